@@ -1,0 +1,33 @@
+"""CPU oracle for the pathpyG lift -> DBGNN hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``pathpyg_b200/`` may import this
+package: only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` do, and only as the checker or as the
+CPU arm that is timed next to the GPU path.
+
+What is restated here (reference paths are relative to ``/root/reference``):
+
+* ``oracle/pyg.py``      torch_geometric 2.7.0 utilities the path calls
+  (``degree``, ``cumsum``, ``coalesce``, ``scatter``, ``add_remaining_self_loops``,
+  ``gcn_norm``) -- third-party, pinned in ``uv.lock:5910-5912``, absent here.
+* ``oracle/lift.py``     ``src/pathpyG/algorithms/lift_order.py`` and
+  ``src/pathpyG/algorithms/temporal.py:17-54``.
+* ``oracle/mom.py``      the four ``MultiOrderModel`` builders
+  (``src/pathpyG/core/multi_order_model.py:83-241,511-554``),
+  ``PathData.append_walks`` (``core/path_data.py:126-159``) and
+  ``generate_bipartite_edge_index`` (``utils/dbgnn.py:10-46``).
+* ``oracle/dbgnn.py``    ``src/pathpyG/nn/dbgnn.py`` + PyG ``GCNConv``.
+
+Pinning status
+--------------
+* lift / indexing (a1-a9): PINNED.  ``tests/golden/make_golden.py`` executes the
+  reference's own ``lift_order.py`` / ``lift_order_temporal`` source (with the
+  four PyG utilities replaced by ``oracle/pyg.py``) in this container and
+  commits the input/output vectors under ``tests/golden/``; the oracle is checked
+  against those and against every known-answer vector in the reference's tests
+  (SURVEY.md section 8c).
+* DBGNN numerics (a10/a11): PARITY UNPINNED.  The reference holds no activation
+  values (``tests/nn/test_dbgnn.py:33-43`` asserts ``out is not None``) and
+  ``GCNConv`` lives in un-vendored PyG, so ``oracle/dbgnn.py`` is a restatement of
+  PyG 2.7.0's published algorithm, not a checked copy.
+"""
