@@ -1,0 +1,161 @@
+/* pathpyg_b200 -- C ABI of the B200 (sm_100a) lift -> DBGNN hot path.
+ *
+ * The reference (pathpy/pathpyG, /root/reference) has no FFI: its hot path is Python calling
+ * torch / torch_geometric ops.  This header is the boundary a maintainer would bind instead
+ * (ctypes stub in INTEGRATION.md): plain device pointers, element counts, a cudaStream_t passed
+ * as void*, int status codes.  No torch types, no hidden global state (last-error text is
+ * thread-local), no host synchronisation except the single count read-back of each
+ * count -> allocate -> fill pair.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with h_ (host);
+ *   - index tensors are int64 and row-major exactly as the reference lays them out
+ *     (edge_index [2,E]: row 0 then row 1; node_sequence [M,k]: row after row);
+ *   - `workspace` comes from the caller (size from the matching *_workspace_bytes); the library
+ *     never allocates device memory, so the caller's allocator (torch's caching allocator) owns it;
+ *   - `stream` is the cudaStream_t the work is enqueued on;
+ *   - return 0 on success; PPG_ERR_INVALID maps to ValueError, everything else to RuntimeError;
+ *     ppg_last_error() holds the message.
+ *
+ * Limits (checked): element counts per call < 2^31; packed sort keys <= 64 bits.
+ */
+#ifndef PATHPYG_B200_H_
+#define PATHPYG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPG_ABI_VERSION 1
+
+#define PPG_OK 0
+#define PPG_ERR_INVALID 1   /* bad argument / id out of range          -> ValueError   */
+#define PPG_ERR_CUDA 2      /* CUDA runtime failure                    -> RuntimeError */
+#define PPG_ERR_WORKSPACE 3 /* workspace too small                     -> RuntimeError */
+#define PPG_ERR_EMPTY 4     /* temporal lift found no pair (reference: torch.cat([]), temporal.py:53) */
+
+/* element types of attribute / weight arrays */
+#define PPG_F32 0
+#define PPG_F64 1
+#define PPG_I64 2
+#define PPG_I32 3
+
+/* aggregate_node_attributes rules (lift_order.py:33-44) */
+#define PPG_PAIR_SRC 0
+#define PPG_PAIR_DST 1
+#define PPG_PAIR_MAX 2
+#define PPG_PAIR_MUL 3
+#define PPG_PAIR_ADD 4
+
+/* coalesce reductions (lift_order.py:139-144 -> torch_geometric.utils.coalesce(reduce=...)) */
+#define PPG_REDUCE_SUM 0
+#define PPG_REDUCE_MEAN 1
+#define PPG_REDUCE_MIN 2
+#define PPG_REDUCE_MAX 3
+
+/* how `t_f <= t_e + delta` is evaluated (torch type promotion at temporal.py:30,43) */
+#define PPG_TIME_I64 0          /* int64 time, integer delta: exact int64 arithmetic            */
+#define PPG_TIME_F64 1          /* float64 time: t_e + (double)(float)delta                     */
+#define PPG_TIME_I64_F32DELTA 2 /* int64 time, float delta: (float)t_f <= (float)t_e + (float)delta */
+
+int ppg_abi_version(void);
+const char* ppg_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a2  lift_order_edge_index            reference: src/pathpyG/algorithms/lift_order.py:48-79
+ *   edge_index [2,E] sorted by row; output [2,E'] with E' = sum_e outdeg(dst e), columns ascending
+ *   in (e, f):  (e, ptr[dst e] + j).
+ * ------------------------------------------------------------------------------------------- */
+size_t ppg_lift_order_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+int ppg_lift_order_count(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, void* workspace,
+                         size_t workspace_bytes, int64_t* h_num_lifted, void* stream);
+int ppg_lift_order_fill(const void* workspace, int64_t num_edges, int64_t num_nodes, int64_t num_lifted,
+                        int64_t* out_index, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3  aggregate_node_attributes        reference: src/pathpyG/algorithms/lift_order.py:10-45
+ *   out[j] = rule(attr[edge_index[0][j]], attr[edge_index[1][j]])
+ * ------------------------------------------------------------------------------------------- */
+int ppg_pair_attributes(const int64_t* edge_index, int64_t num_edges, const void* attr, int64_t num_attr, int dtype,
+                        int rule, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1  lift_order_temporal              reference: src/pathpyG/algorithms/temporal.py:17-54
+ *   edge_index [2,m] and time [m] sorted by time; (e -> f) iff dst(e) == src(f) and
+ *   t_e < t_f <= t_e + delta; output [2,E2] ascending in (e, f).  PPG_ERR_EMPTY if E2 == 0.
+ * ------------------------------------------------------------------------------------------- */
+size_t ppg_lift_temporal_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+int ppg_lift_temporal_count(const int64_t* edge_index, const void* time, int64_t num_edges, int64_t num_nodes,
+                            int time_mode, int64_t delta_i, double delta_f, void* workspace, size_t workspace_bytes,
+                            int64_t* h_num_pairs, void* stream);
+int ppg_lift_temporal_fill(const void* workspace, int64_t num_edges, int64_t num_nodes, int64_t num_pairs,
+                           int64_t* out_index, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4  aggregate_edge_index             reference: src/pathpyG/algorithms/lift_order.py:109-152
+ *   step 1: distinct rows of node_sequence [M,k] in lexicographic order + inverse
+ *           (torch.unique(dim=0, return_inverse=True), :133);
+ *   step 2: map the edge index through a table and coalesce duplicates (PyG coalesce, :139-144),
+ *           output (row, col)-sorted as Graph.__init__ leaves it (core/graph.py:103-105).
+ * ------------------------------------------------------------------------------------------- */
+size_t ppg_rows_minmax_workspace_bytes(int64_t width);
+int ppg_rows_minmax(const int64_t* rows, int64_t num_rows, int64_t width, void* workspace, size_t workspace_bytes,
+                    int64_t* h_col_min, int64_t* h_col_max, int* h_strictly_ascending, void* stream);
+
+/* rows are packed into one key: sum_c (rows[i][c] - h_col_min[c]) << h_col_shift[c], total_bits <= 64 */
+size_t ppg_unique_rows_workspace_bytes(int64_t num_rows, int total_bits);
+int ppg_unique_rows_sort(const int64_t* rows, int64_t num_rows, int64_t width, const int64_t* h_col_min,
+                         const int* h_col_shift, int total_bits, void* workspace, size_t workspace_bytes,
+                         int64_t* out_inverse, int64_t* h_num_unique, void* stream);
+int ppg_unique_rows_gather(const int64_t* rows, int64_t num_rows, int64_t width, const void* workspace, int total_bits,
+                           int64_t num_unique, int64_t* out_rows, void* stream);
+
+/* remap == NULL: edge ids are used as they are; else id -> remap[id] (remap_len entries).
+ * Mapped ids must be < num_nodes (EdgeIndex.validate(), core/graph.py:107) else PPG_ERR_INVALID. */
+size_t ppg_coalesce_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+int ppg_coalesce_sort(const int64_t* edge_index, int64_t num_edges, const int64_t* remap, int64_t remap_len,
+                      int64_t num_nodes, void* workspace, size_t workspace_bytes, int64_t* h_num_out, void* stream);
+/* weights == NULL: unit weights (the reference's torch.ones default, lift_order.py:130-131), out dtype f32 */
+int ppg_coalesce_fill(const void* workspace, int64_t num_edges, int64_t num_nodes, int64_t num_out,
+                      const void* weights, int dtype, int reduce, int64_t* out_edge_index, void* out_weights,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a10/a11  DBGNN.forward building blocks      reference: src/pathpyG/nn/dbgnn.py:32-151 and
+ *   torch_geometric 2.7.0 GCNConv / MessagePassing.propagate (not vendored, see oracle/pyg.py)
+ * ------------------------------------------------------------------------------------------- */
+#define PPG_ACT_NONE 0
+#define PPG_ACT_ELU 1
+
+/* Target-grouped (CSC) view of an edge list [2,E] (stable: original edge order inside a target):
+ * out_colptr [num_targets+1], out_src [E] source node per slot, out_eid [E] original edge per slot. */
+size_t ppg_csc_workspace_bytes(int64_t num_edges, int64_t num_targets);
+int ppg_csc_build(const int64_t* edge_index, int64_t num_edges, int64_t num_sources, int64_t num_targets,
+                  void* workspace, size_t workspace_bytes, int32_t* out_colptr, int32_t* out_src, int32_t* out_eid,
+                  void* stream);
+
+/* gcn_norm with add_remaining_self_loops(fill_value=1): out_val [E] per CSC slot (0 on self-loop
+ * slots), out_self [n] normalised self-loop weight; scratch_dis [n]; edge_weight NULL = ones. */
+int ppg_gcn_norm(const int32_t* colptr, const int32_t* src, const int32_t* eid, const float* edge_weight, int64_t n,
+                 int64_t num_edges, float* scratch_dis, float* out_val, float* out_self, void* stream);
+
+/* out[v] = float(colptr[v+1] - colptr[v]) */
+int ppg_colptr_counts(const int32_t* colptr, int64_t n, float* out, void* stream);
+
+/* out[v,:] = act( sum_{slots i of v} val[i] * X[src[i],:] + self_val[v] * X[v,:] + bias )
+ * val NULL = 1, self_val NULL = no self term, bias NULL = 0;  X [*,F] row-major, out [num_targets,F] */
+int ppg_spmm_csc(const int32_t* colptr, const int32_t* src, const float* val, const float* self_val, const float* X,
+                 int64_t num_targets, int64_t F, const float* bias, int act, float* out, void* stream);
+
+/* out[M,N] = act( A1[M,K1] W1[N,K1]^T + rowscale[M] * (A2[M,K2] W2[N,K2]^T + bias[N]) )
+ * A2 / W2 / bias / rowscale may be NULL (rowscale NULL = 1) */
+int ppg_linear(const float* A1, const float* W1, int64_t M, int64_t K1, const float* A2, const float* W2, int64_t K2,
+               const float* bias, const float* rowscale, int64_t N, int act, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PATHPYG_B200_H_ */

@@ -1,0 +1,15 @@
+from .lift_order import (
+    aggregate_edge_index,
+    aggregate_node_attributes,
+    lift_order_edge_index,
+    lift_order_edge_index_weighted,
+)
+from .temporal import lift_order_temporal
+
+__all__ = [
+    "aggregate_edge_index",
+    "aggregate_node_attributes",
+    "lift_order_edge_index",
+    "lift_order_edge_index_weighted",
+    "lift_order_temporal",
+]

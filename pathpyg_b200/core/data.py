@@ -1,0 +1,199 @@
+"""Minimal stand-ins for ``torch_geometric.data.Data`` and ``torch_geometric.EdgeIndex``.
+
+torch_geometric is a dependency of the reference but not of this package: the hot path only
+needs an attribute container and an edge-index tensor that remembers its sparse size and
+caches its CSR / CSC views.  Only the members the reference's hot path touches are provided
+(``core/graph.py:79-119``, ``core/temporal_graph.py:50-75``, ``core/multi_order_model.py``).
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+
+
+class EdgeIndex(torch.Tensor):
+    """``[2, E]`` int64 tensor with a sparse size; every torch op on it yields a plain tensor."""
+
+    __torch_function__ = torch._C._disabled_torch_function_impl
+
+    @staticmethod
+    def __new__(cls, data, sparse_size=None, sort_order=None, **kwargs):
+        t = torch.as_tensor(data, **kwargs)
+        if isinstance(t, EdgeIndex):
+            t = t.as_subclass(torch.Tensor)
+        if t.dtype != torch.int64:
+            t = t.long()
+        out = torch.Tensor._make_subclass(cls, t)
+        out._sparse_size = tuple(sparse_size) if sparse_size is not None else (None, None)
+        out._sort_order = sort_order
+        out._cache = {}
+        return out
+
+    # ---- PyG-compatible surface
+    def as_tensor(self) -> torch.Tensor:
+        return self.as_subclass(torch.Tensor)
+
+    @property
+    def sparse_size(self):
+        return self._sparse_size
+
+    def get_sparse_size(self, dim: int | None = None):
+        return self._sparse_size if dim is None else self._sparse_size[dim]
+
+    @property
+    def sort_order(self):
+        return self._sort_order
+
+    def validate(self) -> "EdgeIndex":
+        t = self.as_tensor()
+        if t.dim() != 2 or t.size(0) != 2:
+            raise ValueError(f"'EdgeIndex' needs to have a shape of [2, *] (got {list(t.shape)})")
+        if t.numel() > 0:
+            lo, hi = int(t.min()), int(t.max())
+            if lo < 0:
+                raise ValueError(f"'EdgeIndex' contains negative indices (got {lo})")
+            n0, n1 = self._sparse_size
+            if n0 is not None and int(t[0].max()) >= n0:
+                raise ValueError(f"'EdgeIndex' contains larger indices than its number of rows (got {int(t[0].max())}, but expected values smaller than {n0})")
+            if n1 is not None and int(t[1].max()) >= n1:
+                raise ValueError(f"'EdgeIndex' contains larger indices than its number of columns (got {int(t[1].max())}, but expected values smaller than {n1})")
+        return self
+
+    def sort_by(self, sort_order: str = "row", stable: bool = True):
+        """Returns ``(sorted EdgeIndex, permutation)``; the permutation is None if already sorted."""
+        if self._sort_order == sort_order:
+            return self, None
+        t = self.as_tensor()
+        key = t[0] if sort_order == "row" else t[1]
+        if key.numel() < 2 or bool((key[1:] >= key[:-1]).all()):
+            out = EdgeIndex(t, sparse_size=self._sparse_size, sort_order=sort_order)
+            return out, None
+        perm = torch.sort(key, stable=True).indices
+        return EdgeIndex(t[:, perm], sparse_size=self._sparse_size, sort_order=sort_order), perm
+
+    def _ptr(self, ids: torch.Tensor, n: int) -> torch.Tensor:
+        counts = torch.bincount(ids, minlength=n)
+        ptr = counts.new_zeros(n + 1)
+        torch.cumsum(counts, 0, out=ptr[1:])
+        return ptr
+
+    def get_csr(self):
+        """((rowptr, col), perm) -- requires / establishes row order."""
+        if "csr" not in self._cache:
+            t = self.as_tensor()
+            perm = None
+            if self._sort_order != "row":
+                perm = torch.sort(t[0], stable=True).indices
+                t = t[:, perm]
+            n = self._sparse_size[0] if self._sparse_size[0] is not None else (int(t[0].max()) + 1 if t.numel() else 0)
+            self._cache["csr"] = ((self._ptr(t[0], n), t[1]), perm)
+        return self._cache["csr"]
+
+    def get_csc(self):
+        """((colptr, row), perm)."""
+        if "csc" not in self._cache:
+            t = self.as_tensor()
+            perm = None
+            if self._sort_order != "col":
+                perm = torch.sort(t[1], stable=True).indices
+                t = t[:, perm]
+            n = self._sparse_size[1] if self._sparse_size[1] is not None else (int(t[1].max()) + 1 if t.numel() else 0)
+            self._cache["csc"] = ((self._ptr(t[1], n), t[0]), perm)
+        return self._cache["csc"]
+
+    def to(self, *args, **kwargs):  # keep the wrapper across device moves
+        return EdgeIndex(self.as_tensor().to(*args, **kwargs), sparse_size=self._sparse_size, sort_order=self._sort_order)
+
+    def __repr__(self):
+        return f"EdgeIndex({self.as_tensor().tolist()}, sparse_size={self._sparse_size})"
+
+    def __deepcopy__(self, memo):
+        return EdgeIndex(self.as_tensor().clone(), sparse_size=self._sparse_size, sort_order=self._sort_order)
+
+
+class Data:
+    """Attribute bag with the few ``torch_geometric.data.Data`` methods the path uses."""
+
+    def __init__(self, **kwargs):
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    # ---- mapping protocol
+    def __contains__(self, key) -> bool:
+        return key in self.__dict__ and self.__dict__[key] is not None
+
+    def __getitem__(self, key):
+        return self.__dict__[key]
+
+    def __setitem__(self, key, value):
+        self.__dict__[key] = value
+
+    def __getattr__(self, key):
+        # like PyG: unknown attributes read as None
+        if key.startswith("__"):
+            raise AttributeError(key)
+        return None
+
+    def keys(self):
+        return [k for k, v in self.__dict__.items() if v is not None]
+
+    def to_dict(self):
+        return {k: self.__dict__[k] for k in self.keys()}
+
+    # ---- sizes
+    @property
+    def num_edges(self) -> int:
+        ei = self.__dict__.get("edge_index")
+        return 0 if ei is None else int(ei.size(1))
+
+    def edge_attrs(self):
+        """Keys holding one entry per edge (PyG: name contains 'edge', or leading dim == num_edges)."""
+        m = self.num_edges
+        out = []
+        for k, v in self.__dict__.items():
+            if not isinstance(v, torch.Tensor):
+                continue
+            if k == "edge_index" or (k.startswith("edge_") and v.dim() >= 1 and v.size(0) == m):
+                out.append(k)
+            elif k == "time" and v.dim() >= 1 and v.size(0) == m:
+                out.append(k)
+        return out
+
+    def node_attrs(self):
+        n = self.__dict__.get("num_nodes")
+        return [k for k, v in self.__dict__.items()
+                if isinstance(v, torch.Tensor) and k.startswith("node_") and v.dim() >= 1 and v.size(0) == n]
+
+    # ---- time order (TemporalGraph input, multi_order_model.py:148-151)
+    def is_sorted_by_time(self) -> bool:
+        t = self.__dict__.get("time")
+        return t is None or t.numel() < 2 or bool((t[1:] >= t[:-1]).all())
+
+    def sort_by_time(self) -> "Data":
+        perm = torch.sort(self.time, stable=True).indices
+        out = copy.copy(self)
+        for k in self.edge_attrs():
+            v = self.__dict__[k]
+            out.__dict__[k] = v[:, perm] if k == "edge_index" else v[perm]
+        return out
+
+    # ---- device
+    def to(self, device, non_blocking: bool = False) -> "Data":
+        out = copy.copy(self)
+        for k, v in self.__dict__.items():
+            if isinstance(v, EdgeIndex):
+                out.__dict__[k] = v.to(device)
+            elif isinstance(v, torch.Tensor):
+                out.__dict__[k] = v.to(device, non_blocking=non_blocking)
+        return out
+
+    def clone(self) -> "Data":
+        return copy.deepcopy(self)
+
+    def __repr__(self):
+        parts = []
+        for k in self.keys():
+            v = self.__dict__[k]
+            parts.append(f"{k}={list(v.shape)}" if isinstance(v, torch.Tensor) else f"{k}={v}")
+        return "Data(" + ", ".join(parts) + ")"

@@ -1,0 +1,18 @@
+// ABI version and thread-local last-error text.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace ppg {
+static thread_local char g_last_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+}  // namespace ppg
+
+extern "C" int ppg_abi_version(void) { return PPG_ABI_VERSION; }
+extern "C" const char* ppg_last_error(void) { return ppg::g_last_error; }

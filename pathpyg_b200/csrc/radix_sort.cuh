@@ -1,0 +1,281 @@
+// Stable least-significant-digit radix sort, one sweep per 8-bit digit ("onesweep").
+//
+// HBM traffic for n (key, payload) pairs over P digit passes:
+//   histogram pass : read keys once                      (sizeof(Key) * n)
+//   each digit pass: read pairs once, write pairs once   (2 * (sizeof(Key) + 4) * n)
+// The per-pass global scatter offsets come from (a) the up-front histogram of all P digits and
+// (b) a decoupled look-back chain over the per-tile digit counts, so no pass reads its keys twice.
+// Only the significant key bits [0, end_bit) are sorted: P = ceil(end_bit / 8).
+//
+// Within a tile the ranking is stable: a warp ranks its 32*ITEMS keys digit by digit with
+// match.any (lanes holding the same digit elect a leader that bumps the warp's counter in shared
+// memory), the tile is reordered through shared memory, and every digit's run is written out as
+// one contiguous (coalesced) segment.
+//
+// The payload is an optional u32 per key; the first pass can synthesise it as the element index
+// (IOTA) so that an index permutation costs no read.
+#pragma once
+#include "common.cuh"
+
+namespace ppg {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortBlock = 256;  // == kRadix: thread d owns digit d in the per-digit phases
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortBlock * kSortItems;
+constexpr int kMaxPasses = 8;
+
+__host__ __device__ inline int64_t sort_num_tiles(int64_t n) { return n > 0 ? ceil_div(n, kSortTile) : 1; }
+inline int sort_num_passes(int end_bit) { return end_bit <= 0 ? 1 : static_cast<int>(ceil_div(end_bit, kRadixBits)); }
+
+// zero-initialised words a sort needs: [P*256 histogram][P tile counters (u64 each)][tiles*256 look-back words]
+inline size_t sort_state_words(int64_t n, int end_bit) {
+  const size_t P = static_cast<size_t>(sort_num_passes(end_bit));
+  return P * kRadix + P + static_cast<size_t>(sort_num_tiles(n)) * kRadix;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(256)
+radix_histogram_kernel(const KeyT* __restrict__ keys, int64_t n, int num_passes, unsigned long long* __restrict__ ghist) {
+  __shared__ unsigned s_hist[kMaxPasses * kRadix];
+  for (int i = threadIdx.x; i < num_passes * kRadix; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const KeyT k = ld_stream(keys + i);
+    for (int p = 0; p < num_passes; ++p) {
+      const unsigned d = static_cast<unsigned>(k >> (p * kRadixBits)) & (kRadix - 1);
+      // high digits of small-range keys are often identical across a warp: one atomic instead of 32
+      const unsigned active = __activemask();
+      const unsigned d0 = __shfl_sync(active, d, __ffs(active) - 1);
+      if (__all_sync(active, d == d0)) {
+        if (lane_id() == static_cast<unsigned>(__ffs(active) - 1)) atomicAdd(&s_hist[p * kRadix + d], __popc(active));
+      } else {
+        atomicAdd(&s_hist[p * kRadix + d], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < num_passes * kRadix; i += blockDim.x) {
+    const unsigned c = s_hist[i];
+    if (c) atomicAdd(&ghist[i], static_cast<unsigned long long>(c));
+  }
+}
+
+template <typename KeyT, bool HAS_VALUES, bool IOTA>
+__global__ void __launch_bounds__(kSortBlock)
+onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
+                     const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int64_t n, int shift,
+                     const unsigned long long* __restrict__ ghist,  // this pass: 256 digit counts
+                     unsigned* __restrict__ tile_counter, unsigned long long* __restrict__ state,
+                     unsigned code_partial, unsigned code_inclusive) {
+  constexpr int NW = kSortBlock / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + kSortTile);
+  uint32_t* s_whist = s_vals + (HAS_VALUES ? kSortTile : 0);                // [NW][256] per-warp digit counts
+  uint32_t* s_binstart = s_whist + NW * kRadix;                             // [256] first slot of a digit in the tile
+  long long* s_gbase = reinterpret_cast<long long*>(s_binstart + kRadix);   // [256] global slot of tile slot 0 of a digit
+  __shared__ unsigned s_tile;
+  __shared__ unsigned long long s_scan[2 * NW];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const unsigned lane = lane_id();
+
+  for (int i = tid; i < NW * kRadix; i += kSortBlock) s_whist[i] = 0;
+  if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+  __syncthreads();
+  const unsigned tile = s_tile;
+  const int64_t tile_base = static_cast<int64_t>(tile) * kSortTile;
+  const int64_t warp_base = tile_base + static_cast<int64_t>(warp) * (32 * kSortItems);
+  const int64_t remaining = n - tile_base;
+  const int valid_in_tile = remaining >= kSortTile ? kSortTile : static_cast<int>(remaining);
+
+  // ---- load (warp-striped => coalesced; element order inside a warp is (item, lane))
+  KeyT key[kSortItems];
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const int64_t idx = warp_base + i * 32 + lane;
+    key[i] = idx < n ? ld_stream(keys_in + idx) : static_cast<KeyT>(~static_cast<KeyT>(0));
+  }
+
+  // ---- stable rank inside the warp, digit counts per warp
+  uint32_t rank[kSortItems];
+  uint32_t* my_hist = s_whist + warp * kRadix;
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
+    const unsigned peers = __match_any_sync(kFullMask, d);
+    const int leader = 31 - __clz(peers);
+    uint32_t before = 0;
+    if (static_cast<int>(lane) == leader) {
+      before = my_hist[d];
+      my_hist[d] = before + __popc(peers);
+    }
+    before = __shfl_sync(kFullMask, before, leader);
+    rank[i] = before + __popc(peers & lanemask_lt());
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // ---- per digit (thread d): exclusive over warps, tile count, publish, look back
+  unsigned long long count = 0;
+  {
+    uint32_t sum = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const uint32_t t = s_whist[w * kRadix + tid];
+      s_whist[w * kRadix + tid] = sum;
+      sum += t;
+    }
+    // out-of-range slots of the last tile were given all-ones keys: they sit at the very end of the
+    // top digit's run (stable order), so dropping them from that count leaves every valid slot intact
+    if (tid == kRadix - 1) sum -= static_cast<uint32_t>(kSortTile - valid_in_tile);
+    count = sum;
+  }
+  unsigned long long* my_state = state + static_cast<size_t>(tile) * kRadix + tid;
+  unsigned long long prev = 0;  // keys with this digit in earlier tiles
+  if (tile == 0) {
+    state_store(my_state, code_inclusive, count);
+  } else {
+    state_store(my_state, code_partial, count);
+    int64_t q = static_cast<int64_t>(tile) - 1;
+    while (true) {
+      const unsigned long long w = state_load(state + static_cast<size_t>(q) * kRadix + tid);
+      const unsigned code = static_cast<unsigned>(w >> 56);
+      if (code == code_inclusive) {
+        prev += w & kStateValueMask;
+        break;
+      }
+      if (code == code_partial) {
+        prev += w & kStateValueMask;
+        --q;  // tile 0 always publishes an inclusive word, so q never passes 0
+      }
+    }
+    state_store(my_state, code_inclusive, prev + count);
+  }
+
+  // ---- block exclusive scans over the 256 digits: slot of the digit in the tile, and in the output
+  unsigned long long g = ghist[tid];
+  {
+    unsigned long long a = warp_inclusive_sum(count);
+    unsigned long long b = warp_inclusive_sum(g);
+    if (lane == 31) {
+      s_scan[warp] = a;
+      s_scan[NW + warp] = b;
+    }
+    __syncthreads();
+    unsigned long long oa = 0, ob = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      if (w < warp) {
+        oa += s_scan[w];
+        ob += s_scan[NW + w];
+      }
+    }
+    const unsigned long long bin_start = oa + a - count;
+    const unsigned long long out_start = ob + b - g;
+    s_binstart[tid] = static_cast<uint32_t>(bin_start);
+    s_gbase[tid] = static_cast<long long>(out_start + prev) - static_cast<long long>(bin_start);
+  }
+  __syncthreads();
+
+  // ---- reorder the tile through shared memory
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
+    const uint32_t pos = s_binstart[d] + my_hist[d] + rank[i];
+    rank[i] = pos;
+    s_keys[pos] = key[i];
+  }
+  if (HAS_VALUES) {
+#pragma unroll
+    for (int i = 0; i < kSortItems; ++i) {
+      const int64_t idx = warp_base + i * 32 + lane;
+      uint32_t v = 0;
+      if (idx < n) v = IOTA ? static_cast<uint32_t>(idx) : ld_stream(vals_in + idx);
+      s_vals[rank[i]] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- write every digit's run to its global segment
+  for (int j = tid; j < valid_in_tile; j += kSortBlock) {
+    const KeyT k = s_keys[j];
+    const unsigned d = static_cast<unsigned>(k >> shift) & (kRadix - 1);
+    const long long dst = s_gbase[d] + j;
+    keys_out[dst] = k;
+    if (HAS_VALUES) vals_out[dst] = s_vals[j];
+  }
+}
+
+template <typename KeyT, bool HAS_VALUES>
+constexpr size_t onesweep_smem_bytes() {
+  return static_cast<size_t>(kSortTile) * sizeof(KeyT) + (HAS_VALUES ? kSortTile * sizeof(uint32_t) : 0) +
+         (kSortBlock / 32) * kRadix * sizeof(uint32_t) + kRadix * sizeof(uint32_t) + kRadix * sizeof(long long);
+}
+
+template <typename KeyT, bool HAS_VALUES, bool IOTA>
+inline int launch_onesweep_pass(const KeyT* kin, KeyT* kout, const uint32_t* vin, uint32_t* vout, int64_t n, int shift,
+                                const unsigned long long* ghist, unsigned* counter, unsigned long long* state,
+                                unsigned pass, cudaStream_t stream) {
+  auto kern = onesweep_pass_kernel<KeyT, HAS_VALUES, IOTA>;
+  constexpr size_t smem = onesweep_smem_bytes<KeyT, HAS_VALUES>();
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    PPG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  kern<<<static_cast<unsigned>(sort_num_tiles(n)), kSortBlock, smem, stream>>>(
+      kin, kout, vin, vout, n, shift, ghist, counter, state, 2 * pass + 1, 2 * pass + 2);
+  PPG_CUDA_TRY(cudaGetLastError());
+  return PPG_OK;
+}
+
+// Sorts the significant bits [0, end_bit) of keys_a (n elements) with an optional u32 payload.
+//   keys_a/vals_a : input, clobbered (used as the ping buffer)     keys_b/vals_b : pong buffer
+//   vals_a == nullptr with has_values => payload synthesised as the element index on the first pass
+//   zeroed_ws     : sort_state_words(n, end_bit) words, zero on entry
+//   *in_b         : 1 if the sorted result ended in the *_b buffers
+template <typename KeyT>
+inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* vals_b, bool has_values,
+                            bool iota_payload, int64_t n, int end_bit, unsigned long long* zeroed_ws, int* in_b,
+                            cudaStream_t stream) {
+  const int P = sort_num_passes(end_bit);
+  PPG_REQUIRE(P <= kMaxPasses, PPG_ERR_INVALID, "radix sort: %d key bits need more than %d passes", end_bit, kMaxPasses);
+  PPG_REQUIRE(n < (1ll << 31), PPG_ERR_INVALID, "radix sort: %lld elements exceed the 2^31 limit", (long long)n);
+  unsigned long long* ghist = zeroed_ws;
+  unsigned long long* counters = zeroed_ws + static_cast<size_t>(P) * kRadix;
+  unsigned long long* state = counters + P;
+  *in_b = 0;
+  if (n == 0) return PPG_OK;
+
+  radix_histogram_kernel<KeyT><<<grid_for(n, 256 * 8, kNumSMsB200 * 8), 256, 0, stream>>>(keys_a, n, P, ghist);
+  PPG_CUDA_TRY(cudaGetLastError());
+
+  KeyT* kin = keys_a;
+  KeyT* kout = keys_b;
+  uint32_t* vin = vals_a;
+  uint32_t* vout = vals_b;
+  for (int p = 0; p < P; ++p) {
+    unsigned* counter = reinterpret_cast<unsigned*>(counters + p);
+    const unsigned long long* h = ghist + static_cast<size_t>(p) * kRadix;
+    const int shift = p * kRadixBits;
+    if (!has_values) {
+      PPG_TRY((launch_onesweep_pass<KeyT, false, false>(kin, kout, nullptr, nullptr, n, shift, h, counter, state, p, stream)));
+    } else if (p == 0 && iota_payload) {
+      PPG_TRY((launch_onesweep_pass<KeyT, true, true>(kin, kout, nullptr, vout, n, shift, h, counter, state, p, stream)));
+    } else {
+      PPG_TRY((launch_onesweep_pass<KeyT, true, false>(kin, kout, vin, vout, n, shift, h, counter, state, p, stream)));
+    }
+    KeyT* tk = kin; kin = kout; kout = tk;
+    uint32_t* tv = (p == 0 && iota_payload) ? vals_a : vin;
+    vin = vout; vout = tv;
+    *in_b ^= 1;
+  }
+  return PPG_OK;
+}
+
+}  // namespace ppg

@@ -1,0 +1,316 @@
+"""Tensor-level entry points: torch owns device memory and the stream, the C ABI does the work.
+
+Every function here takes CUDA tensors and returns freshly allocated CUDA tensors.  Host
+tensors are handled one level up (``pathpyg_b200.algorithms``), which stages them to the device
+and copies results back, so that the device follows the input as it does in the reference.
+There is no CPU implementation: without a CUDA device or without the built library these raise.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DTYPE_CODES = {torch.float32: _lib.F32, torch.float64: _lib.F64, torch.int64: _lib.I64, torch.int32: _lib.I32}
+
+
+def _ptr(t: torch.Tensor | None) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream(device: torch.device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("pathpyg_b200.ops works on CUDA tensors only (no CPU fallback); got a CPU tensor")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} and {t.device}")
+    return dev
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _edge_index_arg(edge_index: torch.Tensor) -> torch.Tensor:
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError(f"edge_index must have shape [2, E], got {tuple(edge_index.shape)}")
+    if edge_index.dtype != torch.int64:
+        edge_index = edge_index.long()
+    # .as_subclass drops the EdgeIndex wrapper without copying
+    return edge_index.as_subclass(torch.Tensor).contiguous()
+
+
+# --------------------------------------------------------------------------------------- a2
+def lift_order_edge_index(edge_index: torch.Tensor, num_nodes: int) -> torch.Tensor:
+    lib = _lib.load()
+    ei = _edge_index_arg(edge_index)
+    dev = _require_cuda(ei)
+    E = ei.size(1)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_lift_order_workspace_bytes(E, num_nodes), dev)
+        total = ctypes.c_int64(0)
+        _lib.check(lib.ppg_lift_order_count(_ptr(ei), E, num_nodes, _ptr(ws), ws.numel(), ctypes.byref(total), _stream(dev)))
+        out = torch.empty((2, total.value), dtype=torch.int64, device=dev)
+        _lib.check(lib.ppg_lift_order_fill(_ptr(ws), E, num_nodes, total.value, _ptr(out), _stream(dev)))
+    return out
+
+
+# --------------------------------------------------------------------------------------- a3
+def pair_attributes(edge_index: torch.Tensor, node_attribute: torch.Tensor, aggr: str) -> torch.Tensor:
+    if aggr not in _lib.PAIR_RULES:
+        raise ValueError(f"Unknown aggregation method {aggr}")
+    lib = _lib.load()
+    ei = _edge_index_arg(edge_index)
+    dev = _require_cuda(ei, node_attribute)
+    attr = node_attribute.contiguous()
+    if attr.dim() != 1 or attr.dtype not in _DTYPE_CODES:
+        raise TypeError(f"node_attribute must be a 1-D float32/float64/int64/int32 tensor, got {attr.dtype} {tuple(attr.shape)}")
+    E = ei.size(1)
+    out = torch.empty(E, dtype=attr.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_pair_attributes(_ptr(ei), E, _ptr(attr), attr.numel(), _DTYPE_CODES[attr.dtype],
+                                           _lib.PAIR_RULES[aggr], _ptr(out), _stream(dev)))
+    return out
+
+
+# --------------------------------------------------------------------------------------- a1
+def _time_mode(time: torch.Tensor, delta):
+    """Mirror torch's promotion of ``timestamps <= t + torch.tensor(delta)`` (temporal.py:30,43)."""
+    if isinstance(delta, torch.Tensor):
+        delta = delta.item()
+    if time.dtype == torch.int64:
+        if isinstance(delta, int):
+            return time, _lib.TIME_I64, int(delta), 0.0
+        # 0-dim float32 delta: both sides of the comparison are evaluated in float32
+        return time, _lib.TIME_I64_F32DELTA, 0, float(torch.tensor(float(delta), dtype=torch.float32))
+    if time.dtype == torch.float64:
+        d = float(delta) if isinstance(delta, int) else float(torch.tensor(float(delta), dtype=torch.float32))
+        return time, _lib.TIME_F64, 0, d
+    if time.dtype in (torch.int32, torch.int16, torch.int8, torch.uint8):
+        return _time_mode(time.long(), delta)
+    raise TypeError(f"time must be int64 or float64 (got {time.dtype}); float32 time stamps are not supported")
+
+
+def lift_order_temporal(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int) -> torch.Tensor:
+    lib = _lib.load()
+    ei = _edge_index_arg(edge_index)
+    dev = _require_cuda(ei, time)
+    time, mode, delta_i, delta_f = _time_mode(time.contiguous(), delta)
+    m = ei.size(1)
+    if time.numel() != m:
+        raise ValueError("time and edge_index disagree on the number of edges")
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_lift_temporal_workspace_bytes(m, num_nodes), dev)
+        total = ctypes.c_int64(0)
+        _lib.check(lib.ppg_lift_temporal_count(_ptr(ei), _ptr(time), m, num_nodes, mode, delta_i, delta_f, _ptr(ws),
+                                               ws.numel(), ctypes.byref(total), _stream(dev)))
+        out = torch.empty((2, total.value), dtype=torch.int64, device=dev)
+        _lib.check(lib.ppg_lift_temporal_fill(_ptr(ws), m, num_nodes, total.value, _ptr(out), _stream(dev)))
+    return out
+
+
+# --------------------------------------------------------------------------------------- a4
+def rows_minmax(rows: torch.Tensor):
+    lib = _lib.load()
+    dev = _require_cuda(rows)
+    M, k = rows.shape
+    mins = (ctypes.c_int64 * k)()
+    maxs = (ctypes.c_int64 * k)()
+    asc = ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_rows_minmax_workspace_bytes(k), dev)
+        _lib.check(lib.ppg_rows_minmax(_ptr(rows), M, k, _ptr(ws), ws.numel(), mins, maxs, ctypes.byref(asc), _stream(dev)))
+    return list(mins), list(maxs), bool(asc.value)
+
+
+def _unique_stage(rows: torch.Tensor, mins, bits):
+    """One packed-key sort: returns (inverse, num_unique, workspace, total_bits)."""
+    lib = _lib.load()
+    dev = rows.device
+    M, k = rows.shape
+    total_bits = sum(bits)
+    shifts, acc = [], total_bits
+    for b in bits:  # column 0 is the most significant field
+        acc -= b
+        shifts.append(acc)
+    inverse = torch.empty(M, dtype=torch.int64, device=dev)
+    n = ctypes.c_int64(0)
+    ws = _workspace(lib.ppg_unique_rows_workspace_bytes(M, total_bits), dev)
+    _lib.check(lib.ppg_unique_rows_sort(_ptr(rows), M, k, (ctypes.c_int64 * k)(*mins), (ctypes.c_int * k)(*shifts),
+                                        total_bits, _ptr(ws), ws.numel(), _ptr(inverse), ctypes.byref(n), _stream(dev)))
+    return inverse, n.value, ws, total_bits
+
+
+def unique_rows(node_sequence: torch.Tensor):
+    """Distinct rows in lexicographic order and the inverse index (``torch.unique(dim=0, return_inverse=True)``)."""
+    lib = _lib.load()
+    rows = node_sequence.as_subclass(torch.Tensor)
+    if rows.dim() != 2:
+        raise ValueError(f"node_sequence must be 2-D, got shape {tuple(rows.shape)}")
+    if rows.dtype != torch.int64:
+        rows = rows.long()
+    rows = rows.contiguous()
+    dev = _require_cuda(rows)
+    M, k = rows.shape
+    if M == 0 or k == 0:
+        return rows.new_empty((0 if M == 0 else 1, k)), torch.zeros(M, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        mins, maxs, ascending = rows_minmax(rows)
+        if ascending:  # already the sorted distinct rows (e.g. arange(N)[:, None] of layer 1)
+            return rows.clone(), torch.arange(M, dtype=torch.int64, device=dev)
+        bits = [int(hi - lo).bit_length() for lo, hi in zip(mins, maxs)]
+        if any(b > 63 for b in bits):
+            raise ValueError("node_sequence value range exceeds 63 bits")
+        cur, cur_mins, cur_bits = rows, mins, bits
+        while sum(cur_bits) > 64 or cur.size(1) > 64:
+            # rank refinement: the rank of a row is the rank of (rank of its leading columns, the rest)
+            take, acc = 0, 0
+            while take < min(len(cur_bits), 64) and acc + cur_bits[take] <= 64:
+                acc += cur_bits[take]
+                take += 1
+            head_inv, head_n, _, _ = _unique_stage(cur[:, :take].contiguous(), cur_mins[:take], cur_bits[:take])
+            cur = torch.cat([head_inv.unsqueeze(1), cur[:, take:]], dim=1)
+            cur_mins = [0] + cur_mins[take:]
+            cur_bits = [max(head_n - 1, 0).bit_length()] + cur_bits[take:]
+        inverse, n, ws, total_bits = _unique_stage(cur, cur_mins, cur_bits)
+        unique = torch.empty((n, k), dtype=torch.int64, device=dev)
+        # `rep` (first occurrence of every distinct row) indexes the ORIGINAL rows in every stage
+        _lib.check(lib.ppg_unique_rows_gather(_ptr(rows), M, k, _ptr(ws), total_bits, n, _ptr(unique), _stream(dev)))
+    return unique, inverse
+
+
+def coalesce(edge_index: torch.Tensor, remap: torch.Tensor | None, num_nodes: int,
+             edge_weight: torch.Tensor | None, reduce: str = "sum"):
+    """Map edge ids through ``remap`` (or not), merge duplicate (row, col) pairs reducing their weights;
+    result is (row, col)-sorted.  ``edge_weight=None`` means unit float32 weights."""
+    if reduce not in _lib.REDUCTIONS:
+        raise ValueError(f"Unknown reduce {reduce}")
+    lib = _lib.load()
+    ei = _edge_index_arg(edge_index)
+    dev = _require_cuda(ei, remap, edge_weight)
+    E = ei.size(1)
+    if remap is not None:
+        remap = remap.as_subclass(torch.Tensor).contiguous()
+        if remap.dtype != torch.int64:
+            remap = remap.long()
+    if edge_weight is not None:
+        edge_weight = edge_weight.contiguous()
+        if edge_weight.dim() != 1 or edge_weight.numel() != E:
+            raise ValueError("edge_weight must be 1-D with one entry per edge")
+        if edge_weight.dtype not in _DTYPE_CODES:
+            raise TypeError(f"edge_weight dtype {edge_weight.dtype} not supported (float32/float64/int64/int32)")
+    w_dtype = torch.float32 if edge_weight is None else edge_weight.dtype
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_coalesce_workspace_bytes(E, num_nodes), dev)
+        n_out = ctypes.c_int64(0)
+        _lib.check(lib.ppg_coalesce_sort(_ptr(ei), E, _ptr(remap), 0 if remap is None else remap.numel(), num_nodes,
+                                         _ptr(ws), ws.numel(), ctypes.byref(n_out), _stream(dev)))
+        out_ei = torch.empty((2, n_out.value), dtype=torch.int64, device=dev)
+        out_w = torch.empty(n_out.value, dtype=w_dtype, device=dev)
+        _lib.check(lib.ppg_coalesce_fill(_ptr(ws), E, num_nodes, n_out.value, _ptr(edge_weight), _DTYPE_CODES[w_dtype],
+                                         _lib.REDUCTIONS[reduce], _ptr(out_ei), _ptr(out_w), _stream(dev)))
+    return out_ei, out_w
+
+
+# --------------------------------------------------------------------------------------- a10 / a11
+class TargetGroupedEdges:
+    """CSC view of an edge list: incoming edges of every target node, original order inside a target."""
+
+    __slots__ = ("colptr", "src", "eid", "num_sources", "num_targets", "val", "self_val")
+
+    def __init__(self, colptr, src, eid, num_sources, num_targets):
+        self.colptr, self.src, self.eid = colptr, src, eid
+        self.num_sources, self.num_targets = num_sources, num_targets
+        self.val = None       # per-slot coefficient (None = 1)
+        self.self_val = None  # per-target coefficient of the node's own row (None = no self term)
+
+
+def csc_build(edge_index: torch.Tensor, num_sources: int, num_targets: int) -> TargetGroupedEdges:
+    lib = _lib.load()
+    ei = _edge_index_arg(edge_index)
+    dev = _require_cuda(ei)
+    E = ei.size(1)
+    colptr = torch.empty(num_targets + 1, dtype=torch.int32, device=dev)
+    src = torch.empty(E, dtype=torch.int32, device=dev)
+    eid = torch.empty(E, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_csc_workspace_bytes(E, num_targets), dev)
+        _lib.check(lib.ppg_csc_build(_ptr(ei), E, num_sources, num_targets, _ptr(ws), ws.numel(), _ptr(colptr), _ptr(src),
+                                     _ptr(eid), _stream(dev)))
+    return TargetGroupedEdges(colptr, src, eid, num_sources, num_targets)
+
+
+def gcn_prepare(edge_index: torch.Tensor, edge_weight: torch.Tensor | None, num_nodes: int) -> TargetGroupedEdges:
+    """CSC view + symmetric GCN normalisation with remaining self-loops (PyG gcn_norm)."""
+    lib = _lib.load()
+    g = csc_build(edge_index, num_nodes, num_nodes)
+    dev = g.colptr.device
+    E = g.src.numel()
+    if edge_weight is not None:
+        edge_weight = edge_weight.contiguous().float()
+    dis = torch.empty(num_nodes, dtype=torch.float32, device=dev)
+    g.val = torch.empty(E, dtype=torch.float32, device=dev)
+    g.self_val = torch.empty(num_nodes, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_gcn_norm(_ptr(g.colptr), _ptr(g.src), _ptr(g.eid), _ptr(edge_weight), num_nodes, E, _ptr(dis),
+                                    _ptr(g.val), _ptr(g.self_val), _stream(dev)))
+    return g
+
+
+def colptr_counts(g: TargetGroupedEdges) -> torch.Tensor:
+    lib = _lib.load()
+    dev = g.colptr.device
+    out = torch.empty(g.num_targets, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_colptr_counts(_ptr(g.colptr), g.num_targets, _ptr(out), _stream(dev)))
+    return out
+
+
+def spmm_csc(g: TargetGroupedEdges, x: torch.Tensor, bias: torch.Tensor | None = None, act: int = _lib.ACT_NONE) -> torch.Tensor:
+    lib = _lib.load()
+    dev = _require_cuda(x, g.colptr)
+    x = x.contiguous()
+    if x.dtype != torch.float32 or x.dim() != 2:
+        raise TypeError("spmm_csc expects a 2-D float32 feature matrix")
+    if x.size(0) < g.num_sources:
+        raise ValueError(f"feature matrix has {x.size(0)} rows but the graph has {g.num_sources} source nodes")
+    F = x.size(1)
+    out = torch.empty((g.num_targets, F), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_spmm_csc(_ptr(g.colptr), _ptr(g.src), _ptr(g.val), _ptr(g.self_val), _ptr(x), g.num_targets, F,
+                                    _ptr(bias), act, _ptr(out), _stream(dev)))
+    return out
+
+
+def linear(a1: torch.Tensor, w1: torch.Tensor, bias: torch.Tensor | None = None, act: int = _lib.ACT_NONE,
+           a2: torch.Tensor | None = None, w2: torch.Tensor | None = None, rowscale: torch.Tensor | None = None) -> torch.Tensor:
+    """act(a1 @ w1.T + rowscale[:, None] * (a2 @ w2.T + bias))."""
+    lib = _lib.load()
+    dev = _require_cuda(a1, w1, a2, w2, bias, rowscale)
+    a1, w1 = a1.contiguous(), w1.contiguous()
+    M, K1 = a1.shape
+    N = w1.size(0)
+    if w1.size(1) != K1:
+        raise ValueError(f"shape mismatch: {tuple(a1.shape)} @ {tuple(w1.shape)}.T")
+    K2 = 0
+    if a2 is not None:
+        a2, w2 = a2.contiguous(), w2.contiguous()
+        K2 = a2.size(1)
+        if a2.size(0) != M or w2.shape != (N, K2):
+            raise ValueError("shape mismatch in the second operand pair")
+    out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_linear(_ptr(a1), _ptr(w1), M, K1, _ptr(a2), _ptr(w2), K2, _ptr(bias), _ptr(rowscale), N, act,
+                                  _ptr(out), _stream(dev)))
+    return out

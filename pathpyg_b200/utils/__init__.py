@@ -1,0 +1,3 @@
+from .dbgnn import generate_bipartite_edge_index
+
+__all__ = ["generate_bipartite_edge_index"]

@@ -1,0 +1,101 @@
+"""DBGNN forward on the GPU vs the oracle restatement: |a - b| <= 1e-5 * max(1, |b|) per element (north_star: 1e-5 rel fp32)."""
+import pytest
+import torch
+
+import pathpyg_b200 as pp
+from oracle import dbgnn as odbgnn
+from oracle import mom, pyg
+from pathpyg_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def close(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return bool(((a - b).abs() <= RTOL * b.abs().clamp(min=1.0)).all())
+
+
+def test_gcn_norm_and_spmm_vs_oracle(cuda):
+    g = torch.Generator().manual_seed(0)
+    n, e, F = 300, 2500, 64
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei[:, :40] = torch.arange(40).repeat(2, 1)  # explicit self-loops keep their weight
+    key = torch.unique(ei[0] * n + ei[1])       # De Bruijn layers are coalesced: no duplicate edges
+    ei = torch.stack([key // n, key % n])
+    w = torch.randint(1, 6, (ei.size(1),), generator=g).float()
+    x = torch.randn(n, F, generator=g)
+    want_ei, want_norm = pyg.gcn_norm(ei, w, n)
+    want = torch.zeros(n, F, dtype=torch.float64).index_add_(0, want_ei[1], want_norm.double().unsqueeze(1) * x.double()[want_ei[0]])
+    graph = ops.gcn_prepare(ei.to(cuda), w.to(cuda), n)
+    assert close(ops.spmm_csc(graph, x.to(cuda)), want)
+    for F2 in (1, 5, 8, 30, 32, 100, 128, 260):  # every lane-group / vector-width variant
+        x2 = torch.randn(n, F2, generator=g)
+        want2 = torch.zeros(n, F2, dtype=torch.float64).index_add_(0, want_ei[1], want_norm.double().unsqueeze(1) * x2.double()[want_ei[0]])
+        assert close(ops.spmm_csc(graph, x2.to(cuda)), want2), F2
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 1, 1), (7, 5, 3), (64, 64, 64), (1000, 64, 16), (333, 30, 70), (130, 129, 65)])
+def test_linear_vs_torch(cuda, M, K, N):
+    g = torch.Generator().manual_seed(M)
+    a, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+    a2, w2, rs = torch.randn(M, K + 3, generator=g), torch.randn(N, K + 3, generator=g), torch.randint(0, 5, (M,), generator=g).float()
+    want = torch.nn.functional.elu(a.double() @ w.double().t() + b.double())
+    assert close(ops.linear(a.to(cuda), w.to(cuda), b.to(cuda), _lib.ACT_ELU), want)
+    want = a.double() @ w.double().t() + rs.double().unsqueeze(1) * (a2.double() @ w2.double().t() + b.double())
+    assert close(ops.linear(a.to(cuda), w.to(cuda), b.to(cuda), _lib.ACT_NONE, a2=a2.to(cuda), w2=w2.to(cuda), rowscale=rs.to(cuda)), want)
+
+
+def load_params(model, params):
+    model.load_state_dict({k: v.clone() for k, v in params.items()})
+
+
+def test_dbgnn_toy_one_hot_vs_oracle(cuda):
+    """BASELINE config 1 shape: toy temporal graph, order-2 lift, DBGNN with one-hot features exactly as to_dbgnn_data builds them."""
+    g = torch.Generator().manual_seed(0)
+    n, m = 20, 100
+    ei = torch.randint(0, n, (2, m), generator=g)
+    t = torch.sort(torch.randint(0, 50, (m,), generator=g)).values
+    layers = mom.from_temporal_graph(ei, t, n, delta=2, max_order=2)
+    want_data = mom.to_dbgnn_data(layers, max_order=2)
+    params = odbgnn.init_params(3, (want_data["num_nodes"], want_data["num_ho_nodes"]), [16, 16, 16], seed=3)
+    want = odbgnn.dbgnn_forward({k: v.double() for k, v in params.items()},
+                                {k: (v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in want_data.items()})
+
+    tg = pp.TemporalGraph.from_tensors(ei.to(cuda), t.to(cuda), n)
+    model_graph = pp.MultiOrderModel.from_temporal_graph(tg, delta=2, max_order=2)
+    data = model_graph.to_dbgnn_data(max_order=2)
+    assert torch.equal(data.bipartite_edge_index.cpu(), want_data["bipartite_edge_index"])
+    net = pp.nn.DBGNN(num_classes=3, num_features=(data.num_nodes, data.num_ho_nodes), hidden_dims=[16, 16, 16]).to(cuda).eval()
+    load_params(net, params)
+    with torch.no_grad():
+        out = net(data)
+    assert out.shape == (n, 3) and out.is_cuda
+    assert close(out, want)
+
+
+@pytest.mark.parametrize("hidden,classes,mapping", [([16, 32, 8], 4, "last"), ([64, 64, 64], 16, "first"), ([32, 32], 5, "both")])
+def test_dbgnn_dense_features_vs_oracle(cuda, hidden, classes, mapping):
+    g = torch.Generator().manual_seed(len(hidden))
+    n, m = 400, 6000
+    ei = torch.randint(0, n, (2, m), generator=g)
+    t = torch.sort(torch.randint(0, 200, (m,), generator=g)).values
+    layers = mom.from_temporal_graph(ei, t, n, delta=5, max_order=2)
+    F0, F1 = 24, hidden[0]
+    x, x_h = torch.randn(n, F0, generator=g), torch.randn(layers[2].num_nodes, F1, generator=g)
+    want_data = mom.to_dbgnn_data(layers, max_order=2, mapping=mapping, x=x, x_h=x_h)
+    params = odbgnn.init_params(classes, (F0, F1), hidden, seed=11)
+    want = odbgnn.dbgnn_forward({k: v.double() for k, v in params.items()},
+                                {k: (v.double() if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in want_data.items()})
+    fp32 = odbgnn.dbgnn_forward(params, want_data)  # the reference's own precision: shows the tolerance is meaningful
+    assert close(fp32, want)
+
+    tg = pp.TemporalGraph.from_tensors(ei.to(cuda), t.to(cuda), n)
+    mo = pp.MultiOrderModel.from_temporal_graph(tg, delta=5, max_order=2)
+    mo.layers[1].data.x = x.to(cuda)
+    data = mo.to_dbgnn_data(max_order=2, mapping=mapping, x_h=x_h.to(cuda))
+    net = pp.nn.DBGNN(num_classes=classes, num_features=(F0, F1), hidden_dims=hidden).to(cuda).eval()
+    load_params(net, params)
+    with torch.no_grad():
+        out = net(data)
+    assert close(out, want)
