@@ -63,6 +63,8 @@ extern "C" {
 
 int ppg_abi_version(void);
 const char* ppg_last_error(void);
+/* number of kernels this library has launched in this process (monotonic; for bench accounting) */
+unsigned long long ppg_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * a2  lift_order_edge_index            reference: src/pathpyG/algorithms/lift_order.py:48-79
@@ -122,6 +124,13 @@ int ppg_coalesce_sort(const int64_t* edge_index, int64_t num_edges, const int64_
 int ppg_coalesce_fill(const void* workspace, int64_t num_edges, int64_t num_nodes, int64_t num_out,
                       const void* weights, int dtype, int reduce, int64_t* out_edge_index, void* out_weights,
                       void* stream);
+
+/* Stable sort of the low `end_bit` bits of 64-bit keys (in place) + the permutation that sorts them:
+ * the radix sort underneath a4 / the CSC build, exposed for the containers' sort_by and for bench.py.
+ * h_pass_ms (host, nullable, ceil(end_bit/8) floats): CUDA-event time of every digit pass (synchronises). */
+size_t ppg_sort_pairs_workspace_bytes(int64_t n, int end_bit);
+int ppg_sort_pairs_u64(uint64_t* keys, uint32_t* out_perm, int64_t n, int end_bit, void* workspace,
+                       size_t workspace_bytes, float* h_pass_ms, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a10/a11  DBGNN.forward building blocks      reference: src/pathpyG/nn/dbgnn.py:32-151 and

@@ -32,6 +32,7 @@ _ph_int = POINTER(c_int)
 PROTOTYPES = {
     "ppg_abi_version": (c_int, []),
     "ppg_last_error": (c_char_p, []),
+    "ppg_launch_count": (ctypes.c_uint64, []),
     "ppg_lift_order_workspace_bytes": (c_size_t, [_i64, _i64]),
     "ppg_lift_order_count": (c_int, [_p, _i64, _i64, _p, c_size_t, _ph_i64, _p]),
     "ppg_lift_order_fill": (c_int, [_p, _i64, _i64, _i64, _p, _p]),
@@ -47,6 +48,8 @@ PROTOTYPES = {
     "ppg_coalesce_workspace_bytes": (c_size_t, [_i64, _i64]),
     "ppg_coalesce_sort": (c_int, [_p, _i64, _p, _i64, _i64, _p, c_size_t, _ph_i64, _p]),
     "ppg_coalesce_fill": (c_int, [_p, _i64, _i64, _i64, _p, c_int, c_int, _p, _p, _p]),
+    "ppg_sort_pairs_workspace_bytes": (c_size_t, [_i64, c_int]),
+    "ppg_sort_pairs_u64": (c_int, [_p, _p, _i64, c_int, _p, c_size_t, POINTER(ctypes.c_float), _p]),
     "ppg_csc_workspace_bytes": (c_size_t, [_i64, _i64]),
     "ppg_csc_build": (c_int, [_p, _i64, _i64, _i64, _p, c_size_t, _p, _p, _p, _p]),
     "ppg_gcn_norm": (c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),

@@ -277,7 +277,7 @@ static int coalesce_fill_dispatch(const CoalesceLayout& L, int64_t num_out, cons
     default: PPG_REQUIRE(false, PPG_ERR_INVALID, "coalesce: unknown reduce code %d", reduce);
   }
 #undef PPG_FILL
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   return PPG_OK;
 }
 
@@ -302,11 +302,11 @@ extern "C" int ppg_rows_minmax(const int64_t* rows, int64_t M, int64_t width, vo
   int* flag = reinterpret_cast<int*>(maxs + width);
   const int w = static_cast<int>(width);
   init_minmax_kernel<<<static_cast<unsigned>(ceil_div(w, 256)), 256, 0, stream>>>(mins, maxs, flag, w);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   if (M > 0) {
     for (int col0 = 0; col0 < w; col0 += kStatCols) {
       rows_minmax_kernel<<<grid_for(M, 256 * 4, kNumSMsB200 * 8), 256, 0, stream>>>(rows, M, w, col0, mins, maxs, flag);
-      PPG_CUDA_TRY(cudaGetLastError());
+      PPG_LAUNCHED();
     }
   }
   PPG_CUDA_TRY(cudaMemcpyAsync(h_col_min, mins, sizeof(long long) * width, cudaMemcpyDeviceToHost, stream));
@@ -348,7 +348,7 @@ extern "C" int ppg_unique_rows_sort(const int64_t* rows, int64_t M, int64_t widt
     PPG_REQUIRE(h_col_shift[c] >= 0 && h_col_shift[c] < 64, PPG_ERR_INVALID, "unique_rows: bad shift for column %d", c);
   }
   pack_rows_kernel<<<grid_for(M, 256 * 4), 256, 0, stream>>>(rows, M, pp, L.keys_a);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   int in_b = 0;
   PPG_TRY(radix_sort_pairs<unsigned long long>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, M, total_bits,
                                                L.sort_ws, &in_b, stream));
@@ -369,7 +369,7 @@ extern "C" int ppg_unique_rows_gather(const int64_t* rows, int64_t M, int64_t wi
   UniqueLayout L(ws, M, total_bits);
   gather_rows_kernel<<<grid_for(num_unique * width, 256 * 4), 256, 0, stream>>>(rows, L.rep, num_unique,
                                                                                 static_cast<int>(width), out_rows);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   return PPG_OK;
 }
 
@@ -397,7 +397,7 @@ extern "C" int ppg_coalesce_sort(const int64_t* edge_index, int64_t E, const int
 
   edge_keys_kernel<<<grid_for(E, 256 * 4), 256, 0, stream>>>(edge_index, E, remap, remap_len, num_nodes, L.node_bits,
                                                              L.keys_a, &L.result->status);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   int in_b = 0;
   PPG_TRY(radix_sort_pairs<unsigned long long>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, E, 2 * L.node_bits,
                                                L.sort_ws, &in_b, stream));
@@ -430,5 +430,45 @@ extern "C" int ppg_coalesce_fill(const void* workspace, int64_t E, int64_t num_n
     case PPG_I32: return coalesce_fill_dispatch<int, false>(L, num_out, weights, reduce, out_edge_index, out_weights, stream);
     default: PPG_REQUIRE(false, PPG_ERR_INVALID, "coalesce: unsupported dtype code %d", dtype);
   }
+  return PPG_OK;
+}
+
+// =================================================================== stand-alone pair sort (utility + bench probe)
+namespace ppg {
+struct SortLayout {
+  unsigned long long* sort_ws;
+  size_t zero_bytes;
+  unsigned long long* keys_b;
+  uint32_t *vals_a, *vals_b;
+  SortLayout(Workspace& ws, int64_t n, int end_bit) {
+    sort_ws = ws.take<unsigned long long>(sort_state_words(n, end_bit));
+    zero_bytes = ws.used;
+    keys_b = ws.take<unsigned long long>(static_cast<size_t>(n));
+    vals_a = ws.take<uint32_t>(static_cast<size_t>(n));
+    vals_b = ws.take<uint32_t>(static_cast<size_t>(n));
+  }
+};
+}  // namespace ppg
+
+extern "C" size_t ppg_sort_pairs_workspace_bytes(int64_t n, int end_bit) {
+  Workspace ws(nullptr, 0);
+  SortLayout L(ws, n < 0 ? 0 : n, end_bit);
+  return ws.used + 256;
+}
+
+extern "C" int ppg_sort_pairs_u64(uint64_t* keys, uint32_t* out_perm, int64_t n, int end_bit, void* workspace,
+                                  size_t workspace_bytes, float* h_pass_ms, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(n >= 0 && n < (1ll << 31) && end_bit >= 0 && end_bit <= 64, PPG_ERR_INVALID, "sort_pairs: bad arguments");
+  if (n == 0) return PPG_OK;
+  Workspace ws(workspace, workspace_bytes);
+  SortLayout L(ws, n, end_bit);
+  PPG_REQUIRE(ws.fits(), PPG_ERR_WORKSPACE, "sort_pairs: workspace %zu < %zu bytes", workspace_bytes, ws.used);
+  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, L.zero_bytes, stream));
+  int in_b = 0;
+  PPG_TRY(radix_sort_pairs<unsigned long long>(reinterpret_cast<unsigned long long*>(keys), L.keys_b, L.vals_a, L.vals_b,
+                                               true, true, n, end_bit, L.sort_ws, &in_b, stream, h_pass_ms));
+  if (in_b) PPG_CUDA_TRY(cudaMemcpyAsync(keys, L.keys_b, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, stream));
+  PPG_CUDA_TRY(cudaMemcpyAsync(out_perm, in_b ? L.vals_b : L.vals_a, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, stream));
   return PPG_OK;
 }

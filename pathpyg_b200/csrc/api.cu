@@ -5,6 +5,7 @@
 
 namespace ppg {
 static thread_local char g_last_error[512] = "";
+unsigned long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -16,3 +17,4 @@ void set_error(const char* fmt, ...) {
 
 extern "C" int ppg_abi_version(void) { return PPG_ABI_VERSION; }
 extern "C" const char* ppg_last_error(void) { return ppg::g_last_error; }
+extern "C" unsigned long long ppg_launch_count(void) { return ppg::g_launch_count; }

@@ -25,6 +25,14 @@ void set_error(const char* fmt, ...);
     }                                                                                    \
   } while (0)
 
+// after every kernel launch: surface launch errors and count the launch (bench.py reports the count)
+extern unsigned long long g_launch_count;
+#define PPG_LAUNCHED()                                                                   \
+  do {                                                                                   \
+    PPG_CUDA_TRY(cudaGetLastError());                                                    \
+    ++::ppg::g_launch_count;                                                             \
+  } while (0)
+
 #define PPG_REQUIRE(cond, code, ...)                                                     \
   do {                                                                                   \
     if (!(cond)) {                                                                       \

@@ -301,7 +301,7 @@ extern "C" int ppg_csc_build(const int64_t* edge_index, int64_t E, int64_t num_s
   if (E > 0) {
     target_keys_kernel<<<grid_for(E, 256 * 4), 256, 0, stream>>>(edge_index, E, num_sources, num_targets, L.keys_a, L.deg,
                                                                  &L.result->status);
-    PPG_CUDA_TRY(cudaGetLastError());
+    PPG_LAUNCHED();
   }
   PPG_TRY(launch_scan(DegreeProducer32{L.deg}, PointerConsumer32{out_colptr, num_targets}, num_targets, L.scan_ws,
                       nullptr, stream));
@@ -310,7 +310,7 @@ extern "C" int ppg_csc_build(const int64_t* edge_index, int64_t E, int64_t num_s
     PPG_TRY(radix_sort_pairs<uint32_t>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, E, L.sort_bits, L.sort_ws,
                                        &in_b, stream));
     csc_fill_kernel<<<grid_for(E, 256 * 4), 256, 0, stream>>>(edge_index, in_b ? L.vals_b : L.vals_a, E, out_src, out_eid);
-    PPG_CUDA_TRY(cudaGetLastError());
+    PPG_LAUNCHED();
   }
   ResultWords h;
   PPG_TRY(read_back(&h, L.result, stream));
@@ -325,9 +325,9 @@ extern "C" int ppg_gcn_norm(const int32_t* colptr, const int32_t* src, const int
   if (n == 0) return PPG_OK;
   const unsigned grid = static_cast<unsigned>(ceil_div(n, 256));
   gcn_degree_kernel<<<grid, 256, 0, stream>>>(colptr, src, eid, edge_weight, n, scratch_dis, out_self);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   gcn_values_kernel<<<grid, 256, 0, stream>>>(colptr, src, eid, edge_weight, scratch_dis, n, out_val, out_self);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   return PPG_OK;
 }
 
@@ -335,7 +335,7 @@ extern "C" int ppg_colptr_counts(const int32_t* colptr, int64_t n, float* out, v
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n == 0) return PPG_OK;
   colptr_counts_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, stream>>>(colptr, n, out);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   return PPG_OK;
 }
 
@@ -345,7 +345,7 @@ static int launch_spmm(const int32_t* colptr, const int32_t* src, const float* v
   const int64_t threads = n * LPN;
   spmm_csc_kernel<LPN, VEC><<<static_cast<unsigned>(ceil_div(threads, 256)), 256, 0, stream>>>(
       colptr, src, val, self_val, X, n, F, bias, act, out);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   return PPG_OK;
 }
 
@@ -379,6 +379,6 @@ extern "C" int ppg_linear(const float* A1, const float* W1, int64_t M, int64_t K
   PPG_REQUIRE(grid.y < 65536, PPG_ERR_INVALID, "linear: output width %lld too large", (long long)N);
   linear_kernel<<<grid, 256, 0, stream>>>(A1, W1, static_cast<int>(K1), A2, W2, static_cast<int>(K2), bias, rowscale, M,
                                           static_cast<int>(N), act, out);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   return PPG_OK;
 }

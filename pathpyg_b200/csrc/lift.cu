@@ -176,7 +176,7 @@ inline int launch_expand(const unsigned long long* off, int64_t E, int64_t total
   PPG_REQUIRE(tiles < (1ll << 31), PPG_ERR_INVALID, "expand: %lld output columns are too many", (long long)total);
   expand_kernel<<<static_cast<unsigned>(tiles), kExpandBlock, 0, stream>>>(off, E, total, out_index, out_index + total,
                                                                             tail);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   return PPG_OK;
 }
 
@@ -385,7 +385,7 @@ static int pair_attributes_dispatch(const int64_t* ei, int64_t E, const void* at
     case PPG_PAIR_ADD: pair_attributes_kernel<T, PPG_PAIR_ADD><<<grid, 256, 0, stream>>>(ei, E, a, o); break;
     default: PPG_REQUIRE(false, PPG_ERR_INVALID, "Unknown aggregation method %d", rule);
   }
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   return PPG_OK;
 }
 
@@ -420,7 +420,7 @@ extern "C" int ppg_lift_order_count(const int64_t* edge_index, int64_t E, int64_
   PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, L.zero_bytes, stream));
 
   degree_kernel<false><<<grid_for(E, 256 * 4), 256, 0, stream>>>(edge_index, E, N, L.deg, nullptr, &L.result->status);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   PPG_TRY(launch_scan(DegreeProducer{L.deg}, PointerConsumer{L.ptr, N}, N, L.scan_ptr_ws, nullptr, stream));
   PPG_TRY(launch_scan(LiftCountProducer{edge_index + E, L.ptr, L.first, N, &L.result->status}, OffsetConsumer{L.off, E},
                       E, L.scan_off_ws, &L.result->total, stream));
@@ -481,7 +481,7 @@ extern "C" int ppg_lift_temporal_count(const int64_t* edge_index, const void* ti
 
   // CSR over the source node, edges inside a group in time order (stable sort of a time-sorted stream)
   degree_kernel<true><<<grid_for(m, 256 * 4), 256, 0, stream>>>(edge_index, m, N, L.deg, L.keys_a, &L.result->status);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   PPG_TRY(launch_scan(DegreeProducer{L.deg}, PointerConsumer{L.ptr, N}, N, L.scan_ptr_ws, nullptr, stream));
   int in_b = 0;
   PPG_TRY(radix_sort_pairs<uint32_t>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, m, L.sort_bits, L.sort_ws,
@@ -490,7 +490,7 @@ extern "C" int ppg_lift_temporal_count(const int64_t* edge_index, const void* ti
   PPG_REQUIRE(grouped == L.grouped(), PPG_ERR_CUDA, "lift_order_temporal: internal buffer parity mismatch");
   gather64_kernel<<<grid_for(m, 256 * 4), 256, 0, stream>>>(static_cast<const unsigned long long*>(time), grouped, m,
                                                              L.ts_sorted);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
 
   switch (time_mode) {
     case PPG_TIME_I64: PPG_TRY(temporal_count_scan<PPG_TIME_I64>(L, edge_index, time, m, N, delta_i, delta_f, stream)); break;

@@ -230,7 +230,7 @@ inline int launch_onesweep_pass(const KeyT* kin, KeyT* kout, const uint32_t* vin
   }
   kern<<<static_cast<unsigned>(sort_num_tiles(n)), kSortBlock, smem, stream>>>(
       kin, kout, vin, vout, n, shift, ghist, counter, state, 2 * pass + 1, 2 * pass + 2);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   return PPG_OK;
 }
 
@@ -242,8 +242,11 @@ inline int launch_onesweep_pass(const KeyT* kin, KeyT* kout, const uint32_t* vin
 template <typename KeyT>
 inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* vals_b, bool has_values,
                             bool iota_payload, int64_t n, int end_bit, unsigned long long* zeroed_ws, int* in_b,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, float* h_pass_ms = nullptr) {
   const int P = sort_num_passes(end_bit);
+  cudaEvent_t ev[kMaxPasses + 1];
+  if (h_pass_ms != nullptr)
+    for (int p = 0; p <= P && p <= kMaxPasses; ++p) PPG_CUDA_TRY(cudaEventCreate(&ev[p]));
   PPG_REQUIRE(P <= kMaxPasses, PPG_ERR_INVALID, "radix sort: %d key bits need more than %d passes", end_bit, kMaxPasses);
   PPG_REQUIRE(n < (1ll << 31), PPG_ERR_INVALID, "radix sort: %lld elements exceed the 2^31 limit", (long long)n);
   unsigned long long* ghist = zeroed_ws;
@@ -253,12 +256,13 @@ inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32
   if (n == 0) return PPG_OK;
 
   radix_histogram_kernel<KeyT><<<grid_for(n, 256 * 8, kNumSMsB200 * 8), 256, 0, stream>>>(keys_a, n, P, ghist);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
 
   KeyT* kin = keys_a;
   KeyT* kout = keys_b;
   uint32_t* vin = vals_a;
   uint32_t* vout = vals_b;
+  if (h_pass_ms != nullptr) PPG_CUDA_TRY(cudaEventRecord(ev[0], stream));
   for (int p = 0; p < P; ++p) {
     unsigned* counter = reinterpret_cast<unsigned*>(counters + p);
     const unsigned long long* h = ghist + static_cast<size_t>(p) * kRadix;
@@ -274,6 +278,12 @@ inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32
     uint32_t* tv = (p == 0 && iota_payload) ? vals_a : vin;
     vin = vout; vout = tv;
     *in_b ^= 1;
+    if (h_pass_ms != nullptr) PPG_CUDA_TRY(cudaEventRecord(ev[p + 1], stream));
+  }
+  if (h_pass_ms != nullptr) {  // profiling aid for bench.py: CUDA-event time of every digit pass on this stream
+    PPG_CUDA_TRY(cudaStreamSynchronize(stream));
+    for (int p = 0; p < P; ++p) PPG_CUDA_TRY(cudaEventElapsedTime(&h_pass_ms[p], ev[p], ev[p + 1]));
+    for (int p = 0; p <= P; ++p) cudaEventDestroy(ev[p]);
   }
   return PPG_OK;
 }

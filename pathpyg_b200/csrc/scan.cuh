@@ -125,7 +125,7 @@ inline int launch_scan(Producer produce, Consumer consume, int64_t n, unsigned l
   const int64_t tiles = scan_num_tiles(n);
   scan_lookback_kernel<<<static_cast<unsigned>(tiles), kScanBlock, 0, stream>>>(
       produce, consume, n, zeroed_ws, 2 * code - 1, 2 * code, total_out);
-  PPG_CUDA_TRY(cudaGetLastError());
+  PPG_LAUNCHED();
   return PPG_OK;
 }
 

@@ -223,6 +223,20 @@ def coalesce(edge_index: torch.Tensor, remap: torch.Tensor | None, num_nodes: in
     return out_ei, out_w
 
 
+def sort_pairs_u64(keys: torch.Tensor, end_bit: int, time_passes: bool = False):
+    """Stable in-place sort of the low ``end_bit`` bits of int64/uint64 keys; returns (perm int32, per-pass ms or None)."""
+    lib = _lib.load()
+    dev = _require_cuda(keys)
+    n = keys.numel()
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    passes = max(1, -(-end_bit // 8))
+    ms = (ctypes.c_float * passes)() if time_passes else None
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_sort_pairs_workspace_bytes(n, end_bit), dev)
+        _lib.check(lib.ppg_sort_pairs_u64(_ptr(keys), _ptr(perm), n, end_bit, _ptr(ws), ws.numel(), ms, _stream(dev)))
+    return perm, (list(ms) if time_passes else None)
+
+
 # --------------------------------------------------------------------------------------- a10 / a11
 class TargetGroupedEdges:
     """CSC view of an edge list: incoming edges of every target node, original order inside a target."""
