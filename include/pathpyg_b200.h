@@ -164,6 +164,18 @@ int ppg_spmm_csc(const int32_t* colptr, const int32_t* src, const float* val, co
 int ppg_linear(const float* A1, const float* W1, int64_t M, int64_t K1, const float* A2, const float* W2, int64_t K2,
                const float* bias, const float* rowscale, int64_t N, int act, float* out, void* stream);
 
+/* Fused layers for widths F, H in {16, 32, 64} (ppg_gcn_fused_supported): aggregate the 128-node tile in
+ * shared memory, transform it there, apply bias + activation, write the output row once.
+ *   gcn       : out = act( (sum_i val_i X[src_i] + self_v X[v]) W^T + bias )         W [H,F]
+ *   bipartite : out = act( (sum_i X_h[src_i]) W1^T + indeg(v) (X[v] W2^T + bias12) ) W1, W2 [H,F] */
+int ppg_gcn_fused_supported(int64_t F, int64_t H);
+int ppg_gcn_layer_fused(const int32_t* colptr, const int32_t* src, const float* val, const float* self_val,
+                        const float* X, const float* W, const float* bias, int64_t n, int64_t F, int64_t H, int act,
+                        float* out, void* stream);
+int ppg_bipartite_fused(const int32_t* colptr, const int32_t* src, const float* X_h, const float* X, const float* W1,
+                        const float* W2, const float* bias12, int64_t n, int64_t F, int64_t H, int act, float* out,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

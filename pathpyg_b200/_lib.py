@@ -56,6 +56,9 @@ PROTOTYPES = {
     "ppg_colptr_counts": (c_int, [_p, _i64, _p, _p]),
     "ppg_spmm_csc": (c_int, [_p, _p, _p, _p, _p, _i64, _i64, _p, c_int, _p, _p]),
     "ppg_linear": (c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _p, _p, _i64, c_int, _p, _p]),
+    "ppg_gcn_fused_supported": (c_int, [_i64, _i64]),
+    "ppg_gcn_layer_fused": (c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, c_int, _p, _p]),
+    "ppg_bipartite_fused": (c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, c_int, _p, _p]),
 }
 ACT_NONE, ACT_ELU = 0, 1
 

@@ -12,6 +12,14 @@
 // memory), the tile is reordered through shared memory, and every digit's run is written out as
 // one contiguous (coalesced) segment.
 //
+// Look-back: thread d owns digit d and walks the preceding tiles' published words.  A serial walk
+// costs one L2 round trip per hop, which at the sizes of BASELINE config 2 (a few hundred tiles that
+// all start together) dominated the pass; the walk therefore keeps kLookBatch independent loads in
+// flight and consumes them in order.
+//
+// Tile size: 256 threads x 8 keys up to 4M keys (more tiles than SM slots => one balanced wave, short
+// chain hops), 256 x 16 beyond (less look-back state, fewer fixed costs per key).
+//
 // The payload is an optional u32 per key; the first pass can synthesise it as the element index
 // (IOTA) so that an index permutation costs no read.
 #pragma once
@@ -22,11 +30,14 @@ namespace ppg {
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kSortBlock = 256;  // == kRadix: thread d owns digit d in the per-digit phases
-constexpr int kSortItems = 16;
-constexpr int kSortTile = kSortBlock * kSortItems;
 constexpr int kMaxPasses = 8;
+constexpr int kLookBatch = 8;
+constexpr int64_t kSmallSortLimit = 4ll << 20;
 
-__host__ __device__ inline int64_t sort_num_tiles(int64_t n) { return n > 0 ? ceil_div(n, kSortTile) : 1; }
+__host__ __device__ inline int sort_items_for(int64_t n) { return n <= kSmallSortLimit ? 8 : 16; }
+__host__ __device__ inline int64_t sort_num_tiles(int64_t n) {
+  return n > 0 ? ceil_div(n, static_cast<int64_t>(kSortBlock) * sort_items_for(n)) : 1;
+}
 inline int sort_num_passes(int end_bit) { return end_bit <= 0 ? 1 : static_cast<int>(ceil_div(end_bit, kRadixBits)); }
 
 // zero-initialised words a sort needs: [P*256 histogram][P tile counters (u64 each)][tiles*256 look-back words]
@@ -63,7 +74,7 @@ radix_histogram_kernel(const KeyT* __restrict__ keys, int64_t n, int num_passes,
   }
 }
 
-template <typename KeyT, bool HAS_VALUES, bool IOTA>
+template <typename KeyT, bool HAS_VALUES, bool IOTA, int ITEMS>
 __global__ void __launch_bounds__(kSortBlock)
 onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int64_t n, int shift,
@@ -71,10 +82,11 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
                      unsigned* __restrict__ tile_counter, unsigned long long* __restrict__ state,
                      unsigned code_partial, unsigned code_inclusive) {
   constexpr int NW = kSortBlock / 32;
+  constexpr int TILE = kSortBlock * ITEMS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
-  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + kSortTile);
-  uint32_t* s_whist = s_vals + (HAS_VALUES ? kSortTile : 0);                // [NW][256] per-warp digit counts
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);
+  uint32_t* s_whist = s_vals + (HAS_VALUES ? TILE : 0);                     // [NW][256] per-warp digit counts
   uint32_t* s_binstart = s_whist + NW * kRadix;                             // [256] first slot of a digit in the tile
   long long* s_gbase = reinterpret_cast<long long*>(s_binstart + kRadix);   // [256] global slot of tile slot 0 of a digit
   __shared__ unsigned s_tile;
@@ -88,24 +100,24 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
   const unsigned tile = s_tile;
-  const int64_t tile_base = static_cast<int64_t>(tile) * kSortTile;
-  const int64_t warp_base = tile_base + static_cast<int64_t>(warp) * (32 * kSortItems);
+  const int64_t tile_base = static_cast<int64_t>(tile) * TILE;
+  const int64_t warp_base = tile_base + static_cast<int64_t>(warp) * (32 * ITEMS);
   const int64_t remaining = n - tile_base;
-  const int valid_in_tile = remaining >= kSortTile ? kSortTile : static_cast<int>(remaining);
+  const int valid_in_tile = remaining >= TILE ? TILE : static_cast<int>(remaining);
 
   // ---- load (warp-striped => coalesced; element order inside a warp is (item, lane))
-  KeyT key[kSortItems];
+  KeyT key[ITEMS];
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
+  for (int i = 0; i < ITEMS; ++i) {
     const int64_t idx = warp_base + i * 32 + lane;
     key[i] = idx < n ? ld_stream(keys_in + idx) : static_cast<KeyT>(~static_cast<KeyT>(0));
   }
 
   // ---- stable rank inside the warp, digit counts per warp
-  uint32_t rank[kSortItems];
+  uint32_t rank[ITEMS];
   uint32_t* my_hist = s_whist + warp * kRadix;
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
+  for (int i = 0; i < ITEMS; ++i) {
     const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
     const unsigned peers = __match_any_sync(kFullMask, d);
     const int leader = 31 - __clz(peers);
@@ -132,7 +144,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
     }
     // out-of-range slots of the last tile were given all-ones keys: they sit at the very end of the
     // top digit's run (stable order), so dropping them from that count leaves every valid slot intact
-    if (tid == kRadix - 1) sum -= static_cast<uint32_t>(kSortTile - valid_in_tile);
+    if (tid == kRadix - 1) sum -= static_cast<uint32_t>(TILE - valid_in_tile);
     count = sum;
   }
   unsigned long long* my_state = state + static_cast<size_t>(tile) * kRadix + tid;
@@ -141,18 +153,30 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
     state_store(my_state, code_inclusive, count);
   } else {
     state_store(my_state, code_partial, count);
-    int64_t q = static_cast<int64_t>(tile) - 1;
-    while (true) {
-      const unsigned long long w = state_load(state + static_cast<size_t>(q) * kRadix + tid);
-      const unsigned code = static_cast<unsigned>(w >> 56);
-      if (code == code_inclusive) {
-        prev += w & kStateValueMask;
-        break;
+    int64_t q = static_cast<int64_t>(tile) - 1;  // newest tile not yet accounted for
+    bool done = false;
+    while (!done) {
+      unsigned long long w[kLookBatch];
+#pragma unroll
+      for (int j = 0; j < kLookBatch; ++j) {
+        const int64_t qq = q - j;
+        w[j] = qq >= 0 ? state_load(state + static_cast<size_t>(qq) * kRadix + tid) : 0ull;
       }
-      if (code == code_partial) {
-        prev += w & kStateValueMask;
-        --q;  // tile 0 always publishes an inclusive word, so q never passes 0
+      int consumed = 0;
+#pragma unroll
+      for (int j = 0; j < kLookBatch; ++j) {
+        if (!done && consumed == j) {
+          const unsigned code = static_cast<unsigned>(w[j] >> 56);
+          if (code == code_inclusive) {
+            prev += w[j] & kStateValueMask;
+            done = true;
+          } else if (code == code_partial) {
+            prev += w[j] & kStateValueMask;
+            consumed = j + 1;
+          }  // else: not published yet -> poll again from this tile
+        }
       }
+      q -= consumed;  // tile 0 always publishes an inclusive word, so the walk ends at q >= 0
     }
     state_store(my_state, code_inclusive, prev + count);
   }
@@ -184,7 +208,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
 
   // ---- reorder the tile through shared memory
 #pragma unroll
-  for (int i = 0; i < kSortItems; ++i) {
+  for (int i = 0; i < ITEMS; ++i) {
     const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
     const uint32_t pos = s_binstart[d] + my_hist[d] + rank[i];
     rank[i] = pos;
@@ -192,7 +216,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   }
   if (HAS_VALUES) {
 #pragma unroll
-    for (int i = 0; i < kSortItems; ++i) {
+    for (int i = 0; i < ITEMS; ++i) {
       const int64_t idx = warp_base + i * 32 + lane;
       uint32_t v = 0;
       if (idx < n) v = IOTA ? static_cast<uint32_t>(idx) : ld_stream(vals_in + idx);
@@ -211,18 +235,18 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   }
 }
 
-template <typename KeyT, bool HAS_VALUES>
+template <typename KeyT, bool HAS_VALUES, int ITEMS>
 constexpr size_t onesweep_smem_bytes() {
-  return static_cast<size_t>(kSortTile) * sizeof(KeyT) + (HAS_VALUES ? kSortTile * sizeof(uint32_t) : 0) +
+  return static_cast<size_t>(kSortBlock * ITEMS) * sizeof(KeyT) + (HAS_VALUES ? kSortBlock * ITEMS * sizeof(uint32_t) : 0) +
          (kSortBlock / 32) * kRadix * sizeof(uint32_t) + kRadix * sizeof(uint32_t) + kRadix * sizeof(long long);
 }
 
-template <typename KeyT, bool HAS_VALUES, bool IOTA>
-inline int launch_onesweep_pass(const KeyT* kin, KeyT* kout, const uint32_t* vin, uint32_t* vout, int64_t n, int shift,
-                                const unsigned long long* ghist, unsigned* counter, unsigned long long* state,
-                                unsigned pass, cudaStream_t stream) {
-  auto kern = onesweep_pass_kernel<KeyT, HAS_VALUES, IOTA>;
-  constexpr size_t smem = onesweep_smem_bytes<KeyT, HAS_VALUES>();
+template <typename KeyT, bool HAS_VALUES, bool IOTA, int ITEMS>
+inline int launch_onesweep_pass_items(const KeyT* kin, KeyT* kout, const uint32_t* vin, uint32_t* vout, int64_t n,
+                                      int shift, const unsigned long long* ghist, unsigned* counter,
+                                      unsigned long long* state, unsigned pass, cudaStream_t stream) {
+  auto kern = onesweep_pass_kernel<KeyT, HAS_VALUES, IOTA, ITEMS>;
+  constexpr size_t smem = onesweep_smem_bytes<KeyT, HAS_VALUES, ITEMS>();
   static bool configured = false;  // per instantiation
   if (!configured) {
     PPG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -234,21 +258,31 @@ inline int launch_onesweep_pass(const KeyT* kin, KeyT* kout, const uint32_t* vin
   return PPG_OK;
 }
 
+template <typename KeyT, bool HAS_VALUES, bool IOTA>
+inline int launch_onesweep_pass(const KeyT* kin, KeyT* kout, const uint32_t* vin, uint32_t* vout, int64_t n, int shift,
+                                const unsigned long long* ghist, unsigned* counter, unsigned long long* state,
+                                unsigned pass, cudaStream_t stream) {
+  if (sort_items_for(n) == 8)
+    return launch_onesweep_pass_items<KeyT, HAS_VALUES, IOTA, 8>(kin, kout, vin, vout, n, shift, ghist, counter, state, pass, stream);
+  return launch_onesweep_pass_items<KeyT, HAS_VALUES, IOTA, 16>(kin, kout, vin, vout, n, shift, ghist, counter, state, pass, stream);
+}
+
 // Sorts the significant bits [0, end_bit) of keys_a (n elements) with an optional u32 payload.
 //   keys_a/vals_a : input, clobbered (used as the ping buffer)     keys_b/vals_b : pong buffer
 //   vals_a == nullptr with has_values => payload synthesised as the element index on the first pass
 //   zeroed_ws     : sort_state_words(n, end_bit) words, zero on entry
 //   *in_b         : 1 if the sorted result ended in the *_b buffers
+//   h_pass_ms     : optional host array [P]: CUDA-event time of every digit pass (synchronises; bench probe)
 template <typename KeyT>
 inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* vals_b, bool has_values,
                             bool iota_payload, int64_t n, int end_bit, unsigned long long* zeroed_ws, int* in_b,
                             cudaStream_t stream, float* h_pass_ms = nullptr) {
   const int P = sort_num_passes(end_bit);
-  cudaEvent_t ev[kMaxPasses + 1];
-  if (h_pass_ms != nullptr)
-    for (int p = 0; p <= P && p <= kMaxPasses; ++p) PPG_CUDA_TRY(cudaEventCreate(&ev[p]));
   PPG_REQUIRE(P <= kMaxPasses, PPG_ERR_INVALID, "radix sort: %d key bits need more than %d passes", end_bit, kMaxPasses);
   PPG_REQUIRE(n < (1ll << 31), PPG_ERR_INVALID, "radix sort: %lld elements exceed the 2^31 limit", (long long)n);
+  cudaEvent_t ev[kMaxPasses + 1];
+  if (h_pass_ms != nullptr)
+    for (int p = 0; p <= P; ++p) PPG_CUDA_TRY(cudaEventCreate(&ev[p]));
   unsigned long long* ghist = zeroed_ws;
   unsigned long long* counters = zeroed_ws + static_cast<size_t>(P) * kRadix;
   unsigned long long* state = counters + P;
@@ -280,7 +314,7 @@ inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32
     *in_b ^= 1;
     if (h_pass_ms != nullptr) PPG_CUDA_TRY(cudaEventRecord(ev[p + 1], stream));
   }
-  if (h_pass_ms != nullptr) {  // profiling aid for bench.py: CUDA-event time of every digit pass on this stream
+  if (h_pass_ms != nullptr) {
     PPG_CUDA_TRY(cudaStreamSynchronize(stream));
     for (int p = 0; p < P; ++p) PPG_CUDA_TRY(cudaEventElapsedTime(&h_pass_ms[p], ev[p], ev[p + 1]));
     for (int p = 0; p <= P; ++p) cudaEventDestroy(ev[p]);

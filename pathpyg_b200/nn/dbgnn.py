@@ -37,6 +37,8 @@ class GCNConv(nn.Module):
 
     def forward_prepared(self, x: torch.Tensor, graph: ops.TargetGroupedEdges, act: int = _lib.ACT_NONE) -> torch.Tensor:
         w, b = self.lin.weight, self.bias
+        if ops.fused_supported(self.in_channels, self.out_channels):
+            return ops.gcn_layer_fused(graph, x, w, b, act)  # aggregate + transform + bias + act in one kernel
         if self.in_channels <= self.out_channels:      # aggregate the narrower side first
             return ops.linear(ops.spmm_csc(graph, x), w, b, act)
         return ops.spmm_csc(graph, ops.linear(x, w), b, act)
@@ -58,6 +60,9 @@ class BipartiteGraphOperator(nn.Module):
     def forward(self, x, bipartite_index, n_ho: int, n_fo: int, act: int = _lib.ACT_NONE):
         x_h, x_fo = x
         grouped = ops.csc_build(bipartite_index, n_ho, n_fo)
+        if ops.fused_supported(self.lin1.in_features, self.lin1.out_features):
+            return ops.bipartite_fused(grouped, x_h, x_fo, self.lin1.weight, self.lin2.weight,
+                                       self.lin1.bias + self.lin2.bias, act)
         summed = ops.spmm_csc(grouped, x_h)
         indeg = ops.colptr_counts(grouped)
         return ops.linear(summed, self.lin1.weight, self.lin1.bias + self.lin2.bias, act,

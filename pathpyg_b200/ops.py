@@ -328,3 +328,37 @@ def linear(a1: torch.Tensor, w1: torch.Tensor, bias: torch.Tensor | None = None,
         _lib.check(lib.ppg_linear(_ptr(a1), _ptr(w1), M, K1, _ptr(a2), _ptr(w2), K2, _ptr(bias), _ptr(rowscale), N, act,
                                   _ptr(out), _stream(dev)))
     return out
+
+
+def fused_supported(in_width: int, out_width: int) -> bool:
+    return bool(_lib.load().ppg_gcn_fused_supported(in_width, out_width))
+
+
+def gcn_layer_fused(g: TargetGroupedEdges, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None,
+                    act: int = _lib.ACT_NONE) -> torch.Tensor:
+    """act((A_norm x) W^T + b) in one kernel (widths in {16, 32, 64})."""
+    lib = _lib.load()
+    dev = _require_cuda(x, weight, bias, g.colptr)
+    x, weight = x.contiguous(), weight.contiguous()
+    H, F = weight.shape
+    if x.size(1) != F or x.size(0) < g.num_sources:
+        raise ValueError(f"shape mismatch: features {tuple(x.shape)}, weight {tuple(weight.shape)}, graph sources {g.num_sources}")
+    out = torch.empty((g.num_targets, H), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_gcn_layer_fused(_ptr(g.colptr), _ptr(g.src), _ptr(g.val), _ptr(g.self_val), _ptr(x), _ptr(weight),
+                                           _ptr(bias), g.num_targets, F, H, act, _ptr(out), _stream(dev)))
+    return out
+
+
+def bipartite_fused(g: TargetGroupedEdges, x_h: torch.Tensor, x: torch.Tensor, w1: torch.Tensor, w2: torch.Tensor,
+                    bias12: torch.Tensor, act: int = _lib.ACT_NONE) -> torch.Tensor:
+    """act((sum_u x_h[u]) W1^T + indeg (x W2^T + b1 + b2)) in one kernel (widths in {16, 32, 64})."""
+    lib = _lib.load()
+    dev = _require_cuda(x_h, x, w1, w2, bias12, g.colptr)
+    x_h, x, w1, w2 = x_h.contiguous(), x.contiguous(), w1.contiguous(), w2.contiguous()
+    H, F = w1.shape
+    out = torch.empty((g.num_targets, H), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_bipartite_fused(_ptr(g.colptr), _ptr(g.src), _ptr(x_h), _ptr(x), _ptr(w1), _ptr(w2), _ptr(bias12),
+                                           g.num_targets, F, H, act, _ptr(out), _stream(dev)))
+    return out

@@ -102,3 +102,32 @@ def test_dbgnn_dense_features_vs_oracle(cuda, hidden, classes, mapping):
     with torch.no_grad():
         out = net(data)
     assert close(out, want)
+
+
+@pytest.mark.parametrize("F", [16, 32, 64])
+@pytest.mark.parametrize("H", [16, 32, 64])
+def test_fused_layers_vs_oracle(cuda, F, H):
+    """Fused aggregate+transform kernels (all nine width pairs) against float64 dense algebra; n is not a tile multiple."""
+    g = torch.Generator().manual_seed(F * 100 + H)
+    n, e = 1000 + F, 9000
+    ei = torch.randint(0, n, (2, e), generator=g)
+    key = torch.unique(ei[0] * n + ei[1])
+    ei = torch.stack([key // n, key % n])
+    w = torch.randint(1, 4, (ei.size(1),), generator=g).float()
+    x, W, b = torch.randn(n, F, generator=g), torch.randn(H, F, generator=g) / F ** 0.5, torch.randn(H, generator=g)
+    want_ei, want_norm = pyg.gcn_norm(ei, w, n)
+    agg = torch.zeros(n, F, dtype=torch.float64).index_add_(0, want_ei[1], want_norm.double().unsqueeze(1) * x.double()[want_ei[0]])
+    want = torch.nn.functional.elu(agg @ W.double().t() + b.double())
+    graph = ops.gcn_prepare(ei.to(cuda), w.to(cuda), n)
+    assert ops.fused_supported(F, H)
+    assert close(ops.gcn_layer_fused(graph, x.to(cuda), W.to(cuda), b.to(cuda), _lib.ACT_ELU), want)
+
+    n_ho = 3000
+    bip = torch.stack([torch.arange(n_ho), torch.randint(0, n, (n_ho,), generator=g)])
+    bip[1, :50] = 7  # a popular first-order node
+    x_h, W2, b2 = torch.randn(n_ho, F, generator=g), torch.randn(H, F, generator=g) / F ** 0.5, torch.randn(H, generator=g)
+    from oracle import dbgnn as od
+    want = od.bipartite_operator(x_h.double(), x.double(), bip, n, W.double(), b.double(), W2.double(), b2.double())
+    grouped = ops.csc_build(bip.to(cuda), n_ho, n)
+    got = ops.bipartite_fused(grouped, x_h.to(cuda), x.to(cuda), W.to(cuda), W2.to(cuda), (b + b2).to(cuda), _lib.ACT_NONE)
+    assert close(got, want)
