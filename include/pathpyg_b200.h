@@ -116,14 +116,23 @@ int ppg_unique_rows_gather(const int64_t* rows, int64_t num_rows, int64_t width,
                            int64_t num_unique, int64_t* out_rows, void* stream);
 
 /* remap == NULL: edge ids are used as they are; else id -> remap[id] (remap_len entries).
- * Mapped ids must be < num_nodes (EdgeIndex.validate(), core/graph.py:107) else PPG_ERR_INVALID. */
+ * Mapped ids must be < num_nodes (EdgeIndex.validate(), core/graph.py:107) else PPG_ERR_INVALID.
+ * out_inverse (nullable) [num_edges]: the output edge every input edge was merged into.  Because the
+ * distinct edges of layer k-1 in (row, col) order ARE the distinct k-grams in lexicographic order, this is
+ * the `inverse_idx` of layer k (torch.unique(node_sequence, dim=0), lift_order.py:133) -- no second sort. */
 size_t ppg_coalesce_workspace_bytes(int64_t num_edges, int64_t num_nodes);
 int ppg_coalesce_sort(const int64_t* edge_index, int64_t num_edges, const int64_t* remap, int64_t remap_len,
-                      int64_t num_nodes, void* workspace, size_t workspace_bytes, int64_t* h_num_out, void* stream);
+                      int64_t num_nodes, void* workspace, size_t workspace_bytes, int64_t* out_inverse,
+                      int64_t* h_num_out, void* stream);
 /* weights == NULL: unit weights (the reference's torch.ones default, lift_order.py:130-131), out dtype f32 */
 int ppg_coalesce_fill(const void* workspace, int64_t num_edges, int64_t num_nodes, int64_t num_out,
                       const void* weights, int dtype, int reduce, int64_t* out_edge_index, void* out_weights,
                       void* stream);
+
+/* out_rows[j] = prev_rows[edge_index[0][j]] ++ last(prev_rows[edge_index[1][j]])   (multi_order_model.py:114):
+ * node sequences [num_edges, width+1] of the next layer from the distinct edges of this one. */
+int ppg_extend_rows(const int64_t* prev_rows, int64_t num_prev, int64_t width, const int64_t* edge_index,
+                    int64_t num_edges, int64_t* out_rows, void* stream);
 
 /* Stable sort of the low `end_bit` bits of 64-bit keys (in place) + the permutation that sorts them:
  * the radix sort underneath a4 / the CSC build, exposed for the containers' sort_by and for bench.py.
@@ -147,9 +156,11 @@ int ppg_csc_build(const int64_t* edge_index, int64_t num_edges, int64_t num_sour
                   void* stream);
 
 /* gcn_norm with add_remaining_self_loops(fill_value=1): out_val [E] per CSC slot (0 on self-loop
- * slots), out_self [n] normalised self-loop weight; scratch_dis [n]; edge_weight NULL = ones. */
+ * slots), out_self [n] normalised self-loop weight; scratch_dis [n]; edge_weight NULL = ones;
+ * out_val_edge (nullable) [E]: the same coefficient indexed by ORIGINAL edge id (for the backward view). */
 int ppg_gcn_norm(const int32_t* colptr, const int32_t* src, const int32_t* eid, const float* edge_weight, int64_t n,
-                 int64_t num_edges, float* scratch_dis, float* out_val, float* out_self, void* stream);
+                 int64_t num_edges, float* scratch_dis, float* out_val, float* out_self, float* out_val_edge,
+                 void* stream);
 
 /* out[v] = float(colptr[v+1] - colptr[v]) */
 int ppg_colptr_counts(const int32_t* colptr, int64_t n, float* out, void* stream);
@@ -175,6 +186,28 @@ int ppg_gcn_layer_fused(const int32_t* colptr, const int32_t* src, const float* 
 int ppg_bipartite_fused(const int32_t* colptr, const int32_t* src, const float* X_h, const float* X, const float* W1,
                         const float* W2, const float* bias12, int64_t n, int64_t F, int64_t H, int act, float* out,
                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward of a10/a11 (the reference trains through torch autograd of PyG's GCNConv / propagate;
+ * docs/tutorial/dbgnn.ipynb cell 42).  For Y = act(A X W^T + b):
+ *   dPre = dY * act'(pre), db = colsum(dPre)            ppg_act_backward
+ *   G = A^T dPre                                        ppg_spmm_csc on the source-grouped view
+ *   dW = G^T X                                          ppg_atb
+ *   dX = G W                                            ppg_linear
+ * All reductions have a fixed order (no floating-point atomics).
+ * ------------------------------------------------------------------------------------------- */
+/* dPre[M,H] = dY * act'(.) (ELU: 1 if Y > 0 else Y + 1; Y may be NULL for PPG_ACT_NONE); with rowscale:
+ * dPreScaled = rowscale[:,None] * dPre; out_colsum[H] = column sums of dPreScaled if rowscale else of dPre.
+ * dPre / dPreScaled may be NULL (not written). */
+size_t ppg_act_backward_workspace_bytes(int64_t M, int64_t H);
+int ppg_act_backward(const float* dY, const float* Y, const float* rowscale, int64_t M, int64_t H, int act, float* dPre,
+                     float* dPreScaled, float* out_colsum, void* workspace, size_t workspace_bytes, void* stream);
+/* out[H,F] = A[M,H]^T B[M,F] */
+size_t ppg_atb_workspace_bytes(int64_t M, int64_t H, int64_t F);
+int ppg_atb(const float* A, const float* B, int64_t M, int64_t H, int64_t F, float* out, void* workspace,
+            size_t workspace_bytes, void* stream);
+/* out[i] = src[idx[i]] */
+int ppg_gather_f32(const float* src, const int32_t* idx, int64_t n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,19 +46,25 @@ PROTOTYPES = {
     "ppg_unique_rows_sort": (c_int, [_p, _i64, _i64, _ph_i64, _ph_int, c_int, _p, c_size_t, _p, _ph_i64, _p]),
     "ppg_unique_rows_gather": (c_int, [_p, _i64, _i64, _p, c_int, _i64, _p, _p]),
     "ppg_coalesce_workspace_bytes": (c_size_t, [_i64, _i64]),
-    "ppg_coalesce_sort": (c_int, [_p, _i64, _p, _i64, _i64, _p, c_size_t, _ph_i64, _p]),
+    "ppg_coalesce_sort": (c_int, [_p, _i64, _p, _i64, _i64, _p, c_size_t, _p, _ph_i64, _p]),
+    "ppg_extend_rows": (c_int, [_p, _i64, _i64, _p, _i64, _p, _p]),
     "ppg_coalesce_fill": (c_int, [_p, _i64, _i64, _i64, _p, c_int, c_int, _p, _p, _p]),
     "ppg_sort_pairs_workspace_bytes": (c_size_t, [_i64, c_int]),
     "ppg_sort_pairs_u64": (c_int, [_p, _p, _i64, c_int, _p, c_size_t, POINTER(ctypes.c_float), _p]),
     "ppg_csc_workspace_bytes": (c_size_t, [_i64, _i64]),
     "ppg_csc_build": (c_int, [_p, _i64, _i64, _i64, _p, c_size_t, _p, _p, _p, _p]),
-    "ppg_gcn_norm": (c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p]),
+    "ppg_gcn_norm": (c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
     "ppg_colptr_counts": (c_int, [_p, _i64, _p, _p]),
     "ppg_spmm_csc": (c_int, [_p, _p, _p, _p, _p, _i64, _i64, _p, c_int, _p, _p]),
     "ppg_linear": (c_int, [_p, _p, _i64, _i64, _p, _p, _i64, _p, _p, _i64, c_int, _p, _p]),
     "ppg_gcn_fused_supported": (c_int, [_i64, _i64]),
     "ppg_gcn_layer_fused": (c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, c_int, _p, _p]),
     "ppg_bipartite_fused": (c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, c_int, _p, _p]),
+    "ppg_act_backward_workspace_bytes": (c_size_t, [_i64, _i64]),
+    "ppg_act_backward": (c_int, [_p, _p, _p, _i64, _i64, c_int, _p, _p, _p, _p, c_size_t, _p]),
+    "ppg_atb_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
+    "ppg_atb": (c_int, [_p, _p, _i64, _i64, _i64, _p, _p, c_size_t, _p]),
+    "ppg_gather_f32": (c_int, [_p, _p, _i64, _p, _p]),
 }
 ACT_NONE, ACT_ELU = 0, 1
 

@@ -54,6 +54,60 @@ def _lift_step(edge_index, node_sequence, edge_weight, aggr, save):
     return ho_index, node_sequence, edge_weight, gk
 
 
+class _LayerChain:
+    """Builds the De Bruijn layers of consecutive orders with ONE radix sort per order.
+
+    The reference finds the nodes of layer k with ``torch.unique(node_sequence, dim=0)`` over one k-gram
+    row per line-graph edge of level k-1 (lift_order.py:133) and then coalesces the mapped edges
+    (:139-144): two sorts per order, the first over [E, k] int64 rows.  But the k-gram of such an edge is
+    (the (k-1)-gram of its source) ++ (last node of its target), so two edges carry the same k-gram iff they
+    map to the same layer-(k-1) edge, and k-grams ordered lexicographically are ordered like
+    (rank of prefix, rank of suffix) = the (row, col) order of the coalesced layer-(k-1) edges.  Hence
+
+        nodes of layer k        = distinct edges of layer k-1, in their (row, col) order,
+        inverse_idx of layer k  = the output edge every level-(k-1) edge was merged into,
+        node_sequence of layer k= extend_rows(node_sequence of layer k-1, edge_index of layer k-1),
+
+    and the [E, k] row matrix of the reference (multi_order_model.py:114) is never materialised.
+    """
+
+    def __init__(self, model: "MultiOrderModel", cached: bool, max_order: int):
+        self.model, self.cached, self.max_order = model, cached, max_order
+        self.order = 0
+        self.edge_index = self.node_sequence = self.inverse_next = None
+
+    def _store(self, agg_index, agg_weight, n, node_sequence, inverse_idx) -> None:
+        if self.cached or self.order == self.max_order:
+            data = Data(edge_index=EdgeIndex(agg_index, sparse_size=(n, n), sort_order="row"), num_nodes=n,
+                        node_sequence=node_sequence, edge_weight=agg_weight, inverse_idx=inverse_idx)
+            self.model.layers[self.order] = Graph._from_sorted(data)
+
+    def first_layer(self, edge_index, remap, n, node_sequence, inverse_idx, edge_weight) -> None:
+        self.order = 1
+        more = self.max_order > 1
+        res = ops.coalesce(edge_index, remap, n, edge_weight, "sum", return_inverse=more)
+        self._store(res[0], res[1], n, node_sequence, inverse_idx)
+        if more:
+            # layer-1 ids are the node values themselves, so the 2-grams are the coalesced edges transposed
+            self.edge_index, self.inverse_next = res[0], res[2]
+            self.node_sequence = None
+
+    def next_layer(self, line_index, edge_weight) -> None:
+        """``line_index`` [2, E_k]: the line graph whose nodes are the level-(k-1) edges."""
+        self.order += 1
+        more = self.order < self.max_order
+        if self.node_sequence is None:
+            node_sequence = self.edge_index.t().contiguous()
+        else:
+            node_sequence = ops.extend_rows(self.node_sequence, self.edge_index)
+        n = int(node_sequence.size(0))
+        inverse_idx = self.inverse_next
+        res = ops.coalesce(line_index, inverse_idx, n, edge_weight, "sum", return_inverse=more)
+        self._store(res[0], res[1], n, node_sequence, inverse_idx)
+        self.edge_index, self.node_sequence = res[0], node_sequence
+        self.inverse_next = res[2] if more else None
+
+
 class MultiOrderModel:
     """Higher-order De Bruijn graph layers keyed by order (``layers: dict[int, Graph]``)."""
 
@@ -89,52 +143,44 @@ class MultiOrderModel:
     @staticmethod
     def from_temporal_graph(g: TemporalGraph, delta: float | int = 1, max_order: int = 1, weight: str = "edge_weight",
                             cached: bool = True, event_graph: torch.Tensor | None = None) -> "MultiOrderModel":
-        """multi_order_model.py:124-192."""
+        """multi_order_model.py:124-192, one radix sort per order (see ``_LayerChain``)."""
         m = MultiOrderModel()
         data = g.data if g.data.is_sorted_by_time() else g.data.sort_by_time()
         dev, to_host = _staging.compute_device(data.edge_index, data.time)
         edge_index = _plain(_staging.up(data.edge_index, dev)).long()
-        time = _staging.up(data.time, dev)
         n = int(data.num_nodes)
-        node_sequence = torch.arange(n, device=dev).unsqueeze(1)
         edge_weight = _staging.up(data[weight], dev) if weight in data else None  # None == ones(m), :154-157
 
-        if cached or max_order == 1:
-            m.layers[1] = _aggregate(edge_index, node_sequence, edge_weight)
-            m.layers[1].mapping = g.mapping
-
+        chain = _LayerChain(m, cached, max_order)
+        chain.first_layer(edge_index, None, n, torch.arange(n, device=dev).unsqueeze(1), torch.arange(n, device=dev),
+                          edge_weight)
         if max_order > 1:
-            node_sequence = _extend_node_sequence(node_sequence, edge_index)
             if event_graph is None:
                 # the reference passes `g`, not the locally re-sorted data (:167); identical unless the
                 # caller shuffled time stamps after construction, in which case `g.data` is what counts
                 src_ei = edge_index if data is g.data else _plain(_staging.up(g.data.edge_index, dev)).long()
-                src_t = time if data is g.data else _staging.up(g.data.time, dev)
-                edge_index = ops.lift_order_temporal(src_ei, src_t, delta, n)
+                src_t = _staging.up(data.time if data is g.data else g.data.time, dev)
+                line_index = ops.lift_order_temporal(src_ei, src_t, delta, n)
             else:
-                edge_index = _plain(_staging.up(event_graph, dev)).long()
+                line_index = _plain(_staging.up(event_graph, dev)).long()
             if edge_weight is not None:
-                edge_weight = ops.pair_attributes(edge_index, edge_weight, "src")
-            if cached or max_order == 2:
-                m.layers[2] = _aggregate(edge_index, node_sequence, edge_weight)
-            for k in range(3, max_order + 1):
-                save = cached or k == max_order
-                edge_index, node_sequence, edge_weight, gk = _lift_step(edge_index, node_sequence, edge_weight, "src", save)
-                if save:
-                    m.layers[k] = gk
-
-        for k, layer in m.layers.items():
-            if to_host:
-                layer.to("cpu")
-            if k > 1:
-                layer.mapping = HigherOrderIndexMap(g.mapping, layer.data.node_sequence)
+                edge_weight = ops.pair_attributes(line_index, edge_weight, "src")
+            chain.next_layer(line_index, edge_weight)
+            num_line_nodes = edge_index.size(1)
+            for _ in range(3, max_order + 1):
+                nxt = ops.lift_order_edge_index(line_index, num_line_nodes)
+                if edge_weight is not None:
+                    edge_weight = ops.pair_attributes(nxt, edge_weight, "src")
+                num_line_nodes, line_index = line_index.size(1), nxt
+                chain.next_layer(line_index, edge_weight)
+        m._finish(g.mapping, to_host)
         return m
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
     def from_path_data(path_data: PathData, max_order: int = 1, mode: str = "propagation",
                        cached: bool = True) -> "MultiOrderModel":
-        """multi_order_model.py:194-241."""
+        """multi_order_model.py:194-241, one radix sort per order (see ``_LayerChain``)."""
         m = MultiOrderModel()
         pg = path_data.data
         dev, to_host = _staging.compute_device(pg.edge_index, pg.node_sequence)
@@ -150,19 +196,25 @@ class MultiOrderModel:
         else:
             raise ValueError(f"Unknown mode {mode}")  # the reference dies with a NameError here (:218-224)
 
-        m.layers[1] = _aggregate(edge_index, node_sequence, edge_weight)
-        m.layers[1].mapping = path_data.mapping
-        for k in range(2, max_order + 1):
-            save = cached or k == max_order
-            edge_index, node_sequence, edge_weight, gk = _lift_step(edge_index, node_sequence, edge_weight, aggr, save)
-            if save:
-                m.layers[k] = gk
-        for k, layer in m.layers.items():
+        chain = _LayerChain(m, cached, max_order)
+        unique_nodes, inverse_idx = ops.unique_rows(node_sequence)
+        # first order: the VALUES of node_sequence are the node ids (lift_order.py:135-136)
+        chain.first_layer(edge_index, node_sequence.reshape(-1), int(unique_nodes.size(0)), unique_nodes, inverse_idx,
+                          edge_weight)
+        line_index, num_line_nodes = edge_index, node_sequence.size(0)
+        for _ in range(2, max_order + 1):
+            nxt = ops.lift_order_edge_index(line_index, num_line_nodes)
+            edge_weight = ops.pair_attributes(nxt, edge_weight, aggr)
+            num_line_nodes, line_index = line_index.size(1), nxt
+            chain.next_layer(line_index, edge_weight)
+        m._finish(path_data.mapping, to_host)
+        return m
+
+    def _finish(self, mapping, to_host: bool) -> None:
+        for k, layer in self.layers.items():
             if to_host:
                 layer.to("cpu")
-            if k > 1:
-                layer.mapping = HigherOrderIndexMap(path_data.mapping, layer.data.node_sequence)
-        return m
+            layer.mapping = mapping if k == 1 else HigherOrderIndexMap(mapping, layer.data.node_sequence)
 
     # ------------------------------------------------------------------------------------------
     def to_dbgnn_data(self, max_order: int = 2, mapping: str = "last", x_h: torch.Tensor | None = None) -> Data:

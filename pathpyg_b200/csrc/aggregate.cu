@@ -212,11 +212,30 @@ edge_keys_kernel(const int64_t* __restrict__ ei, int64_t E, const int64_t* __res
 struct RunStartConsumer {
   uint32_t* run_start;
   int64_t n;
+  const uint32_t* perm;  // with `inverse`: the run (= output edge) every input edge fell into
+  int64_t* inverse;      // nullable
   __device__ void operator()(int64_t i, unsigned long long head, unsigned long long prefix) const {
     if (head) run_start[prefix] = static_cast<uint32_t>(i);
     if (i == n - 1) run_start[prefix + head] = static_cast<uint32_t>(n);
+    if (inverse != nullptr) inverse[perm[i]] = static_cast<int64_t>(prefix + head - 1);
   }
 };
+
+// k-gram of every edge of a layer: the (k-1)-gram of its source node + the last node of its target node
+// (multi_order_model.py:114 applied to the DISTINCT edges: these rows are the next layer's node sequences)
+__global__ void __launch_bounds__(256)
+extend_rows_kernel(const int64_t* __restrict__ prev, int width, const int64_t* __restrict__ ei, int64_t n,
+                   int64_t* __restrict__ out) {
+  const int ow = width + 1;
+  const int64_t total = n * ow;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const int64_t j = t / ow;
+    const int c = static_cast<int>(t - j * ow);
+    const int64_t v = c < width ? prev[ei[j] * width + c] : prev[ei[n + j] * width + (width - 1)];
+    st_stream(out + t, v);
+  }
+}
 
 __device__ __forceinline__ float mean_of(float s, uint32_t n) { return s / static_cast<float>(n); }
 __device__ __forceinline__ double mean_of(double s, uint32_t n) { return s / static_cast<double>(n); }
@@ -381,8 +400,8 @@ extern "C" size_t ppg_coalesce_workspace_bytes(int64_t num_edges, int64_t num_no
 }
 
 extern "C" int ppg_coalesce_sort(const int64_t* edge_index, int64_t E, const int64_t* remap, int64_t remap_len,
-                                 int64_t num_nodes, void* workspace, size_t workspace_bytes, int64_t* h_num_out,
-                                 void* stream_) {
+                                 int64_t num_nodes, void* workspace, size_t workspace_bytes, int64_t* out_inverse,
+                                 int64_t* h_num_out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PPG_REQUIRE(E >= 0 && E < (1ll << 31), PPG_ERR_INVALID, "coalesce: %lld edges outside [0, 2^31)", (long long)E);
   PPG_REQUIRE(num_nodes >= 0 && num_nodes <= (1ll << 32), PPG_ERR_INVALID, "coalesce: num_nodes %lld outside [0, 2^32]",
@@ -402,8 +421,8 @@ extern "C" int ppg_coalesce_sort(const int64_t* edge_index, int64_t E, const int
   PPG_TRY(radix_sort_pairs<unsigned long long>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, E, 2 * L.node_bits,
                                                L.sort_ws, &in_b, stream));
   PPG_REQUIRE((in_b != 0) == ((L.passes & 1) != 0), PPG_ERR_CUDA, "coalesce: internal buffer parity mismatch");
-  PPG_TRY(launch_scan(RunHeadProducer{L.sorted_keys()}, RunStartConsumer{L.run_start, E}, E, L.scan_ws,
-                      &L.result->total, stream));
+  PPG_TRY(launch_scan(RunHeadProducer{L.sorted_keys()}, RunStartConsumer{L.run_start, E, L.sorted_perm(), out_inverse}, E,
+                      L.scan_ws, &L.result->total, stream));
   ResultWords h;
   PPG_TRY(read_back(&h, L.result, stream));
   PPG_REQUIRE((h.status & kStatusIdOutOfRange) == 0, PPG_ERR_INVALID,
@@ -430,6 +449,18 @@ extern "C" int ppg_coalesce_fill(const void* workspace, int64_t E, int64_t num_n
     case PPG_I32: return coalesce_fill_dispatch<int, false>(L, num_out, weights, reduce, out_edge_index, out_weights, stream);
     default: PPG_REQUIRE(false, PPG_ERR_INVALID, "coalesce: unsupported dtype code %d", dtype);
   }
+  return PPG_OK;
+}
+
+extern "C" int ppg_extend_rows(const int64_t* prev_rows, int64_t num_prev, int64_t width, const int64_t* edge_index,
+                               int64_t num_edges, int64_t* out_rows, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  (void)num_prev;
+  PPG_REQUIRE(width >= 1 && width < (1 << 20) && num_edges >= 0, PPG_ERR_INVALID, "extend_rows: bad shape");
+  if (num_edges == 0) return PPG_OK;
+  extend_rows_kernel<<<grid_for(num_edges * (width + 1), 256 * 4), 256, 0, stream>>>(prev_rows, static_cast<int>(width),
+                                                                                     edge_index, num_edges, out_rows);
+  PPG_LAUNCHED();
   return PPG_OK;
 }
 

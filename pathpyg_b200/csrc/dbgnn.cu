@@ -109,14 +109,17 @@ gcn_degree_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict_
 __global__ void __launch_bounds__(256)
 gcn_values_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ src, const int32_t* __restrict__ eid,
                   const float* __restrict__ w, const float* __restrict__ dis, int64_t n, float* __restrict__ val,
-                  float* __restrict__ self_val /* in: loop weight, out: normalised loop weight */) {
+                  float* __restrict__ self_val /* in: loop weight, out: normalised loop weight */,
+                  float* __restrict__ val_edge /* nullable: the same coefficient by ORIGINAL edge id */) {
   const int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (v >= n) return;
   const float dv = dis[v];
   for (int32_t i = colptr[v]; i < colptr[v + 1]; ++i) {
     const int32_t u = src[i];
     const float x = w ? w[eid[i]] : 1.f;
-    val[i] = (u == v) ? 0.f : dis[u] * x * dv;
+    const float c = (u == v) ? 0.f : dis[u] * x * dv;
+    val[i] = c;
+    if (val_edge != nullptr) val_edge[eid[i]] = c;
   }
   self_val[v] = dv * self_val[v] * dv;
 }
@@ -319,14 +322,15 @@ extern "C" int ppg_csc_build(const int64_t* edge_index, int64_t E, int64_t num_s
 }
 
 extern "C" int ppg_gcn_norm(const int32_t* colptr, const int32_t* src, const int32_t* eid, const float* edge_weight,
-                            int64_t n, int64_t E, float* scratch_dis, float* out_val, float* out_self, void* stream_) {
+                            int64_t n, int64_t E, float* scratch_dis, float* out_val, float* out_self,
+                            float* out_val_edge, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   (void)E;
   if (n == 0) return PPG_OK;
   const unsigned grid = static_cast<unsigned>(ceil_div(n, 256));
   gcn_degree_kernel<<<grid, 256, 0, stream>>>(colptr, src, eid, edge_weight, n, scratch_dis, out_self);
   PPG_LAUNCHED();
-  gcn_values_kernel<<<grid, 256, 0, stream>>>(colptr, src, eid, edge_weight, scratch_dis, n, out_val, out_self);
+  gcn_values_kernel<<<grid, 256, 0, stream>>>(colptr, src, eid, edge_weight, scratch_dis, n, out_val, out_self, out_val_edge);
   PPG_LAUNCHED();
   return PPG_OK;
 }

@@ -19,6 +19,81 @@ from torch import nn
 from .. import _lib, _staging, ops
 
 
+def _gcn_forward(x, w, b, graph, act):
+    F_in, H = w.size(1), w.size(0)
+    if ops.fused_supported(F_in, H):
+        return ops.gcn_layer_fused(graph, x, w, b, act)  # aggregate + transform + bias + act in one kernel
+    if F_in <= H:                                        # aggregate the narrower side first
+        return ops.linear(ops.spmm_csc(graph, x), w, b, act)
+    return ops.spmm_csc(graph, ops.linear(x, w), b, act)
+
+
+class _GCNLayerFn(torch.autograd.Function):
+    """Y = act(A X W^T + b);  backward: dPre = dY act', G = A^T dPre, dW = G^T X, dX = G W, db = colsum(dPre)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, graph, act):
+        y = _gcn_forward(x, weight, bias, graph, act)
+        ctx.save_for_backward(x, weight, y)
+        ctx.graph, ctx.act = graph, act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        dpre, _, db = ops.act_backward(dy, y, ctx.act)
+        g = ops.spmm_csc(ctx.graph.transposed(), dpre)
+        dw = ops.atb(g, x) if ctx.needs_input_grad[1] else None
+        dx = ops.linear(g, weight.t().contiguous()) if ctx.needs_input_grad[0] else None
+        return dx, dw, (db if ctx.needs_input_grad[2] else None), None, None
+
+
+class _BipartiteFn(torch.autograd.Function):
+    """out = act(S W1^T + c (X W2^T + b1 + b2)), S[v] = sum_{u->v} X_h[u], c = indeg."""
+
+    @staticmethod
+    def forward(ctx, x_h, x, w1, b1, w2, b2, graph, act):
+        if ops.fused_supported(w1.size(1), w1.size(0)):
+            out = ops.bipartite_fused(graph, x_h, x, w1, w2, b1 + b2, act)
+        else:
+            out = ops.linear(ops.spmm_csc(graph, x_h), w1, b1 + b2, act, a2=x, w2=w2, rowscale=ops.colptr_counts(graph))
+        ctx.save_for_backward(x_h, x, w1, w2, out)
+        ctx.graph, ctx.act = graph, act
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x_h, x, w1, w2, out = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        indeg = ops.colptr_counts(ctx.graph)
+        dpre, scaled, db = ops.act_backward(dout, out, ctx.act, rowscale=indeg)
+        g_h = ops.spmm_csc(ctx.graph.transposed(), dpre)            # [n_ho, H]: dPre of the target(s) of every HO node
+        dw1 = ops.atb(g_h, x_h) if need[2] else None
+        dx_h = ops.linear(g_h, w1.t().contiguous()) if need[0] else None
+        dw2 = ops.atb(scaled, x) if need[4] else None
+        dx = ops.linear(scaled, w2.t().contiguous()) if need[1] else None
+        return dx_h, dx, dw1, (db if need[3] else None), dw2, (db if need[5] else None), None, None
+
+
+class _LinearFn(torch.autograd.Function):
+    """out = X W^T + b on the kernels of this package (forward ppg_linear, backward ppg_atb / ppg_linear)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return ops.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dout = dout.contiguous()
+        db = ops.act_backward(dout, None, _lib.ACT_NONE, want_dpre=False)[2] if need[2] else None
+        dw = ops.atb(dout, x) if need[1] else None
+        dx = ops.linear(dout, weight.t().contiguous()) if need[0] else None
+        return dx, dw, db
+
+
 class GCNConv(nn.Module):
     """PyG ``GCNConv(in, out)`` with its defaults (normalize, add_self_loops, bias, not cached):
     ``out = D^-1/2 (A + I) D^-1/2 X W^T + b`` aggregated at the edge target."""
@@ -36,15 +111,10 @@ class GCNConv(nn.Module):
         nn.init.zeros_(self.bias)
 
     def forward_prepared(self, x: torch.Tensor, graph: ops.TargetGroupedEdges, act: int = _lib.ACT_NONE) -> torch.Tensor:
-        w, b = self.lin.weight, self.bias
-        if ops.fused_supported(self.in_channels, self.out_channels):
-            return ops.gcn_layer_fused(graph, x, w, b, act)  # aggregate + transform + bias + act in one kernel
-        if self.in_channels <= self.out_channels:      # aggregate the narrower side first
-            return ops.linear(ops.spmm_csc(graph, x), w, b, act)
-        return ops.spmm_csc(graph, ops.linear(x, w), b, act)
+        return _GCNLayerFn.apply(x, self.lin.weight, self.bias, graph, act)
 
     def forward(self, x, edge_index, edge_weight=None):
-        graph = ops.gcn_prepare(edge_index, edge_weight, x.size(0))
+        graph = ops.gcn_prepare(edge_index, edge_weight, x.size(0), keep_edge_values=torch.is_grad_enabled())
         return self.forward_prepared(x, graph)
 
 
@@ -60,13 +130,7 @@ class BipartiteGraphOperator(nn.Module):
     def forward(self, x, bipartite_index, n_ho: int, n_fo: int, act: int = _lib.ACT_NONE):
         x_h, x_fo = x
         grouped = ops.csc_build(bipartite_index, n_ho, n_fo)
-        if ops.fused_supported(self.lin1.in_features, self.lin1.out_features):
-            return ops.bipartite_fused(grouped, x_h, x_fo, self.lin1.weight, self.lin2.weight,
-                                       self.lin1.bias + self.lin2.bias, act)
-        summed = ops.spmm_csc(grouped, x_h)
-        indeg = ops.colptr_counts(grouped)
-        return ops.linear(summed, self.lin1.weight, self.lin1.bias + self.lin2.bias, act,
-                          a2=x_fo, w2=self.lin2.weight, rowscale=indeg)
+        return _BipartiteFn.apply(x_h, x_fo, self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias, grouped, act)
 
 
 class DBGNN(nn.Module):
@@ -88,8 +152,7 @@ class DBGNN(nn.Module):
         self.lin = nn.Linear(hidden_dims[-1], num_classes)
 
     def forward(self, data) -> torch.Tensor:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("pathpyg_b200.nn.DBGNN: backward pass not built yet -- call under torch.no_grad()")
+        grad = torch.is_grad_enabled()
         dev, to_host = _staging.compute_device(data.x, data.x_h, data.edge_index)
         x, x_h = _staging.up(data.x, dev).float(), _staging.up(data.x_h, dev).float()
         ei, ei_h = _staging.up(data.edge_index, dev), _staging.up(data.edge_index_higher_order, dev)
@@ -98,12 +161,12 @@ class DBGNN(nn.Module):
         n_fo, n_ho = int(data.num_nodes), int(data.num_ho_nodes)
         drop = self.training and self.p_dropout > 0.0
 
-        fo_graph = ops.gcn_prepare(ei, w, n_fo)
+        fo_graph = ops.gcn_prepare(ei, w, n_fo, keep_edge_values=grad)
         for layer in self.first_order_layers:
             if drop:
                 x = F.dropout(x, p=self.p_dropout, training=True)
             x = layer.forward_prepared(x, fo_graph, _lib.ACT_ELU)
-        ho_graph = ops.gcn_prepare(ei_h, w_h, n_ho)
+        ho_graph = ops.gcn_prepare(ei_h, w_h, n_ho, keep_edge_values=grad)
         for layer in self.higher_order_layers:
             if drop:
                 x_h = F.dropout(x_h, p=self.p_dropout, training=True)
@@ -114,5 +177,5 @@ class DBGNN(nn.Module):
         x = self.bipartite_layer((x_h, x), bip, n_ho, n_fo, _lib.ACT_ELU)
         if drop:
             x = F.dropout(x, p=self.p_dropout, training=True)
-        out = ops.linear(x, self.lin.weight, self.lin.bias)
+        out = _LinearFn.apply(x, self.lin.weight, self.lin.bias)
         return _staging.down(out, to_host)

@@ -191,9 +191,10 @@ def unique_rows(node_sequence: torch.Tensor):
 
 
 def coalesce(edge_index: torch.Tensor, remap: torch.Tensor | None, num_nodes: int,
-             edge_weight: torch.Tensor | None, reduce: str = "sum"):
+             edge_weight: torch.Tensor | None, reduce: str = "sum", return_inverse: bool = False):
     """Map edge ids through ``remap`` (or not), merge duplicate (row, col) pairs reducing their weights;
-    result is (row, col)-sorted.  ``edge_weight=None`` means unit float32 weights."""
+    result is (row, col)-sorted.  ``edge_weight=None`` means unit float32 weights.  With
+    ``return_inverse`` a third result gives, per input edge, the output edge it was merged into."""
     if reduce not in _lib.REDUCTIONS:
         raise ValueError(f"Unknown reduce {reduce}")
     lib = _lib.load()
@@ -214,13 +215,29 @@ def coalesce(edge_index: torch.Tensor, remap: torch.Tensor | None, num_nodes: in
     with torch.cuda.device(dev):
         ws = _workspace(lib.ppg_coalesce_workspace_bytes(E, num_nodes), dev)
         n_out = ctypes.c_int64(0)
+        inverse = torch.empty(E, dtype=torch.int64, device=dev) if return_inverse else None
         _lib.check(lib.ppg_coalesce_sort(_ptr(ei), E, _ptr(remap), 0 if remap is None else remap.numel(), num_nodes,
-                                         _ptr(ws), ws.numel(), ctypes.byref(n_out), _stream(dev)))
+                                         _ptr(ws), ws.numel(), _ptr(inverse), ctypes.byref(n_out), _stream(dev)))
         out_ei = torch.empty((2, n_out.value), dtype=torch.int64, device=dev)
         out_w = torch.empty(n_out.value, dtype=w_dtype, device=dev)
         _lib.check(lib.ppg_coalesce_fill(_ptr(ws), E, num_nodes, n_out.value, _ptr(edge_weight), _DTYPE_CODES[w_dtype],
                                          _lib.REDUCTIONS[reduce], _ptr(out_ei), _ptr(out_w), _stream(dev)))
+    if return_inverse:
+        return out_ei, out_w, inverse
     return out_ei, out_w
+
+
+def extend_rows(prev_rows: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+    """``cat([prev[ei[0]], prev[ei[1]][:, -1:]], 1)`` (multi_order_model.py:114) in one kernel."""
+    lib = _lib.load()
+    ei = _edge_index_arg(edge_index)
+    prev = prev_rows.as_subclass(torch.Tensor).contiguous()
+    dev = _require_cuda(ei, prev)
+    n, w = ei.size(1), prev.size(1)
+    out = torch.empty((n, w + 1), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_extend_rows(_ptr(prev), prev.size(0), w, _ptr(ei), n, _ptr(out), _stream(dev)))
+    return out
 
 
 def sort_pairs_u64(keys: torch.Tensor, end_bit: int, time_passes: bool = False):
@@ -241,13 +258,28 @@ def sort_pairs_u64(keys: torch.Tensor, end_bit: int, time_passes: bool = False):
 class TargetGroupedEdges:
     """CSC view of an edge list: incoming edges of every target node, original order inside a target."""
 
-    __slots__ = ("colptr", "src", "eid", "num_sources", "num_targets", "val", "self_val")
+    __slots__ = ("colptr", "src", "eid", "num_sources", "num_targets", "val", "self_val", "val_edge", "edge_index",
+                 "_transposed")
 
     def __init__(self, colptr, src, eid, num_sources, num_targets):
         self.colptr, self.src, self.eid = colptr, src, eid
         self.num_sources, self.num_targets = num_sources, num_targets
         self.val = None       # per-slot coefficient (None = 1)
         self.self_val = None  # per-target coefficient of the node's own row (None = no self term)
+        self.val_edge = None  # the per-slot coefficient indexed by original edge id (kept for the backward view)
+        self.edge_index = None
+        self._transposed = None
+
+    def transposed(self) -> "TargetGroupedEdges":
+        """The same edges grouped by SOURCE node (what the backward pass reduces over): A^T."""
+        if self._transposed is None:
+            t = csc_build(self.edge_index.flip(0), self.num_targets, self.num_sources)
+            if self.val_edge is not None:
+                t.val = gather_f32(self.val_edge, t.eid)
+            t.self_val = self.self_val
+            t._transposed = self
+            self._transposed = t
+        return self._transposed
 
 
 def csc_build(edge_index: torch.Tensor, num_sources: int, num_targets: int) -> TargetGroupedEdges:
@@ -262,10 +294,13 @@ def csc_build(edge_index: torch.Tensor, num_sources: int, num_targets: int) -> T
         ws = _workspace(lib.ppg_csc_workspace_bytes(E, num_targets), dev)
         _lib.check(lib.ppg_csc_build(_ptr(ei), E, num_sources, num_targets, _ptr(ws), ws.numel(), _ptr(colptr), _ptr(src),
                                      _ptr(eid), _stream(dev)))
-    return TargetGroupedEdges(colptr, src, eid, num_sources, num_targets)
+    g = TargetGroupedEdges(colptr, src, eid, num_sources, num_targets)
+    g.edge_index = ei
+    return g
 
 
-def gcn_prepare(edge_index: torch.Tensor, edge_weight: torch.Tensor | None, num_nodes: int) -> TargetGroupedEdges:
+def gcn_prepare(edge_index: torch.Tensor, edge_weight: torch.Tensor | None, num_nodes: int,
+                keep_edge_values: bool = False) -> TargetGroupedEdges:
     """CSC view + symmetric GCN normalisation with remaining self-loops (PyG gcn_norm)."""
     lib = _lib.load()
     g = csc_build(edge_index, num_nodes, num_nodes)
@@ -276,10 +311,56 @@ def gcn_prepare(edge_index: torch.Tensor, edge_weight: torch.Tensor | None, num_
     dis = torch.empty(num_nodes, dtype=torch.float32, device=dev)
     g.val = torch.empty(E, dtype=torch.float32, device=dev)
     g.self_val = torch.empty(num_nodes, dtype=torch.float32, device=dev)
+    if keep_edge_values:
+        g.val_edge = torch.empty(E, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.ppg_gcn_norm(_ptr(g.colptr), _ptr(g.src), _ptr(g.eid), _ptr(edge_weight), num_nodes, E, _ptr(dis),
-                                    _ptr(g.val), _ptr(g.self_val), _stream(dev)))
+                                    _ptr(g.val), _ptr(g.self_val), _ptr(g.val_edge), _stream(dev)))
     return g
+
+
+def gather_f32(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """out[i] = src[idx[i]] (float32 values, int32 indices)."""
+    lib = _lib.load()
+    dev = _require_cuda(src, idx)
+    out = torch.empty(idx.numel(), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_gather_f32(_ptr(src), _ptr(idx), idx.numel(), _ptr(out), _stream(dev)))
+    return out
+
+
+def act_backward(dy: torch.Tensor, y: torch.Tensor | None, act: int, rowscale: torch.Tensor | None = None,
+                 want_dpre: bool = True):
+    """(dPre, dPreScaled, colsum): dPre = dy * act'(.), dPreScaled = rowscale[:, None] * dPre (None without
+    rowscale), colsum = column sums of dPreScaled if rowscale is given else of dPre."""
+    lib = _lib.load()
+    dev = _require_cuda(dy, y, rowscale)
+    dy = dy.contiguous()
+    M, H = dy.shape
+    dpre = torch.empty_like(dy) if want_dpre else None
+    scaled = torch.empty_like(dy) if rowscale is not None else None
+    colsum = torch.empty(H, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_act_backward_workspace_bytes(M, H), dev)
+        _lib.check(lib.ppg_act_backward(_ptr(dy), _ptr(y), _ptr(rowscale), M, H, act, _ptr(dpre), _ptr(scaled), _ptr(colsum),
+                                        _ptr(ws), ws.numel(), _stream(dev)))
+    return dpre, scaled, colsum
+
+
+def atb(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a^T @ b for tall-skinny float32 a [M,H], b [M,F] (weight gradients: reduction over the node dimension)."""
+    lib = _lib.load()
+    dev = _require_cuda(a, b)
+    a, b = a.contiguous(), b.contiguous()
+    M, H = a.shape
+    F = b.size(1)
+    if b.size(0) != M:
+        raise ValueError(f"shape mismatch: {tuple(a.shape)}.T @ {tuple(b.shape)}")
+    out = torch.empty((H, F), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_atb_workspace_bytes(M, H, F), dev)
+        _lib.check(lib.ppg_atb(_ptr(a), _ptr(b), M, H, F, _ptr(out), _ptr(ws), ws.numel(), _stream(dev)))
+    return out
 
 
 def colptr_counts(g: TargetGroupedEdges) -> torch.Tensor:

@@ -131,3 +131,113 @@ def test_fused_layers_vs_oracle(cuda, F, H):
     grouped = ops.csc_build(bip.to(cuda), n_ho, n)
     got = ops.bipartite_fused(grouped, x_h.to(cuda), x.to(cuda), W.to(cuda), W2.to(cuda), (b + b2).to(cuda), _lib.ACT_NONE)
     assert close(got, want)
+
+
+# ------------------------------------------------------------------ backward (autograd of a10 / a11)
+def close_norm(a, b, rtol=RTOL):
+    """Gradient tensors: |a - b| <= rtol * max(1, max|b|) -- sums over all nodes, so the bound is norm-wise."""
+    a, b = a.double().cpu(), b.double().cpu()
+    return bool(((a - b).abs() <= rtol * max(1.0, float(b.abs().max()))).all())
+
+
+@pytest.mark.parametrize("M,H,F", [(1, 1, 1), (5, 3, 7), (1000, 64, 64), (4097, 16, 32), (70000, 64, 16), (333, 70, 130)])
+def test_atb_vs_torch(cuda, M, H, F):
+    g = torch.Generator().manual_seed(M + H)
+    a, b = torch.randn(M, H, generator=g), torch.randn(M, F, generator=g)
+    want = a.double().t() @ b.double()
+    scale = a.double().abs().t() @ b.double().abs()
+    got = ops.atb(a.to(cuda), b.to(cuda)).double().cpu()
+    assert bool(((got - want).abs() <= RTOL * scale.clamp(min=1.0)).all())
+
+
+@pytest.mark.parametrize("M,H", [(1, 1), (77, 5), (1000, 64), (5000, 16), (20000, 100)])
+def test_act_backward_vs_torch(cuda, M, H):
+    g = torch.Generator().manual_seed(M)
+    pre = torch.randn(M, H, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(M, H, generator=g)
+    rs = torch.randint(0, 4, (M,), generator=g).float()
+    y = torch.nn.functional.elu(pre)
+    y.backward(dy.double())
+    dpre, scaled, colsum = ops.act_backward(dy.to(cuda), y.detach().float().to(cuda), _lib.ACT_ELU, rowscale=rs.to(cuda))
+    assert close(dpre, pre.grad)
+    assert close(scaled, rs.double().unsqueeze(1) * pre.grad)
+    want = (rs.double().unsqueeze(1) * pre.grad).sum(0)
+    scale = (rs.double().unsqueeze(1) * pre.grad).abs().sum(0)
+    assert bool(((colsum.double().cpu() - want).abs() <= RTOL * scale.clamp(min=1.0)).all())
+    dpre2, none, colsum2 = ops.act_backward(dy.to(cuda), None, _lib.ACT_NONE)
+    assert none is None and torch.equal(dpre2.cpu(), dy)
+    assert bool(((colsum2.double().cpu() - dy.double().sum(0)).abs() <= RTOL * dy.double().abs().sum(0).clamp(min=1.0)).all())
+
+
+@pytest.mark.parametrize("hidden,classes,mapping", [([16, 32, 8], 4, "last"), ([64, 64, 64], 16, "first"), ([32, 32], 5, "both")])
+def test_dbgnn_backward_vs_autograd(cuda, hidden, classes, mapping):
+    """Gradients of every parameter (and of the input features) against torch autograd through the float64 oracle."""
+    g = torch.Generator().manual_seed(100 + len(hidden))
+    n, m = 400, 6000
+    ei = torch.randint(0, n, (2, m), generator=g)
+    t = torch.sort(torch.randint(0, 200, (m,), generator=g)).values
+    layers = mom.from_temporal_graph(ei, t, n, delta=5, max_order=2)
+    F0, F1 = 24, hidden[0]
+    x, x_h = torch.randn(n, F0, generator=g), torch.randn(layers[2].num_nodes, F1, generator=g)
+    y = torch.randint(0, classes, (n,), generator=g)
+    want_data = mom.to_dbgnn_data(layers, max_order=2, mapping=mapping, x=x, x_h=x_h)
+    params = odbgnn.init_params(classes, (F0, F1), hidden, seed=13)
+    for k in params:  # GCN biases are zero-initialised: make them matter
+        if k.endswith(".bias"):
+            params[k] = params[k] + 0.1 * torch.randn(params[k].shape, generator=g)
+
+    def oracle_grads(dtype):
+        p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in params.items()}
+        d = {k: (v.to(dtype) if isinstance(v, torch.Tensor) and v.is_floating_point() else v) for k, v in want_data.items()}
+        d["x"] = d["x"].clone().requires_grad_(True)
+        d["x_h"] = d["x_h"].clone().requires_grad_(True)
+        loss = torch.nn.functional.cross_entropy(odbgnn.dbgnn_forward(p, d), y)
+        loss.backward()
+        grads = {k: v.grad for k, v in p.items()}
+        grads["x"], grads["x_h"] = d["x"].grad, d["x_h"].grad
+        return loss.detach(), grads
+
+    loss64, want = oracle_grads(torch.float64)
+    loss32, ref32 = oracle_grads(torch.float32)
+    for k in want:  # the reference's own precision meets the bar, so the bar is meaningful
+        assert close_norm(ref32[k], want[k]), k
+
+    tg = pp.TemporalGraph.from_tensors(ei.to(cuda), t.to(cuda), n)
+    mo = pp.MultiOrderModel.from_temporal_graph(tg, delta=5, max_order=2)
+    mo.layers[1].data.x = x.to(cuda).requires_grad_(True)
+    xh_dev = x_h.to(cuda).requires_grad_(True)
+    data = mo.to_dbgnn_data(max_order=2, mapping=mapping, x_h=xh_dev)
+    net = pp.nn.DBGNN(num_classes=classes, num_features=(F0, F1), hidden_dims=hidden).to(cuda).train()
+    load_params(net, params)
+    out = net(data)
+    loss = torch.nn.functional.cross_entropy(out, y.to(cuda))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(loss64)) <= 1e-5 * max(1.0, abs(float(loss64)))
+    for name, p in net.named_parameters():
+        assert p.grad is not None, name
+        assert close_norm(p.grad, want[name]), name
+    assert close_norm(data.x.grad, want["x"])
+    assert close_norm(xh_dev.grad, want["x_h"])
+
+
+def test_dbgnn_training_reduces_loss(cuda):
+    """A few Adam steps on the toy configuration (BASELINE config 1 shape): the loss falls, as in the tutorial."""
+    g = torch.Generator().manual_seed(5)
+    n, m = 30, 400
+    ei = torch.randint(0, n, (2, m), generator=g)
+    t = torch.sort(torch.randint(0, 100, (m,), generator=g)).values
+    tg = pp.TemporalGraph.from_tensors(ei.to(cuda), t.to(cuda), n)
+    mo = pp.MultiOrderModel.from_temporal_graph(tg, delta=3, max_order=2)
+    data = mo.to_dbgnn_data(max_order=2)
+    y = (torch.arange(n) % 3).to(cuda)
+    torch.manual_seed(0)
+    net = pp.nn.DBGNN(num_classes=3, num_features=(data.num_nodes, data.num_ho_nodes), hidden_dims=[16, 32, 8], p_dropout=0.1).to(cuda)
+    opt = torch.optim.Adam(net.parameters(), lr=0.01)
+    losses = []
+    for _ in range(40):
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(net(data), y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < 0.7 * losses[0], losses[::8]
