@@ -187,6 +187,13 @@ int ppg_bipartite_fused(const int32_t* colptr, const int32_t* src, const float* 
                         const float* W2, const float* bias12, int64_t n, int64_t F, int64_t H, int act, float* out,
                         void* stream);
 
+/* The same GCN layer with the dense transform on the tcgen05 tensor cores (3xTF32 split, fp32-accurate),
+ * accumulator in TMEM; F in {32, 64}, H in {16, 32, 64} (ppg_gcn_tc_supported). */
+int ppg_gcn_tc_supported(int64_t F, int64_t H);
+int ppg_gcn_layer_tc(const int32_t* colptr, const int32_t* src, const float* val, const float* self_val, const float* X,
+                     const float* W, const float* bias, int64_t n, int64_t F, int64_t H, int act, float* out,
+                     void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Backward of a10/a11 (the reference trains through torch autograd of PyG's GCNConv / propagate;
  * docs/tutorial/dbgnn.ipynb cell 42).  For Y = act(A X W^T + b):

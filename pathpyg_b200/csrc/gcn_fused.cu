@@ -8,8 +8,9 @@
 // layer) disappears and the output row is written exactly once, bias and ELU applied in registers.
 //
 // One persistent CTA (256 threads) per SM slot loops over 128-node tiles:
-//   phase 1  F/4 lanes per node walk the node's CSC segment, gather source rows with 16-byte loads
-//            (4 edges in flight per lane group) and park the aggregated row in shared memory;
+//   phase 1  lane groups of F/4 lanes own a few consecutive nodes each and walk the contiguous CSC slot range
+//            of those nodes as one flat list, 8 source-row gathers (16-byte loads) in flight per group
+//            independent of the node degrees, parking every finished node's row in shared memory;
 //   phase 2  128 x H x K tile product on the FMA pipe from shared memory (W^T staged once per CTA),
 //            (H/8) x 4 register micro-tile per thread, float4 epilogue stores.
 // Per-layer HBM traffic: 8 e + (4F) e_sl gathered + 4F n (self rows) + 4H n written.
@@ -19,6 +20,7 @@ namespace ppg {
 
 constexpr int kFusedTile = 128;
 constexpr int kFusedThreads = 256;
+constexpr int kGatherBatch = 8;  // row gathers a lane group keeps in flight
 
 __device__ __forceinline__ float fused_activate(float x, int act) {
   return (act == PPG_ACT_ELU && x <= 0.f) ? expm1f(x) : x;
@@ -40,7 +42,8 @@ gcn_fused_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__
   constexpr int K = BIP ? 2 * F : F;
   constexpr int LDA = K + 4;            // row stride of the aggregated tile (floats): 16-byte aligned rows
   constexpr int LPN = F / 4;            // lanes per node
-  constexpr int GPW = 32 / LPN;         // nodes a warp aggregates concurrently
+  constexpr int GPW = 32 / LPN;         // lane groups per warp
+  constexpr int NPG = kFusedTile / ((kFusedThreads / 32) * GPW);  // consecutive nodes owned by a lane group
   constexpr int CG = H / 4;             // column groups (4 output columns per thread)
   constexpr int RG = kFusedThreads / CG;
   constexpr int RPT = kFusedTile / RG;  // output rows per thread
@@ -49,6 +52,7 @@ gcn_fused_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__
   extern __shared__ __align__(16) float smem[];
   float* sA = smem;                    // [128][LDA]
   float* sW = sA + kFusedTile * LDA;   // [K][H] = W^T (bipartite: [W1 | W2]^T)
+  __shared__ int32_t s_ptr[kFusedTile + 1];  // CSC pointers of the tile's nodes
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -72,44 +76,89 @@ gcn_fused_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__
     const int64_t row0 = tile * kFusedTile;
 
     // ---------------- phase 1: segment-reduce the incoming rows of 128 target nodes
-    for (int r = warp * GPW + grp; r < kFusedTile; r += (kFusedThreads / 32) * GPW) {
-      const int64_t v = row0 + r;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 own = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (v < n) {
-        const int32_t a = colptr[v];
-        const int32_t b = colptr[v + 1];
-        int32_t i = a;
-        for (; i + 4 <= b; i += 4) {
-          int32_t s[4];
-          float c[4];
-          float4 x[4];
+    // Each lane group owns NPG consecutive nodes and walks THEIR contiguous CSC slot range as one flat
+    // list, kGatherBatch row gathers in flight at a time, whatever the individual in-degrees are (mean
+    // in-degree of a De Bruijn layer is 2-3: a per-node loop would expose one DRAM latency per edge).
+    // A node's edges are summed in slot order by one lane group (deterministic), its own row first.
+    if (tid <= kFusedTile) {
+      const int64_t v = row0 + tid;
+      s_ptr[tid] = colptr[v < n ? v : n];
+    }
+    __syncthreads();
+    {
+      const int r_lo = (warp * GPW + grp) * NPG;
+      const int32_t e_lo = s_ptr[r_lo];
+      const int32_t e_hi = s_ptr[r_lo + NPG];
+      // own rows: sA[r] = self_v X[v]   (bipartite: sA[r] = [0 | indeg(v) X2[v]])
+      {
+        float4 own[NPG];
+        float coef[NPG];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            s[u] = src[i + u];
-            c[u] = val != nullptr ? val[i + u] : 1.f;
+        for (int q = 0; q < NPG; ++q) {
+          const int64_t v = row0 + r_lo + q;
+          own[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          coef[q] = 0.f;
+          if (v < n) {
+            if (BIP) {
+              own[q] = *reinterpret_cast<const float4*>(X2 + v * F + g * 4);
+              coef[q] = static_cast<float>(s_ptr[r_lo + q + 1] - s_ptr[r_lo + q]);
+            } else if (self_val != nullptr) {
+              own[q] = *reinterpret_cast<const float4*>(X + v * F + g * 4);
+              coef[q] = self_val[v];
+            }
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const float4*>(X + static_cast<int64_t>(s[u]) * F + g * 4);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) fma4(acc, c[u], x[u]);
         }
-        for (; i < b; ++i) {
-          const float c = val != nullptr ? val[i] : 1.f;
-          const float4 x = *reinterpret_cast<const float4*>(X + static_cast<int64_t>(src[i]) * F + g * 4);
-          fma4(acc, c, x);
-        }
-        if (BIP) {
-          const float deg = static_cast<float>(b - a);
-          const float4 x = *reinterpret_cast<const float4*>(X2 + v * F + g * 4);
-          own = make_float4(deg * x.x, deg * x.y, deg * x.z, deg * x.w);
-        } else if (self_val != nullptr) {
-          const float4 x = *reinterpret_cast<const float4*>(X + v * F + g * 4);
-          fma4(acc, self_val[v], x);
+#pragma unroll
+        for (int q = 0; q < NPG; ++q) {
+          const float4 o4 = make_float4(coef[q] * own[q].x, coef[q] * own[q].y, coef[q] * own[q].z, coef[q] * own[q].w);
+          float* dst = sA + (r_lo + q) * LDA + g * 4;
+          if (BIP) {
+            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dst + F) = o4;
+          } else {
+            *reinterpret_cast<float4*>(dst) = o4;
+          }
         }
       }
-      *reinterpret_cast<float4*>(sA + r * LDA + g * 4) = acc;
-      if (BIP) *reinterpret_cast<float4*>(sA + r * LDA + F + g * 4) = own;
+      int r = r_lo;
+      int32_t nb = s_ptr[r + 1];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int32_t i = e_lo; i < e_hi; i += kGatherBatch) {
+        int32_t sidx[kGatherBatch];
+        float c[kGatherBatch];
+        float4 x[kGatherBatch];
+#pragma unroll
+        for (int u = 0; u < kGatherBatch; ++u) {
+          const bool in = i + u < e_hi;
+          sidx[u] = in ? src[i + u] : 0;
+          c[u] = in ? (val != nullptr ? val[i + u] : 1.f) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kGatherBatch; ++u)
+          x[u] = (i + u < e_hi) ? *reinterpret_cast<const float4*>(X + static_cast<int64_t>(sidx[u]) * F + g * 4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < kGatherBatch; ++u) {
+          if (i + u < e_hi) {
+            while (i + u >= nb) {  // the slot belongs to a later node: park the finished one
+              float4* dst = reinterpret_cast<float4*>(sA + r * LDA + g * 4);
+              float4 t = *dst;
+              t.x += acc.x; t.y += acc.y; t.z += acc.z; t.w += acc.w;
+              *dst = t;
+              acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              ++r;
+              nb = s_ptr[r + 1];
+            }
+            fma4(acc, c[u], x[u]);
+          }
+        }
+      }
+      if (e_hi > e_lo) {  // the node the walk ended in (nodes after it have no edges)
+        float4* dst = reinterpret_cast<float4*>(sA + r * LDA + g * 4);
+        float4 t = *dst;
+        t.x += acc.x; t.y += acc.y; t.z += acc.z; t.w += acc.w;
+        *dst = t;
+      }
     }
     __syncthreads();
 

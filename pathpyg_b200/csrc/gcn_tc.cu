@@ -1,0 +1,352 @@
+// Fused GCN layer with the dense transform on the 5th-generation tensor cores (tcgen05, accumulator in TMEM).
+//
+//   out[v,:] = act( (sum_i val_i X[src_i,:] + self_v X[v,:]) W^T + b )        F in {32, 64}, H in {16, 32, 64}
+//
+// Same tiling as gcn_fused.cu (persistent CTAs over 128-node tiles; phase 1 = flat segmented walk over the
+// tile's CSC slots with 8 row gathers in flight per lane group), but the [128 x F] . [F x H] product of
+// phase 2 no longer runs on the FMA pipe, where it costs as much time as the gathers (2*128*64*64 flop per
+// tile = 4096 FMA-pipe cycles per SM): one thread issues tcgen05.mma (kind::tf32, M = 128, N = H, K = 8
+// per instruction) on operands staged in shared memory in the canonical K-major SWIZZLE_128B layout, the
+// accumulator lives in TMEM, and the epilogue reads it back with tcgen05.ld (bias + ELU in registers).
+//
+// fp32 accuracy (north_star: 1e-5 relative): TF32 keeps 10 mantissa bits, so every operand is split
+// x = hi + lo with hi = x truncated to TF32 (exactly representable) and lo = x - hi (exact in fp32), and
+// three MMAs accumulate A_hi W_hi + A_lo W_hi + A_hi W_lo into the same TMEM tile; the dropped term
+// A_lo W_lo is below 2^-21 relative, products of 11-bit significands are exact in the fp32 accumulator.
+#include "common.cuh"
+
+namespace ppg {
+
+constexpr int kTcTile = 128;
+constexpr int kTcThreads = 256;
+constexpr int kTcGatherBatch = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// byte offset of element (row, k) of a [rows x K] fp32 operand in the K-major SWIZZLE_128B canonical layout:
+// 128-byte K blocks (32 floats) are the outer dimension; inside a block every row is 128 contiguous bytes
+// and the 16-byte chunk index is XORed with (row % 8)  (Swizzle<3,4,3> on byte addresses).
+__device__ __forceinline__ uint32_t swz_offset(int rows, int row, int k) {
+  const int kb = k >> 5, kk = k & 31;
+  return static_cast<uint32_t>(kb * rows * 128 + row * 128 + ((((kk >> 2) ^ (row & 7)) << 4) | ((kk & 3) << 2)));
+}
+
+// shared-memory matrix descriptor (sm_100): start address >> 4 in [0,14), leading byte offset [16,30) (unused for
+// swizzled K-major), stride byte offset [32,46) = 8 rows * 128 B, version 1 at [46,48), SWIZZLE_128B = 2 at [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+// instruction descriptor: D = F32 (1 at [4,6)), A = B = TF32 (2 at [7,10) and [10,13)), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  int spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1 << 26)) __trap();  // a lost commit must fail loudly, not hang the device
+  }
+}
+
+template <int N>
+struct TmemLoad;
+template <>
+struct TmemLoad<8> {
+  __device__ static void run(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+  }
+};
+template <>
+struct TmemLoad<16> {
+  __device__ static void run(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+  }
+};
+template <>
+struct TmemLoad<32> {
+  __device__ static void run(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+        "[%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+  }
+};
+
+__device__ __forceinline__ float tc_activate(float x, int act) { return (act == PPG_ACT_ELU && x <= 0.f) ? expm1f(x) : x; }
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = x - hi;
+}
+
+template <int F, int H>
+__global__ void __launch_bounds__(kTcThreads, 2)
+gcn_tc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ src, const float* __restrict__ val,
+              const float* __restrict__ self_val, const float* __restrict__ X, const float* __restrict__ W,
+              const float* __restrict__ bias, int64_t n, int act, float* __restrict__ out) {
+  static_assert(F % 32 == 0 && (H == 16 || H == 32 || H == 64), "unsupported width");
+  constexpr int LPN = F / 4;                                   // lanes per lane group (one float4 each)
+  constexpr int GPW = 32 / LPN;                                // lane groups per warp
+  constexpr int NPG = kTcTile / ((kTcThreads / 32) * GPW);     // consecutive nodes owned by a lane group
+  constexpr int A_BYTES = kTcTile * F * 4;
+  constexpr int W_BYTES = H * F * 4;
+  constexpr int TMEM_COLS = H < 32 ? 32 : H;
+  constexpr int CPT = H / 2;                                   // accumulator columns per thread in the epilogue
+  constexpr uint32_t IDESC = umma_idesc_tf32(kTcTile, H);
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  unsigned char* sAhi = base;
+  unsigned char* sAlo = base + A_BYTES;
+  unsigned char* sWhi = base + 2 * A_BYTES;
+  unsigned char* sWlo = sWhi + W_BYTES;
+  __shared__ __align__(8) unsigned long long s_mbar;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ int32_t s_ptr[kTcTile + 1];
+  __shared__ float s_bias[H];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  // ---- one-time setup: W^T split into TF32 hi / lo parts, bias, TMEM allocation, completion barrier
+  for (int idx = tid; idx < H * F; idx += kTcThreads) {
+    const int h = idx / F, k = idx % F;
+    float hi, lo;
+    split_tf32(W[idx], hi, lo);
+    const uint32_t off = swz_offset(H, h, k);
+    *reinterpret_cast<float*>(sWhi + off) = hi;
+    *reinterpret_cast<float*>(sWlo + off) = lo;
+  }
+  if (tid < H) s_bias[tid] = bias != nullptr ? bias[tid] : 0.f;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem_base;
+  const uint32_t mbar = smem_u32(&s_mbar);
+  uint32_t parity = 0;
+
+  const int g = lane % LPN;
+  const int grp = lane / LPN;
+  const int64_t num_tiles = ceil_div(n, kTcTile);
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kTcTile;
+
+    // ---------------- phase 1: segment-reduce the incoming rows of 128 target nodes (see gcn_fused.cu)
+    if (tid <= kTcTile) {
+      const int64_t v = row0 + tid;
+      s_ptr[tid] = colptr[v < n ? v : n];
+    }
+    __syncthreads();
+    {
+      const int r_lo = (warp * GPW + grp) * NPG;
+      const int32_t e_lo = s_ptr[r_lo];
+      const int32_t e_hi = s_ptr[r_lo + NPG];
+      // own rows first: self_v X[v], parked (full fp32) in the hi buffer until the node is finished
+      {
+        float4 own[NPG];
+        float coef[NPG];
+#pragma unroll
+        for (int q = 0; q < NPG; ++q) {
+          const int64_t v = row0 + r_lo + q;
+          own[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          coef[q] = 0.f;
+          if (v < n && self_val != nullptr) {
+            own[q] = *reinterpret_cast<const float4*>(X + v * F + g * 4);
+            coef[q] = self_val[v];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < NPG; ++q)
+          *reinterpret_cast<float4*>(sAhi + swz_offset(kTcTile, r_lo + q, g * 4)) =
+              make_float4(coef[q] * own[q].x, coef[q] * own[q].y, coef[q] * own[q].z, coef[q] * own[q].w);
+      }
+      int r = r_lo;
+      int32_t nb = s_ptr[r + 1];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto finish_node = [&](int row, const float4& a) {
+        const uint32_t off = swz_offset(kTcTile, row, g * 4);
+        const float4 o = *reinterpret_cast<const float4*>(sAhi + off);
+        float4 hi, lo;
+        split_tf32(o.x + a.x, hi.x, lo.x);
+        split_tf32(o.y + a.y, hi.y, lo.y);
+        split_tf32(o.z + a.z, hi.z, lo.z);
+        split_tf32(o.w + a.w, hi.w, lo.w);
+        *reinterpret_cast<float4*>(sAhi + off) = hi;
+        *reinterpret_cast<float4*>(sAlo + off) = lo;
+      };
+      for (int32_t i = e_lo; i < e_hi; i += kTcGatherBatch) {
+        int32_t sidx[kTcGatherBatch];
+        float c[kTcGatherBatch];
+        float4 x[kTcGatherBatch];
+#pragma unroll
+        for (int u = 0; u < kTcGatherBatch; ++u) {
+          const bool in = i + u < e_hi;
+          sidx[u] = in ? src[i + u] : 0;
+          c[u] = in ? (val != nullptr ? val[i + u] : 1.f) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < kTcGatherBatch; ++u)
+          x[u] = (i + u < e_hi) ? *reinterpret_cast<const float4*>(X + static_cast<int64_t>(sidx[u]) * F + g * 4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < kTcGatherBatch; ++u) {
+          if (i + u < e_hi) {
+            while (i + u >= nb) {  // the slot belongs to a later node: finish the current one
+              finish_node(r, acc);
+              acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              ++r;
+              nb = s_ptr[r + 1];
+            }
+            acc.x = fmaf(c[u], x[u].x, acc.x);
+            acc.y = fmaf(c[u], x[u].y, acc.y);
+            acc.z = fmaf(c[u], x[u].z, acc.z);
+            acc.w = fmaf(c[u], x[u].w, acc.w);
+          }
+        }
+      }
+      for (; r < r_lo + NPG; ++r) {  // the node the walk ended in, and the edge-less nodes after it
+        finish_node(r, acc);
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    // generic-proxy writes of the operands -> visible to the tensor core (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    // ---------------- phase 2: D[128 x H] (TMEM) = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T, one issuing thread
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), w_hi = smem_u32(sWhi), w_lo = smem_u32(sWlo);
+      uint32_t accumulate = 0;
+#pragma unroll
+      for (int j = 0; j < F / 8; ++j) {  // K = 8 per tf32 instruction: 32 bytes along the 128-byte swizzled row
+        const uint32_t a_off = (j >> 2) * (kTcTile * 128) + (j & 3) * 32;
+        const uint32_t w_off = (j >> 2) * (H * 128) + (j & 3) * 32;
+        umma_tf32(tmem_base, umma_desc(a_hi + a_off), umma_desc(w_hi + w_off), IDESC, accumulate);
+        accumulate = 1;
+        umma_tf32(tmem_base, umma_desc(a_lo + a_off), umma_desc(w_hi + w_off), IDESC, 1);
+        umma_tf32(tmem_base, umma_desc(a_hi + a_off), umma_desc(w_lo + w_off), IDESC, 1);
+      }
+      // arrives on the barrier when all MMAs above have completed (implies tcgen05.fence::before_thread_sync)
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+    }
+    mbar_wait(mbar, parity);
+    parity ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---------------- epilogue: TMEM -> registers (thread = one row, CPT consecutive columns) -> bias + act -> HBM
+    {
+      uint32_t d[CPT];
+      const int col0 = (warp >> 2) * CPT;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(col0);
+      TmemLoad<CPT>::run(taddr, d);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int64_t v = row0 + (warp & 3) * 32 + lane;
+      if (v < n) {
+        float* o = out + v * H + col0;
+#pragma unroll
+        for (int c = 0; c < CPT; c += 4) {
+          float4 r4;
+          r4.x = tc_activate(__uint_as_float(d[c + 0]) + s_bias[col0 + c + 0], act);
+          r4.y = tc_activate(__uint_as_float(d[c + 1]) + s_bias[col0 + c + 1], act);
+          r4.z = tc_activate(__uint_as_float(d[c + 2]) + s_bias[col0 + c + 2], act);
+          r4.w = tc_activate(__uint_as_float(d[c + 3]) + s_bias[col0 + c + 3], act);
+          *reinterpret_cast<float4*>(o + c) = r4;
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // TMEM tile and operand buffers are free for the next tile
+  }
+
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int F, int H>
+static int launch_tc(const int32_t* colptr, const int32_t* src, const float* val, const float* self_val, const float* X,
+                     const float* W, const float* bias, int64_t n, int act, float* out, cudaStream_t stream) {
+  constexpr size_t smem = 2 * static_cast<size_t>(kTcTile) * F * 4 + 2 * static_cast<size_t>(H) * F * 4 + 1024;
+  auto kern = gcn_tc_kernel<F, H>;
+  static bool configured = false;
+  if (!configured) {
+    PPG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  const int64_t tiles = ceil_div(n, kTcTile);
+  const int64_t slots = static_cast<int64_t>(kNumSMsB200) * 2;
+  const unsigned grid = static_cast<unsigned>(tiles < slots ? tiles : slots);
+  kern<<<grid, kTcThreads, smem, stream>>>(colptr, src, val, self_val, X, W, bias, n, act, out);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
+}  // namespace ppg
+
+using namespace ppg;
+
+extern "C" int ppg_gcn_tc_supported(int64_t F, int64_t H) {
+  return ((F == 32 || F == 64) && (H == 16 || H == 32 || H == 64)) ? 1 : 0;
+}
+
+extern "C" int ppg_gcn_layer_tc(const int32_t* colptr, const int32_t* src, const float* val, const float* self_val,
+                                const float* X, const float* W, const float* bias, int64_t n, int64_t F, int64_t H,
+                                int act, float* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n == 0) return PPG_OK;
+#define PPG_TC_CASE(FF, HH) \
+  if (F == FF && H == HH) return launch_tc<FF, HH>(colptr, src, val, self_val, X, W, bias, n, act, out, stream)
+  PPG_TC_CASE(32, 16); PPG_TC_CASE(32, 32); PPG_TC_CASE(32, 64);
+  PPG_TC_CASE(64, 16); PPG_TC_CASE(64, 32); PPG_TC_CASE(64, 64);
+#undef PPG_TC_CASE
+  PPG_REQUIRE(false, PPG_ERR_INVALID, "tensor-core layer: widths F=%lld H=%lld not supported", (long long)F, (long long)H);
+}

@@ -12,10 +12,8 @@
 // memory), the tile is reordered through shared memory, and every digit's run is written out as
 // one contiguous (coalesced) segment.
 //
-// Look-back: thread d owns digit d and walks the preceding tiles' published words.  A serial walk
-// costs one L2 round trip per hop, which at the sizes of BASELINE config 2 (a few hundred tiles that
-// all start together) dominated the pass; the walk therefore keeps kLookBatch independent loads in
-// flight and consumes them in order.
+// Look-back: thread d owns digit d.  Two levels (tiles inside a group of 16, then groups), every walk with
+// kLookBatch independent loads in flight consumed in order -- see the comment in the kernel.
 //
 // Tile size: 256 threads x 8 keys up to 4M keys (more tiles than SM slots => one balanced wave, short
 // chain hops), 256 x 16 beyond (less look-back state, fewer fixed costs per key).
@@ -23,6 +21,8 @@
 // The payload is an optional u32 per key; the first pass can synthesise it as the element index
 // (IOTA) so that an index permutation costs no read.
 #pragma once
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ppg {
@@ -32,18 +32,33 @@ constexpr int kRadix = 1 << kRadixBits;
 constexpr int kSortBlock = 256;  // == kRadix: thread d owns digit d in the per-digit phases
 constexpr int kMaxPasses = 8;
 constexpr int kLookBatch = 8;
+constexpr int kLookGroup = 16;  // tiles per look-back group
 constexpr int64_t kSmallSortLimit = 4ll << 20;
 
-__host__ __device__ inline int sort_items_for(int64_t n) { return n <= kSmallSortLimit ? 8 : 16; }
-__host__ __device__ inline int64_t sort_num_tiles(int64_t n) {
+// development override: PPG_SORT_ITEMS=8|16 forces the tile size
+inline int sort_items_override() {
+  static const int v = [] {
+    const char* e = getenv("PPG_SORT_ITEMS");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+inline int sort_items_for(int64_t n) {
+  const int o = sort_items_override();
+  if (o == 8 || o == 16) return o;
+  return n <= kSmallSortLimit ? 8 : 16;
+}
+inline int64_t sort_num_tiles(int64_t n) {
   return n > 0 ? ceil_div(n, static_cast<int64_t>(kSortBlock) * sort_items_for(n)) : 1;
 }
 inline int sort_num_passes(int end_bit) { return end_bit <= 0 ? 1 : static_cast<int>(ceil_div(end_bit, kRadixBits)); }
 
-// zero-initialised words a sort needs: [P*256 histogram][P tile counters (u64 each)][tiles*256 look-back words]
+inline size_t sort_num_groups(int64_t n) { return static_cast<size_t>(ceil_div(sort_num_tiles(n), kLookGroup)); }
+// zero-initialised words a sort needs:
+// [P*256 histogram][P tile counters (u64 each)][tiles*256 tile words][groups*256 group words]
 inline size_t sort_state_words(int64_t n, int end_bit) {
   const size_t P = static_cast<size_t>(sort_num_passes(end_bit));
-  return P * kRadix + P + static_cast<size_t>(sort_num_tiles(n)) * kRadix;
+  return P * kRadix + P + (static_cast<size_t>(sort_num_tiles(n)) + sort_num_groups(n)) * kRadix;
 }
 
 template <typename KeyT>
@@ -80,7 +95,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                      const unsigned long long* __restrict__ ghist,  // this pass: 256 digit counts
                      unsigned* __restrict__ tile_counter, unsigned long long* __restrict__ state,
-                     unsigned code_partial, unsigned code_inclusive) {
+                     unsigned long long* __restrict__ gstate, unsigned code_partial, unsigned code_inclusive) {
   constexpr int NW = kSortBlock / 32;
   constexpr int TILE = kSortBlock * ITEMS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -114,21 +129,26 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   }
 
   // ---- stable rank inside the warp, digit counts per warp
+  // All match.any are issued before the first is consumed (their latency overlaps); the counter updates
+  // that follow are one shared-memory atomic per distinct digit per round, in item order (=> stable).
   uint32_t rank[ITEMS];
   uint32_t* my_hist = s_whist + warp * kRadix;
+  {
+    unsigned peers[ITEMS];
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
-    const unsigned peers = __match_any_sync(kFullMask, d);
-    const int leader = 31 - __clz(peers);
-    uint32_t before = 0;
-    if (static_cast<int>(lane) == leader) {
-      before = my_hist[d];
-      my_hist[d] = before + __popc(peers);
+    for (int i = 0; i < ITEMS; ++i) {
+      const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
+      peers[i] = __match_any_sync(kFullMask, d);
     }
-    before = __shfl_sync(kFullMask, before, leader);
-    rank[i] = before + __popc(peers & lanemask_lt());
-    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
+      const int leader = 31 - __clz(peers[i]);
+      uint32_t before = 0;
+      if (static_cast<int>(lane) == leader) before = atomicAdd(&my_hist[d], static_cast<uint32_t>(__popc(peers[i])));
+      before = __shfl_sync(kFullMask, before, leader);
+      rank[i] = before + __popc(peers[i] & lanemask_lt());
+    }
   }
   __syncthreads();
 
@@ -147,20 +167,53 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
     if (tid == kRadix - 1) sum -= static_cast<uint32_t>(TILE - valid_in_tile);
     count = sum;
   }
-  unsigned long long* my_state = state + static_cast<size_t>(tile) * kRadix + tid;
-  unsigned long long prev = 0;  // keys with this digit in earlier tiles
-  if (tile == 0) {
-    state_store(my_state, code_inclusive, count);
+  // ---- two-level decoupled look-back (thread d owns digit d)
+  // Tiles are grouped by kLookGroup.  A tile sums the partial counts of the earlier tiles of its own group
+  // (all loads independent), the last tile of a group publishes the group aggregate, and the prefix over
+  // earlier groups comes from a look-back over the group words (aggregate -> inclusive, as in single-level
+  // decoupled look-back).  When all tiles of a sort start together (n up to a few million keys: tiles ~ SM
+  // slots) a single-level walk is a dependent chain of ~tiles/16 L2 round trips and reads ~tiles^2/4 words;
+  // here it is <= 2 + groups/8 round trips and <= (kLookGroup + groups) words per tile and digit.
+  const unsigned grp_id = tile / kLookGroup;
+  const unsigned in_grp = tile % kLookGroup;
+  state_store(state + static_cast<size_t>(tile) * kRadix + tid, code_partial, count);
+  unsigned long long within = 0;  // keys with this digit in the earlier tiles of this group
+  {
+    int64_t q = static_cast<int64_t>(tile) - 1;
+    const int64_t stop = static_cast<int64_t>(grp_id) * kLookGroup;
+    while (q >= stop) {
+      unsigned long long w[kLookBatch];
+#pragma unroll
+      for (int j = 0; j < kLookBatch; ++j) {
+        const int64_t qq = q - j;
+        w[j] = qq >= stop ? state_load(state + static_cast<size_t>(qq) * kRadix + tid) : 0ull;
+      }
+      int consumed = 0;
+#pragma unroll
+      for (int j = 0; j < kLookBatch; ++j) {
+        if (consumed == j && q - j >= stop && static_cast<unsigned>(w[j] >> 56) == code_partial) {
+          within += w[j] & kStateValueMask;
+          consumed = j + 1;
+        }
+      }
+      q -= consumed;  // unpublished words are polled again
+    }
+  }
+  const bool closes_group = in_grp == kLookGroup - 1;
+  unsigned long long* my_group = gstate + static_cast<size_t>(grp_id) * kRadix + tid;
+  unsigned long long before_group = 0;  // keys with this digit in earlier groups
+  if (grp_id == 0) {
+    if (closes_group) state_store(my_group, code_inclusive, within + count);
   } else {
-    state_store(my_state, code_partial, count);
-    int64_t q = static_cast<int64_t>(tile) - 1;  // newest tile not yet accounted for
+    if (closes_group) state_store(my_group, code_partial, within + count);
+    int64_t q = static_cast<int64_t>(grp_id) - 1;
     bool done = false;
     while (!done) {
       unsigned long long w[kLookBatch];
 #pragma unroll
       for (int j = 0; j < kLookBatch; ++j) {
         const int64_t qq = q - j;
-        w[j] = qq >= 0 ? state_load(state + static_cast<size_t>(qq) * kRadix + tid) : 0ull;
+        w[j] = qq >= 0 ? state_load(gstate + static_cast<size_t>(qq) * kRadix + tid) : 0ull;
       }
       int consumed = 0;
 #pragma unroll
@@ -168,18 +221,19 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
         if (!done && consumed == j) {
           const unsigned code = static_cast<unsigned>(w[j] >> 56);
           if (code == code_inclusive) {
-            prev += w[j] & kStateValueMask;
+            before_group += w[j] & kStateValueMask;
             done = true;
           } else if (code == code_partial) {
-            prev += w[j] & kStateValueMask;
+            before_group += w[j] & kStateValueMask;
             consumed = j + 1;
-          }  // else: not published yet -> poll again from this tile
+          }  // else: not published yet -> poll again from this group
         }
       }
-      q -= consumed;  // tile 0 always publishes an inclusive word, so the walk ends at q >= 0
+      q -= consumed;  // group 0 always ends up inclusive, so the walk ends at q >= 0
     }
-    state_store(my_state, code_inclusive, prev + count);
+    if (closes_group) state_store(my_group, code_inclusive, before_group + within + count);
   }
+  const unsigned long long prev = before_group + within;  // keys with this digit in earlier tiles
 
   // ---- block exclusive scans over the 256 digits: slot of the digit in the tile, and in the output
   unsigned long long g = ghist[tid];
@@ -244,7 +298,8 @@ constexpr size_t onesweep_smem_bytes() {
 template <typename KeyT, bool HAS_VALUES, bool IOTA, int ITEMS>
 inline int launch_onesweep_pass_items(const KeyT* kin, KeyT* kout, const uint32_t* vin, uint32_t* vout, int64_t n,
                                       int shift, const unsigned long long* ghist, unsigned* counter,
-                                      unsigned long long* state, unsigned pass, cudaStream_t stream) {
+                                      unsigned long long* state, unsigned long long* gstate, unsigned pass,
+                                      cudaStream_t stream) {
   auto kern = onesweep_pass_kernel<KeyT, HAS_VALUES, IOTA, ITEMS>;
   constexpr size_t smem = onesweep_smem_bytes<KeyT, HAS_VALUES, ITEMS>();
   static bool configured = false;  // per instantiation
@@ -253,7 +308,7 @@ inline int launch_onesweep_pass_items(const KeyT* kin, KeyT* kout, const uint32_
     configured = true;
   }
   kern<<<static_cast<unsigned>(sort_num_tiles(n)), kSortBlock, smem, stream>>>(
-      kin, kout, vin, vout, n, shift, ghist, counter, state, 2 * pass + 1, 2 * pass + 2);
+      kin, kout, vin, vout, n, shift, ghist, counter, state, gstate, 2 * pass + 1, 2 * pass + 2);
   PPG_LAUNCHED();
   return PPG_OK;
 }
@@ -261,10 +316,10 @@ inline int launch_onesweep_pass_items(const KeyT* kin, KeyT* kout, const uint32_
 template <typename KeyT, bool HAS_VALUES, bool IOTA>
 inline int launch_onesweep_pass(const KeyT* kin, KeyT* kout, const uint32_t* vin, uint32_t* vout, int64_t n, int shift,
                                 const unsigned long long* ghist, unsigned* counter, unsigned long long* state,
-                                unsigned pass, cudaStream_t stream) {
+                                unsigned long long* gstate, unsigned pass, cudaStream_t stream) {
   if (sort_items_for(n) == 8)
-    return launch_onesweep_pass_items<KeyT, HAS_VALUES, IOTA, 8>(kin, kout, vin, vout, n, shift, ghist, counter, state, pass, stream);
-  return launch_onesweep_pass_items<KeyT, HAS_VALUES, IOTA, 16>(kin, kout, vin, vout, n, shift, ghist, counter, state, pass, stream);
+    return launch_onesweep_pass_items<KeyT, HAS_VALUES, IOTA, 8>(kin, kout, vin, vout, n, shift, ghist, counter, state, gstate, pass, stream);
+  return launch_onesweep_pass_items<KeyT, HAS_VALUES, IOTA, 16>(kin, kout, vin, vout, n, shift, ghist, counter, state, gstate, pass, stream);
 }
 
 // Sorts the significant bits [0, end_bit) of keys_a (n elements) with an optional u32 payload.
@@ -286,6 +341,7 @@ inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32
   unsigned long long* ghist = zeroed_ws;
   unsigned long long* counters = zeroed_ws + static_cast<size_t>(P) * kRadix;
   unsigned long long* state = counters + P;
+  unsigned long long* gstate = state + static_cast<size_t>(sort_num_tiles(n)) * kRadix;
   *in_b = 0;
   if (n == 0) return PPG_OK;
 
@@ -302,11 +358,11 @@ inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32
     const unsigned long long* h = ghist + static_cast<size_t>(p) * kRadix;
     const int shift = p * kRadixBits;
     if (!has_values) {
-      PPG_TRY((launch_onesweep_pass<KeyT, false, false>(kin, kout, nullptr, nullptr, n, shift, h, counter, state, p, stream)));
+      PPG_TRY((launch_onesweep_pass<KeyT, false, false>(kin, kout, nullptr, nullptr, n, shift, h, counter, state, gstate, p, stream)));
     } else if (p == 0 && iota_payload) {
-      PPG_TRY((launch_onesweep_pass<KeyT, true, true>(kin, kout, nullptr, vout, n, shift, h, counter, state, p, stream)));
+      PPG_TRY((launch_onesweep_pass<KeyT, true, true>(kin, kout, nullptr, vout, n, shift, h, counter, state, gstate, p, stream)));
     } else {
-      PPG_TRY((launch_onesweep_pass<KeyT, true, false>(kin, kout, vin, vout, n, shift, h, counter, state, p, stream)));
+      PPG_TRY((launch_onesweep_pass<KeyT, true, false>(kin, kout, vin, vout, n, shift, h, counter, state, gstate, p, stream)));
     }
     KeyT* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = (p == 0 && iota_payload) ? vals_a : vin;

@@ -21,6 +21,8 @@ from .. import _lib, _staging, ops
 
 def _gcn_forward(x, w, b, graph, act):
     F_in, H = w.size(1), w.size(0)
+    if ops.tc_supported(F_in, H):
+        return ops.gcn_layer_tc(graph, x, w, b, act)     # aggregate + tcgen05 transform + bias + act in one kernel
     if ops.fused_supported(F_in, H):
         return ops.gcn_layer_fused(graph, x, w, b, act)  # aggregate + transform + bias + act in one kernel
     if F_in <= H:                                        # aggregate the narrower side first

@@ -8,6 +8,7 @@ There is no CPU implementation: without a CUDA device or without the built libra
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -428,6 +429,30 @@ def gcn_layer_fused(g: TargetGroupedEdges, x: torch.Tensor, weight: torch.Tensor
     with torch.cuda.device(dev):
         _lib.check(lib.ppg_gcn_layer_fused(_ptr(g.colptr), _ptr(g.src), _ptr(g.val), _ptr(g.self_val), _ptr(x), _ptr(weight),
                                            _ptr(bias), g.num_targets, F, H, act, _ptr(out), _stream(dev)))
+    return out
+
+
+def tc_supported(in_width: int, out_width: int) -> bool:
+    """Widths for which the layer runs its dense transform on the tcgen05 tensor cores.
+    ``PPG_GCN_FMA=1`` in the environment selects the FMA-pipe kernel instead (A/B comparison)."""
+    if os.environ.get("PPG_GCN_FMA", "0") == "1":
+        return False
+    return bool(_lib.load().ppg_gcn_tc_supported(in_width, out_width))
+
+
+def gcn_layer_tc(g: TargetGroupedEdges, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None,
+                 act: int = _lib.ACT_NONE) -> torch.Tensor:
+    """act((A_norm x) W^T + b): segment-reduce gather + tcgen05 (3xTF32) transform in one kernel."""
+    lib = _lib.load()
+    dev = _require_cuda(x, weight, bias, g.colptr)
+    x, weight = x.contiguous(), weight.contiguous()
+    H, F = weight.shape
+    if x.size(1) != F or x.size(0) < g.num_sources:
+        raise ValueError(f"shape mismatch: features {tuple(x.shape)}, weight {tuple(weight.shape)}, graph sources {g.num_sources}")
+    out = torch.empty((g.num_targets, H), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_gcn_layer_tc(_ptr(g.colptr), _ptr(g.src), _ptr(g.val), _ptr(g.self_val), _ptr(x), _ptr(weight),
+                                        _ptr(bias), g.num_targets, F, H, act, _ptr(out), _stream(dev)))
     return out
 
 

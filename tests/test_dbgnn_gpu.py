@@ -241,3 +241,38 @@ def test_dbgnn_training_reduces_loss(cuda):
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < 0.7 * losses[0], losses[::8]
+
+
+@pytest.mark.parametrize("F", [32, 64])
+@pytest.mark.parametrize("H", [16, 32, 64])
+def test_tensor_core_layer_vs_oracle(cuda, F, H):
+    """tcgen05 (3xTF32 split) GCN layer against float64 dense algebra: the same 1e-5 bar as the FMA kernels.
+    Rows without edges, several tiles, n not a tile multiple, a heavy-tailed in-degree."""
+    g = torch.Generator().manual_seed(F * 7 + H)
+    n, e = 1000 + F, 12000
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei[1, :3000] = torch.randint(0, 5, (3000,), generator=g)   # a few nodes with ~600 in-edges
+    ei = ei[:, ei[1] % 7 != 3]                                 # some nodes without any in-edge
+    key = torch.unique(ei[0] * n + ei[1])
+    ei = torch.stack([key // n, key % n])
+    w = torch.randint(1, 4, (ei.size(1),), generator=g).float()
+    x, W, b = torch.randn(n, F, generator=g) * 3.0, torch.randn(H, F, generator=g) / F ** 0.5, torch.randn(H, generator=g)
+    want_ei, want_norm = pyg.gcn_norm(ei, w, n)
+    agg = torch.zeros(n, F, dtype=torch.float64).index_add_(0, want_ei[1], want_norm.double().unsqueeze(1) * x.double()[want_ei[0]])
+    pre = agg @ W.double().t() + b.double()
+    graph = ops.gcn_prepare(ei.to(cuda), w.to(cuda), n)
+    assert ops.tc_supported(F, H)
+    for act, want in ((_lib.ACT_ELU, torch.nn.functional.elu(pre)), (_lib.ACT_NONE, pre)):
+        got = ops.gcn_layer_tc(graph, x.to(cuda), W.to(cuda), b.to(cuda), act)
+        # condition-aware bound: the dot products cancel, so the error scales with sum |a_k w_k|
+        scale = (agg.abs() @ W.double().abs().t() + b.double().abs()).clamp(min=1.0)
+        assert bool(((got.double().cpu() - want).abs() <= RTOL * scale).all()), (F, H, act)
+        assert close(got, ops.gcn_layer_fused(graph, x.to(cuda), W.to(cuda), b.to(cuda), act))
+    # no bias, no self term (plain segment sum) and repeated launches (TMEM alloc / dealloc, barrier phases)
+    graph.self_val = None
+    for _ in range(3):
+        got = ops.gcn_layer_tc(graph, x.to(cuda), W.to(cuda), None, _lib.ACT_NONE)
+    mask = want_ei[0] != want_ei[1]
+    agg2 = torch.zeros(n, F, dtype=torch.float64).index_add_(0, want_ei[1][mask], want_norm.double()[mask].unsqueeze(1) * x.double()[want_ei[0][mask]])
+    scale = (agg2.abs() @ W.double().abs().t()).clamp(min=1.0)
+    assert bool(((got.double().cpu() - agg2 @ W.double().t()).abs() <= RTOL * scale).all())
