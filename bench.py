@@ -159,12 +159,14 @@ def run_gpu(args, cfg, rank, world, local_rank):
         with torch.no_grad():
             return net(data)
 
+    resident = pp.TemporalGraph.from_tensors(ei, t, cfg["n"])  # the input container, resident in HBM before the timed region
+
     def one_step(timed):
         flush.fill_(1)  # evict L2 between steps
         e0, e1, e2_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         c0 = lib.ppg_launch_count()
         e0.record(stream)
-        model = lift_step(ei, t)
+        model = pp.MultiOrderModel.from_temporal_graph(resident, delta=cfg["delta"], max_order=K)
         e1.record(stream)
         c1 = lib.ppg_launch_count()
         out = dbgnn_step(model)
@@ -234,6 +236,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
 
     # ---- dominant kernel, timed live with CUDA events on the launch stream: one onesweep digit pass
     roofline = measure_sort_pass(pp, dev, e2, layers[K][0])
+    at_scale = measure_sort_pass(pp, dev, 64_000_000, 1 << 20) if rank == 0 else None
 
     times = torch.tensor([lift_ms, dbgnn_ms, e2e_lift_ms, e2e_dbgnn_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -273,7 +276,8 @@ def run_gpu(args, cfg, rank, world, local_rank):
                   "e2e": {"value": world * nodes / (e2e_dbgnn_ms / 1e3), "unit": "nodes/s", "h2d_bytes_per_step": 0,
                           "d2h_bytes_per_step": d2h_dbgnn}},
         "lift_stage_roofline": stage_roofline(lift_bytes, lift_ms / steps, peaks),
-        "roofline": roofline_entry(roofline, peaks),
+        "roofline": roofline_entry(roofline, peaks, traffic_key="pairs_1.8M"),
+        "roofline_at_scale": roofline_entry(at_scale, peaks, traffic_key="pairs_64M"),
         "e2e": {"value": world * lifted / (e2e_lift_ms / 1e3), "unit": "lifted edges/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h_lift, "ms_per_step": e2e_lift_ms},
         "gpu_launches": launches,
@@ -325,10 +329,21 @@ def measure_sort_pass(pp, dev, num_pairs, num_nodes):
             "launch_ms": sum(per_pass) / len(per_pass), "bytes_per_launch": 2 * 12 * num_pairs}
 
 
-def roofline_entry(r, peaks):
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the probe kernel, from the committed
+    `ncu --set full` capture of the same probe (profiles/r01_sort_traffic.json); None if not captured."""
+    path = os.path.join(ROOT, "profiles", "r01_sort_traffic.json")
+    if not os.path.isfile(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get(key, {}).get("dram_bytes_per_launch")
+
+
+def roofline_entry(r, peaks, traffic_key=None):
     achieved = r["bytes_per_launch"] / (r["launch_ms"] / 1e3) / 1e9
-    return {"bound": "hbm", "kernel": r["kernel"], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes_per_launch": r["bytes_per_launch"],
+    return {"bound": "hbm", "kernel": r["kernel"], "pairs": r["pairs"], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(traffic_key) if traffic_key else None,
+            "algorithmic_bytes_per_launch": r["bytes_per_launch"],
             "launch_ms": r["launch_ms"], "launches_averaged": r["passes"] * 5,
             "how": "CUDA events around every digit pass on the launch stream; bytes = read + write of (8 B key + 4 B payload) per pair",
             "peak_source": peaks["source"]}

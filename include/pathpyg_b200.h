@@ -62,6 +62,10 @@ extern "C" {
 #define PPG_TIME_I64_F32DELTA 2 /* int64 time, float delta: (float)t_f <= (float)t_e + (float)delta */
 
 int ppg_abi_version(void);
+/* Deferred count read-back.  ppg_lift_order_count, ppg_lift_temporal_count and ppg_coalesce_sort accept a NULL
+ * host count pointer: they then only enqueue their kernels, and the host collects {count, status bits}
+ * (bit 0: a node id was out of range) later with this call -- one synchronisation for several pending ops. */
+int ppg_result_read(const void* workspace, int64_t* h_total, int* h_status_bits, void* stream);
 const char* ppg_last_error(void);
 /* number of kernels this library has launched in this process (monotonic; for bench accounting) */
 unsigned long long ppg_launch_count(void);

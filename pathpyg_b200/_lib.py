@@ -12,7 +12,7 @@ import subprocess
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libpathpyg_b200.so")
+LIB_PATH = os.environ.get("PATHPYG_B200_LIB", os.path.join(_HERE, "_C", "libpathpyg_b200.so"))  # override: instrumented builds
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_EMPTY = 0, 1, 2, 3, 4
@@ -33,6 +33,7 @@ PROTOTYPES = {
     "ppg_abi_version": (c_int, []),
     "ppg_last_error": (c_char_p, []),
     "ppg_launch_count": (ctypes.c_uint64, []),
+    "ppg_result_read": (c_int, [_p, _ph_i64, _ph_int, _p]),
     "ppg_lift_order_workspace_bytes": (c_size_t, [_i64, _i64]),
     "ppg_lift_order_count": (c_int, [_p, _i64, _i64, _p, c_size_t, _ph_i64, _p]),
     "ppg_lift_order_fill": (c_int, [_p, _i64, _i64, _i64, _p, _p]),

@@ -75,6 +75,7 @@ class _LayerChain:
         self.model, self.cached, self.max_order = model, cached, max_order
         self.order = 0
         self.edge_index = self.node_sequence = self.inverse_next = None
+        self.overlapped = None
 
     def _store(self, agg_index, agg_weight, n, node_sequence, inverse_idx) -> None:
         if self.cached or self.order == self.max_order:
@@ -82,17 +83,21 @@ class _LayerChain:
                         node_sequence=node_sequence, edge_weight=agg_weight, inverse_idx=inverse_idx)
             self.model.layers[self.order] = Graph._from_sorted(data)
 
-    def first_layer(self, edge_index, remap, n, node_sequence, inverse_idx, edge_weight) -> None:
+    def first_layer(self, edge_index, remap, n, node_sequence, inverse_idx, edge_weight, overlap=None) -> None:
+        """``overlap``: a pending count -> fill operation (the temporal / line-graph lift of the next level) that
+        is already enqueued; it is finished right after this layer's sort, under the same synchronisation."""
         self.order = 1
         more = self.max_order > 1
-        res = ops.coalesce(edge_index, remap, n, edge_weight, "sum", return_inverse=more)
+        pending = ops.coalesce_begin(edge_index, remap, n, edge_weight, "sum", return_inverse=more)
+        res = pending.finish()
+        self.overlapped = overlap.finish() if overlap is not None else None
         self._store(res[0], res[1], n, node_sequence, inverse_idx)
         if more:
             # layer-1 ids are the node values themselves, so the 2-grams are the coalesced edges transposed
             self.edge_index, self.inverse_next = res[0], res[2]
             self.node_sequence = None
 
-    def next_layer(self, line_index, edge_weight) -> None:
+    def next_layer(self, line_index, edge_weight, overlap=None) -> None:
         """``line_index`` [2, E_k]: the line graph whose nodes are the level-(k-1) edges."""
         self.order += 1
         more = self.order < self.max_order
@@ -102,7 +107,9 @@ class _LayerChain:
             node_sequence = ops.extend_rows(self.node_sequence, self.edge_index)
         n = int(node_sequence.size(0))
         inverse_idx = self.inverse_next
-        res = ops.coalesce(line_index, inverse_idx, n, edge_weight, "sum", return_inverse=more)
+        pending = ops.coalesce_begin(line_index, inverse_idx, n, edge_weight, "sum", return_inverse=more)
+        res = pending.finish()
+        self.overlapped = overlap.finish() if overlap is not None else None
         self._store(res[0], res[1], n, node_sequence, inverse_idx)
         self.edge_index, self.node_sequence = res[0], node_sequence
         self.inverse_next = res[2] if more else None
@@ -145,34 +152,36 @@ class MultiOrderModel:
                             cached: bool = True, event_graph: torch.Tensor | None = None) -> "MultiOrderModel":
         """multi_order_model.py:124-192, one radix sort per order (see ``_LayerChain``)."""
         m = MultiOrderModel()
-        data = g.data if g.data.is_sorted_by_time() else g.data.sort_by_time()
+        known_sorted = getattr(g, "time_is_known_sorted", lambda: False)()
+        data = g.data if known_sorted or g.data.is_sorted_by_time() else g.data.sort_by_time()
         dev, to_host = _staging.compute_device(data.edge_index, data.time)
         edge_index = _plain(_staging.up(data.edge_index, dev)).long()
         n = int(data.num_nodes)
         edge_weight = _staging.up(data[weight], dev) if weight in data else None  # None == ones(m), :154-157
 
         chain = _LayerChain(m, cached, max_order)
-        chain.first_layer(edge_index, None, n, torch.arange(n, device=dev).unsqueeze(1), torch.arange(n, device=dev),
-                          edge_weight)
+        pending = None
+        if max_order > 1 and event_graph is None:
+            # the reference passes `g`, not the locally re-sorted data (:167); identical unless the
+            # caller shuffled time stamps after construction, in which case `g.data` is what counts
+            src_ei = edge_index if data is g.data else _plain(_staging.up(g.data.edge_index, dev)).long()
+            src_t = _staging.up(data.time if data is g.data else g.data.time, dev)
+            pending = ops.lift_order_temporal_begin(src_ei, src_t, delta, n)   # count pass runs behind the layer-1 sort
+        ids = torch.arange(n, device=dev)
+        chain.first_layer(edge_index, None, n, ids.unsqueeze(1), ids, edge_weight, overlap=pending)
         if max_order > 1:
-            if event_graph is None:
-                # the reference passes `g`, not the locally re-sorted data (:167); identical unless the
-                # caller shuffled time stamps after construction, in which case `g.data` is what counts
-                src_ei = edge_index if data is g.data else _plain(_staging.up(g.data.edge_index, dev)).long()
-                src_t = _staging.up(data.time if data is g.data else g.data.time, dev)
-                line_index = ops.lift_order_temporal(src_ei, src_t, delta, n)
-            else:
-                line_index = _plain(_staging.up(event_graph, dev)).long()
+            line_index = chain.overlapped if event_graph is None else _plain(_staging.up(event_graph, dev)).long()
             if edge_weight is not None:
                 edge_weight = ops.pair_attributes(line_index, edge_weight, "src")
-            chain.next_layer(line_index, edge_weight)
             num_line_nodes = edge_index.size(1)
-            for _ in range(3, max_order + 1):
-                nxt = ops.lift_order_edge_index(line_index, num_line_nodes)
-                if edge_weight is not None:
-                    edge_weight = ops.pair_attributes(nxt, edge_weight, "src")
-                num_line_nodes, line_index = line_index.size(1), nxt
-                chain.next_layer(line_index, edge_weight)
+            for k in range(2, max_order + 1):
+                pending = ops.lift_order_edge_index_begin(line_index, num_line_nodes) if k < max_order else None
+                chain.next_layer(line_index, edge_weight, overlap=pending)
+                if k < max_order:
+                    nxt = chain.overlapped
+                    if edge_weight is not None:
+                        edge_weight = ops.pair_attributes(nxt, edge_weight, "src")
+                    num_line_nodes, line_index = line_index.size(1), nxt
         m._finish(g.mapping, to_host)
         return m
 

@@ -32,6 +32,21 @@ class TemporalGraph(Graph):
         self.mapping = mapping if mapping is not None else IndexMap()
         self._edge_to_index = None
         self._tedge_to_index = None
+        self._sorted_token = self._time_token()  # the time tensor this object has verified / put in order
+
+    def _time_token(self):
+        t = self.data.time
+        return (t.data_ptr(), t._version, t.numel(), str(t.device))
+
+    def time_is_known_sorted(self) -> bool:
+        """True if ``data.time`` is still the tensor the constructor checked (no device pass needed again)."""
+        return self._sorted_token is not None and self._sorted_token == self._time_token()
+
+    def to(self, device) -> "TemporalGraph":
+        known = self.time_is_known_sorted()
+        self.data = self.data.to(device)
+        self._sorted_token = self._time_token() if known else None
+        return self
 
     @property
     def edge_to_index(self) -> dict:

@@ -406,7 +406,7 @@ extern "C" int ppg_coalesce_sort(const int64_t* edge_index, int64_t E, const int
   PPG_REQUIRE(E >= 0 && E < (1ll << 31), PPG_ERR_INVALID, "coalesce: %lld edges outside [0, 2^31)", (long long)E);
   PPG_REQUIRE(num_nodes >= 0 && num_nodes <= (1ll << 32), PPG_ERR_INVALID, "coalesce: num_nodes %lld outside [0, 2^32]",
               (long long)num_nodes);
-  *h_num_out = 0;
+  if (h_num_out != nullptr) *h_num_out = 0;
   if (E == 0) return PPG_OK;
   PPG_REQUIRE(num_nodes > 0, PPG_ERR_INVALID, "coalesce: edges present but num_nodes == 0");
   Workspace ws(workspace, workspace_bytes);
@@ -423,6 +423,7 @@ extern "C" int ppg_coalesce_sort(const int64_t* edge_index, int64_t E, const int
   PPG_REQUIRE((in_b != 0) == ((L.passes & 1) != 0), PPG_ERR_CUDA, "coalesce: internal buffer parity mismatch");
   PPG_TRY(launch_scan(RunHeadProducer{L.sorted_keys()}, RunStartConsumer{L.run_start, E, L.sorted_perm(), out_inverse}, E,
                       L.scan_ws, &L.result->total, stream));
+  if (h_num_out == nullptr) return PPG_OK;  // deferred: ppg_result_read
   ResultWords h;
   PPG_TRY(read_back(&h, L.result, stream));
   PPG_REQUIRE((h.status & kStatusIdOutOfRange) == 0, PPG_ERR_INVALID,

@@ -123,20 +123,36 @@ gcn_fused_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__
       int r = r_lo;
       int32_t nb = s_ptr[r + 1];
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      // software pipeline: the (src, val) words of the NEXT batch are requested before the rows of the current
+      // batch are consumed, so every batch after the first costs one memory latency (the row gather), not two
+      int32_t sidx_n[kGatherBatch];
+      float c_n[kGatherBatch];
+#pragma unroll
+      for (int u = 0; u < kGatherBatch; ++u) {
+        const bool in = e_lo + u < e_hi;
+        sidx_n[u] = in ? src[e_lo + u] : 0;
+        c_n[u] = in ? (val != nullptr ? val[e_lo + u] : 1.f) : 0.f;
+      }
       for (int32_t i = e_lo; i < e_hi; i += kGatherBatch) {
         int32_t sidx[kGatherBatch];
         float c[kGatherBatch];
         float4 x[kGatherBatch];
 #pragma unroll
         for (int u = 0; u < kGatherBatch; ++u) {
-          const bool in = i + u < e_hi;
-          sidx[u] = in ? src[i + u] : 0;
-          c[u] = in ? (val != nullptr ? val[i + u] : 1.f) : 0.f;
+          sidx[u] = sidx_n[u];
+          c[u] = c_n[u];
         }
 #pragma unroll
         for (int u = 0; u < kGatherBatch; ++u)
           x[u] = (i + u < e_hi) ? *reinterpret_cast<const float4*>(X + static_cast<int64_t>(sidx[u]) * F + g * 4)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < kGatherBatch; ++u) {
+          const int32_t nx = i + kGatherBatch + u;
+          const bool in = nx < e_hi;
+          sidx_n[u] = in ? src[nx] : 0;
+          c_n[u] = in ? (val != nullptr ? val[nx] : 1.f) : 0.f;
+        }
 #pragma unroll
         for (int u = 0; u < kGatherBatch; ++u) {
           if (i + u < e_hi) {

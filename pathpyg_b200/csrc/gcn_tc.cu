@@ -75,6 +75,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+__host__ __device__ constexpr int tc_a_region_bytes(int F, int H) {
+  const int a = 2 * kTcTile * F * 4, o = kTcTile * (H + 4) * 4;
+  return ((a > o ? a : o) + 1023) / 1024 * 1024;
+}
+
 template <int N>
 struct TmemLoad;
 template <>
@@ -110,7 +115,21 @@ struct TmemLoad<32> {
   }
 };
 
-__device__ __forceinline__ float tc_activate(float x, int act) { return (act == PPG_ACT_ELU && x <= 0.f) ? expm1f(x) : x; }
+// ELU: expm1 for x <= 0 without the slow library path.  |x| < 0.5: degree-8 Taylor polynomial (truncation
+// < 3e-8 relative); below: exp(x) - 1 with ex2.approx (result magnitude >= 0.39, so no cancellation).
+__device__ __forceinline__ float tc_activate(float x, int act) {
+  if (act != PPG_ACT_ELU || x > 0.f) return x;
+  float p = fmaf(x, 1.f / 40320.f, 1.f / 5040.f);
+  p = fmaf(p, x, 1.f / 720.f);
+  p = fmaf(p, x, 1.f / 120.f);
+  p = fmaf(p, x, 1.f / 24.f);
+  p = fmaf(p, x, 1.f / 6.f);
+  p = fmaf(p, x, 0.5f);
+  p = fmaf(p, x, 1.f);
+  p *= x;
+  const float e = __expf(x) - 1.f;
+  return x > -0.5f ? p : e;
+}
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
@@ -131,12 +150,13 @@ gcn_tc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ sr
   constexpr int TMEM_COLS = H < 32 ? 32 : H;
   constexpr int CPT = H / 2;                                   // accumulator columns per thread in the epilogue
   constexpr uint32_t IDESC = umma_idesc_tf32(kTcTile, H);
+  constexpr int A_REGION = tc_a_region_bytes(F, H);  // both A parts, or the staged output tile if that is larger
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   unsigned char* sAhi = base;
   unsigned char* sAlo = base + A_BYTES;
-  unsigned char* sWhi = base + 2 * A_BYTES;
+  unsigned char* sWhi = base + A_REGION;
   unsigned char* sWlo = sWhi + W_BYTES;
   __shared__ __align__(8) unsigned long long s_mbar;
   __shared__ uint32_t s_tmem_base;
@@ -222,20 +242,36 @@ gcn_tc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ sr
         *reinterpret_cast<float4*>(sAhi + off) = hi;
         *reinterpret_cast<float4*>(sAlo + off) = lo;
       };
+      // software pipeline: the (src, val) words of the NEXT batch are requested before the rows of the current
+      // batch are consumed, so every batch after the first costs one memory latency (the row gather), not two
+      int32_t sidx_n[kTcGatherBatch];
+      float c_n[kTcGatherBatch];
+#pragma unroll
+      for (int u = 0; u < kTcGatherBatch; ++u) {
+        const bool in = e_lo + u < e_hi;
+        sidx_n[u] = in ? src[e_lo + u] : 0;
+        c_n[u] = in ? (val != nullptr ? val[e_lo + u] : 1.f) : 0.f;
+      }
       for (int32_t i = e_lo; i < e_hi; i += kTcGatherBatch) {
         int32_t sidx[kTcGatherBatch];
         float c[kTcGatherBatch];
         float4 x[kTcGatherBatch];
 #pragma unroll
         for (int u = 0; u < kTcGatherBatch; ++u) {
-          const bool in = i + u < e_hi;
-          sidx[u] = in ? src[i + u] : 0;
-          c[u] = in ? (val != nullptr ? val[i + u] : 1.f) : 0.f;
+          sidx[u] = sidx_n[u];
+          c[u] = c_n[u];
         }
 #pragma unroll
         for (int u = 0; u < kTcGatherBatch; ++u)
           x[u] = (i + u < e_hi) ? *reinterpret_cast<const float4*>(X + static_cast<int64_t>(sidx[u]) * F + g * 4)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < kTcGatherBatch; ++u) {
+          const int32_t nx = i + kTcGatherBatch + u;
+          const bool in = nx < e_hi;
+          sidx_n[u] = in ? src[nx] : 0;
+          c_n[u] = in ? (val != nullptr ? val[nx] : 1.f) : 0.f;
+        }
 #pragma unroll
         for (int u = 0; u < kTcGatherBatch; ++u) {
           if (i + u < e_hi) {
@@ -282,25 +318,33 @@ gcn_tc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ sr
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---------------- epilogue: TMEM -> registers (thread = one row, CPT consecutive columns) -> bias + act -> HBM
+    // ---------------- epilogue: TMEM -> registers (thread = one row, CPT consecutive columns) -> bias + act ->
+    // shared memory (the operand buffers are idle once the MMAs have completed) -> coalesced 16-byte stores
     {
+      constexpr int LDO = H + 4;  // padded row stride (floats) of the staged output tile
+      float* sOut = reinterpret_cast<float*>(base);
       uint32_t d[CPT];
       const int col0 = (warp >> 2) * CPT;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(col0);
       TmemLoad<CPT>::run(taddr, d);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int64_t v = row0 + (warp & 3) * 32 + lane;
-      if (v < n) {
-        float* o = out + v * H + col0;
+      float* so = sOut + ((warp & 3) * 32 + lane) * LDO + col0;
 #pragma unroll
-        for (int c = 0; c < CPT; c += 4) {
-          float4 r4;
-          r4.x = tc_activate(__uint_as_float(d[c + 0]) + s_bias[col0 + c + 0], act);
-          r4.y = tc_activate(__uint_as_float(d[c + 1]) + s_bias[col0 + c + 1], act);
-          r4.z = tc_activate(__uint_as_float(d[c + 2]) + s_bias[col0 + c + 2], act);
-          r4.w = tc_activate(__uint_as_float(d[c + 3]) + s_bias[col0 + c + 3], act);
-          *reinterpret_cast<float4*>(o + c) = r4;
-        }
+      for (int c = 0; c < CPT; c += 4) {
+        float4 r4;
+        r4.x = tc_activate(__uint_as_float(d[c + 0]) + s_bias[col0 + c + 0], act);
+        r4.y = tc_activate(__uint_as_float(d[c + 1]) + s_bias[col0 + c + 1], act);
+        r4.z = tc_activate(__uint_as_float(d[c + 2]) + s_bias[col0 + c + 2], act);
+        r4.w = tc_activate(__uint_as_float(d[c + 3]) + s_bias[col0 + c + 3], act);
+        *reinterpret_cast<float4*>(so + c) = r4;
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      const int64_t rows_here = n - row0 < kTcTile ? n - row0 : kTcTile;
+      float* o = out + row0 * H;
+      for (int idx = tid; idx < kTcTile * (H / 4); idx += kTcThreads) {
+        const int r = idx / (H / 4), c4 = idx % (H / 4);
+        if (r < rows_here) *reinterpret_cast<float4*>(o + static_cast<int64_t>(r) * H + c4 * 4) = *reinterpret_cast<const float4*>(sOut + r * LDO + c4 * 4);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -315,7 +359,7 @@ gcn_tc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ sr
 template <int F, int H>
 static int launch_tc(const int32_t* colptr, const int32_t* src, const float* val, const float* self_val, const float* X,
                      const float* W, const float* bias, int64_t n, int act, float* out, cudaStream_t stream) {
-  constexpr size_t smem = 2 * static_cast<size_t>(kTcTile) * F * 4 + 2 * static_cast<size_t>(H) * F * 4 + 1024;
+  constexpr size_t smem = static_cast<size_t>(tc_a_region_bytes(F, H)) + 2 * static_cast<size_t>(H) * F * 4 + 1024;
   auto kern = gcn_tc_kernel<F, H>;
   static bool configured = false;
   if (!configured) {

@@ -411,7 +411,7 @@ extern "C" int ppg_lift_order_count(const int64_t* edge_index, int64_t E, int64_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PPG_REQUIRE(E >= 0 && N >= 0 && E < (1ll << 31) && N < (1ll << 31), PPG_ERR_INVALID,
               "lift_order: sizes E=%lld N=%lld outside [0, 2^31)", (long long)E, (long long)N);
-  *h_num_lifted = 0;
+  if (h_num_lifted != nullptr) *h_num_lifted = 0;
   if (E == 0) return PPG_OK;
   PPG_REQUIRE(N > 0, PPG_ERR_INVALID, "lift_order: num_nodes must be positive for a non-empty edge index");
   Workspace ws(workspace, workspace_bytes);
@@ -424,6 +424,7 @@ extern "C" int ppg_lift_order_count(const int64_t* edge_index, int64_t E, int64_
   PPG_TRY(launch_scan(DegreeProducer{L.deg}, PointerConsumer{L.ptr, N}, N, L.scan_ptr_ws, nullptr, stream));
   PPG_TRY(launch_scan(LiftCountProducer{edge_index + E, L.ptr, L.first, N, &L.result->status}, OffsetConsumer{L.off, E},
                       E, L.scan_off_ws, &L.result->total, stream));
+  if (h_num_lifted == nullptr) return PPG_OK;  // deferred: the caller collects the count with ppg_result_read
   ResultWords h;
   PPG_TRY(read_back(&h, L.result, stream));
   PPG_TRY(check_result(h, "lift_order_edge_index"));
@@ -472,7 +473,7 @@ extern "C" int ppg_lift_temporal_count(const int64_t* edge_index, const void* ti
               "lift_order_temporal: sizes m=%lld N=%lld outside [0, 2^31)", (long long)m, (long long)N);
   PPG_REQUIRE(time_mode >= PPG_TIME_I64 && time_mode <= PPG_TIME_I64_F32DELTA, PPG_ERR_INVALID,
               "lift_order_temporal: unknown time mode %d", time_mode);
-  *h_num_pairs = 0;
+  if (h_num_pairs != nullptr) *h_num_pairs = 0;
   PPG_REQUIRE(m > 0 && N > 0, PPG_ERR_EMPTY, "lift_order_temporal: no time-respecting pair (empty input)");
   Workspace ws(workspace, workspace_bytes);
   TemporalLayout L(ws, m, N);
@@ -497,6 +498,7 @@ extern "C" int ppg_lift_temporal_count(const int64_t* edge_index, const void* ti
     case PPG_TIME_F64: PPG_TRY(temporal_count_scan<PPG_TIME_F64>(L, edge_index, time, m, N, delta_i, delta_f, stream)); break;
     default: PPG_TRY(temporal_count_scan<PPG_TIME_I64_F32DELTA>(L, edge_index, time, m, N, delta_i, delta_f, stream)); break;
   }
+  if (h_num_pairs == nullptr) return PPG_OK;  // deferred: ppg_result_read
   ResultWords h;
   PPG_TRY(read_back(&h, L.result, stream));
   PPG_TRY(check_result(h, "lift_order_temporal"));
@@ -512,4 +514,18 @@ extern "C" int ppg_lift_temporal_fill(const void* workspace, int64_t m, int64_t 
   Workspace ws(const_cast<void*>(workspace), ~static_cast<size_t>(0));
   TemporalLayout L(ws, m, N);
   return launch_expand(L.off, m, num_pairs, out_index, TemporalTail{L.first, L.grouped()}, stream);
+}
+
+// =================================================================== deferred count read-back
+// Every workspace of a count -> fill pair starts with {total, status}.  A *_count / *_sort call with a NULL
+// host pointer only enqueues its kernels; several such calls can be in flight on the stream before the
+// host collects their results here with one synchronisation.
+extern "C" int ppg_result_read(const void* workspace, int64_t* h_total, int* h_status_bits, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ResultWords h;
+  PPG_TRY(read_back(&h, static_cast<const ResultWords*>(workspace), stream));
+  *h_total = static_cast<int64_t>(h.total);
+  *h_status_bits = static_cast<int>(h.status);
+  PPG_REQUIRE(h.total < (1ull << 62), PPG_ERR_INVALID, "result_read: output size overflow");
+  return PPG_OK;
 }

@@ -7,9 +7,9 @@
 // (b) a decoupled look-back chain over the per-tile digit counts, so no pass reads its keys twice.
 // Only the significant key bits [0, end_bit) are sorted: P = ceil(end_bit / 8).
 //
-// Within a tile the ranking is stable: a warp ranks its 32*ITEMS keys digit by digit with
-// match.any (lanes holding the same digit elect a leader that bumps the warp's counter in shared
-// memory), the tile is reordered through shared memory, and every digit's run is written out as
+// Within a tile the ranking is stable: a warp ranks its 32*ITEMS keys round by round; lanes holding the
+// same digit are found with one ballot per digit bit and elect a leader that bumps the warp's counter in
+// shared memory; the tile is reordered through shared memory, and every digit's run is written out as
 // one contiguous (coalesced) segment.
 //
 // Look-back: thread d owns digit d.  Two levels (tiles inside a group of 16, then groups), every walk with
@@ -26,6 +26,21 @@
 #include "common.cuh"
 
 namespace ppg {
+
+// development aid: per-tile phase time stamps (globaltimer, ns) of the digit passes; enabled with -DPPG_SORT_TRACE
+#ifdef PPG_SORT_TRACE
+extern __device__ unsigned long long* g_sort_trace;  // [tiles][8]
+__device__ __forceinline__ void sort_trace(unsigned tile, int slot) {
+  if (threadIdx.x == 0 && g_sort_trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_sort_trace[static_cast<size_t>(tile) * 8 + slot] = t;
+  }
+}
+#define PPG_TRACE(tile, slot) sort_trace(tile, slot)
+#else
+#define PPG_TRACE(tile, slot)
+#endif
 
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
@@ -120,6 +135,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   const int64_t remaining = n - tile_base;
   const int valid_in_tile = remaining >= TILE ? TILE : static_cast<int>(remaining);
 
+  PPG_TRACE(tile, 0);
   // ---- load (warp-striped => coalesced; element order inside a warp is (item, lane))
   KeyT key[ITEMS];
 #pragma unroll
@@ -128,30 +144,33 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
     key[i] = idx < n ? ld_stream(keys_in + idx) : static_cast<KeyT>(~static_cast<KeyT>(0));
   }
 
+  PPG_TRACE(tile, 1);  // (issue point only: the loads complete at their first use)
   // ---- stable rank inside the warp, digit counts per warp
-  // All match.any are issued before the first is consumed (their latency overlaps); the counter updates
-  // that follow are one shared-memory atomic per distinct digit per round, in item order (=> stable).
+  // Lanes holding the same digit are found with one ballot per digit bit (8 votes + 8 logic ops per key).
+  // match.any would be a single instruction, but its cost grows with the number of DISTINCT values in the
+  // warp (~30 for random digits: measured 5 us per 8 keys), the ballots are fixed-cost and pipelined.
+  // The counter updates are one shared-memory atomic per distinct digit per round, in item order (=> stable).
   uint32_t rank[ITEMS];
   uint32_t* my_hist = s_whist + warp * kRadix;
-  {
-    unsigned peers[ITEMS];
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
-      peers[i] = __match_any_sync(kFullMask, d);
-    }
+  for (int i = 0; i < ITEMS; ++i) {
+    const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
+    unsigned peers = kFullMask;
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
-      const int leader = 31 - __clz(peers[i]);
-      uint32_t before = 0;
-      if (static_cast<int>(lane) == leader) before = atomicAdd(&my_hist[d], static_cast<uint32_t>(__popc(peers[i])));
-      before = __shfl_sync(kFullMask, before, leader);
-      rank[i] = before + __popc(peers[i] & lanemask_lt());
+    for (int b = 0; b < kRadixBits; ++b) {
+      const bool bit = (d >> b) & 1u;
+      const unsigned vote = __ballot_sync(kFullMask, bit);
+      peers &= bit ? vote : ~vote;
     }
+    const int leader = 31 - __clz(peers);
+    uint32_t before = 0;
+    if (static_cast<int>(lane) == leader) before = atomicAdd(&my_hist[d], static_cast<uint32_t>(__popc(peers)));
+    before = __shfl_sync(kFullMask, before, leader);
+    rank[i] = before + __popc(peers & lanemask_lt());
   }
   __syncthreads();
 
+  PPG_TRACE(tile, 2);
   // ---- per digit (thread d): exclusive over warps, tile count, publish, look back
   unsigned long long count = 0;
   {
@@ -235,6 +254,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   }
   const unsigned long long prev = before_group + within;  // keys with this digit in earlier tiles
 
+  PPG_TRACE(tile, 3);
   // ---- block exclusive scans over the 256 digits: slot of the digit in the tile, and in the output
   unsigned long long g = ghist[tid];
   {
@@ -260,6 +280,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   }
   __syncthreads();
 
+  PPG_TRACE(tile, 4);
   // ---- reorder the tile through shared memory
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
@@ -279,6 +300,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   }
   __syncthreads();
 
+  PPG_TRACE(tile, 5);
   // ---- write every digit's run to its global segment
   for (int j = tid; j < valid_in_tile; j += kSortBlock) {
     const KeyT k = s_keys[j];
@@ -287,6 +309,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
     keys_out[dst] = k;
     if (HAS_VALUES) vals_out[dst] = s_vals[j];
   }
+  PPG_TRACE(tile, 6);
 }
 
 template <typename KeyT, bool HAS_VALUES, int ITEMS>
@@ -305,6 +328,8 @@ inline int launch_onesweep_pass_items(const KeyT* kin, KeyT* kout, const uint32_
   static bool configured = false;  // per instantiation
   if (!configured) {
     PPG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    // all resident-CTA slots the register file allows must also fit in shared memory (one wave at cfg2 sizes)
+    PPG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   kern<<<static_cast<unsigned>(sort_num_tiles(n)), kSortBlock, smem, stream>>>(

@@ -52,19 +52,47 @@ def _edge_index_arg(edge_index: torch.Tensor) -> torch.Tensor:
     return edge_index.as_subclass(torch.Tensor).contiguous()
 
 
-# --------------------------------------------------------------------------------------- a2
-def lift_order_edge_index(edge_index: torch.Tensor, num_nodes: int) -> torch.Tensor:
-    lib = _lib.load()
-    ei = _edge_index_arg(edge_index)
-    dev = _require_cuda(ei)
-    E = ei.size(1)
+# --------------------------------------------------------------------------------------- deferred counts
+def _read_result(ws: torch.Tensor, dev: torch.device, what: str) -> int:
+    """Collect {count, status} of a pending count -> fill operation (synchronises the stream)."""
+    total, status = ctypes.c_int64(0), ctypes.c_int(0)
     with torch.cuda.device(dev):
-        ws = _workspace(lib.ppg_lift_order_workspace_bytes(E, num_nodes), dev)
-        total = ctypes.c_int64(0)
-        _lib.check(lib.ppg_lift_order_count(_ptr(ei), E, num_nodes, _ptr(ws), ws.numel(), ctypes.byref(total), _stream(dev)))
-        out = torch.empty((2, total.value), dtype=torch.int64, device=dev)
-        _lib.check(lib.ppg_lift_order_fill(_ptr(ws), E, num_nodes, total.value, _ptr(out), _stream(dev)))
-    return out
+        _lib.check(_lib.load().ppg_result_read(_ptr(ws), ctypes.byref(total), ctypes.byref(status), _stream(dev)))
+    if status.value & 1:
+        raise ValueError(f"{what}: node id outside [0, num_nodes)")
+    return total.value
+
+
+# --------------------------------------------------------------------------------------- a2
+class PendingLift:
+    """lift_order_edge_index whose count pass is enqueued; ``finish()`` reads the size, allocates and fills."""
+
+    def __init__(self, ei, num_nodes):
+        self.ei, self.num_nodes, self.dev, self.E = ei, num_nodes, ei.device, ei.size(1)
+        self.ws = None
+        if self.E:
+            lib = _lib.load()
+            with torch.cuda.device(self.dev):
+                self.ws = _workspace(lib.ppg_lift_order_workspace_bytes(self.E, num_nodes), self.dev)
+                _lib.check(lib.ppg_lift_order_count(_ptr(ei), self.E, num_nodes, _ptr(self.ws), self.ws.numel(), None, _stream(self.dev)))
+
+    def finish(self) -> torch.Tensor:
+        total = _read_result(self.ws, self.dev, "lift_order_edge_index") if self.E else 0
+        out = torch.empty((2, total), dtype=torch.int64, device=self.dev)
+        if total:
+            with torch.cuda.device(self.dev):
+                _lib.check(_lib.load().ppg_lift_order_fill(_ptr(self.ws), self.E, self.num_nodes, total, _ptr(out), _stream(self.dev)))
+        return out
+
+
+def lift_order_edge_index_begin(edge_index: torch.Tensor, num_nodes: int) -> PendingLift:
+    ei = _edge_index_arg(edge_index)
+    _require_cuda(ei)
+    return PendingLift(ei, int(num_nodes))
+
+
+def lift_order_edge_index(edge_index: torch.Tensor, num_nodes: int) -> torch.Tensor:
+    return lift_order_edge_index_begin(edge_index, num_nodes).finish()
 
 
 # --------------------------------------------------------------------------------------- a3
@@ -103,22 +131,40 @@ def _time_mode(time: torch.Tensor, delta):
     raise TypeError(f"time must be int64 or float64 (got {time.dtype}); float32 time stamps are not supported")
 
 
-def lift_order_temporal(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int) -> torch.Tensor:
-    lib = _lib.load()
+class PendingTemporalLift:
+    def __init__(self, ei, time, mode, delta_i, delta_f, num_nodes):
+        self.dev, self.m, self.num_nodes = ei.device, ei.size(1), num_nodes
+        self.keep = (ei, time)  # inputs stay alive until the kernels have run
+        lib = _lib.load()
+        with torch.cuda.device(self.dev):
+            self.ws = _workspace(lib.ppg_lift_temporal_workspace_bytes(self.m, num_nodes), self.dev)
+            _lib.check(lib.ppg_lift_temporal_count(_ptr(ei), _ptr(time), self.m, num_nodes, mode, delta_i, delta_f, _ptr(self.ws),
+                                                   self.ws.numel(), None, _stream(self.dev)))
+
+    def finish(self) -> torch.Tensor:
+        total = _read_result(self.ws, self.dev, "lift_order_temporal")
+        if total == 0:
+            raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors "
+                                      "(lift_order_temporal: no time-respecting pair for this delta)")
+        out = torch.empty((2, total), dtype=torch.int64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.load().ppg_lift_temporal_fill(_ptr(self.ws), self.m, self.num_nodes, total, _ptr(out), _stream(self.dev)))
+        return out
+
+
+def lift_order_temporal_begin(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int) -> PendingTemporalLift:
     ei = _edge_index_arg(edge_index)
-    dev = _require_cuda(ei, time)
+    _require_cuda(ei, time)
     time, mode, delta_i, delta_f = _time_mode(time.contiguous(), delta)
-    m = ei.size(1)
-    if time.numel() != m:
+    if time.numel() != ei.size(1):
         raise ValueError("time and edge_index disagree on the number of edges")
-    with torch.cuda.device(dev):
-        ws = _workspace(lib.ppg_lift_temporal_workspace_bytes(m, num_nodes), dev)
-        total = ctypes.c_int64(0)
-        _lib.check(lib.ppg_lift_temporal_count(_ptr(ei), _ptr(time), m, num_nodes, mode, delta_i, delta_f, _ptr(ws),
-                                               ws.numel(), ctypes.byref(total), _stream(dev)))
-        out = torch.empty((2, total.value), dtype=torch.int64, device=dev)
-        _lib.check(lib.ppg_lift_temporal_fill(_ptr(ws), m, num_nodes, total.value, _ptr(out), _stream(dev)))
-    return out
+    if ei.size(1) == 0 or num_nodes <= 0:
+        raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors (lift_order_temporal: empty input)")
+    return PendingTemporalLift(ei, time, mode, delta_i, delta_f, int(num_nodes))
+
+
+def lift_order_temporal(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int) -> torch.Tensor:
+    return lift_order_temporal_begin(edge_index, time, delta, num_nodes).finish()
 
 
 # --------------------------------------------------------------------------------------- a4
@@ -191,16 +237,42 @@ def unique_rows(node_sequence: torch.Tensor):
     return unique, inverse
 
 
-def coalesce(edge_index: torch.Tensor, remap: torch.Tensor | None, num_nodes: int,
-             edge_weight: torch.Tensor | None, reduce: str = "sum", return_inverse: bool = False):
-    """Map edge ids through ``remap`` (or not), merge duplicate (row, col) pairs reducing their weights;
-    result is (row, col)-sorted.  ``edge_weight=None`` means unit float32 weights.  With
-    ``return_inverse`` a third result gives, per input edge, the output edge it was merged into."""
+class PendingCoalesce:
+    def __init__(self, ei, remap, num_nodes, edge_weight, reduce, return_inverse):
+        self.dev, self.E, self.num_nodes = ei.device, ei.size(1), num_nodes
+        self.edge_weight, self.reduce, self.return_inverse = edge_weight, reduce, return_inverse
+        self.keep = (ei, remap)
+        self.ws, self.inverse = None, None
+        if return_inverse:
+            self.inverse = torch.empty(self.E, dtype=torch.int64, device=self.dev)
+        if self.E:
+            lib = _lib.load()
+            with torch.cuda.device(self.dev):
+                self.ws = _workspace(lib.ppg_coalesce_workspace_bytes(self.E, num_nodes), self.dev)
+                _lib.check(lib.ppg_coalesce_sort(_ptr(ei), self.E, _ptr(remap), 0 if remap is None else remap.numel(), num_nodes,
+                                                 _ptr(self.ws), self.ws.numel(), _ptr(self.inverse), None, _stream(self.dev)))
+
+    def finish(self):
+        n_out = _read_result(self.ws, self.dev, "coalesce (EdgeIndex.validate)") if self.E else 0
+        w_dtype = torch.float32 if self.edge_weight is None else self.edge_weight.dtype
+        out_ei = torch.empty((2, n_out), dtype=torch.int64, device=self.dev)
+        out_w = torch.empty(n_out, dtype=w_dtype, device=self.dev)
+        if n_out:
+            with torch.cuda.device(self.dev):
+                _lib.check(_lib.load().ppg_coalesce_fill(_ptr(self.ws), self.E, self.num_nodes, n_out, _ptr(self.edge_weight),
+                                                         _DTYPE_CODES[w_dtype], _lib.REDUCTIONS[self.reduce], _ptr(out_ei), _ptr(out_w),
+                                                         _stream(self.dev)))
+        if self.return_inverse:
+            return out_ei, out_w, self.inverse
+        return out_ei, out_w
+
+
+def coalesce_begin(edge_index: torch.Tensor, remap: torch.Tensor | None, num_nodes: int,
+                   edge_weight: torch.Tensor | None, reduce: str = "sum", return_inverse: bool = False) -> PendingCoalesce:
     if reduce not in _lib.REDUCTIONS:
         raise ValueError(f"Unknown reduce {reduce}")
-    lib = _lib.load()
     ei = _edge_index_arg(edge_index)
-    dev = _require_cuda(ei, remap, edge_weight)
+    _require_cuda(ei, remap, edge_weight)
     E = ei.size(1)
     if remap is not None:
         remap = remap.as_subclass(torch.Tensor).contiguous()
@@ -212,20 +284,15 @@ def coalesce(edge_index: torch.Tensor, remap: torch.Tensor | None, num_nodes: in
             raise ValueError("edge_weight must be 1-D with one entry per edge")
         if edge_weight.dtype not in _DTYPE_CODES:
             raise TypeError(f"edge_weight dtype {edge_weight.dtype} not supported (float32/float64/int64/int32)")
-    w_dtype = torch.float32 if edge_weight is None else edge_weight.dtype
-    with torch.cuda.device(dev):
-        ws = _workspace(lib.ppg_coalesce_workspace_bytes(E, num_nodes), dev)
-        n_out = ctypes.c_int64(0)
-        inverse = torch.empty(E, dtype=torch.int64, device=dev) if return_inverse else None
-        _lib.check(lib.ppg_coalesce_sort(_ptr(ei), E, _ptr(remap), 0 if remap is None else remap.numel(), num_nodes,
-                                         _ptr(ws), ws.numel(), _ptr(inverse), ctypes.byref(n_out), _stream(dev)))
-        out_ei = torch.empty((2, n_out.value), dtype=torch.int64, device=dev)
-        out_w = torch.empty(n_out.value, dtype=w_dtype, device=dev)
-        _lib.check(lib.ppg_coalesce_fill(_ptr(ws), E, num_nodes, n_out.value, _ptr(edge_weight), _DTYPE_CODES[w_dtype],
-                                         _lib.REDUCTIONS[reduce], _ptr(out_ei), _ptr(out_w), _stream(dev)))
-    if return_inverse:
-        return out_ei, out_w, inverse
-    return out_ei, out_w
+    return PendingCoalesce(ei, remap, int(num_nodes), edge_weight, reduce, return_inverse)
+
+
+def coalesce(edge_index: torch.Tensor, remap: torch.Tensor | None, num_nodes: int,
+             edge_weight: torch.Tensor | None, reduce: str = "sum", return_inverse: bool = False):
+    """Map edge ids through ``remap`` (or not), merge duplicate (row, col) pairs reducing their weights;
+    result is (row, col)-sorted.  ``edge_weight=None`` means unit float32 weights.  With
+    ``return_inverse`` a third result gives, per input edge, the output edge it was merged into."""
+    return coalesce_begin(edge_index, remap, num_nodes, edge_weight, reduce, return_inverse).finish()
 
 
 def extend_rows(prev_rows: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:

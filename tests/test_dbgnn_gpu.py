@@ -239,7 +239,7 @@ def test_dbgnn_training_reduces_loss(cuda):
         loss = torch.nn.functional.cross_entropy(net(data), y)
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[-1] < 0.7 * losses[0], losses[::8]
 
 
