@@ -220,6 +220,35 @@ int ppg_atb(const float* A, const float* B, int64_t M, int64_t H, int64_t F, flo
 /* out[i] = src[idx[i]] */
 int ppg_gather_f32(const float* src, const int32_t* idx, int64_t n, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Consumers of the built layers
+ *   Graph.degrees / transition_probabilities      reference: src/pathpyG/core/graph.py:486-533
+ *   MultiOrderModel.get_mon_dof                   reference: src/pathpyG/core/multi_order_model.py:243-312
+ *   MultiOrderModel.get_*_log_likelihood          reference: src/pathpyG/core/multi_order_model.py:314-409
+ * ------------------------------------------------------------------------------------------- */
+/* out_ptr[v] = first slot with sorted_ids[slot] >= v, v in [0, num_nodes]: the CSR pointer of a SORTED id column */
+int ppg_sorted_ids_ptr(const int64_t* sorted_ids, int64_t num_ids, int64_t num_nodes, int32_t* out_ptr, void* stream);
+/* out[s] = sum_{i in [ptr[s], ptr[s+1])} weights[perm ? perm[i] : i], added in slot order (the order of a sequential
+ * scatter_add); weights NULL: out[s] = ptr[s+1] - ptr[s].  Segments longer than 64 slots use a fixed fp64 tree. */
+size_t ppg_segment_sum_workspace_bytes(int64_t num_slots);
+int ppg_segment_sum(const int32_t* ptr, const int32_t* perm, const float* weights, int64_t num_segments, int64_t num_slots,
+                    void* workspace, size_t workspace_bytes, float* out, void* stream);
+/* out[e] = (weights ? weights[e] : 1) / denom[ids[e]]     (graph.py:531-533) */
+int ppg_edge_ratio(const int64_t* ids, const float* weights, const float* denom, int64_t num_edges, float* out, void* stream);
+/* h_num_walks[k-1]   = number of walks with k edges          (= columns of the k-th line-graph lift, :285-291),
+ * h_num_sources[k-1] = number of nodes that start such a walk (= non-empty rows of A^k, :294-303), k = 1..max_len.
+ * Counts are exact below 2^64.  Synchronises (host outputs). */
+size_t ppg_walk_counts_workspace_bytes(int64_t num_nodes, int max_len);
+int ppg_walk_counts(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int max_len, void* workspace,
+                    size_t workspace_bytes, int64_t* h_num_walks, int64_t* h_num_sources, void* stream);
+/* *h_out = sum_i freq[i] * logf(prob[j]),  j = i, idx[i] or idx2[idx[i]] (idx / idx2 nullable): every term formed in
+ * fp32 like torch.mul(frequencies, torch.log(p[...])) (:339,367-368,395-396), accumulated in fp64 in a fixed order.
+ * PPG_ERR_INVALID if an index is out of range.  Synchronises (host output). */
+size_t ppg_weighted_log_sum_workspace_bytes(void);
+int ppg_weighted_log_sum(const float* freq, const float* prob, const int64_t* idx, const int64_t* idx2, int64_t n,
+                         int64_t prob_len, int64_t idx2_len, void* workspace, size_t workspace_bytes, double* h_out,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,3 +136,105 @@ class TemporalInput:
 
 def ref_lift_order_temporal(edge_index, time, delta):
     return temporal_module().lift_order_temporal(TemporalInput(edge_index, time), delta)
+
+
+# ----------------------------------------------------------------------------------------------
+# model-selection statistics: the reference's own method bodies (multi_order_model.py:243-509)
+# ----------------------------------------------------------------------------------------------
+class _RefEdgeIndex(torch.Tensor):
+    """Stand-in for torch_geometric.EdgeIndex with the two members get_mon_dof touches
+    (``sort_by("row")`` and ``matmul``, multi_order_model.py:298-301); unit edge values."""
+
+    __torch_function__ = torch._C._disabled_torch_function_impl
+
+    @staticmethod
+    def wrap(t, num_nodes):
+        out = torch.Tensor._make_subclass(_RefEdgeIndex, t)
+        out.num_nodes = num_nodes
+        return out
+
+    def sort_by(self, order):
+        assert order == "row"
+        t = self.as_subclass(torch.Tensor)
+        perm = torch.sort(t[0], stable=True).indices
+        return _RefEdgeIndex.wrap(t[:, perm], self.num_nodes), perm
+
+    def matmul(self, other):
+        import warnings
+
+        n = self.num_nodes
+        a, b = self.as_subclass(torch.Tensor), other.as_subclass(torch.Tensor)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            A = torch.sparse_coo_tensor(a, torch.ones(a.size(1)), (n, n))
+            B = torch.sparse_coo_tensor(b, torch.ones(b.size(1)), (n, n))
+            C = torch.sparse.mm(A, B).coalesce()
+        return _RefEdgeIndex.wrap(C.indices(), n), C.values()
+
+
+class _RefLayer:
+    """What the statistics read from ``self.layers[k]``: ``.data`` fields and ``transition_probabilities`` -- the
+    latter executes the reference's own ``Graph.degrees`` / ``Graph.transition_probabilities`` bodies."""
+
+    def __init__(self, layer, graph_methods):
+        self.data = _Data(edge_index=_RefEdgeIndex.wrap(layer.edge_index, layer.num_nodes), num_nodes=layer.num_nodes,
+                          num_edges=layer.edge_index.size(1), edge_weight=layer.edge_weight, inverse_idx=layer.inverse_idx,
+                          node_sequence=layer.node_sequence)
+        self.n = layer.num_nodes
+        self._m = graph_methods
+
+    def degrees(self, *a, **k):
+        return self._m["degrees"](self, *a, **k)
+
+    def transition_probabilities(self, *a, **k):
+        return self._m["transition_probabilities"](self, *a, **k)
+
+
+def _methods_of(rel_path: str, class_name: str, names, env: dict) -> dict:
+    """Compile the named methods of one class from a reference file, unmodified, into ``env``."""
+    import ast
+
+    path = os.path.join(REFERENCE_ROOT, rel_path)
+    tree = ast.parse(open(path).read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name)
+    picked = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    module = ast.Module(body=picked, type_ignores=[])
+    exec(compile(module, path, "exec"), env)
+    return {n: env[n] for n in names}
+
+
+def selection_methods():
+    """``(model_factory, methods)``: ``model_factory(layers)`` builds the object the reference's statistics see as
+    ``self``; ``methods`` maps name -> the reference's own function (call as ``methods[name](model, ...)``)."""
+    if "selection" not in _cache:
+        import logging
+        import typing
+
+        from scipy.stats import chi2
+
+        tg = types.SimpleNamespace(utils=types.SimpleNamespace(
+            degree=lambda index, num_nodes=None, dtype=None: pyg.degree(index, num_nodes, dtype or torch.float)))
+        genv = dict(torch=torch, torch_geometric=tg, scatter=lambda src, index, dim=0, dim_size=None, reduce="sum":
+                    pyg.scatter(src, index, dim_size, reduce), Union=typing.Union, Dict=typing.Dict, Any=typing.Any)
+        graph_methods = _methods_of("src/pathpyG/core/graph.py", "Graph", ["degrees", "transition_probabilities"], genv)
+        menv = dict(torch=torch, cumsum=pyg.cumsum, chi2=chi2, Optional=typing.Optional, Data=_Data, PathData=object,
+                    logger=logging.getLogger("ref"), lift_order_edge_index=lift_order_module().lift_order_edge_index)
+        names = ["get_mon_dof", "get_zeroth_order_log_likelihood", "get_intermediate_order_log_likelihood",
+                 "get_mon_log_likelihood", "likelihood_ratio_test"]
+        methods = _methods_of("src/pathpyG/core/multi_order_model.py", "MultiOrderModel", names, menv)
+
+        class Model:
+            def __init__(self, layers):
+                self.layers = {k: _RefLayer(v, graph_methods) for k, v in layers.items()}
+
+        for name, fn in methods.items():
+            setattr(Model, name, fn)
+        _cache["selection"] = (Model, methods)
+    return _cache["selection"]
+
+
+def ref_walks_data(walks):
+    """The ``dag_graph`` argument of the statistics: the fields of ``PathData.data``."""
+    return _Data(edge_index=walks.edge_index, node_sequence=walks.node_sequence, dag_weight=walks.dag_weight,
+                 dag_num_edges=walks.dag_num_edges, dag_num_nodes=walks.dag_num_nodes,
+                 num_nodes=int(walks.node_sequence.size(0)))

@@ -68,6 +68,14 @@ PROTOTYPES = {
     "ppg_atb_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
     "ppg_atb": (c_int, [_p, _p, _i64, _i64, _i64, _p, _p, c_size_t, _p]),
     "ppg_gather_f32": (c_int, [_p, _p, _i64, _p, _p]),
+    "ppg_sorted_ids_ptr": (c_int, [_p, _i64, _i64, _p, _p]),
+    "ppg_segment_sum_workspace_bytes": (c_size_t, [_i64]),
+    "ppg_segment_sum": (c_int, [_p, _p, _p, _i64, _i64, _p, c_size_t, _p, _p]),
+    "ppg_edge_ratio": (c_int, [_p, _p, _p, _i64, _p, _p]),
+    "ppg_walk_counts_workspace_bytes": (c_size_t, [_i64, c_int]),
+    "ppg_walk_counts": (c_int, [_p, _i64, _i64, c_int, _p, c_size_t, _ph_i64, _ph_i64, _p]),
+    "ppg_weighted_log_sum_workspace_bytes": (c_size_t, []),
+    "ppg_weighted_log_sum": (c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _p, c_size_t, POINTER(c_double), _p]),
 }
 ACT_NONE, ACT_ELU = 0, 1
 

@@ -7,13 +7,16 @@ Differences that matter for speed, not for results:
   ``core/graph.py:110-112``) and the CSR / CSC views are built on first access;
 * layers produced by ``aggregate_edge_index`` are already (row, col)-sorted and validated on the
   device, so ``Graph._from_sorted`` skips the sort and the validation pass.
-Generic graph utilities of the reference (degrees, Laplacian, ``__add__`` ...) are out of scope.
+``degrees`` / ``transition_probabilities`` (graph.py:486-533) feed the model-selection statistics of
+``MultiOrderModel`` and run on the device (``csrc/selection.cu``); the other generic graph utilities of the
+reference (Laplacian, ``__add__`` ...) are out of scope.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 
+from .. import _staging, ops
 from .data import Data, EdgeIndex
 from .index_map import IndexMap
 
@@ -148,6 +151,52 @@ class Graph:
     def get_predecessors(self, col_idx: int) -> torch.Tensor:
         ptr = self.col_ptr
         return self.row[ptr[col_idx]: ptr[col_idx + 1]]
+
+    # ---- degrees / transition probabilities (graph.py:486-533) -----------------------------
+    def _degree_tensor(self, mode: str, edge_attr: str | None) -> torch.Tensor:
+        ei = self.data.edge_index
+        dev, to_host = _staging.compute_device(ei)
+        t = _staging.up(ei, dev).as_subclass(torch.Tensor)
+        w = None
+        if edge_attr:
+            w = getattr(self.data, edge_attr, None)
+            if w is None:
+                raise AttributeError(f"edge attribute {edge_attr} not found")
+            w = _staging.up(w, dev)
+        if mode == "in":
+            grouped = ops.csc_build(t, self.n, self.n)          # stable: slots keep the edge order inside a target
+            ptr, perm = grouped.colptr, grouped.eid
+        else:
+            ptr, perm = ops.sorted_ids_ptr(t[0], self.n), None  # Graph keeps edge_index sorted by row
+        if w is None:
+            d = (ptr[1:] - ptr[:-1]).to(torch.int32)            # torch_geometric.utils.degree(..., dtype=torch.int)
+        else:
+            d = ops.segment_sum(ptr, w, perm)
+            if w.dtype.is_floating_point and w.dtype != torch.float32:
+                d = d.to(w.dtype)
+        return _staging.down(d, to_host)
+
+    def degrees(self, mode: str = "in", edge_attr: str | None = None, return_tensor: bool = False):
+        d = self._degree_tensor(mode, edge_attr)
+        if return_tensor:
+            return d
+        return {node: degree.item() for node, degree in zip(self.nodes, d)}
+
+    def in_degrees(self) -> dict:
+        return self.degrees(mode="in")
+
+    def out_degrees(self) -> dict:
+        return self.degrees(mode="out")
+
+    def transition_probabilities(self, edge_attr: str | None = None) -> torch.Tensor:
+        """edge weight / (weighted) out-degree of the edge's source, one value per edge (graph.py:518-533)."""
+        ei = self.data.edge_index
+        dev, to_host = _staging.compute_device(ei)
+        t = _staging.up(ei, dev).as_subclass(torch.Tensor)
+        w = _staging.up(getattr(self.data, edge_attr, None), dev) if edge_attr is not None else None
+        ptr = ops.sorted_ids_ptr(t[0], self.n)
+        denom = ops.segment_sum(ptr, w)
+        return _staging.down(ops.edge_ratio(t[0], w, denom), to_host)
 
     def is_edge(self, v, w) -> bool:
         return (self.mapping.to_idx(v), self.mapping.to_idx(w)) in self.edge_to_index

@@ -1,7 +1,8 @@
 """``MultiOrderModel`` builders (reference ``src/pathpyG/core/multi_order_model.py``):
 ``iterate_lift_order`` (:83-122), ``from_temporal_graph`` (:124-192), ``from_path_data`` (:194-241),
-``to_dbgnn_data`` (:511-554).  The degrees-of-freedom / likelihood part (:243-509) consumes the
-layers built here and is outside the hot path.
+``to_dbgnn_data`` (:511-554), and the model-selection statistics that consume the built layers
+(SURVEY.md 8f rank 3): ``get_mon_dof`` (:243-312), the log-likelihoods (:314-409),
+``likelihood_ratio_test`` (:411-459) and ``estimate_order`` (:461-509).
 
 All tensors of one build stay on the GPU from the first kernel to the last; host inputs are staged
 once at entry and the finished layers are moved back once at exit.
@@ -224,6 +225,130 @@ class MultiOrderModel:
             if to_host:
                 layer.to("cpu")
             layer.mapping = mapping if k == 1 else HigherOrderIndexMap(mapping, layer.data.node_sequence)
+
+    # ------------------------------------------------------------------------------------------
+    def get_mon_dof(self, max_order: int | None = None, assumption: str = "paths") -> int:
+        """multi_order_model.py:243-312.  Under "paths" the reference materialises every line graph up to
+        ``max_order`` only to read its number of columns (:285-291) and multiplies sparse adjacency powers only to
+        count their non-empty rows (:294-303).  Both are counts of walks: #columns of the k-th lift = number of
+        walks with k edges, non-empty rows of A^k = nodes that start one.  One pass per order over the first-order
+        edges computes c_k[v] = sum over out-edges (v, w) of c_{k-1}[w] in exact integers (``ops.walk_counts``)."""
+        if max_order is None:
+            max_order = max(self.layers)
+        if max_order > max(self.layers):
+            logger.error("max_order cannot be larger than maximum order of multi-order network")
+            raise ValueError("max_order cannot be larger than maximum order of multi-order network")
+        n = int(self.layers[1].data.num_nodes)
+        dof = n - 1
+        if assumption == "paths":
+            if max_order >= 1:
+                ei = self.layers[1].data.edge_index
+                dev, _ = _staging.compute_device(ei)
+                walks, sources = ops.walk_counts(_plain(_staging.up(ei, dev)), n, max_order)
+                dof += sum(walks) - sum(sources)
+        elif assumption == "ngrams":
+            for order in range(1, max_order + 1):
+                dof += (n ** order) * (n - 1)
+        else:
+            logger.error("Unknown assumption %s. Only 'path' and 'ngram' are accepted.", assumption)
+            raise ValueError(f"Unknown assumption {assumption}. Only 'path' and 'ngram' are accepted.")
+        return int(dof)
+
+    @staticmethod
+    def _node_counts(node_sequence: torch.Tensor) -> torch.Tensor:
+        """``torch.unique(node_sequence, return_counts=True)[1]`` (:335): occurrence counts of the node ids that
+        occur, in ascending id order -- ids that never occur are SKIPPED, as in the reference (:336-337)."""
+        ids = node_sequence.reshape(-1)
+        counts = torch.bincount(ids)
+        return counts if bool((counts > 0).all()) else counts[counts > 0]
+
+    def get_zeroth_order_log_likelihood(self, dag_graph: Data) -> float:
+        """multi_order_model.py:314-339: sum over walks of weight * log(relative frequency of the start node)."""
+        dev, _ = _staging.compute_device(dag_graph.edge_index, dag_graph.node_sequence)
+        ei = _plain(_staging.up(dag_graph.edge_index, dev))
+        ns = _plain(_staging.up(dag_graph.node_sequence, dev)).reshape(-1)
+        is_start = torch.ones(int(dag_graph.num_nodes), dtype=torch.bool, device=dev)
+        is_start[ei[1]] = False                                                   # :329-330
+        start_nodes = ns[is_start]                                                # :331
+        counts = self._node_counts(ns)                                            # :335
+        prob = counts / counts.sum()                                              # :338 (int64 / int64 -> float32)
+        return ops.weighted_log_sum(_staging.up(dag_graph.dag_weight, dev), prob, start_nodes)    # :339
+
+    def get_intermediate_order_log_likelihood(self, dag_graph: Data, order: int) -> float:
+        """multi_order_model.py:341-369: the first transition of every walk in layer ``order``, found through
+        ``inverse_idx`` of layer ``order + 1`` at the walk's first position in the order-``order`` line graph."""
+        dev, _ = _staging.compute_device(dag_graph.dag_weight, self.layers[order].data.edge_index)
+        freq = _staging.up(dag_graph.dag_weight, dev)
+        shrunk = _staging.up(dag_graph.dag_num_nodes, dev) - order                # :354-356
+        keep = shrunk > 0
+        lengths = shrunk[keep]                                                    # :358
+        freq = freq[keep]                                                         # :359
+        starts = torch.cumsum(lengths, 0) - lengths                               # cumsum(.)[:-1] of the zero-prefixed sum, :361
+        prob = self.layers[order].transition_probabilities()                      # unweighted, as in the reference (:363)
+        inverse = _staging.up(self.layers[order + 1].data.inverse_idx, dev)
+        return ops.weighted_log_sum(freq, _staging.up(prob, dev), starts, inverse)    # :363-369
+
+    def get_mon_log_likelihood(self, dag_graph: Data, max_order: int = 1) -> float:
+        """multi_order_model.py:371-409."""
+        if max_order > 0:
+            llh = self.get_zeroth_order_log_likelihood(dag_graph)                 # :386
+            for order in range(1, max_order):
+                llh += self.get_intermediate_order_log_likelihood(dag_graph, order)   # :389-390
+            layer = self.layers[max_order]
+            dev, _ = _staging.compute_device(layer.data.edge_index)
+            prob = layer.transition_probabilities(edge_attr="edge_weight")        # :394
+            llh += ops.weighted_log_sum(_staging.up(layer.data.edge_weight, dev), _staging.up(prob, dev))   # :395-397
+            return llh
+        # zeroth-order model: weighted node frequencies (:402-407)
+        dev, _ = _staging.compute_device(dag_graph.node_sequence, dag_graph.dag_weight)
+        ns = _plain(_staging.up(dag_graph.node_sequence, dev)).reshape(-1)
+        w = _staging.up(dag_graph.dag_weight, dev).repeat_interleave(_staging.up(dag_graph.dag_num_nodes, dev))
+        n_ids = int(ns.max()) + 1 if ns.numel() else 0
+        # torch.bincount(ids, weights) adds the weights of a node in position order: group the positions by node
+        # (stable) and sum every group in slot order
+        grouped = ops.csc_build(torch.stack([torch.arange(ns.numel(), device=dev), ns]), ns.numel(), n_ids)
+        counts = ops.segment_sum(grouped.colptr, w, grouped.eid)                  # :403-405
+        prob = counts / counts.sum()                                              # :406
+        return ops.weighted_log_sum(counts, prob)                                 # :407
+
+    def likelihood_ratio_test(self, dag_graph: Data, max_order_null: int = 0, max_order: int = 1,
+                              assumption: str = "paths", significance_threshold: float = 0.01) -> tuple:
+        """multi_order_model.py:411-459."""
+        from scipy.stats import chi2
+
+        if max_order_null >= max_order:
+            logger.error("order of null hypothesis must be smaller than order of alternative hypothesis")
+            raise ValueError("order of null hypothesis must be smaller than order of alternative hypothesis")
+        if max_order > max(self.layers):
+            logger.error("order of hypotheses must be smaller than max. order of MultiOrderModel")
+            raise ValueError(f"order of hypotheses ({max_order_null} and {max_order}) must be smaller than max. order of "
+                             f"MultiOrderModel {max(self.layers)}")
+        x = -2 * (self.get_mon_log_likelihood(dag_graph, max_order=max_order_null)
+                  - self.get_mon_log_likelihood(dag_graph, max_order=max_order))
+        dof_diff = self.get_mon_dof(max_order, assumption=assumption) - self.get_mon_dof(max_order_null, assumption=assumption)
+        p = 1 - chi2.cdf(x, dof_diff)
+        return (p < significance_threshold), p
+
+    def estimate_order(self, dag_data: PathData, max_order: int | None = None, significance_threshold: float = 0.01) -> int:
+        """multi_order_model.py:461-509."""
+        if max_order is None:
+            max_order = max(self.layers)
+        if max_order > max(self.layers):
+            logger.error("max_order cannot be larger than maximum order of multi-order network")
+            raise ValueError("max_order cannot be larger than maximum order of multi-order network")
+        if max_order <= 1:
+            logger.error("max_order must be larger than one")
+            raise ValueError("max_order must be larger than one")
+        if not set(dag_data.mapping.node_ids).issubset(set(self.layers[1].mapping.node_ids)):
+            logger.error("Input paths do not have same set of nodes as multi-order network")
+            raise ValueError("Input paths do not have same set of nodes as multi-order network")
+        max_accepted_order = 1
+        dag_graph = dag_data.data
+        for k in range(2, max_order + 1):
+            if self.likelihood_ratio_test(dag_graph, max_order_null=k - 1, max_order=k,
+                                          significance_threshold=significance_threshold)[0]:
+                max_accepted_order = k
+        return max_accepted_order
 
     # ------------------------------------------------------------------------------------------
     def to_dbgnn_data(self, max_order: int = 2, mapping: str = "last", x_h: torch.Tensor | None = None) -> Data:

@@ -8,15 +8,15 @@
 // Only the significant key bits [0, end_bit) are sorted: P = ceil(end_bit / 8).
 //
 // Within a tile the ranking is stable: a warp ranks its 32*ITEMS keys round by round; lanes holding the
-// same digit are found with one ballot per digit bit and elect a leader that bumps the warp's counter in
-// shared memory; the tile is reordered through shared memory, and every digit's run is written out as
-// one contiguous (coalesced) segment.
+// same digit find each other through a per-warp mask word in shared memory (atomic OR of the lane bit) and
+// the highest of them bumps the warp's digit counter; the tile is reordered through shared memory, and
+// every digit's run is written out as one contiguous (coalesced) segment.
 //
 // Look-back: thread d owns digit d.  Two levels (tiles inside a group of 16, then groups), every walk with
 // kLookBatch independent loads in flight consumed in order -- see the comment in the kernel.
 //
-// Tile size: 256 threads x 8 keys up to 4M keys (more tiles than SM slots => one balanced wave, short
-// chain hops), 256 x 16 beyond (less look-back state, fewer fixed costs per key).
+// Tile size: 256 threads x 16 keys (the per-tile fixed costs -- look-back, digit scans, counter reset -- are
+// amortised over 4096 keys); 256 x 8 up to 512K keys, where more tiles fill more SMs.
 //
 // The payload is an optional u32 per key; the first pass can synthesise it as the element index
 // (IOTA) so that an index permutation costs no read.
@@ -48,7 +48,7 @@ constexpr int kSortBlock = 256;  // == kRadix: thread d owns digit d in the per-
 constexpr int kMaxPasses = 8;
 constexpr int kLookBatch = 8;
 constexpr int kLookGroup = 16;  // tiles per look-back group
-constexpr int64_t kSmallSortLimit = 4ll << 20;
+constexpr int64_t kSmallSortLimit = 512ll << 10;
 
 // development override: PPG_SORT_ITEMS=8|16 forces the tile size
 inline int sort_items_override() {
@@ -104,8 +104,17 @@ radix_histogram_kernel(const KeyT* __restrict__ keys, int64_t n, int num_passes,
   }
 }
 
-template <typename KeyT, bool HAS_VALUES, bool IOTA, int ITEMS>
-__global__ void __launch_bounds__(kSortBlock)
+// Resident CTAs per SM the register allocation is capped for: the phases of a tile (load, rank, look-back, scan,
+// reorder, write) are a dependent chain, so throughput comes from tiles in different phases sharing an SM.
+// 16 keys per thread: 3 CTAs (<= 85 registers, 59 KB shared memory each; measured on B200 at 64M pairs: 608 us per
+// pass against 704 us at 2 CTAs and 641 us at 4 CTAs with spills); 8 keys: 4 CTAs (64 registers).
+template <int ITEMS>
+struct SortMinCtas {
+  static constexpr int value = ITEMS >= 16 ? 3 : 4;
+};
+
+template <typename KeyT, bool HAS_VALUES, bool IOTA, int ITEMS, int MIN_CTAS>
+__global__ void __launch_bounds__(kSortBlock, MIN_CTAS)
 onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                      const unsigned long long* __restrict__ ghist,  // this pass: 256 digit counts
@@ -119,6 +128,9 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   uint32_t* s_whist = s_vals + (HAS_VALUES ? TILE : 0);                     // [NW][256] per-warp digit counts
   uint32_t* s_binstart = s_whist + NW * kRadix;                             // [256] first slot of a digit in the tile
   long long* s_gbase = reinterpret_cast<long long*>(s_binstart + kRadix);   // [256] global slot of tile slot 0 of a digit
+  // [NW][2][256] per-warp peer masks of the ranking rounds: they are dead before the tile is reordered, so they
+  // live in the buffer the reorder fills (TILE * 8 bytes >= NW * 2 * 256 * 4 for every ITEMS >= 4)
+  uint32_t* s_wmask = reinterpret_cast<uint32_t*>(smem_raw);
   __shared__ unsigned s_tile;
   __shared__ unsigned long long s_scan[2 * NW];
 
@@ -126,7 +138,11 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   const int warp = tid >> 5;
   const unsigned lane = lane_id();
 
-  for (int i = tid; i < NW * kRadix; i += kSortBlock) s_whist[i] = 0;
+  for (int i = tid; i < NW * kRadix; i += kSortBlock) {
+    s_whist[i] = 0;
+    s_wmask[i] = 0;
+    s_wmask[NW * kRadix + i] = 0;
+  }
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
   const unsigned tile = s_tile;
@@ -146,26 +162,27 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
 
   PPG_TRACE(tile, 1);  // (issue point only: the loads complete at their first use)
   // ---- stable rank inside the warp, digit counts per warp
-  // Lanes holding the same digit are found with one ballot per digit bit (8 votes + 8 logic ops per key).
-  // match.any would be a single instruction, but its cost grows with the number of DISTINCT values in the
-  // warp (~30 for random digits: measured 5 us per 8 keys), the ballots are fixed-cost and pipelined.
-  // The counter updates are one shared-memory atomic per distinct digit per round, in item order (=> stable).
+  // Lanes holding the same digit find each other through shared memory: every lane ORs its lane bit into the
+  // warp's mask word of its digit, the warp synchronises, and the word read back IS the peer set (one RED.OR +
+  // one LDS per key instead of 8 ballots + 8 logic ops).  The highest peer bumps the warp's digit counter and
+  // clears the mask word; the mask arrays alternate between rounds, so the clear of round i is ordered before
+  // the ORs of round i + 2 by the warp barriers of round i + 1.  Rounds run in item order => stable.
   uint32_t rank[ITEMS];
   uint32_t* my_hist = s_whist + warp * kRadix;
+  uint32_t* my_mask = s_wmask + warp * (2 * kRadix);
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
-    unsigned peers = kFullMask;
-#pragma unroll
-    for (int b = 0; b < kRadixBits; ++b) {
-      const bool bit = (d >> b) & 1u;
-      const unsigned vote = __ballot_sync(kFullMask, bit);
-      peers &= bit ? vote : ~vote;
+    uint32_t* m = my_mask + (i & 1) * kRadix + d;
+    atomicOr(m, 1u << lane);
+    __syncwarp();
+    const unsigned peers = *m;
+    const uint32_t before = my_hist[d];
+    __syncwarp();
+    if (lane == static_cast<unsigned>(31 - __clz(peers))) {
+      my_hist[d] = before + static_cast<uint32_t>(__popc(peers));
+      *m = 0;
     }
-    const int leader = 31 - __clz(peers);
-    uint32_t before = 0;
-    if (static_cast<int>(lane) == leader) before = atomicAdd(&my_hist[d], static_cast<uint32_t>(__popc(peers)));
-    before = __shfl_sync(kFullMask, before, leader);
     rank[i] = before + __popc(peers & lanemask_lt());
   }
   __syncthreads();
@@ -323,7 +340,7 @@ inline int launch_onesweep_pass_items(const KeyT* kin, KeyT* kout, const uint32_
                                       int shift, const unsigned long long* ghist, unsigned* counter,
                                       unsigned long long* state, unsigned long long* gstate, unsigned pass,
                                       cudaStream_t stream) {
-  auto kern = onesweep_pass_kernel<KeyT, HAS_VALUES, IOTA, ITEMS>;
+  auto kern = onesweep_pass_kernel<KeyT, HAS_VALUES, IOTA, ITEMS, SortMinCtas<ITEMS>::value>;
   constexpr size_t smem = onesweep_smem_bytes<KeyT, HAS_VALUES, ITEMS>();
   static bool configured = false;  // per instantiation
   if (!configured) {

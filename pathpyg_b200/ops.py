@@ -535,3 +535,75 @@ def bipartite_fused(g: TargetGroupedEdges, x_h: torch.Tensor, x: torch.Tensor, w
         _lib.check(lib.ppg_bipartite_fused(_ptr(g.colptr), _ptr(g.src), _ptr(x_h), _ptr(x), _ptr(w1), _ptr(w2), _ptr(bias12),
                                            g.num_targets, F, H, act, _ptr(out), _stream(dev)))
     return out
+
+
+# --------------------------------------------------------------------------------------- layer consumers
+def sorted_ids_ptr(sorted_ids: torch.Tensor, num_nodes: int) -> torch.Tensor:
+    """CSR pointer (int32, ``num_nodes + 1`` entries) of an ascending int64 id column."""
+    lib = _lib.load()
+    ids = sorted_ids.as_subclass(torch.Tensor).contiguous()
+    dev = _require_cuda(ids)
+    ptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_sorted_ids_ptr(_ptr(ids), ids.numel(), num_nodes, _ptr(ptr), _stream(dev)))
+    return ptr
+
+
+def segment_sum(ptr: torch.Tensor, weights: torch.Tensor | None, perm: torch.Tensor | None = None) -> torch.Tensor:
+    """float32 sums of ``weights`` over the slots of every segment of ``ptr`` (counts if ``weights`` is None)."""
+    lib = _lib.load()
+    dev = _require_cuda(ptr, weights, perm)
+    n = ptr.numel() - 1
+    if weights is not None:
+        weights = weights.contiguous().float()
+    slots = (perm.numel() if perm is not None else weights.numel()) if weights is not None else 0
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_segment_sum_workspace_bytes(slots), dev)
+        _lib.check(lib.ppg_segment_sum(_ptr(ptr), _ptr(perm), _ptr(weights), n, slots, _ptr(ws), ws.numel(), _ptr(out), _stream(dev)))
+    return out
+
+
+def edge_ratio(ids: torch.Tensor, weights: torch.Tensor | None, denom: torch.Tensor) -> torch.Tensor:
+    """out[e] = (weights[e] or 1) / denom[ids[e]] (float32)."""
+    lib = _lib.load()
+    ids = ids.as_subclass(torch.Tensor).contiguous()
+    dev = _require_cuda(ids, weights, denom)
+    if weights is not None:
+        weights = weights.contiguous().float()
+    denom = denom.contiguous().float()
+    out = torch.empty(ids.numel(), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_edge_ratio(_ptr(ids), _ptr(weights), _ptr(denom), ids.numel(), _ptr(out), _stream(dev)))
+    return out
+
+
+def walk_counts(edge_index: torch.Tensor, num_nodes: int, max_len: int):
+    """([#walks with k edges], [#nodes starting one]) for k = 1..max_len, as Python ints."""
+    lib = _lib.load()
+    ei = _edge_index_arg(edge_index)
+    dev = _require_cuda(ei)
+    walks, sources = (ctypes.c_int64 * max_len)(), (ctypes.c_int64 * max_len)()
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_walk_counts_workspace_bytes(num_nodes, max_len), dev)
+        _lib.check(lib.ppg_walk_counts(_ptr(ei), ei.size(1), num_nodes, max_len, _ptr(ws), ws.numel(), walks, sources, _stream(dev)))
+    return list(walks), list(sources)
+
+
+def weighted_log_sum(freq: torch.Tensor, prob: torch.Tensor, idx: torch.Tensor | None = None,
+                     idx2: torch.Tensor | None = None) -> float:
+    """sum_i freq[i] * log(prob[j]) with j = i, idx[i] or idx2[idx[i]]; fp32 terms, fp64 fixed-order accumulation."""
+    lib = _lib.load()
+    dev = _require_cuda(freq, prob, idx, idx2)
+    freq, prob = freq.contiguous().float(), prob.contiguous().float()
+    idx = None if idx is None else idx.as_subclass(torch.Tensor).contiguous().long()
+    idx2 = None if idx2 is None else idx2.as_subclass(torch.Tensor).contiguous().long()
+    out = ctypes.c_double(0.0)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_weighted_log_sum_workspace_bytes(), dev)
+        try:
+            _lib.check(lib.ppg_weighted_log_sum(_ptr(freq), _ptr(prob), _ptr(idx), _ptr(idx2), freq.numel(), prob.numel(),
+                                                0 if idx2 is None else idx2.numel(), _ptr(ws), ws.numel(), ctypes.byref(out), _stream(dev)))
+        except ValueError as e:  # torch raises IndexError for an out-of-range index
+            raise IndexError(str(e)) from None
+    return out.value

@@ -13,7 +13,7 @@ bits = 8  # one pass
 dev = torch.device("cuda", 0)
 lib = _lib.load()
 lib.ppg_debug_set_sort_trace.argtypes = [ctypes.c_void_p]
-items = 8 if n <= (4 << 20) else 16
+items = int(os.environ.get("PPG_SORT_ITEMS", 8 if n <= (512 << 10) else 16))
 tiles = -(-n // (256 * items))
 trace = torch.zeros(tiles * 8, dtype=torch.int64, device=dev)
 g = torch.Generator().manual_seed(0)
