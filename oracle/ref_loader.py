@@ -25,6 +25,7 @@ import sys
 import types
 from contextlib import contextmanager
 
+import numpy as np
 import torch
 
 from . import pyg
@@ -238,3 +239,72 @@ def ref_walks_data(walks):
     return _Data(edge_index=walks.edge_index, node_sequence=walks.node_sequence, dag_weight=walks.dag_weight,
                  dag_num_edges=walks.dag_num_edges, dag_num_nodes=walks.dag_num_nodes,
                  num_nodes=int(walks.node_sequence.size(0)))
+
+
+# ----------------------------------------------------------------------------------------------
+# ingest: the reference's own io/pandas.py, core/index_map.py and core/path_data.py
+# ----------------------------------------------------------------------------------------------
+class _RefTemporalGraph:
+    """Stand-in for pathpyG.TemporalGraph in io/pandas.py: applies the time ordering of the real constructor
+    (temporal_graph.py:58-63) with a STABLE sort (the reference's argsort leaves the order of ties unspecified)."""
+
+    def __init__(self, data, mapping=None):
+        order = torch.sort(data.time, stable=True).indices
+        m = data.edge_index.size(1)
+        for k, v in list(data.__dict__.items()):
+            if k == "edge_index":
+                data.edge_index = v[:, order]
+            elif isinstance(v, torch.Tensor) and v.dim() >= 1 and v.size(0) == m and (k == "time" or k.startswith("edge_")):
+                data.__dict__[k] = v[order]
+            elif isinstance(v, np.ndarray) and k.startswith("edge_") and v.shape[0] == m:
+                data.__dict__[k] = v[order.numpy()]
+        self.data, self.mapping = data, mapping
+        self.n, self.m = data.num_nodes, m
+
+
+class _SettableData(_Data):
+    def __setitem__(self, key, value):
+        self.__dict__[key] = value
+
+
+def io_module():
+    """The reference's ``io/pandas.py`` executed as a module, with its own ``IndexMap`` and ``PathData``."""
+    if "io" not in _cache:
+        import numpy  # noqa: F401
+
+        to_numpy = lambda t: t.numpy() if isinstance(t, torch.Tensor) else np.asarray(t)  # noqa: E731
+        names = {}
+
+        def mod(name, **attrs):
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            names[name] = m
+            return m
+
+        mod("torch_geometric")
+        mod("torch_geometric.data", Data=_SettableData)
+        mod("torch_geometric.utils", cumsum=pyg.cumsum)
+        mod("pathpyG")
+        mod("pathpyG.utils", to_numpy=to_numpy)
+        mod("pathpyG.utils.convert", to_numpy=to_numpy)
+        mod("pathpyG.core")
+        mod("pathpyG.core.graph", Graph=_Graph)
+        mod("pathpyG.core.temporal_graph", TemporalGraph=_RefTemporalGraph)
+        saved = {k: sys.modules.get(k) for k in list(names) + ["pathpyG.core.index_map", "pathpyG.core.path_data"]}
+        sys.modules.update(names)
+        try:
+            for rel, name in (("src/pathpyG/core/index_map.py", "pathpyG.core.index_map"),
+                              ("src/pathpyG/core/path_data.py", "pathpyG.core.path_data"),
+                              ("src/pathpyG/io/pandas.py", "_ref_io_pandas")):
+                spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE_ROOT, rel))
+                module = importlib.util.module_from_spec(spec)
+                sys.modules[name] = module
+                spec.loader.exec_module(module)
+            _cache["io"] = sys.modules.pop("_ref_io_pandas")
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    sys.modules.pop(k, None)
+                else:
+                    sys.modules[k] = v
+    return _cache["io"]

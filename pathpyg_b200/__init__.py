@@ -7,9 +7,9 @@ De Bruijn lift -> DBGNN hot path, behind pathpyG's own Python operator surface.
     data = m.to_dbgnn_data(max_order=2)
     out = pp.nn.DBGNN(...)(data)
 """
-from . import algorithms, nn, utils
+from . import algorithms, io, nn, utils
 from .core import Data, EdgeIndex, Graph, HigherOrderIndexMap, IndexMap, MultiOrderModel, PathData, TemporalGraph
 
 __version__ = "0.1.0"
-__all__ = ["algorithms", "nn", "utils", "Data", "EdgeIndex", "Graph", "IndexMap", "HigherOrderIndexMap",
+__all__ = ["algorithms", "io", "nn", "utils", "Data", "EdgeIndex", "Graph", "IndexMap", "HigherOrderIndexMap",
            "MultiOrderModel", "PathData", "TemporalGraph"]

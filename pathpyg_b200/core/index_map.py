@@ -80,6 +80,13 @@ class IndexMap:
         else:
             self._id_to_idx.update({v: start + i for i, v in enumerate(new.tolist())})
 
+    def _sorted_order(self) -> np.ndarray:
+        cached = getattr(self, "_order_cache", None)
+        if cached is None or cached[0] != len(self.node_ids):
+            cached = (len(self.node_ids), np.argsort(self.node_ids, kind="stable"))
+            self._order_cache = cached
+        return cached[1]
+
     def to_id(self, idx: int):
         if not self.has_ids:
             return idx
@@ -104,6 +111,18 @@ class IndexMap:
         arr = _as_numpy(nodes)
         lut = self.id_to_idx
         if self.id_shape == (-1,):
+            if arr.size >= 64 and arr.dtype.kind == self.node_ids.dtype.kind and arr.dtype.kind in "iufUS":
+                # bulk look-up: one binary search per id over the sorted ids instead of one dictionary probe
+                # (reference core/index_map.py:368); unknown ids raise KeyError like the dictionary would
+                ids = self.node_ids
+                order = self._sorted_order()
+                pos = np.searchsorted(ids, arr.reshape(-1), sorter=order)
+                pos[pos == len(ids)] = 0
+                hit = order[pos]
+                bad = ids[hit] != arr.reshape(-1)
+                if bad.any():
+                    raise KeyError(arr.reshape(-1)[bad][0].item())
+                return torch.from_numpy(hit.astype(np.int64)).to(device).reshape(arr.shape)
             flat = [lut[v] for v in arr.reshape(-1).tolist()]
             return torch.tensor(flat, device=device).reshape(arr.shape)
         k = len(self.id_shape) - 1

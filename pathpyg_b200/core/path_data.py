@@ -7,6 +7,7 @@ device (5M walks in BASELINE config 4): no per-walk Python, no dictionary look-u
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from .data import Data
@@ -52,8 +53,9 @@ class PathData:
 
     def append_walks(self, node_seqs, weights) -> None:
         dev = self.data.edge_index.device
-        flat = torch.cat([self.mapping.to_idxs(seq, device=dev) for seq in node_seqs])
         lengths = torch.tensor([len(seq) for seq in node_seqs], device=dev)
+        # one vectorised id look-up over all walks (the reference maps walk by walk, path_data.py:139-142)
+        flat = self.mapping.to_idxs(np.concatenate([np.asarray(seq) for seq in node_seqs]), device=dev)
         self.append_index_walks(flat, lengths, torch.tensor(weights, device=dev))
 
     def append_index_walks(self, flat_nodes: torch.Tensor, lengths: torch.Tensor, weights: torch.Tensor) -> None:

@@ -19,10 +19,16 @@ class TemporalGraph(Graph):
         if not isinstance(data.edge_index, EdgeIndex):
             data.edge_index = EdgeIndex(data.edge_index.contiguous(), sparse_size=(data.num_nodes, data.num_nodes))
         # reorder by time (temporal_graph.py:58-63; the reference's argsort is not stable, so any
-        # tie order is a valid instance -- a stable one is used here)
+        # tie order is a valid instance -- a stable one is used here).  On the GPU the order comes from the
+        # library's radix sort over the significant bits of the time range.
         t = data.time
         if t.numel() > 1 and not bool((t[1:] >= t[:-1]).all()):
-            order = torch.sort(t, stable=True).indices
+            if t.is_cuda and t.dtype in (torch.int64, torch.float64):
+                from .. import ops
+
+                order = ops.stable_argsort(t)
+            else:
+                order = torch.sort(t, stable=True).indices
             for attr in set(data.edge_attrs()).union({"time"}):
                 if attr == "edge_index":
                     data.edge_index = EdgeIndex(data.edge_index.as_tensor()[:, order].contiguous(),

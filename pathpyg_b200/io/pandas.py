@@ -1,0 +1,141 @@
+"""The step in front of the lift: ``df_to_temporal_graph`` (reference
+``src/pathpyG/io/pandas.py:318-396``), ``read_csv_temporal_graph`` (``:511-545``), ``read_csv_path_data``
+(``:572-599``), the column parsers they share (``:28-109``) and ``temporal_graph_to_df`` (``:437-471``).
+
+Same results as the reference, different mechanics:
+* node ids are factorised ONCE with ``np.unique(return_inverse=True)`` instead of one dictionary look-up per
+  end point (``IndexMap.to_idxs``, reference ``core/index_map.py:368``, 1-2 us per id);
+* with ``device=`` the index tensors go straight to the GPU and ``TemporalGraph`` puts them in time order there
+  with the library's radix sort (``ops.stable_argsort``) -- the reference sorts on the host with ``torch.argsort``;
+* n-gram files are parsed in one pass and handed to ``PathData.append_index_walks`` as one flat tensor.
+"""
+from __future__ import annotations
+
+import ast
+import csv
+import logging
+import re
+from typing import Any
+
+import numpy as np
+import pandas as pd
+import torch
+
+from ..core.data import Data
+from ..core.index_map import IndexMap
+from ..core.path_data import PathData
+from ..core.temporal_graph import TemporalGraph
+
+logger = logging.getLogger("root")
+
+# the reference's column classifiers (io/pandas.py:22-25)
+_iterable_re = re.compile(r"^\s*[\[\(\{].*[\]\)\}]\s*$")
+_number_re = re.compile(r"^\s*[+-]?(\d+(\.\d*)?|\.\d+)([eE][+-]?\d+)?\s*$")
+_integer_re = re.compile(r"^\s*[+-]?\d+\s*$")
+
+
+def _parse_timestamp(df: pd.DataFrame, timestamp_format: str = "%Y-%m-%d %H:%M:%S", time_rescale: int = 1) -> None:
+    """io/pandas.py:28-57 -- in place on column ``t``."""
+    if pd.api.types.is_string_dtype(df["t"]):
+        df["t"] = pd.to_datetime(df["t"], format=timestamp_format)
+        df["t"] = df["t"].astype("int64") // time_rescale
+        df["t"] = df["t"] - df["t"].min()
+    elif df["t"].dtype == "int64" or df["t"].dtype == "float64":
+        df["t"] = df["t"] // time_rescale
+    elif pd.api.types.is_datetime64_any_dtype(df["t"]):
+        df["t"] = df["t"].astype("int64") // time_rescale
+        df["t"] = df["t"] - df["t"].min()
+    else:
+        raise ValueError("Column `t` must be of type `object`, `int64`, `float64`, or a datetime type. "
+                         f"Found {df['t'].dtype} instead.")
+
+
+def _parse_df_column(df: pd.DataFrame, data: Data, attr: str, idx=None, prefix: str = "") -> None:
+    """io/pandas.py:60-109 -- one DataFrame column -> ``data[prefix + attr]`` (tensor, or numpy array for text)."""
+    if idx is None:
+        idx = np.arange(len(df))
+    dev = data.edge_index.device
+    col = df[attr]
+    if col.dtype == "object" or pd.api.types.is_string_dtype(col):
+        first = col.values[0]
+        if isinstance(first, str):
+            if _iterable_re.match(str(first)):
+                data[prefix + attr] = torch.tensor([ast.literal_eval(x) for x in col.values[idx]], device=dev)
+            elif _number_re.match(str(first)):
+                kind = int if _integer_re.match(str(first)) else float
+                data[prefix + attr] = torch.tensor(col.values.astype(kind)[idx], device=dev)
+            else:
+                data[prefix + attr] = np.array(col.values.astype(str)[idx])
+        elif isinstance(first, (list, tuple)):
+            data[prefix + attr] = torch.tensor(np.array([np.array(x) for x in col.values[idx]]))
+        else:
+            raise ValueError(f"Unsupported data type for attribute '{attr}': {type(first)}")
+    else:
+        data[prefix + attr] = torch.tensor(col.values[idx], device=dev)
+
+
+def df_to_temporal_graph(df: pd.DataFrame, multiedges: bool = False, timestamp_format="%Y-%m-%d %H:%M:%S", time_rescale=1,
+                         num_nodes: int | None = None, device=None) -> TemporalGraph:
+    """io/pandas.py:318-396.  ``device`` (extension): where the index tensors are created; with a CUDA device the
+    time ordering of ``TemporalGraph`` runs there."""
+    if all(isinstance(x, int) for x in df.columns.values.tolist()):
+        logger.info("Interpreting first three columns as v, w, t")
+        df.columns = ["v", "w", "t"] + [f"edge_attr_{i - 2}" for i in range(3, len(df.columns))]
+    _parse_timestamp(df=df, timestamp_format=timestamp_format, time_rescale=time_rescale)
+    if not multiedges:
+        df = df.drop_duplicates(subset=["v", "w", "t"])
+    # np.unique sorts the ids like the reference's IndexMap(np.unique(...)) (:376); the inverse IS mapping.to_idxs
+    node_ids, inverse = np.unique(df[["v", "w"]].values, return_inverse=True)
+    mapping = IndexMap(node_ids)
+    edge_index = torch.from_numpy(np.ascontiguousarray(inverse.reshape(-1, 2).T.astype(np.int64)))
+    time = torch.tensor(df["t"].values)
+    if device is not None:
+        edge_index, time = edge_index.to(device), time.to(device)
+    data = Data(edge_index=edge_index, time=time, num_nodes=num_nodes if num_nodes is not None else int(node_ids.shape[0]))
+    for col in [c for c in df.columns if c not in ("v", "w", "t")]:
+        _parse_df_column(df=df, data=data, attr=col, prefix="" if col.startswith("edge_") else "edge_")
+    return TemporalGraph(data=data, mapping=mapping)
+
+
+def read_csv_temporal_graph(filename: str, sep: str = ",", header: bool = True, timestamp_format: str = "%Y-%m-%d %H:%M:%S",
+                            time_rescale: int = 1, **kwargs: Any) -> TemporalGraph:
+    """io/pandas.py:511-545."""
+    df = pd.read_csv(filename, header=0 if header else None, sep=sep)
+    return df_to_temporal_graph(df, timestamp_format=timestamp_format, time_rescale=time_rescale, **kwargs)
+
+
+def temporal_graph_to_df(graph: TemporalGraph, node_indices: bool = False) -> pd.DataFrame:
+    """io/pandas.py:437-471: one row per time-stamped edge, edge attributes as extra columns."""
+    ei = graph.data.edge_index.as_tensor().cpu().numpy()
+    if node_indices:
+        v, w = ei[0], ei[1]
+    else:
+        v, w = graph.mapping.to_ids(ei[0]), graph.mapping.to_ids(ei[1])
+    df = pd.DataFrame({"v": v, "w": w, "t": graph.data.time.cpu().numpy()})
+    for attr in graph.edge_attrs():
+        if attr in ("edge_index", "time"):
+            continue
+        val = graph.data[attr]
+        df[attr] = val.cpu().numpy().tolist() if isinstance(val, torch.Tensor) else list(val)
+    return df
+
+
+def read_csv_path_data(path_or_buf: Any = None, weight: bool = True, sep=",", device=None) -> PathData:
+    """io/pandas.py:572-599: one walk per line, optionally followed by its count."""
+    with open(path_or_buf, "r") as f:
+        rows = list(csv.reader(f, delimiter=sep))
+    if weight:
+        paths = [row[:-1] for row in rows]
+        weights = [ast.literal_eval(row[-1]) for row in rows]
+    else:
+        paths, weights = rows, [1.0] * len(rows)
+    flat = np.hstack(paths) if paths else np.empty(0, dtype=str)
+    node_ids, inverse = np.unique(flat, return_inverse=True)     # sorted ids + index of every occurrence (:591-592)
+    mapping = IndexMap()
+    mapping.add_ids(node_ids)
+    pathdata = PathData(mapping, device)
+    if paths:
+        lengths = torch.tensor([len(p) for p in paths], device=device)
+        pathdata.append_index_walks(torch.from_numpy(inverse.astype(np.int64)).to(device) if device is not None
+                                    else torch.from_numpy(inverse.astype(np.int64)), lengths, torch.tensor(weights, device=device))
+    return pathdata

@@ -322,6 +322,40 @@ def sort_pairs_u64(keys: torch.Tensor, end_bit: int, time_passes: bool = False):
     return perm, (list(ms) if time_passes else None)
 
 
+def stable_argsort(values: torch.Tensor) -> torch.Tensor:
+    """Permutation (int64) that puts a 1-D int64 / float64 CUDA tensor in ascending order, equal values keeping
+    their input order.  Keys are made unsigned and as narrow as the value range allows, so time stamps spanning
+    2^b cost ceil(b / 8) digit passes of the onesweep radix sort instead of 8 (TemporalGraph.__init__,
+    reference core/temporal_graph.py:58)."""
+    _require_cuda(values)
+    v = values.as_subclass(torch.Tensor).contiguous()
+    if v.dim() != 1:
+        raise ValueError("stable_argsort expects a 1-D tensor")
+    n = v.numel()
+    if n >= 1 << 31:
+        raise ValueError("stable_argsort: more than 2^31 - 1 elements")
+    if n < 2:
+        return torch.arange(n, device=v.device)
+    if v.dtype == torch.float64:
+        if bool(torch.isnan(v).any()):
+            raise ValueError("stable_argsort: NaN time stamps have no order")
+        bits = (v + 0.0).view(torch.int64)                                  # + 0.0 turns -0.0 into +0.0
+        # order-preserving map to unsigned: negative values flip all bits, the others flip the sign bit
+        keys, end_bit = bits ^ ((bits >> 63) | torch.tensor(-1 << 63, dtype=torch.int64, device=v.device)), 64
+    elif v.dtype in (torch.int64, torch.int32, torch.int16, torch.int8, torch.uint8):
+        v = v.long()
+        lo, hi = int(v.min()), int(v.max())
+        span = hi - lo
+        if span >= 1 << 63:
+            keys, end_bit = v ^ torch.tensor(-1 << 63, dtype=torch.int64, device=v.device), 64
+        else:
+            keys, end_bit = v - lo, max(1, span.bit_length())
+    else:
+        raise TypeError(f"stable_argsort supports int64 and float64 (got {v.dtype})")
+    perm, _ = sort_pairs_u64(keys, end_bit)  # keys is a fresh tensor in every branch (sorted in place)
+    return perm.long()
+
+
 # --------------------------------------------------------------------------------------- a10 / a11
 class TargetGroupedEdges:
     """CSC view of an edge list: incoming edges of every target node, original order inside a target."""
