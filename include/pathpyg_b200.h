@@ -249,6 +249,24 @@ int ppg_weighted_log_sum(const float* freq, const float* prob, const int64_t* id
                          int64_t prob_len, int64_t idx2_len, void* workspace, size_t workspace_bytes, double* h_out,
                          void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Shortest time-respecting paths   reference: src/pathpyG/algorithms/temporal.py:57-107
+ *   edge_index [2,m] time-sorted events, event_graph [2,num_pairs] = the a1 output for the same delta.
+ *   For the sources [source_begin, source_end) (source_begin a multiple of 32):
+ *     out_dist [source_end - source_begin, n] float64: fewest events on a time-respecting path s -> v
+ *              (0 on the diagonal, +inf if there is none);
+ *     out_pred [same] int64: source node of the event that ends such a path (the one with the largest event
+ *              index, which is what scipy's dijkstra reports for the reference's augmented graph), s itself on
+ *              the diagonal, -1 if unreachable.
+ *   h_levels (nullable): number of breadth-first levels run.  Synchronises once per level.
+ * ------------------------------------------------------------------------------------------- */
+size_t ppg_temporal_paths_workspace_bytes(int64_t num_events, int64_t num_nodes, int64_t chunk_sources);
+int ppg_temporal_paths(const int64_t* edge_index, int64_t num_events, int64_t num_nodes, const int64_t* event_graph,
+                       int64_t num_pairs, int64_t source_begin, int64_t source_end, void* workspace,
+                       size_t workspace_bytes, double* out_dist, int64_t* out_pred, int* h_levels, void* stream);
+/* out[v] = sum_{x != v} (n - 1) / dist[x, v] in ascending x (temporal_closeness_centrality, centrality.py:320-322) */
+int ppg_temporal_closeness(const double* dist, int64_t num_nodes, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

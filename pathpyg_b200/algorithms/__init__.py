@@ -4,7 +4,8 @@ from .lift_order import (
     lift_order_edge_index,
     lift_order_edge_index_weighted,
 )
-from .temporal import lift_order_temporal
+from .centrality import temporal_closeness_centrality
+from .temporal import lift_order_temporal, temporal_shortest_paths
 
 __all__ = [
     "aggregate_edge_index",
@@ -12,4 +13,6 @@ __all__ = [
     "lift_order_edge_index",
     "lift_order_edge_index_weighted",
     "lift_order_temporal",
+    "temporal_shortest_paths",
+    "temporal_closeness_centrality",
 ]

@@ -129,14 +129,19 @@ class Graph:
 
     @property
     def order(self) -> int:
-        return int(self.data.node_sequence.size(1))
+        ns = self.data.node_sequence
+        return 1 if ns is None else int(ns.size(1))
 
     @property
     def nodes(self) -> list:
-        ids = self.mapping.to_ids(self.data.node_sequence.cpu().numpy()) if self.mapping.has_ids else self.data.node_sequence.cpu().numpy()
-        if self.order == 1:
-            return [v[0] if not isinstance(v[0], np.str_) else str(v[0]) for v in ids]
-        return [tuple(v.tolist()) for v in ids]
+        """IDs (or indices without a mapping) of all nodes, tuples for higher-order graphs (graph.py:329-342)."""
+        if self.order > 1:
+            seq = self.data.node_sequence.cpu().numpy()
+            ids = self.mapping.to_ids(np.arange(self.n)) if isinstance(self.mapping.node_ids, np.ndarray) and \
+                self.mapping.id_shape != (-1,) else seq
+            return [tuple(v.tolist()) for v in ids]
+        ids = self.mapping.to_ids(np.arange(self.n))
+        return [str(v) if isinstance(v, np.str_) else (v.item() if isinstance(v, np.generic) else v) for v in ids]
 
     @property
     def edges(self) -> list:

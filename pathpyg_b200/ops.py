@@ -641,3 +641,43 @@ def weighted_log_sum(freq: torch.Tensor, prob: torch.Tensor, idx: torch.Tensor |
         except ValueError as e:  # torch raises IndexError for an out-of-range index
             raise IndexError(str(e)) from None
     return out.value
+
+
+# --------------------------------------------------------------------------------------- shortest time-respecting paths
+def temporal_paths(edge_index: torch.Tensor, event_graph: torch.Tensor | None, num_nodes: int,
+                   max_workspace_bytes: int = 8 << 30):
+    """(dist [n, n] float64, pred [n, n] int64) on the device: bit-parallel multi-source BFS over the event graph,
+    sources processed in chunks (multiples of 32) sized so that the frontier state stays below
+    ``max_workspace_bytes``."""
+    lib = _lib.load()
+    ei = _edge_index_arg(edge_index)
+    dev = _require_cuda(ei, event_graph)
+    m, n = ei.size(1), int(num_nodes)
+    eg = _edge_index_arg(event_graph) if event_graph is not None and event_graph.numel() else None
+    pairs = 0 if eg is None else eg.size(1)
+    dist = torch.empty((n, n), dtype=torch.float64, device=dev)
+    pred = torch.empty((n, n), dtype=torch.int64, device=dev)
+    if n == 0:
+        return dist, pred
+    per_word = 12 * max(m, 1) + 32 * 8 * n                      # frontier + visited + next words, best rows
+    chunk = max(32, min((n + 31) // 32 * 32, max_workspace_bytes // per_word * 32))
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_temporal_paths_workspace_bytes(m, n, min(chunk, n)), dev)
+        for s0 in range(0, n, chunk):
+            s1 = min(n, s0 + chunk)
+            _lib.check(lib.ppg_temporal_paths(_ptr(ei), m, n, _ptr(eg), pairs, s0, s1, _ptr(ws), ws.numel(),
+                                              ctypes.c_void_p(dist.data_ptr() + s0 * n * 8),
+                                              ctypes.c_void_p(pred.data_ptr() + s0 * n * 8), None, _stream(dev)))
+    return dist, pred
+
+
+def temporal_closeness(dist: torch.Tensor) -> torch.Tensor:
+    """closeness[v] = sum over x != v of (n - 1) / dist[x, v] (float64, added in ascending x)."""
+    lib = _lib.load()
+    dev = _require_cuda(dist)
+    dist = dist.contiguous()
+    n = dist.size(0)
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_temporal_closeness(_ptr(dist), n, _ptr(out), _stream(dev)))
+    return out
