@@ -17,6 +17,11 @@ What is restated here (reference paths are relative to ``/root/reference``):
   ``PathData.append_walks`` (``core/path_data.py:126-159``) and
   ``generate_bipartite_edge_index`` (``utils/dbgnn.py:10-46``).
 * ``oracle/dbgnn.py``    ``src/pathpyG/nn/dbgnn.py`` + PyG ``GCNConv``.
+* ``oracle/selection.py`` ``Graph.degrees`` / ``transition_probabilities`` (``core/graph.py:486-533``) and the
+  model-selection statistics of ``MultiOrderModel`` (``core/multi_order_model.py:243-509``).
+* ``oracle/ingest.py``   ``df_to_temporal_graph`` / ``read_csv_path_data`` (``io/pandas.py``).
+* ``oracle/paths.py``    ``temporal_shortest_paths`` (``algorithms/temporal.py:57-107``) and
+  ``temporal_closeness_centrality`` (``algorithms/centrality.py:303-324``).
 
 Pinning status
 --------------
@@ -26,6 +31,9 @@ Pinning status
   commits the input/output vectors under ``tests/golden/``; the oracle is checked
   against those and against every known-answer vector in the reference's tests
   (SURVEY.md section 8c).
+* statistics, ingest, shortest paths: PINNED the same way -- ``oracle/ref_loader.py`` compiles the
+  reference's own method bodies / modules from ``/root/reference`` and ``tests/golden/make_selection_golden.py`` /
+  ``make_ingest_golden.py`` commit their outputs; known answers of the reference's tests are test cases.
 * DBGNN numerics (a10/a11): PARITY UNPINNED.  The reference holds no activation
   values (``tests/nn/test_dbgnn.py:33-43`` asserts ``out is not None``) and
   ``GCNConv`` lives in un-vendored PyG, so ``oracle/dbgnn.py`` is a restatement of
