@@ -92,15 +92,25 @@ struct PackParams {
 };
 
 __global__ void __launch_bounds__(256)
-pack_rows_kernel(const int64_t* __restrict__ rows, int64_t M, PackParams pp, unsigned long long* __restrict__ keys) {
+pack_rows_kernel(const int64_t* __restrict__ rows, int64_t M, PackParams pp, unsigned long long* __restrict__ keys,
+                 unsigned long long* __restrict__ ghist0) {
+  __shared__ unsigned s_hist[kRadix];
+  Digit0Counter digit0;
+  digit0.begin(s_hist);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < M; i += stride) {
-    const int64_t* r = rows + i * pp.width;
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * blockDim.x; base < M; base += stride) {
+    const int64_t i = base + threadIdx.x;
+    const bool valid = i < M;
     unsigned long long k = 0;
-    for (int c = 0; c < pp.width; ++c)
-      k |= static_cast<unsigned long long>(ld_stream(r + c) - pp.col_min[c]) << pp.col_shift[c];
-    keys[i] = k;
+    if (valid) {
+      const int64_t* r = rows + i * pp.width;
+      for (int c = 0; c < pp.width; ++c)
+        k |= static_cast<unsigned long long>(ld_stream(r + c) - pp.col_min[c]) << pp.col_shift[c];
+      keys[i] = k;
+    }
+    digit0.count(static_cast<unsigned>(k) & (kRadix - 1), valid);
   }
+  digit0.end(ghist0);
 }
 
 struct UniqueLayout {
@@ -189,24 +199,35 @@ struct CoalesceLayout {
 __global__ void __launch_bounds__(256)
 edge_keys_kernel(const int64_t* __restrict__ ei, int64_t E, const int64_t* __restrict__ remap, int64_t remap_len,
                  int64_t num_nodes, int node_bits, unsigned long long* __restrict__ keys,
-                 unsigned long long* __restrict__ status) {
+                 unsigned long long* __restrict__ status, unsigned long long* __restrict__ ghist0) {
+  __shared__ unsigned s_hist[kRadix];
+  Digit0Counter digit0;
+  digit0.begin(s_hist);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < E; j += stride) {
-    int64_t r = ld_stream(ei + j);
-    int64_t c = ld_stream(ei + E + j);
-    bool ok = true;
-    if (remap != nullptr) {
-      ok = r >= 0 && r < remap_len && c >= 0 && c < remap_len;
-      r = ok ? remap[r] : 0;
-      c = ok ? remap[c] : 0;
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * blockDim.x; base < E; base += stride) {
+    const int64_t j = base + threadIdx.x;
+    const bool valid = j < E;
+    unsigned long long key = 0;
+    if (valid) {
+      int64_t r = ld_stream(ei + j);
+      int64_t c = ld_stream(ei + E + j);
+      bool ok = true;
+      if (remap != nullptr) {
+        ok = r >= 0 && r < remap_len && c >= 0 && c < remap_len;
+        r = ok ? remap[r] : 0;
+        c = ok ? remap[c] : 0;
+      }
+      ok = ok && r >= 0 && r < num_nodes && c >= 0 && c < num_nodes;
+      if (!ok) {
+        atomicOr(reinterpret_cast<unsigned*>(status), kStatusIdOutOfRange);
+        r = c = 0;
+      }
+      key = (static_cast<unsigned long long>(r) << node_bits) | static_cast<unsigned long long>(c);
+      keys[j] = key;
     }
-    ok = ok && r >= 0 && r < num_nodes && c >= 0 && c < num_nodes;
-    if (!ok) {
-      atomicOr(reinterpret_cast<unsigned*>(status), kStatusIdOutOfRange);
-      r = c = 0;
-    }
-    keys[j] = (static_cast<unsigned long long>(r) << node_bits) | static_cast<unsigned long long>(c);
+    digit0.count(static_cast<unsigned>(key) & (kRadix - 1), valid);
   }
+  digit0.end(ghist0);
 }
 
 struct RunStartConsumer {
@@ -366,11 +387,11 @@ extern "C" int ppg_unique_rows_sort(const int64_t* rows, int64_t M, int64_t widt
     pp.col_shift[c] = h_col_shift[c];
     PPG_REQUIRE(h_col_shift[c] >= 0 && h_col_shift[c] < 64, PPG_ERR_INVALID, "unique_rows: bad shift for column %d", c);
   }
-  pack_rows_kernel<<<grid_for(M, 256 * 4), 256, 0, stream>>>(rows, M, pp, L.keys_a);
+  pack_rows_kernel<<<grid_for(M, 256 * 4), 256, 0, stream>>>(rows, M, pp, L.keys_a, L.sort_ws);
   PPG_LAUNCHED();
   int in_b = 0;
   PPG_TRY(radix_sort_pairs<unsigned long long>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, M, total_bits,
-                                               L.sort_ws, &in_b, stream));
+                                               L.sort_ws, &in_b, stream, nullptr, true));
   PPG_REQUIRE((in_b != 0) == ((L.passes & 1) != 0), PPG_ERR_CUDA, "unique_rows: internal buffer parity mismatch");
   PPG_TRY(launch_scan(RunHeadProducer{L.sorted_keys()}, RankScatterConsumer{L.sorted_perm(), out_inverse, L.rep}, M,
                       L.scan_ws, &L.result->total, stream));
@@ -415,11 +436,11 @@ extern "C" int ppg_coalesce_sort(const int64_t* edge_index, int64_t E, const int
   PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, L.zero_bytes, stream));
 
   edge_keys_kernel<<<grid_for(E, 256 * 4), 256, 0, stream>>>(edge_index, E, remap, remap_len, num_nodes, L.node_bits,
-                                                             L.keys_a, &L.result->status);
+                                                             L.keys_a, &L.result->status, L.sort_ws);
   PPG_LAUNCHED();
   int in_b = 0;
   PPG_TRY(radix_sort_pairs<unsigned long long>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, E, 2 * L.node_bits,
-                                               L.sort_ws, &in_b, stream));
+                                               L.sort_ws, &in_b, stream, nullptr, true));
   PPG_REQUIRE((in_b != 0) == ((L.passes & 1) != 0), PPG_ERR_CUDA, "coalesce: internal buffer parity mismatch");
   PPG_TRY(launch_scan(RunHeadProducer{L.sorted_keys()}, RunStartConsumer{L.run_start, E, L.sorted_perm(), out_inverse}, E,
                       L.scan_ws, &L.result->total, stream));

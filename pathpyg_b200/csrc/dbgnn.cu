@@ -51,16 +51,28 @@ struct CscLayout {
 
 __global__ void __launch_bounds__(256)
 target_keys_kernel(const int64_t* __restrict__ ei, int64_t E, int64_t num_sources, int64_t num_targets,
-                   uint32_t* __restrict__ keys, uint32_t* __restrict__ deg, unsigned long long* __restrict__ status) {
+                   uint32_t* __restrict__ keys, uint32_t* __restrict__ deg, unsigned long long* __restrict__ status,
+                   unsigned long long* __restrict__ ghist0) {
+  __shared__ unsigned s_hist[kRadix];
+  Digit0Counter digit0;
+  digit0.begin(s_hist);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < E; j += stride) {
-    const int64_t r = ld_stream(ei + j);
-    const int64_t c = ld_stream(ei + E + j);
-    const bool ok = r >= 0 && r < num_sources && c >= 0 && c < num_targets;
-    if (!ok) atomicOr(reinterpret_cast<unsigned*>(status), kStatusIdOutOfRange);
-    keys[j] = ok ? static_cast<uint32_t>(c) : 0u;
-    if (ok) atomicAdd(&deg[c], 1u);
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * blockDim.x; base < E; base += stride) {
+    const int64_t j = base + threadIdx.x;
+    const bool valid = j < E;
+    uint32_t key = 0;
+    if (valid) {
+      const int64_t r = ld_stream(ei + j);
+      const int64_t c = ld_stream(ei + E + j);
+      const bool ok = r >= 0 && r < num_sources && c >= 0 && c < num_targets;
+      if (!ok) atomicOr(reinterpret_cast<unsigned*>(status), kStatusIdOutOfRange);
+      key = ok ? static_cast<uint32_t>(c) : 0u;
+      keys[j] = key;
+      if (ok) atomicAdd(&deg[c], 1u);
+    }
+    digit0.count(key & (kRadix - 1), valid);
   }
+  digit0.end(ghist0);
 }
 
 struct DegreeProducer32 {
@@ -303,7 +315,7 @@ extern "C" int ppg_csc_build(const int64_t* edge_index, int64_t E, int64_t num_s
   }
   if (E > 0) {
     target_keys_kernel<<<grid_for(E, 256 * 4), 256, 0, stream>>>(edge_index, E, num_sources, num_targets, L.keys_a, L.deg,
-                                                                 &L.result->status);
+                                                                 &L.result->status, L.sort_ws);
     PPG_LAUNCHED();
   }
   PPG_TRY(launch_scan(DegreeProducer32{L.deg}, PointerConsumer32{out_colptr, num_targets}, num_targets, L.scan_ws,
@@ -311,7 +323,7 @@ extern "C" int ppg_csc_build(const int64_t* edge_index, int64_t E, int64_t num_s
   if (E > 0) {
     int in_b = 0;
     PPG_TRY(radix_sort_pairs<uint32_t>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, E, L.sort_bits, L.sort_ws,
-                                       &in_b, stream));
+                                       &in_b, stream, nullptr, true));
     csc_fill_kernel<<<grid_for(E, 256 * 4), 256, 0, stream>>>(edge_index, in_b ? L.vals_b : L.vals_a, E, out_src, out_eid);
     PPG_LAUNCHED();
   }

@@ -34,21 +34,33 @@ struct ResultWords {
 template <bool EMIT_KEYS>
 __global__ void __launch_bounds__(256)
 degree_kernel(const int64_t* __restrict__ ids, int64_t n, int64_t num_nodes, uint32_t* __restrict__ deg,
-              uint32_t* __restrict__ keys_out, unsigned long long* __restrict__ status) {
+              uint32_t* __restrict__ keys_out, unsigned long long* __restrict__ status,
+              unsigned long long* __restrict__ ghist0) {
+  __shared__ unsigned s_hist[kRadix];
+  Digit0Counter digit0;
+  if (EMIT_KEYS) digit0.begin(s_hist);
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int64_t v = ld_stream(ids + i);
-    const bool ok = v >= 0 && v < num_nodes;
-    if (EMIT_KEYS) keys_out[i] = ok ? static_cast<uint32_t>(v) : 0u;
-    const unsigned active = __activemask();
-    const unsigned tag = ok ? static_cast<unsigned>(v) : 0xffffffffu;
-    const unsigned peers = __match_any_sync(active, tag);
-    if (!ok) {
-      atomicOr(reinterpret_cast<unsigned*>(status), kStatusIdOutOfRange);
-    } else if (lane_id() == static_cast<unsigned>(__ffs(peers) - 1)) {
-      atomicAdd(&deg[v], static_cast<uint32_t>(__popc(peers)));
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * blockDim.x; base < n; base += stride) {
+    const int64_t i = base + threadIdx.x;
+    const bool valid = i < n;
+    uint32_t key = 0;
+    if (valid) {
+      const int64_t v = ld_stream(ids + i);
+      const bool ok = v >= 0 && v < num_nodes;
+      key = ok ? static_cast<uint32_t>(v) : 0u;
+      if (EMIT_KEYS) keys_out[i] = key;
+      const unsigned active = __activemask();
+      const unsigned tag = ok ? static_cast<unsigned>(v) : 0xffffffffu;
+      const unsigned peers = __match_any_sync(active, tag);
+      if (!ok) {
+        atomicOr(reinterpret_cast<unsigned*>(status), kStatusIdOutOfRange);
+      } else if (lane_id() == static_cast<unsigned>(__ffs(peers) - 1)) {
+        atomicAdd(&deg[v], static_cast<uint32_t>(__popc(peers)));
+      }
     }
+    if (EMIT_KEYS) digit0.count(key & (kRadix - 1), valid);  // the keys feed a radix sort: count its first digit here
   }
+  if (EMIT_KEYS) digit0.end(ghist0);
 }
 
 struct DegreeProducer {
@@ -419,7 +431,7 @@ extern "C" int ppg_lift_order_count(const int64_t* edge_index, int64_t E, int64_
   PPG_REQUIRE(ws.fits(), PPG_ERR_WORKSPACE, "lift_order: workspace %zu < %zu bytes", workspace_bytes, ws.used);
   PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, L.zero_bytes, stream));
 
-  degree_kernel<false><<<grid_for(E, 256 * 4), 256, 0, stream>>>(edge_index, E, N, L.deg, nullptr, &L.result->status);
+  degree_kernel<false><<<grid_for(E, 256 * 4), 256, 0, stream>>>(edge_index, E, N, L.deg, nullptr, &L.result->status, nullptr);
   PPG_LAUNCHED();
   PPG_TRY(launch_scan(DegreeProducer{L.deg}, PointerConsumer{L.ptr, N}, N, L.scan_ptr_ws, nullptr, stream));
   PPG_TRY(launch_scan(LiftCountProducer{edge_index + E, L.ptr, L.first, N, &L.result->status}, OffsetConsumer{L.off, E},
@@ -481,12 +493,13 @@ extern "C" int ppg_lift_temporal_count(const int64_t* edge_index, const void* ti
   PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, L.zero_bytes, stream));
 
   // CSR over the source node, edges inside a group in time order (stable sort of a time-sorted stream)
-  degree_kernel<true><<<grid_for(m, 256 * 4), 256, 0, stream>>>(edge_index, m, N, L.deg, L.keys_a, &L.result->status);
+  degree_kernel<true><<<grid_for(m, 256 * 4), 256, 0, stream>>>(edge_index, m, N, L.deg, L.keys_a, &L.result->status,
+                                                                L.sort_ws);
   PPG_LAUNCHED();
   PPG_TRY(launch_scan(DegreeProducer{L.deg}, PointerConsumer{L.ptr, N}, N, L.scan_ptr_ws, nullptr, stream));
   int in_b = 0;
   PPG_TRY(radix_sort_pairs<uint32_t>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, m, L.sort_bits, L.sort_ws,
-                                     &in_b, stream));
+                                     &in_b, stream, nullptr, true));
   const uint32_t* grouped = in_b ? L.vals_b : L.vals_a;
   PPG_REQUIRE(grouped == L.grouped(), PPG_ERR_CUDA, "lift_order_temporal: internal buffer parity mismatch");
   gather64_kernel<<<grid_for(m, 256 * 4), 256, 0, stream>>>(static_cast<const unsigned long long*>(time), grouped, m,

@@ -1,10 +1,11 @@
 // Stable least-significant-digit radix sort, one sweep per 8-bit digit ("onesweep").
 //
 // HBM traffic for n (key, payload) pairs over P digit passes:
-//   histogram pass : read keys once                      (sizeof(Key) * n)
+//   histogram pass : read keys once, count digit 0       (sizeof(Key) * n)
 //   each digit pass: read pairs once, write pairs once   (2 * (sizeof(Key) + 4) * n)
-// The per-pass global scatter offsets come from (a) the up-front histogram of all P digits and
-// (b) a decoupled look-back chain over the per-tile digit counts, so no pass reads its keys twice.
+// The per-pass global scatter offsets come from (a) the digit histogram of the pass -- digit 0 is counted up front,
+// every pass counts the digits of the NEXT pass while it holds the keys in registers -- and (b) a decoupled
+// look-back chain over the per-tile digit counts, so no pass reads its keys twice.
 // Only the significant key bits [0, end_bit) are sorted: P = ceil(end_bit / 8).
 //
 // Within a tile the ranking is stable: a warp ranks its 32*ITEMS keys round by round; lanes holding the
@@ -76,6 +77,36 @@ inline size_t sort_state_words(int64_t n, int end_bit) {
   return P * kRadix + P + (static_cast<size_t>(sort_num_tiles(n)) + sort_num_groups(n)) * kRadix;
 }
 
+// Digit-0 counts taken by the kernel that PRODUCES the keys (one shared-memory atomic per key, one global atomic
+// per non-empty bin and CTA), so that a sort never reads its keys just to count them.  count() must be reached
+// by all 32 lanes of a warp (pass valid = false for lanes past the end).
+struct Digit0Counter {
+  unsigned* s;
+  __device__ __forceinline__ void begin(unsigned* smem256) {
+    s = smem256;
+    for (int i = threadIdx.x; i < kRadix; i += blockDim.x) s[i] = 0;
+    __syncthreads();
+  }
+  __device__ __forceinline__ void count(unsigned digit, bool valid) {
+    const unsigned live = __ballot_sync(kFullMask, valid);
+    if (live == 0) return;
+    const int first = __ffs(live) - 1;
+    const unsigned d0 = __shfl_sync(kFullMask, digit, first);
+    if (__all_sync(kFullMask, !valid || digit == d0)) {
+      if (static_cast<int>(lane_id()) == first) atomicAdd(&s[digit], static_cast<unsigned>(__popc(live)));
+    } else if (valid) {
+      atomicAdd(&s[digit], 1u);
+    }
+  }
+  __device__ __forceinline__ void end(unsigned long long* ghist) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kRadix; i += blockDim.x) {
+      const unsigned c = s[i];
+      if (c) atomicAdd(&ghist[i], static_cast<unsigned long long>(c));
+    }
+  }
+};
+
 template <typename KeyT>
 __global__ void __launch_bounds__(256)
 radix_histogram_kernel(const KeyT* __restrict__ keys, int64_t n, int num_passes, unsigned long long* __restrict__ ghist) {
@@ -118,6 +149,7 @@ __global__ void __launch_bounds__(kSortBlock, MIN_CTAS)
 onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
                      const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out, int64_t n, int shift,
                      const unsigned long long* __restrict__ ghist,  // this pass: 256 digit counts
+                     unsigned long long* __restrict__ ghist_next,   // next pass: accumulated here (nullptr on the last pass)
                      unsigned* __restrict__ tile_counter, unsigned long long* __restrict__ state,
                      unsigned long long* __restrict__ gstate, unsigned code_partial, unsigned code_inclusive) {
   constexpr int NW = kSortBlock / 32;
@@ -133,6 +165,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   uint32_t* s_wmask = reinterpret_cast<uint32_t*>(smem_raw);
   __shared__ unsigned s_tile;
   __shared__ unsigned long long s_scan[2 * NW];
+  __shared__ unsigned s_next[kRadix];  // digit counts of this tile for the NEXT pass
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -143,6 +176,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
     s_wmask[i] = 0;
     s_wmask[NW * kRadix + i] = 0;
   }
+  s_next[tid] = 0;
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
   const unsigned tile = s_tile;
@@ -158,6 +192,25 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   for (int i = 0; i < ITEMS; ++i) {
     const int64_t idx = warp_base + i * 32 + lane;
     key[i] = idx < n ? ld_stream(keys_in + idx) : static_cast<KeyT>(~static_cast<KeyT>(0));
+  }
+
+  // ---- digit counts for the next pass, taken while the keys are in registers: the sort reads its keys once per
+  // pass and never for a histogram of its own (only digit 0 is counted up front).  High digits of small-range keys
+  // are often identical across a warp: one shared-memory atomic instead of 32.
+  if (ghist_next != nullptr) {
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const bool valid = warp_base + i * 32 + lane < n;
+      const unsigned d1 = static_cast<unsigned>(key[i] >> (shift + kRadixBits)) & (kRadix - 1);
+      const unsigned live = __ballot_sync(kFullMask, valid);
+      if (live == 0) continue;
+      const unsigned d0 = __shfl_sync(kFullMask, d1, __ffs(live) - 1);
+      if (__all_sync(kFullMask, !valid || d1 == d0)) {
+        if (lane == static_cast<unsigned>(__ffs(live) - 1)) atomicAdd(&s_next[d1], static_cast<unsigned>(__popc(live)));
+      } else if (valid) {
+        atomicAdd(&s_next[d1], 1u);
+      }
+    }
   }
 
   PPG_TRACE(tile, 1);  // (issue point only: the loads complete at their first use)
@@ -188,6 +241,10 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   __syncthreads();
 
   PPG_TRACE(tile, 2);
+  if (ghist_next != nullptr) {
+    const unsigned c = s_next[tid];
+    if (c) atomicAdd(&ghist_next[tid], static_cast<unsigned long long>(c));
+  }
   // ---- per digit (thread d): exclusive over warps, tile count, publish, look back
   unsigned long long count = 0;
   {
@@ -337,9 +394,9 @@ constexpr size_t onesweep_smem_bytes() {
 
 template <typename KeyT, bool HAS_VALUES, bool IOTA, int ITEMS>
 inline int launch_onesweep_pass_items(const KeyT* kin, KeyT* kout, const uint32_t* vin, uint32_t* vout, int64_t n,
-                                      int shift, const unsigned long long* ghist, unsigned* counter,
-                                      unsigned long long* state, unsigned long long* gstate, unsigned pass,
-                                      cudaStream_t stream) {
+                                      int shift, const unsigned long long* ghist, unsigned long long* ghist_next,
+                                      unsigned* counter, unsigned long long* state, unsigned long long* gstate,
+                                      unsigned pass, cudaStream_t stream) {
   auto kern = onesweep_pass_kernel<KeyT, HAS_VALUES, IOTA, ITEMS, SortMinCtas<ITEMS>::value>;
   constexpr size_t smem = onesweep_smem_bytes<KeyT, HAS_VALUES, ITEMS>();
   static bool configured = false;  // per instantiation
@@ -350,18 +407,18 @@ inline int launch_onesweep_pass_items(const KeyT* kin, KeyT* kout, const uint32_
     configured = true;
   }
   kern<<<static_cast<unsigned>(sort_num_tiles(n)), kSortBlock, smem, stream>>>(
-      kin, kout, vin, vout, n, shift, ghist, counter, state, gstate, 2 * pass + 1, 2 * pass + 2);
+      kin, kout, vin, vout, n, shift, ghist, ghist_next, counter, state, gstate, 2 * pass + 1, 2 * pass + 2);
   PPG_LAUNCHED();
   return PPG_OK;
 }
 
 template <typename KeyT, bool HAS_VALUES, bool IOTA>
 inline int launch_onesweep_pass(const KeyT* kin, KeyT* kout, const uint32_t* vin, uint32_t* vout, int64_t n, int shift,
-                                const unsigned long long* ghist, unsigned* counter, unsigned long long* state,
-                                unsigned long long* gstate, unsigned pass, cudaStream_t stream) {
+                                const unsigned long long* ghist, unsigned long long* ghist_next, unsigned* counter,
+                                unsigned long long* state, unsigned long long* gstate, unsigned pass, cudaStream_t stream) {
   if (sort_items_for(n) == 8)
-    return launch_onesweep_pass_items<KeyT, HAS_VALUES, IOTA, 8>(kin, kout, vin, vout, n, shift, ghist, counter, state, gstate, pass, stream);
-  return launch_onesweep_pass_items<KeyT, HAS_VALUES, IOTA, 16>(kin, kout, vin, vout, n, shift, ghist, counter, state, gstate, pass, stream);
+    return launch_onesweep_pass_items<KeyT, HAS_VALUES, IOTA, 8>(kin, kout, vin, vout, n, shift, ghist, ghist_next, counter, state, gstate, pass, stream);
+  return launch_onesweep_pass_items<KeyT, HAS_VALUES, IOTA, 16>(kin, kout, vin, vout, n, shift, ghist, ghist_next, counter, state, gstate, pass, stream);
 }
 
 // Sorts the significant bits [0, end_bit) of keys_a (n elements) with an optional u32 payload.
@@ -370,10 +427,11 @@ inline int launch_onesweep_pass(const KeyT* kin, KeyT* kout, const uint32_t* vin
 //   zeroed_ws     : sort_state_words(n, end_bit) words, zero on entry
 //   *in_b         : 1 if the sorted result ended in the *_b buffers
 //   h_pass_ms     : optional host array [P]: CUDA-event time of every digit pass (synchronises; bench probe)
+//   digit0_counted: the producer of the keys already added the digit-0 counts to zeroed_ws[0..255] (Digit0Counter)
 template <typename KeyT>
 inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* vals_b, bool has_values,
                             bool iota_payload, int64_t n, int end_bit, unsigned long long* zeroed_ws, int* in_b,
-                            cudaStream_t stream, float* h_pass_ms = nullptr) {
+                            cudaStream_t stream, float* h_pass_ms = nullptr, bool digit0_counted = false) {
   const int P = sort_num_passes(end_bit);
   PPG_REQUIRE(P <= kMaxPasses, PPG_ERR_INVALID, "radix sort: %d key bits need more than %d passes", end_bit, kMaxPasses);
   PPG_REQUIRE(n < (1ll << 31), PPG_ERR_INVALID, "radix sort: %lld elements exceed the 2^31 limit", (long long)n);
@@ -387,8 +445,11 @@ inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32
   *in_b = 0;
   if (n == 0) return PPG_OK;
 
-  radix_histogram_kernel<KeyT><<<grid_for(n, 256 * 8, kNumSMsB200 * 8), 256, 0, stream>>>(keys_a, n, P, ghist);
-  PPG_LAUNCHED();
+  // digit 0 only: every pass counts the digits of the next one while it holds the keys
+  if (!digit0_counted) {
+    radix_histogram_kernel<KeyT><<<grid_for(n, 256 * 8, kNumSMsB200 * 8), 256, 0, stream>>>(keys_a, n, 1, ghist);
+    PPG_LAUNCHED();
+  }
 
   KeyT* kin = keys_a;
   KeyT* kout = keys_b;
@@ -398,13 +459,14 @@ inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32
   for (int p = 0; p < P; ++p) {
     unsigned* counter = reinterpret_cast<unsigned*>(counters + p);
     const unsigned long long* h = ghist + static_cast<size_t>(p) * kRadix;
+    unsigned long long* hn = p + 1 < P ? ghist + static_cast<size_t>(p + 1) * kRadix : nullptr;
     const int shift = p * kRadixBits;
     if (!has_values) {
-      PPG_TRY((launch_onesweep_pass<KeyT, false, false>(kin, kout, nullptr, nullptr, n, shift, h, counter, state, gstate, p, stream)));
+      PPG_TRY((launch_onesweep_pass<KeyT, false, false>(kin, kout, nullptr, nullptr, n, shift, h, hn, counter, state, gstate, p, stream)));
     } else if (p == 0 && iota_payload) {
-      PPG_TRY((launch_onesweep_pass<KeyT, true, true>(kin, kout, nullptr, vout, n, shift, h, counter, state, gstate, p, stream)));
+      PPG_TRY((launch_onesweep_pass<KeyT, true, true>(kin, kout, nullptr, vout, n, shift, h, hn, counter, state, gstate, p, stream)));
     } else {
-      PPG_TRY((launch_onesweep_pass<KeyT, true, false>(kin, kout, vin, vout, n, shift, h, counter, state, gstate, p, stream)));
+      PPG_TRY((launch_onesweep_pass<KeyT, true, false>(kin, kout, vin, vout, n, shift, h, hn, counter, state, gstate, p, stream)));
     }
     KeyT* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = (p == 0 && iota_payload) ? vals_a : vin;
