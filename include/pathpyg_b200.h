@@ -158,6 +158,12 @@ size_t ppg_csc_workspace_bytes(int64_t num_edges, int64_t num_targets);
 int ppg_csc_build(const int64_t* edge_index, int64_t num_edges, int64_t num_sources, int64_t num_targets,
                   void* workspace, size_t workspace_bytes, int32_t* out_colptr, int32_t* out_src, int32_t* out_eid,
                   void* stream);
+/* Same without the host synchronisation: the kernels are only enqueued (so the call can sit inside a CUDA graph),
+ * out-of-range ids are clamped to 0 in the outputs and flagged in the workspace head; collect the flag later with
+ * ppg_result_read(workspace, ...) (status bit 0). */
+int ppg_csc_build_async(const int64_t* edge_index, int64_t num_edges, int64_t num_sources, int64_t num_targets,
+                        void* workspace, size_t workspace_bytes, int32_t* out_colptr, int32_t* out_src, int32_t* out_eid,
+                        void* stream);
 
 /* gcn_norm with add_remaining_self_loops(fill_value=1): out_val [E] per CSC slot (0 on self-loop
  * slots), out_self [n] normalised self-loop weight; scratch_dis [n]; edge_weight NULL = ones;

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "ppg_sort_pairs_u64": (c_int, [_p, _p, _i64, c_int, _p, c_size_t, POINTER(ctypes.c_float), _p]),
     "ppg_csc_workspace_bytes": (c_size_t, [_i64, _i64]),
     "ppg_csc_build": (c_int, [_p, _i64, _i64, _i64, _p, c_size_t, _p, _p, _p, _p]),
+    "ppg_csc_build_async": (c_int, [_p, _i64, _i64, _i64, _p, c_size_t, _p, _p, _p, _p]),
     "ppg_gcn_norm": (c_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p]),
     "ppg_colptr_counts": (c_int, [_p, _i64, _p, _p]),
     "ppg_spmm_csc": (c_int, [_p, _p, _p, _p, _p, _i64, _i64, _p, c_int, _p, _p]),

@@ -89,13 +89,16 @@ struct PointerConsumer32 {
 };
 
 __global__ void __launch_bounds__(256)
-csc_fill_kernel(const int64_t* __restrict__ ei, const uint32_t* __restrict__ perm, int64_t E, int32_t* __restrict__ src,
-                int32_t* __restrict__ eid) {
+csc_fill_kernel(const int64_t* __restrict__ ei, const uint32_t* __restrict__ perm, int64_t E, int64_t num_sources,
+                int32_t* __restrict__ src, int32_t* __restrict__ eid) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < E; i += stride) {
     const uint32_t e = perm[i];
     eid[i] = static_cast<int32_t>(e);
-    src[i] = static_cast<int32_t>(ei[e]);
+    // an out-of-range source id was flagged by target_keys_kernel; it is clamped here so that consumers running
+    // before a deferred status check stay inside their arrays
+    const int64_t r = ei[e];
+    src[i] = r >= 0 && r < num_sources ? static_cast<int32_t>(r) : 0;
   }
 }
 
@@ -298,7 +301,7 @@ extern "C" size_t ppg_csc_workspace_bytes(int64_t num_edges, int64_t num_targets
   return ws.used + 256;
 }
 
-extern "C" int ppg_csc_build(const int64_t* edge_index, int64_t E, int64_t num_sources, int64_t num_targets,
+extern "C" int ppg_csc_build_async(const int64_t* edge_index, int64_t E, int64_t num_sources, int64_t num_targets,
                              void* workspace, size_t workspace_bytes, int32_t* out_colptr, int32_t* out_src,
                              int32_t* out_eid, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -324,11 +327,19 @@ extern "C" int ppg_csc_build(const int64_t* edge_index, int64_t E, int64_t num_s
     int in_b = 0;
     PPG_TRY(radix_sort_pairs<uint32_t>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, E, L.sort_bits, L.sort_ws,
                                        &in_b, stream, nullptr, true));
-    csc_fill_kernel<<<grid_for(E, 256 * 4), 256, 0, stream>>>(edge_index, in_b ? L.vals_b : L.vals_a, E, out_src, out_eid);
+    csc_fill_kernel<<<grid_for(E, 256 * 4), 256, 0, stream>>>(edge_index, in_b ? L.vals_b : L.vals_a, E, num_sources, out_src,
+                                                              out_eid);
     PPG_LAUNCHED();
   }
+  return PPG_OK;  // status bits stay in the workspace head: ppg_result_read
+}
+
+extern "C" int ppg_csc_build(const int64_t* edge_index, int64_t E, int64_t num_sources, int64_t num_targets, void* workspace,
+                             size_t workspace_bytes, int32_t* out_colptr, int32_t* out_src, int32_t* out_eid, void* stream_) {
+  PPG_TRY(ppg_csc_build_async(edge_index, E, num_sources, num_targets, workspace, workspace_bytes, out_colptr, out_src,
+                              out_eid, stream_));
   ResultWords h;
-  PPG_TRY(read_back(&h, L.result, stream));
+  PPG_TRY(read_back(&h, static_cast<const ResultWords*>(workspace), static_cast<cudaStream_t>(stream_)));
   PPG_REQUIRE((h.status & kStatusIdOutOfRange) == 0, PPG_ERR_INVALID, "csc_build: node id out of range");
   return PPG_OK;
 }

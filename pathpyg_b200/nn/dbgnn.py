@@ -11,6 +11,7 @@ segment-reduce SpMM + dense transform in the sm_100a kernels of ``csrc/dbgnn.cu`
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -129,10 +130,12 @@ class BipartiteGraphOperator(nn.Module):
         self.lin1 = nn.Linear(in_ch, out_ch)
         self.lin2 = nn.Linear(in_ch, out_ch)
 
-    def forward(self, x, bipartite_index, n_ho: int, n_fo: int, act: int = _lib.ACT_NONE):
+    def forward_prepared(self, x, grouped: ops.TargetGroupedEdges, act: int = _lib.ACT_NONE):
         x_h, x_fo = x
-        grouped = ops.csc_build(bipartite_index, n_ho, n_fo)
         return _BipartiteFn.apply(x_h, x_fo, self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias, grouped, act)
+
+    def forward(self, x, bipartite_index, n_ho: int, n_fo: int, act: int = _lib.ACT_NONE):
+        return self.forward_prepared(x, ops.csc_build(bipartite_index, n_ho, n_fo), act)
 
 
 class DBGNN(nn.Module):
@@ -160,15 +163,22 @@ class DBGNN(nn.Module):
         ei, ei_h = _staging.up(data.edge_index, dev), _staging.up(data.edge_index_higher_order, dev)
         w, w_h = _staging.up(data.edge_weights, dev), _staging.up(data.edge_weights_higher_order, dev)
         bip = _staging.up(data.bipartite_edge_index, dev)
-        n_fo, n_ho = int(data.num_nodes), int(data.num_ho_nodes)
+        sizes = (int(data.num_nodes), int(data.num_ho_nodes))
         drop = self.training and self.p_dropout > 0.0
+        if grad or drop or to_host or os.environ.get("PPG_NO_GRAPH", "0") == "1":
+            return _staging.down(self._run(x, x_h, ei, ei_h, w, w_h, bip, sizes, grad, drop, validate=True), to_host)
+        return self._replay(x, x_h, ei, ei_h, w, w_h, bip, sizes)
 
-        fo_graph = ops.gcn_prepare(ei, w, n_fo, keep_edge_values=grad)
+    def _run(self, x, x_h, ei, ei_h, w, w_h, bip, sizes, grad, drop, validate) -> torch.Tensor:
+        """nn/dbgnn.py:121-151.  The three target-grouped views are built without host synchronisation; their id
+        checks are collected once, after every kernel of the forward pass has been enqueued."""
+        n_fo, n_ho = sizes
+        fo_graph = ops.gcn_prepare(ei, w, n_fo, keep_edge_values=grad, defer_check=True)
         for layer in self.first_order_layers:
             if drop:
                 x = F.dropout(x, p=self.p_dropout, training=True)
             x = layer.forward_prepared(x, fo_graph, _lib.ACT_ELU)
-        ho_graph = ops.gcn_prepare(ei_h, w_h, n_ho, keep_edge_values=grad)
+        ho_graph = ops.gcn_prepare(ei_h, w_h, n_ho, keep_edge_values=grad, defer_check=True)
         for layer in self.higher_order_layers:
             if drop:
                 x_h = F.dropout(x_h, p=self.p_dropout, training=True)
@@ -176,8 +186,42 @@ class DBGNN(nn.Module):
         if drop:
             x = F.dropout(x, p=self.p_dropout, training=True)
             x_h = F.dropout(x_h, p=self.p_dropout, training=True)
-        x = self.bipartite_layer((x_h, x), bip, n_ho, n_fo, _lib.ACT_ELU)
+        bip_graph = ops.csc_build(bip, n_ho, n_fo, defer_check=True)
+        x = self.bipartite_layer.forward_prepared((x_h, x), bip_graph, _lib.ACT_ELU)
         if drop:
             x = F.dropout(x, p=self.p_dropout, training=True)
         out = _LinearFn.apply(x, self.lin.weight, self.lin.bias)
-        return _staging.down(out, to_host)
+        if validate:
+            for g in (fo_graph, ho_graph, bip_graph):
+                g.check()
+        else:
+            fo_graph.pending_ws = ho_graph.pending_ws = bip_graph.pending_ws = None
+        return out
+
+    def _replay(self, x, x_h, ei, ei_h, w, w_h, bip, sizes) -> torch.Tensor:
+        """Repeated inference on the same device-resident graph: the forward pass is ~30 short kernels whose launches
+        cost as much host time as the kernels take, so the SECOND call with the same (graph tensors, parameters) is
+        captured into a CUDA graph and later calls replay it -- every kernel runs on every call, only the launch
+        work is saved.  The capture is keyed on the addresses and in-place versions of the index tensors (validated
+        eagerly first); feature and parameter VALUES are read at replay time.  A graph seen once runs eagerly."""
+        ident = lambda t: None if t is None else (t.data_ptr(), tuple(t.shape), t.dtype)  # noqa: E731
+        ver = lambda t: None if t is None else t._version  # noqa: E731
+        key = (ident(x), ident(x_h), ident(w), ident(w_h), sizes,
+               tuple((ident(t), ver(t)) for t in (ei, ei_h, bip)),
+               tuple(ident(p) for p in self.parameters()))
+        cache = self.__dict__.setdefault("_graphs", {})
+        args = (x, x_h, ei, ei_h, w, w_h, bip, sizes)
+        if key not in cache:
+            if len(cache) >= 4:
+                cache.pop(next(iter(cache)))
+            cache[key] = None                                            # first sight: eager (and validated)
+            return self._run(*args, grad=False, drop=False, validate=True)
+        entry = cache[key]
+        if entry is None:
+            torch.cuda.synchronize(x.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._run(*args, grad=False, drop=False, validate=False)
+            entry = cache[key] = (graph, static_out, args)               # args keep the captured tensors alive
+        entry[0].replay()
+        return entry[1].clone()

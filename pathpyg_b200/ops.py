@@ -361,7 +361,7 @@ class TargetGroupedEdges:
     """CSC view of an edge list: incoming edges of every target node, original order inside a target."""
 
     __slots__ = ("colptr", "src", "eid", "num_sources", "num_targets", "val", "self_val", "val_edge", "edge_index",
-                 "_transposed")
+                 "_transposed", "pending_ws")
 
     def __init__(self, colptr, src, eid, num_sources, num_targets):
         self.colptr, self.src, self.eid = colptr, src, eid
@@ -371,6 +371,13 @@ class TargetGroupedEdges:
         self.val_edge = None  # the per-slot coefficient indexed by original edge id (kept for the backward view)
         self.edge_index = None
         self._transposed = None
+        self.pending_ws = None  # workspace whose status word has not been checked yet (deferred csc_build)
+
+    def check(self) -> None:
+        """Raise ValueError if the deferred build saw a node id out of range (synchronises the stream)."""
+        if self.pending_ws is not None:
+            ws, self.pending_ws = self.pending_ws, None
+            _read_result(ws, ws.device, "csc_build")
 
     def transposed(self) -> "TargetGroupedEdges":
         """The same edges grouped by SOURCE node (what the backward pass reduces over): A^T."""
@@ -384,7 +391,9 @@ class TargetGroupedEdges:
         return self._transposed
 
 
-def csc_build(edge_index: torch.Tensor, num_sources: int, num_targets: int) -> TargetGroupedEdges:
+def csc_build(edge_index: torch.Tensor, num_sources: int, num_targets: int, defer_check: bool = False) -> TargetGroupedEdges:
+    """``defer_check``: only enqueue the kernels (no host synchronisation); the caller validates the ids later with
+    ``graph.check()`` -- out-of-range ids are clamped meanwhile, so consumers stay memory-safe."""
     lib = _lib.load()
     ei = _edge_index_arg(edge_index)
     dev = _require_cuda(ei)
@@ -394,18 +403,21 @@ def csc_build(edge_index: torch.Tensor, num_sources: int, num_targets: int) -> T
     eid = torch.empty(E, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         ws = _workspace(lib.ppg_csc_workspace_bytes(E, num_targets), dev)
-        _lib.check(lib.ppg_csc_build(_ptr(ei), E, num_sources, num_targets, _ptr(ws), ws.numel(), _ptr(colptr), _ptr(src),
-                                     _ptr(eid), _stream(dev)))
+        build = lib.ppg_csc_build_async if defer_check else lib.ppg_csc_build
+        _lib.check(build(_ptr(ei), E, num_sources, num_targets, _ptr(ws), ws.numel(), _ptr(colptr), _ptr(src), _ptr(eid),
+                         _stream(dev)))
     g = TargetGroupedEdges(colptr, src, eid, num_sources, num_targets)
     g.edge_index = ei
+    if defer_check:
+        g.pending_ws = ws
     return g
 
 
 def gcn_prepare(edge_index: torch.Tensor, edge_weight: torch.Tensor | None, num_nodes: int,
-                keep_edge_values: bool = False) -> TargetGroupedEdges:
+                keep_edge_values: bool = False, defer_check: bool = False) -> TargetGroupedEdges:
     """CSC view + symmetric GCN normalisation with remaining self-loops (PyG gcn_norm)."""
     lib = _lib.load()
-    g = csc_build(edge_index, num_nodes, num_nodes)
+    g = csc_build(edge_index, num_nodes, num_nodes, defer_check=defer_check)
     dev = g.colptr.device
     E = g.src.numel()
     if edge_weight is not None:

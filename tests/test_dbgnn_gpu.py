@@ -276,3 +276,34 @@ def test_tensor_core_layer_vs_oracle(cuda, F, H):
     agg2 = torch.zeros(n, F, dtype=torch.float64).index_add_(0, want_ei[1][mask], want_norm.double()[mask].unsqueeze(1) * x.double()[want_ei[0][mask]])
     scale = (agg2.abs() @ W.double().abs().t()).clamp(min=1.0)
     assert bool(((got.double().cpu() - agg2 @ W.double().t()).abs() <= RTOL * scale).all())
+
+
+def test_graph_replay_matches_eager(cuda, monkeypatch):
+    """Repeated no-grad inference on the same device-resident graph replays a captured CUDA graph: bit-identical to
+    the eager pass, follows feature / parameter VALUES, re-validates when an index tensor is modified in place."""
+    g = torch.Generator().manual_seed(21)
+    n, m, H = 3000, 40000, 64
+    ei = torch.randint(0, n, (2, m), generator=g)
+    t = torch.sort(torch.randint(0, 400, (m,), generator=g)).values
+    mo = pp.MultiOrderModel.from_temporal_graph(pp.TemporalGraph.from_tensors(ei.to(cuda), t.to(cuda), n), delta=4, max_order=2)
+    mo.layers[1].data.x = torch.randn(n, H, generator=g).to(cuda)
+    data = mo.to_dbgnn_data(max_order=2, x_h=torch.randn(mo.layers[2].n, H, generator=g).to(cuda))
+    net = pp.nn.DBGNN(num_classes=7, num_features=(H, H), hidden_dims=[H, H, H]).to(cuda).eval()
+    with torch.no_grad():
+        monkeypatch.setenv("PPG_NO_GRAPH", "1")
+        eager = net(data)
+        monkeypatch.setenv("PPG_NO_GRAPH", "0")
+        first, second, third = net(data), net(data), net(data)      # eager, capture + replay, replay
+        assert net._graphs and any(v is not None for v in net._graphs.values())
+        assert torch.equal(first, eager) and torch.equal(second, eager) and torch.equal(third, eager)
+        data.x_h.mul_(0.5)
+        net.lin.bias.add_(1.0)
+        replayed = net(data)
+        monkeypatch.setenv("PPG_NO_GRAPH", "1")
+        assert torch.equal(replayed, net(data)) and not torch.equal(replayed, eager)
+        monkeypatch.setenv("PPG_NO_GRAPH", "0")
+        data.edge_index_higher_order.as_tensor()[0, 3] = mo.layers[2].n + 5   # in place: new version -> eager + validated
+        with pytest.raises(ValueError):
+            net(data)
+    out = net(data.__class__(**{**data.to_dict(), "edge_index_higher_order": mo.layers[2].data.edge_index.as_tensor().clone().clamp_(max=mo.layers[2].n - 1)}))
+    assert out.requires_grad                                        # grad mode never takes the graph path
