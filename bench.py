@@ -210,6 +210,8 @@ def run_gpu(args, cfg, rank, world, local_rank):
     launches = timed[-1][3] + timed[-1][4]
 
     # ---- e2e: the public call with HOST (pinned) inputs; H2D of the inputs and D2H of the result inside the timed region
+    out_pin = torch.empty((cfg["n"], cfg["classes"]), dtype=torch.float32).pin_memory()   # host buffer the activations land in
+
     def e2e_step():
         flush.fill_(1)
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
@@ -219,7 +221,7 @@ def run_gpu(args, cfg, rank, world, local_rank):
         model_ = lift_step(ei_d, t_d)
         sizes = torch.tensor([g.m for g in model_.layers.values()], device=dev).cpu()  # result read-back of the lift
         b.record(stream)
-        out_h = dbgnn_step(model_).cpu()  # result read-back of the forward
+        out_h = out_pin.copy_(dbgnn_step(model_), non_blocking=True)  # result read-back of the forward
         c.record(stream)
         return a, b, c, out_h, sizes
 

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -204,24 +205,25 @@ class DBGNN(nn.Module):
         captured into a CUDA graph and later calls replay it -- every kernel runs on every call, only the launch
         work is saved.  The capture is keyed on the addresses and in-place versions of the index tensors (validated
         eagerly first); feature and parameter VALUES are read at replay time.  A graph seen once runs eagerly."""
-        ident = lambda t: None if t is None else (t.data_ptr(), tuple(t.shape), t.dtype)  # noqa: E731
-        ver = lambda t: None if t is None else t._version  # noqa: E731
-        key = (ident(x), ident(x_h), ident(w), ident(w_h), sizes,
-               tuple((ident(t), ver(t)) for t in (ei, ei_h, bip)),
-               tuple(ident(p) for p in self.parameters()))
+        tensors = (x, x_h, ei, ei_h, w, w_h, bip) + tuple(self.parameters())
+        # identity of the tensor OBJECTS (ids are confirmed through weak references: the allocator hands the addresses
+        # -- and Python the ids -- of freed tensors out again, and a pipeline that rebuilds its graph on every call
+        # must stay on the eager path), their storage addresses / shapes, and the in-place versions of the indices
+        key = tuple(id(t) for t in tensors) + sizes
+        stamp = (tuple((t.data_ptr(), tuple(t.shape), t.dtype) for t in tensors), tuple(t._version for t in (ei, ei_h, bip)))
         cache = self.__dict__.setdefault("_graphs", {})
         args = (x, x_h, ei, ei_h, w, w_h, bip, sizes)
-        if key not in cache:
+        entry = cache.get(key)
+        if entry is None or entry["stamp"] != stamp or any(r() is not t for r, t in zip(entry["refs"], tensors)):
             if len(cache) >= 4:
                 cache.pop(next(iter(cache)))
-            cache[key] = None                                            # first sight: eager (and validated)
-            return self._run(*args, grad=False, drop=False, validate=True)
-        entry = cache[key]
-        if entry is None:
+            cache[key] = {"stamp": stamp, "refs": [weakref.ref(t) for t in tensors], "graph": None}
+            return self._run(*args, grad=False, drop=False, validate=True)   # first sight: eager (and validated)
+        if entry["graph"] is None:
             torch.cuda.synchronize(x.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_out = self._run(*args, grad=False, drop=False, validate=False)
-            entry = cache[key] = (graph, static_out, args)               # args keep the captured tensors alive
-        entry[0].replay()
-        return entry[1].clone()
+            entry["graph"], entry["out"], entry["args"] = graph, static_out, args   # args keep the captured tensors alive
+        entry["graph"].replay()
+        return entry["out"].clone()

@@ -294,7 +294,7 @@ def test_graph_replay_matches_eager(cuda, monkeypatch):
         eager = net(data)
         monkeypatch.setenv("PPG_NO_GRAPH", "0")
         first, second, third = net(data), net(data), net(data)      # eager, capture + replay, replay
-        assert net._graphs and any(v is not None for v in net._graphs.values())
+        assert net._graphs and any(v["graph"] is not None for v in net._graphs.values())
         assert torch.equal(first, eager) and torch.equal(second, eager) and torch.equal(third, eager)
         data.x_h.mul_(0.5)
         net.lin.bias.add_(1.0)
@@ -305,5 +305,12 @@ def test_graph_replay_matches_eager(cuda, monkeypatch):
         data.edge_index_higher_order.as_tensor()[0, 3] = mo.layers[2].n + 5   # in place: new version -> eager + validated
         with pytest.raises(ValueError):
             net(data)
+        # a pipeline that rebuilds its inputs on every call (new tensor objects, possibly at recycled addresses) stays eager
+        for _ in range(4):
+            fresh = mo.to_dbgnn_data(max_order=2, x_h=data.x_h)
+            fresh.edge_index_higher_order = mo.layers[2].data.edge_index.as_tensor().clone().clamp_(max=mo.layers[2].n - 1)
+            net(fresh)
+            del fresh
+        assert sum(v["graph"] is not None for v in net._graphs.values()) <= 1
     out = net(data.__class__(**{**data.to_dict(), "edge_index_higher_order": mo.layers[2].data.edge_index.as_tensor().clone().clamp_(max=mo.layers[2].n - 1)}))
     assert out.requires_grad                                        # grad mode never takes the graph path
