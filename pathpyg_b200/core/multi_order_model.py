@@ -24,6 +24,16 @@ from .temporal_graph import TemporalGraph
 logger = logging.getLogger("root")
 
 
+_copy_streams: dict = {}
+
+
+def _copy_stream(dev: torch.device) -> torch.cuda.Stream:
+    """One side stream per device for uploads that overlap compute."""
+    if dev not in _copy_streams:
+        _copy_streams[dev] = torch.cuda.Stream(dev)
+    return _copy_streams[dev]
+
+
 def _plain(t):
     return t.as_subclass(torch.Tensor) if isinstance(t, torch.Tensor) else t
 
@@ -85,11 +95,13 @@ class _LayerChain:
             self.model.layers[self.order] = Graph._from_sorted(data)
 
     def first_layer(self, edge_index, remap, n, node_sequence, inverse_idx, edge_weight, overlap=None) -> None:
-        """``overlap``: a pending count -> fill operation (the temporal / line-graph lift of the next level) that
-        is already enqueued; it is finished right after this layer's sort, under the same synchronisation."""
+        """``overlap``: a pending count -> fill operation (the temporal / line-graph lift of the next level), or a
+        callable that enqueues one; it is finished right after this layer's sort, under the same synchronisation."""
         self.order = 1
         more = self.max_order > 1
         pending = ops.coalesce_begin(edge_index, remap, n, edge_weight, "sum", return_inverse=more)
+        if callable(overlap):
+            overlap = overlap()  # enqueued BEHIND the layer sort: whatever it still waits for (a staged copy) is hidden
         res = pending.finish()
         self.overlapped = overlap.finish() if overlap is not None else None
         self._store(res[0], res[1], n, node_sequence, inverse_idx)
@@ -150,13 +162,32 @@ class MultiOrderModel:
     # ------------------------------------------------------------------------------------------
     @staticmethod
     def from_temporal_graph(g: TemporalGraph, delta: float | int = 1, max_order: int = 1, weight: str = "edge_weight",
-                            cached: bool = True, event_graph: torch.Tensor | None = None) -> "MultiOrderModel":
-        """multi_order_model.py:124-192, one radix sort per order (see ``_LayerChain``)."""
+                            cached: bool = True, event_graph: torch.Tensor | None = None, device=None) -> "MultiOrderModel":
+        """multi_order_model.py:124-192, one radix sort per order (see ``_LayerChain``).
+
+        ``device`` (extension): build on this CUDA device from a HOST graph and leave the layers there.  The edge
+        index is uploaded first; the time stamps follow on a copy stream while the first-order layer is already
+        being sorted, and the temporal lift -- the first consumer of the time stamps -- is enqueued behind that sort."""
         m = MultiOrderModel()
         known_sorted = getattr(g, "time_is_known_sorted", lambda: False)()
         data = g.data if known_sorted or g.data.is_sorted_by_time() else g.data.sort_by_time()
         dev, to_host = _staging.compute_device(data.edge_index, data.time)
-        edge_index = _plain(_staging.up(data.edge_index, dev)).long()
+        staged = device is not None and to_host
+        if staged:
+            dev, to_host = torch.device(device), False
+            if dev.index is None:
+                dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            edge_index = _plain(_staging.up(data.edge_index, dev)).long()
+            time_ready = None
+            if staged and max_order > 1 and event_graph is None and data is g.data:
+                main = torch.cuda.current_stream(dev)
+                side = _copy_stream(dev)
+                side.wait_stream(main)                   # after the edge index: that copy keeps the full link rate
+                with torch.cuda.stream(side):
+                    time_dev = _staging.up(data.time, dev)
+                    time_ready = torch.cuda.Event()
+                    time_ready.record(side)
         n = int(data.num_nodes)
         edge_weight = _staging.up(data[weight], dev) if weight in data else None  # None == ones(m), :154-157
 
@@ -166,8 +197,14 @@ class MultiOrderModel:
             # the reference passes `g`, not the locally re-sorted data (:167); identical unless the
             # caller shuffled time stamps after construction, in which case `g.data` is what counts
             src_ei = edge_index if data is g.data else _plain(_staging.up(g.data.edge_index, dev)).long()
-            src_t = _staging.up(data.time if data is g.data else g.data.time, dev)
-            pending = ops.lift_order_temporal_begin(src_ei, src_t, delta, n)   # count pass runs behind the layer-1 sort
+            if time_ready is not None:
+                def pending():  # called by the chain once the layer-1 sort is enqueued
+                    main.wait_event(time_ready)
+                    time_dev.record_stream(main)
+                    return ops.lift_order_temporal_begin(src_ei, time_dev, delta, n)
+            else:
+                src_t = _staging.up(data.time if data is g.data else g.data.time, dev)
+                pending = ops.lift_order_temporal_begin(src_ei, src_t, delta, n)   # count pass runs with the layer-1 sort
         ids = torch.arange(n, device=dev)
         chain.first_layer(edge_index, None, n, ids.unsqueeze(1), ids, edge_weight, overlap=pending)
         if max_order > 1:

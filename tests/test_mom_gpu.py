@@ -125,3 +125,26 @@ def test_from_path_data_vs_oracle(cuda, mode):
             assert torch.equal(d.edge_weight.cpu(), layer.edge_weight), k
         else:
             assert torch.allclose(d.edge_weight.cpu(), layer.edge_weight, rtol=1e-5), k
+
+
+def test_from_temporal_graph_staged_from_host(cuda):
+    """Host graph + ``device=``: edge index and time stamps are uploaded by the call (time stamps on a copy stream
+    behind the layer-1 sort), the layers stay on the GPU and equal the device-resident build."""
+    g = torch.Generator().manual_seed(12)
+    n, m = 5000, 200_000
+    ei = torch.randint(0, n, (2, m), generator=g).pin_memory()
+    t = torch.sort(torch.randint(0, 600, (m,), generator=g)).values.pin_memory()
+    w = torch.randint(1, 4, (m,), generator=g).float()
+    host = pp.TemporalGraph.from_tensors(ei, t, n, edge_weight=w)
+    want = pp.MultiOrderModel.from_temporal_graph(pp.TemporalGraph.from_tensors(ei.to(cuda), t.to(cuda), n, edge_weight=w.to(cuda)),
+                                                  delta=6, max_order=3)
+    for _ in range(3):
+        got = pp.MultiOrderModel.from_temporal_graph(host, delta=6, max_order=3, device=cuda)
+        for k in (1, 2, 3):
+            a, b = got.layers[k].data, want.layers[k].data
+            assert a.edge_index.is_cuda
+            assert torch.equal(a.edge_index.as_tensor(), b.edge_index.as_tensor()) and torch.equal(a.edge_weight, b.edge_weight)
+            assert torch.equal(a.node_sequence, b.node_sequence) and torch.equal(a.inverse_idx, b.inverse_idx)
+    back = pp.MultiOrderModel.from_temporal_graph(host, delta=6, max_order=2)      # without device=: results return to the host
+    assert not back.layers[2].data.edge_index.is_cuda
+    assert torch.equal(back.layers[2].data.edge_index.as_tensor(), want.layers[2].data.edge_index.as_tensor().cpu())
