@@ -139,9 +139,12 @@ radix_histogram_kernel(const KeyT* __restrict__ keys, int64_t n, int num_passes,
 // reorder, write) are a dependent chain, so throughput comes from tiles in different phases sharing an SM.
 // 16 keys per thread: 3 CTAs (<= 85 registers, 59 KB shared memory each; measured on B200 at 64M pairs: 608 us per
 // pass against 704 us at 2 CTAs and 641 us at 4 CTAs with spills); 8 keys: 4 CTAs (64 registers).
+#ifndef PPG_SORT_CTAS16
+#define PPG_SORT_CTAS16 3
+#endif
 template <int ITEMS>
 struct SortMinCtas {
-  static constexpr int value = ITEMS >= 16 ? 3 : 4;
+  static constexpr int value = ITEMS >= 16 ? PPG_SORT_CTAS16 : 4;
 };
 
 template <typename KeyT, bool HAS_VALUES, bool IOTA, int ITEMS, int MIN_CTAS>
@@ -157,8 +160,9 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
   uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);
-  uint32_t* s_whist = s_vals + (HAS_VALUES ? TILE : 0);                     // [NW][256] per-warp digit counts
-  uint32_t* s_binstart = s_whist + NW * kRadix;                             // [256] first slot of a digit in the tile
+  // [NW][256] per-warp digit counts: a warp holds at most 32 * ITEMS <= 512 keys of one digit, a tile 4096: 16 bits
+  uint16_t* s_whist = reinterpret_cast<uint16_t*>(s_vals + (HAS_VALUES ? TILE : 0));
+  uint32_t* s_binstart = reinterpret_cast<uint32_t*>(s_whist + NW * kRadix);  // [256] first slot of a digit in the tile
   long long* s_gbase = reinterpret_cast<long long*>(s_binstart + kRadix);   // [256] global slot of tile slot 0 of a digit
   // [NW][2][256] per-warp peer masks of the ranking rounds: they are dead before the tile is reordered, so they
   // live in the buffer the reorder fills (TILE * 8 bytes >= NW * 2 * 256 * 4 for every ITEMS >= 4)
@@ -172,10 +176,10 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   const unsigned lane = lane_id();
 
   for (int i = tid; i < NW * kRadix; i += kSortBlock) {
-    s_whist[i] = 0;
     s_wmask[i] = 0;
     s_wmask[NW * kRadix + i] = 0;
   }
+  for (int i = tid; i < NW * kRadix / 2; i += kSortBlock) reinterpret_cast<uint32_t*>(s_whist)[i] = 0;
   s_next[tid] = 0;
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
@@ -220,8 +224,9 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   // one LDS per key instead of 8 ballots + 8 logic ops).  The highest peer bumps the warp's digit counter and
   // clears the mask word; the mask arrays alternate between rounds, so the clear of round i is ordered before
   // the ORs of round i + 2 by the warp barriers of round i + 1.  Rounds run in item order => stable.
-  uint32_t rank[ITEMS];
-  uint32_t* my_hist = s_whist + warp * kRadix;
+  // ranks (< 512 inside the warp, < 4096 inside the tile) are kept two per register
+  uint32_t rank2[ITEMS / 2];
+  uint16_t* my_hist = s_whist + warp * kRadix;
   uint32_t* my_mask = s_wmask + warp * (2 * kRadix);
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
@@ -233,10 +238,11 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
     const uint32_t before = my_hist[d];
     __syncwarp();
     if (lane == static_cast<unsigned>(31 - __clz(peers))) {
-      my_hist[d] = before + static_cast<uint32_t>(__popc(peers));
+      my_hist[d] = static_cast<uint16_t>(before + static_cast<uint32_t>(__popc(peers)));
       *m = 0;
     }
-    rank[i] = before + __popc(peers & lanemask_lt());
+    const uint32_t r = before + __popc(peers & lanemask_lt());
+    rank2[i >> 1] = (i & 1) ? (rank2[i >> 1] | (r << 16)) : r;
   }
   __syncthreads();
 
@@ -252,7 +258,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
       const uint32_t t = s_whist[w * kRadix + tid];
-      s_whist[w * kRadix + tid] = sum;
+      s_whist[w * kRadix + tid] = static_cast<uint16_t>(sum);
       sum += t;
     }
     // out-of-range slots of the last tile were given all-ones keys: they sit at the very end of the
@@ -359,8 +365,9 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
-    const uint32_t pos = s_binstart[d] + my_hist[d] + rank[i];
-    rank[i] = pos;
+    const uint32_t r = (i & 1) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu);
+    const uint32_t pos = s_binstart[d] + my_hist[d] + r;
+    rank2[i >> 1] = (i & 1) ? ((rank2[i >> 1] & 0xffffu) | (pos << 16)) : ((rank2[i >> 1] & 0xffff0000u) | pos);
     s_keys[pos] = key[i];
   }
   if (HAS_VALUES) {
@@ -369,7 +376,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
       const int64_t idx = warp_base + i * 32 + lane;
       uint32_t v = 0;
       if (idx < n) v = IOTA ? static_cast<uint32_t>(idx) : ld_stream(vals_in + idx);
-      s_vals[rank[i]] = v;
+      s_vals[(i & 1) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu)] = v;
     }
   }
   __syncthreads();
@@ -389,7 +396,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
 template <typename KeyT, bool HAS_VALUES, int ITEMS>
 constexpr size_t onesweep_smem_bytes() {
   return static_cast<size_t>(kSortBlock * ITEMS) * sizeof(KeyT) + (HAS_VALUES ? kSortBlock * ITEMS * sizeof(uint32_t) : 0) +
-         (kSortBlock / 32) * kRadix * sizeof(uint32_t) + kRadix * sizeof(uint32_t) + kRadix * sizeof(long long);
+         (kSortBlock / 32) * kRadix * sizeof(uint16_t) + kRadix * sizeof(uint32_t) + kRadix * sizeof(long long);
 }
 
 template <typename KeyT, bool HAS_VALUES, bool IOTA, int ITEMS>
