@@ -60,6 +60,7 @@ extern "C" {
 #define PPG_TIME_I64 0          /* int64 time, integer delta: exact int64 arithmetic            */
 #define PPG_TIME_F64 1          /* float64 time: t_e + (double)(float)delta                     */
 #define PPG_TIME_I64_F32DELTA 2 /* int64 time, float delta: (float)t_f <= (float)t_e + (float)delta */
+#define PPG_TIME_GROUPED 0x100  /* or'ed into time_mode: ppg_lift_temporal_group already ran on this workspace */
 
 int ppg_abi_version(void);
 /* Deferred count read-back.  ppg_lift_order_count, ppg_lift_temporal_count and ppg_coalesce_sort accept a NULL
@@ -94,6 +95,11 @@ int ppg_pair_attributes(const int64_t* edge_index, int64_t num_edges, const void
  *   t_e < t_f <= t_e + delta; output [2,E2] ascending in (e, f).  PPG_ERR_EMPTY if E2 == 0.
  * ------------------------------------------------------------------------------------------- */
 size_t ppg_lift_temporal_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+/* Optional first half of ppg_lift_temporal_count: groups the events by source node.  It reads the SOURCE row only
+ * (edge_index[0], num_edges entries), so a caller that uploads its inputs can start it while the target row and the
+ * time stamps are still being copied; pass time_mode | PPG_TIME_GROUPED to the count call on the same workspace. */
+int ppg_lift_temporal_group(const int64_t* source_row, int64_t num_edges, int64_t num_nodes, void* workspace,
+                            size_t workspace_bytes, void* stream);
 int ppg_lift_temporal_count(const int64_t* edge_index, const void* time, int64_t num_edges, int64_t num_nodes,
                             int time_mode, int64_t delta_i, double delta_f, void* workspace, size_t workspace_bytes,
                             int64_t* h_num_pairs, void* stream);

@@ -22,6 +22,7 @@ F32, F64, I64, I32 = 0, 1, 2, 3
 PAIR_RULES = {"src": 0, "dst": 1, "max": 2, "mul": 3, "add": 4}
 REDUCTIONS = {"sum": 0, "add": 0, "mean": 1, "min": 2, "max": 3}
 TIME_I64, TIME_F64, TIME_I64_F32DELTA = 0, 1, 2
+TIME_GROUPED = 0x100
 
 _p = c_void_p
 _i64 = c_int64
@@ -39,6 +40,7 @@ PROTOTYPES = {
     "ppg_lift_order_fill": (c_int, [_p, _i64, _i64, _i64, _p, _p]),
     "ppg_pair_attributes": (c_int, [_p, _i64, _p, _i64, c_int, c_int, _p, _p]),
     "ppg_lift_temporal_workspace_bytes": (c_size_t, [_i64, _i64]),
+    "ppg_lift_temporal_group": (c_int, [_p, _i64, _i64, _p, c_size_t, _p]),
     "ppg_lift_temporal_count": (c_int, [_p, _p, _i64, _i64, c_int, _i64, c_double, _p, c_size_t, _ph_i64, _p]),
     "ppg_lift_temporal_fill": (c_int, [_p, _i64, _i64, _i64, _p, _p]),
     "ppg_rows_minmax_workspace_bytes": (c_size_t, [_i64]),

@@ -177,18 +177,30 @@ class MultiOrderModel:
             dev, to_host = torch.device(device), False
             if dev.index is None:
                 dev = torch.device("cuda", torch.cuda.current_device())
+        n = int(data.num_nodes)
+        time_ready = rows_ready = grouped_ws = None
         with torch.cuda.device(dev):
-            edge_index = _plain(_staging.up(data.edge_index, dev)).long()
-            time_ready = None
-            if staged and max_order > 1 and event_graph is None and data is g.data:
-                main = torch.cuda.current_stream(dev)
-                side = _copy_stream(dev)
-                side.wait_stream(main)                   # after the edge index: that copy keeps the full link rate
+            host_ei = _plain(data.edge_index)
+            if staged and max_order > 1 and event_graph is None and data is g.data and host_ei.dtype == torch.int64 \
+                    and host_ei.size(1) > 0 and n > 0:
+                # upload pipeline: source row (main stream) -> group the events by source while the target row and then
+                # the time stamps arrive on the copy stream; every consumer waits for exactly the rows it reads
+                main, side = torch.cuda.current_stream(dev), _copy_stream(dev)
+                edge_index = torch.empty(host_ei.shape, dtype=torch.int64, device=dev)
+                edge_index[0].copy_(host_ei[0], non_blocking=True)
+                side.wait_stream(main)                   # the copies follow each other: each keeps the full link rate
+                edge_index.record_stream(side)
                 with torch.cuda.stream(side):
+                    edge_index[1].copy_(host_ei[1], non_blocking=True)
+                    rows_ready = torch.cuda.Event()
+                    rows_ready.record(side)
                     time_dev = _staging.up(data.time, dev)
                     time_ready = torch.cuda.Event()
                     time_ready.record(side)
-        n = int(data.num_nodes)
+                grouped_ws = ops.lift_order_temporal_group(edge_index, n)
+                main.wait_event(rows_ready)
+            else:
+                edge_index = _plain(_staging.up(data.edge_index, dev)).long()
         edge_weight = _staging.up(data[weight], dev) if weight in data else None  # None == ones(m), :154-157
 
         chain = _LayerChain(m, cached, max_order)
@@ -201,7 +213,7 @@ class MultiOrderModel:
                 def pending():  # called by the chain once the layer-1 sort is enqueued
                     main.wait_event(time_ready)
                     time_dev.record_stream(main)
-                    return ops.lift_order_temporal_begin(src_ei, time_dev, delta, n)
+                    return ops.lift_order_temporal_begin(src_ei, time_dev, delta, n, grouped_ws=grouped_ws)
             else:
                 src_t = _staging.up(data.time if data is g.data else g.data.time, dev)
                 pending = ops.lift_order_temporal_begin(src_ei, src_t, delta, n)   # count pass runs with the layer-1 sort

@@ -477,10 +477,38 @@ extern "C" size_t ppg_lift_temporal_workspace_bytes(int64_t num_edges, int64_t n
   return ws.used + 256;
 }
 
+// CSR over the source node, edges inside a group in time order (stable sort of a time-sorted stream).  Reads the
+// SOURCE row only, so it can run while the target row and the time stamps are still on their way to the device.
+static int temporal_group(TemporalLayout& L, const int64_t* src_row, int64_t m, int64_t N, void* workspace, cudaStream_t stream) {
+  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, L.zero_bytes, stream));
+  degree_kernel<true><<<grid_for(m, 256 * 4), 256, 0, stream>>>(src_row, m, N, L.deg, L.keys_a, &L.result->status, L.sort_ws);
+  PPG_LAUNCHED();
+  PPG_TRY(launch_scan(DegreeProducer{L.deg}, PointerConsumer{L.ptr, N}, N, L.scan_ptr_ws, nullptr, stream));
+  int in_b = 0;
+  PPG_TRY(radix_sort_pairs<uint32_t>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, m, L.sort_bits, L.sort_ws,
+                                     &in_b, stream, nullptr, true));
+  const uint32_t* grouped = in_b ? L.vals_b : L.vals_a;
+  PPG_REQUIRE(grouped == L.grouped(), PPG_ERR_CUDA, "lift_order_temporal: internal buffer parity mismatch");
+  return PPG_OK;
+}
+
+extern "C" int ppg_lift_temporal_group(const int64_t* src_row, int64_t m, int64_t N, void* workspace, size_t workspace_bytes,
+                                       void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(m > 0 && N > 0 && m < (1ll << 31) && N < (1ll << 31), PPG_ERR_INVALID,
+              "lift_order_temporal: sizes m=%lld N=%lld outside (0, 2^31)", (long long)m, (long long)N);
+  Workspace ws(workspace, workspace_bytes);
+  TemporalLayout L(ws, m, N);
+  PPG_REQUIRE(ws.fits(), PPG_ERR_WORKSPACE, "lift_order_temporal: workspace %zu < %zu bytes", workspace_bytes, ws.used);
+  return temporal_group(L, src_row, m, N, workspace, stream);
+}
+
 extern "C" int ppg_lift_temporal_count(const int64_t* edge_index, const void* time, int64_t m, int64_t N, int time_mode,
                                        int64_t delta_i, double delta_f, void* workspace, size_t workspace_bytes,
                                        int64_t* h_num_pairs, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool grouped_already = (time_mode & PPG_TIME_GROUPED) != 0;
+  time_mode &= ~PPG_TIME_GROUPED;
   PPG_REQUIRE(m >= 0 && N >= 0 && m < (1ll << 31) && N < (1ll << 31), PPG_ERR_INVALID,
               "lift_order_temporal: sizes m=%lld N=%lld outside [0, 2^31)", (long long)m, (long long)N);
   PPG_REQUIRE(time_mode >= PPG_TIME_I64 && time_mode <= PPG_TIME_I64_F32DELTA, PPG_ERR_INVALID,
@@ -490,18 +518,8 @@ extern "C" int ppg_lift_temporal_count(const int64_t* edge_index, const void* ti
   Workspace ws(workspace, workspace_bytes);
   TemporalLayout L(ws, m, N);
   PPG_REQUIRE(ws.fits(), PPG_ERR_WORKSPACE, "lift_order_temporal: workspace %zu < %zu bytes", workspace_bytes, ws.used);
-  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, L.zero_bytes, stream));
-
-  // CSR over the source node, edges inside a group in time order (stable sort of a time-sorted stream)
-  degree_kernel<true><<<grid_for(m, 256 * 4), 256, 0, stream>>>(edge_index, m, N, L.deg, L.keys_a, &L.result->status,
-                                                                L.sort_ws);
-  PPG_LAUNCHED();
-  PPG_TRY(launch_scan(DegreeProducer{L.deg}, PointerConsumer{L.ptr, N}, N, L.scan_ptr_ws, nullptr, stream));
-  int in_b = 0;
-  PPG_TRY(radix_sort_pairs<uint32_t>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, true, m, L.sort_bits, L.sort_ws,
-                                     &in_b, stream, nullptr, true));
-  const uint32_t* grouped = in_b ? L.vals_b : L.vals_a;
-  PPG_REQUIRE(grouped == L.grouped(), PPG_ERR_CUDA, "lift_order_temporal: internal buffer parity mismatch");
+  if (!grouped_already) PPG_TRY(temporal_group(L, edge_index, m, N, workspace, stream));
+  const uint32_t* grouped = L.grouped();
   gather64_kernel<<<grid_for(m, 256 * 4), 256, 0, stream>>>(static_cast<const unsigned long long*>(time), grouped, m,
                                                              L.ts_sorted);
   PPG_LAUNCHED();

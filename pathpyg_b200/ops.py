@@ -132,12 +132,15 @@ def _time_mode(time: torch.Tensor, delta):
 
 
 class PendingTemporalLift:
-    def __init__(self, ei, time, mode, delta_i, delta_f, num_nodes):
+    def __init__(self, ei, time, mode, delta_i, delta_f, num_nodes, grouped_ws=None):
         self.dev, self.m, self.num_nodes = ei.device, ei.size(1), num_nodes
         self.keep = (ei, time)  # inputs stay alive until the kernels have run
         lib = _lib.load()
         with torch.cuda.device(self.dev):
-            self.ws = _workspace(lib.ppg_lift_temporal_workspace_bytes(self.m, num_nodes), self.dev)
+            if grouped_ws is None:
+                self.ws = _workspace(lib.ppg_lift_temporal_workspace_bytes(self.m, num_nodes), self.dev)
+            else:
+                self.ws, mode = grouped_ws, mode | _lib.TIME_GROUPED
             _lib.check(lib.ppg_lift_temporal_count(_ptr(ei), _ptr(time), self.m, num_nodes, mode, delta_i, delta_f, _ptr(self.ws),
                                                    self.ws.numel(), None, _stream(self.dev)))
 
@@ -152,7 +155,24 @@ class PendingTemporalLift:
         return out
 
 
-def lift_order_temporal_begin(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int) -> PendingTemporalLift:
+def lift_order_temporal_group(edge_index: torch.Tensor, num_nodes: int) -> torch.Tensor:
+    """First half of the temporal lift (grouping the events by source node): needs ``edge_index[0]`` only, so it can
+    be enqueued while ``edge_index[1]`` and the time stamps are still being uploaded.  Returns the workspace to hand
+    to ``lift_order_temporal_begin(..., grouped_ws=...)``."""
+    lib = _lib.load()
+    ei = _edge_index_arg(edge_index)
+    dev = _require_cuda(ei)
+    m = ei.size(1)
+    if m == 0 or num_nodes <= 0:
+        raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors (lift_order_temporal: empty input)")
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_lift_temporal_workspace_bytes(m, int(num_nodes)), dev)
+        _lib.check(lib.ppg_lift_temporal_group(_ptr(ei), m, int(num_nodes), _ptr(ws), ws.numel(), _stream(dev)))
+    return ws
+
+
+def lift_order_temporal_begin(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int,
+                              grouped_ws: torch.Tensor | None = None) -> PendingTemporalLift:
     ei = _edge_index_arg(edge_index)
     _require_cuda(ei, time)
     time, mode, delta_i, delta_f = _time_mode(time.contiguous(), delta)
@@ -160,7 +180,7 @@ def lift_order_temporal_begin(edge_index: torch.Tensor, time: torch.Tensor, delt
         raise ValueError("time and edge_index disagree on the number of edges")
     if ei.size(1) == 0 or num_nodes <= 0:
         raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors (lift_order_temporal: empty input)")
-    return PendingTemporalLift(ei, time, mode, delta_i, delta_f, int(num_nodes))
+    return PendingTemporalLift(ei, time, mode, delta_i, delta_f, int(num_nodes), grouped_ws)
 
 
 def lift_order_temporal(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int) -> torch.Tensor:
