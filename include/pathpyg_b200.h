@@ -276,6 +276,17 @@ size_t ppg_temporal_paths_workspace_bytes(int64_t num_events, int64_t num_nodes,
 int ppg_temporal_paths(const int64_t* edge_index, int64_t num_events, int64_t num_nodes, const int64_t* event_graph,
                        int64_t num_pairs, int64_t source_begin, int64_t source_end, void* workspace,
                        size_t workspace_bytes, double* out_dist, int64_t* out_pred, int* h_levels, void* stream);
+/* temporal_betweenness_centrality (centrality.py:164-300: Brandes on the event DAG), one batch of source nodes:
+ *   group_off [num_groups+1]: boundaries of the runs of equal time stamps in the time-sorted event list;
+ *   succ_ptr [m+1] / succ: CSR of the event graph (the a1 output is sorted by its first row: succ = its second row);
+ *   pred_ptr [m+1] / pred: its CSC (ppg_csc_build);  in_ptr [n+1] / in_event: the events grouped by target node;
+ *   sources [batch]: node ids in ascending order;  inout_bw [n] float64: the batch's contributions are ADDED.
+ * All sums run in a fixed order (no floating-point atomics).  Does not synchronise. */
+size_t ppg_temporal_betweenness_workspace_bytes(int64_t num_events, int64_t num_nodes, int64_t batch_sources);
+int ppg_temporal_betweenness(const int64_t* edge_index, int64_t num_events, int64_t num_nodes, const int32_t* group_off,
+                             int64_t num_groups, const int32_t* succ_ptr, const int64_t* succ, const int32_t* pred_ptr,
+                             const int32_t* pred, const int32_t* in_ptr, const int32_t* in_event, const int32_t* sources,
+                             int64_t batch_sources, void* workspace, size_t workspace_bytes, double* inout_bw, void* stream);
 /* out[v] = sum_{x != v} (n - 1) / dist[x, v] in ascending x (temporal_closeness_centrality, centrality.py:320-322) */
 int ppg_temporal_closeness(const double* dist, int64_t num_nodes, double* out, void* stream);
 

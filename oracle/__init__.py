@@ -20,8 +20,8 @@ What is restated here (reference paths are relative to ``/root/reference``):
 * ``oracle/selection.py`` ``Graph.degrees`` / ``transition_probabilities`` (``core/graph.py:486-533``) and the
   model-selection statistics of ``MultiOrderModel`` (``core/multi_order_model.py:243-509``).
 * ``oracle/ingest.py``   ``df_to_temporal_graph`` / ``read_csv_path_data`` (``io/pandas.py``).
-* ``oracle/paths.py``    ``temporal_shortest_paths`` (``algorithms/temporal.py:57-107``) and
-  ``temporal_closeness_centrality`` (``algorithms/centrality.py:303-324``).
+* ``oracle/paths.py``    ``temporal_shortest_paths`` (``algorithms/temporal.py:57-107``),
+  ``temporal_closeness_centrality`` and ``temporal_betweenness_centrality`` (``algorithms/centrality.py:164-324``).
 
 Pinning status
 --------------

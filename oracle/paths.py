@@ -5,13 +5,14 @@ TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).
 Reference (relative to ``/root/reference``):
 * ``src/pathpyG/algorithms/temporal.py:57-107``      temporal_shortest_paths
 * ``src/pathpyG/algorithms/centrality.py:303-324``   temporal_closeness_centrality
+* ``src/pathpyG/algorithms/centrality.py:164-300``   temporal_betweenness_centrality
 
 ``scipy.sparse.csgraph.dijkstra`` (scipy is a dependency of the reference and present here) is called exactly as
 the reference calls it.  Distances are unique; the predecessor matrix is NOT: where several shortest paths reach a
 node, scipy reports whichever predecessor its heap settles first, which is an implementation detail of scipy.
 ``is_valid_pred`` states the property every correct predecessor matrix has.
 Pinned by the known answers of ``tests/algorithms/test_temporal.py:20-93`` and
-``tests/algorithms/test_centrality.py`` (closeness).
+``tests/algorithms/test_centrality.py:45-70`` (betweenness, closeness).
 """
 from __future__ import annotations
 
@@ -77,3 +78,63 @@ def is_valid_pred(edge_index: torch.Tensor, time: torch.Tensor, delta, dist: np.
                 if not ok.any():
                     return False
     return True
+
+
+def temporal_betweenness_centrality(edge_index: torch.Tensor, time: torch.Tensor, num_nodes: int, delta) -> np.ndarray:
+    """centrality.py:164-300 (Brandes on the event DAG, Buss et al.) as an array over node indices; pure-Python
+    loops in the reference's own order of operations -- small cases only."""
+    from collections import defaultdict, deque
+    from math import isnan
+
+    m, n = edge_index.size(1), num_nodes
+    event_graph = lift.lift_order_temporal(edge_index, time, delta)                                # :196
+    src_edges = torch.stack([edge_index[0] + m, torch.arange(m)])                                  # :200-204
+    aug = torch.cat([event_graph, src_edges], dim=1)                                               # :205
+    order = torch.sort(aug[0], stable=True).indices                                                # Graph.__init__ row sort
+    aug = aug[:, order]
+    succ = defaultdict(list)
+    for v, w in aug.t().tolist():
+        succ[v].append(w)
+    src_indices = torch.unique(src_edges[0]).tolist()                                              # :206
+    e_i = edge_index.numpy()
+    fo = lambda v: int(e_i[1, v]) if v < m else v - m                                              # noqa: E731  (:212-217)
+    bw = defaultdict(float)
+    for s in src_indices:                                                                          # :222
+        delta_ = defaultdict(float)
+        sigma = defaultdict(float)
+        sigma[s] = 1.0
+        sigma_fo = defaultdict(float)
+        sigma_fo[fo(s)] = 1.0
+        dist = defaultdict(lambda: -1)
+        dist[s] = 0
+        dist_fo = defaultdict(lambda: -1)
+        dist_fo[fo(s)] = 0
+        P = defaultdict(set)
+        Q, S = deque([s]), []
+        while Q:                                                                                   # :253-271
+            v = Q.popleft()
+            for w in succ[v]:
+                if dist[w] == -1:
+                    dist[w] = dist[v] + 1
+                    if dist_fo[fo(w)] == -1:
+                        dist_fo[fo(w)] = dist[v] + 1
+                    S.append(w)
+                    Q.append(w)
+                if dist[w] == dist[v] + 1:
+                    sigma[w] += sigma[v]
+                    P[w].add(v)
+                    if dist[w] == dist_fo[fo(w)]:
+                        sigma_fo[fo(w)] += sigma[v]
+        c = sum(1.0 for i in list(dist_fo) if dist_fo[i] >= 0)                                     # :273-276
+        bw[fo(s)] = bw[fo(s)] - c + 1.0                                                            # :277
+        while S:                                                                                   # :279-293
+            w = S.pop()
+            if dist[w] == dist_fo[fo(w)]:
+                x = sigma[w] / sigma_fo[fo(w)]
+                delta_[w] += 0.0 if isnan(x) else x
+            for v in P[w]:
+                x = sigma[v] / sigma[w]
+                x = 0.0 if isnan(x) else x
+                delta_[v] += x * delta_[w]
+                bw[fo(v)] += delta_[w] * x
+    return np.array([float(bw[i]) if i in bw else 0.0 for i in range(n)])

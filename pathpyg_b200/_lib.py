@@ -80,6 +80,8 @@ PROTOTYPES = {
     "ppg_temporal_paths_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
     "ppg_temporal_paths": (c_int, [_p, _i64, _i64, _p, _i64, _i64, _i64, _p, c_size_t, _p, _p, _ph_int, _p]),
     "ppg_temporal_closeness": (c_int, [_p, _i64, _p, _p]),
+    "ppg_temporal_betweenness_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
+    "ppg_temporal_betweenness": (c_int, [_p, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _i64, _p, c_size_t, _p, _p]),
     "ppg_weighted_log_sum_workspace_bytes": (c_size_t, []),
     "ppg_weighted_log_sum": (c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _p, c_size_t, POINTER(c_double), _p]),
 }

@@ -4,7 +4,7 @@ from .lift_order import (
     lift_order_edge_index,
     lift_order_edge_index_weighted,
 )
-from .centrality import temporal_closeness_centrality
+from .centrality import temporal_betweenness_centrality, temporal_closeness_centrality
 from .temporal import lift_order_temporal, temporal_shortest_paths
 
 __all__ = [
@@ -15,4 +15,5 @@ __all__ = [
     "lift_order_temporal",
     "temporal_shortest_paths",
     "temporal_closeness_centrality",
+    "temporal_betweenness_centrality",
 ]

@@ -1,6 +1,6 @@
 """``temporal_closeness_centrality`` (reference ``src/pathpyG/algorithms/centrality.py:303-324``): a consumer of
-the shortest time-respecting path distances.  ``temporal_betweenness_centrality`` (``:164-300``, Brandes over the
-event DAG with per-source path counts) is not built."""
+the shortest time-respecting path distances, and ``temporal_betweenness_centrality`` (``:164-300``): Brandes'
+dependency accumulation over the event DAG."""
 from __future__ import annotations
 
 from .. import _staging, ops
@@ -18,3 +18,23 @@ def temporal_closeness_centrality(graph, delta: int) -> dict:
     dist, _ = ops.temporal_paths(ei, event_graph, n)
     closeness = ops.temporal_closeness(dist).cpu().tolist()
     return {x: float(closeness[graph.mapping.to_idx(x)]) for x in graph.nodes}
+
+
+def temporal_betweenness_centrality(graph, delta: int = 1) -> dict:
+    """Temporal betweenness of the nodes over shortest time-respecting paths (path length = number of traversed
+    edges, waiting time at most ``delta``), centrality.py:164-300.  The reference walks the event DAG in Python once
+    per source node; here every source is one CTA sweeping the time groups of the event list forward (distances and
+    path counts) and backward (dependencies).  Returns ``{node id: value}``; nodes that get no contribution read 0.0
+    (the reference returns a ``defaultdict`` with the same values)."""
+    from collections import defaultdict
+
+    edge_index, time = graph.data.edge_index, graph.data.time
+    dev, _ = _staging.compute_device(edge_index, time)
+    ei, t = _staging.up(edge_index, dev), _staging.up(time, dev)
+    n = int(graph.data.num_nodes)
+    event_graph = ops.lift_order_temporal(ei, t, delta, n)
+    bw = ops.temporal_betweenness(ei, t, event_graph, n).cpu().tolist()
+    out = defaultdict(lambda: 0.0)
+    for idx, value in enumerate(bw):
+        out[graph.mapping.to_id(idx)] = float(value)
+    return out

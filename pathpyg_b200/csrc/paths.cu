@@ -136,6 +136,158 @@ closeness_kernel(const double* __restrict__ dist, int64_t n, double* __restrict_
   out[v] = acc;
 }
 
+__device__ __forceinline__ double block_sum_f64_paths(double x, double* s_part) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(kFullMask, x, d);
+  if (lane_id() == 0) s_part[threadIdx.x >> 5] = x;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) t += s_part[w];  // every thread: same order, same value
+  __syncthreads();
+  return t;
+}
+
+// ------------------------------------------------------------------ temporal betweenness (Brandes on the event DAG)
+// Reference: src/pathpyG/algorithms/centrality.py:164-300.  One CTA per source node.  The event graph is a DAG whose
+// edges run forward in time, and events sharing a time stamp never continue each other, so the time groups of the
+// time-sorted event list are the levels of a topological order:
+//   forward  (groups ascending) : dist[f] = fewest events from the source, sigma[f] = number of such shortest paths,
+//                                 pulled from the predecessors of f (CSC of the event graph);
+//   per node                    : dist_fo[x] = min dist over the events ending in x, sigma_fo[x] = their path count;
+//   backward (groups descending): delta[v] = own(v) + sum over successors w one level deeper of
+//                                 sigma[v] / sigma[w] * delta[w]   (CSR of the event graph),
+//                                 own(v) = sigma[v] / sigma_fo[dst v] if v ends a shortest path to its node;
+//   contrib[x] = sum of the pulled parts of the events ending in x (+ the source's own share and 1 - #reachable).
+// Every sum runs over a fixed list in a fixed order: no floating-point atomics.
+constexpr int kUnreachedDist = 0x3fffffff;
+constexpr int kBrandesBlock = 256;
+
+__global__ void __launch_bounds__(kBrandesBlock)
+temporal_brandes_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t m, int64_t n,
+                        const int32_t* __restrict__ group_off, int num_groups,
+                        const int32_t* __restrict__ succ_ptr, const int64_t* __restrict__ succ,      // CSR of the event graph
+                        const int32_t* __restrict__ pred_ptr, const int32_t* __restrict__ pred,      // CSC of the event graph
+                        const int32_t* __restrict__ in_ptr, const int32_t* __restrict__ in_event,    // events grouped by dst
+                        const int32_t* __restrict__ sources, int batch,
+                        int32_t* __restrict__ dist_all, double* __restrict__ sigma_all, double* __restrict__ delta_all,
+                        double* __restrict__ pull_all, int32_t* __restrict__ dist_fo_all, double* __restrict__ sigma_fo_all,
+                        double* __restrict__ contrib_all) {
+  __shared__ double s_part[kBrandesBlock / 32];
+  const int b = blockIdx.x;
+  if (b >= batch) return;
+  const int64_t s = sources[b];
+  int32_t* dist = dist_all + static_cast<int64_t>(b) * m;
+  double* sigma = sigma_all + static_cast<int64_t>(b) * m;
+  double* delta = delta_all + static_cast<int64_t>(b) * m;
+  double* pull = pull_all + static_cast<int64_t>(b) * m;
+  int32_t* dist_fo = dist_fo_all + static_cast<int64_t>(b) * n;
+  double* sigma_fo = sigma_fo_all + static_cast<int64_t>(b) * n;
+  double* contrib = contrib_all + static_cast<int64_t>(b) * n;
+  const int tid = threadIdx.x;
+
+  // ---- forward: shortest distances and path counts, one time group after the other
+  for (int g = 0; g < num_groups; ++g) {
+    for (int32_t f = group_off[g] + tid; f < group_off[g + 1]; f += kBrandesBlock) {
+      const bool first = src[f] == s;
+      int32_t d = first ? 1 : kUnreachedDist;
+      const int32_t p0 = pred_ptr[f], p1 = pred_ptr[f + 1];
+      for (int32_t i = p0; i < p1; ++i) d = min(d, dist[pred[i]] + 1);
+      double sg = 0.0;
+      if (d < kUnreachedDist) {
+        if (first && d == 1) sg = 1.0;
+        for (int32_t i = p0; i < p1; ++i) {
+          const int32_t e = pred[i];
+          if (dist[e] + 1 == d) sg += sigma[e];
+        }
+      } else {
+        d = kUnreachedDist;
+      }
+      dist[f] = d;
+      sigma[f] = sg;
+    }
+    __syncthreads();
+  }
+
+  // ---- first-order nodes: distance and number of shortest paths, number of reachable nodes
+  int reach = 0;
+  for (int64_t x = tid; x < n; x += kBrandesBlock) {
+    int32_t d = kUnreachedDist;
+    double sg = 0.0;
+    if (x == s) {
+      d = 0;
+      sg = 1.0;
+    } else {
+      const int32_t i0 = in_ptr[x], i1 = in_ptr[x + 1];
+      for (int32_t i = i0; i < i1; ++i) d = min(d, dist[in_event[i]]);
+      if (d < kUnreachedDist)
+        for (int32_t i = i0; i < i1; ++i) {
+          const int32_t w = in_event[i];
+          if (dist[w] == d) sg += sigma[w];
+        }
+    }
+    dist_fo[x] = d;
+    sigma_fo[x] = sg;
+    reach += d < kUnreachedDist;
+  }
+  __syncthreads();
+
+  // ---- backward: dependencies, one time group after the other
+  for (int g = num_groups - 1; g >= 0; --g) {
+    for (int32_t v = group_off[g] + tid; v < group_off[g + 1]; v += kBrandesBlock) {
+      const int32_t dv = dist[v];
+      double p = 0.0, own = 0.0;
+      if (dv < kUnreachedDist) {
+        const double sv = sigma[v];
+        for (int32_t i = succ_ptr[v]; i < succ_ptr[v + 1]; ++i) {
+          const int64_t w = succ[i];
+          if (dist[w] == dv + 1) p += sv / sigma[w] * delta[w];
+        }
+        const int64_t x = dst[v];
+        if (x != s && dv == dist_fo[x]) own = sv / sigma_fo[x];
+      }
+      pull[v] = p;
+      delta[v] = own + p;
+    }
+    __syncthreads();
+  }
+
+  // ---- contributions of this source to every node
+  for (int64_t x = tid; x < n; x += kBrandesBlock) {
+    double c = 0.0;
+    for (int32_t i = in_ptr[x]; i < in_ptr[x + 1]; ++i) {
+      const int32_t v = in_event[i];
+      if (dist[v] < kUnreachedDist) c += pull[v];
+    }
+    contrib[x] = c;
+  }
+  // the source itself: its first events (dist 1, sigma 1) hand their dependency back, minus the reachable others
+  double own_share = 0.0;
+  for (int64_t e = tid; e < m; e += kBrandesBlock)
+    if (src[e] == s) own_share += delta[e] / sigma[e];
+  const double total = block_sum_f64_paths(own_share, s_part);
+  __shared__ int s_reach[kBrandesBlock / 32];
+  int r = reach;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) r += __shfl_xor_sync(kFullMask, r, d);
+  if (lane_id() == 0) s_reach[tid >> 5] = r;
+  __syncthreads();
+  if (tid == 0) {
+    int rt = 0;
+    for (int w = 0; w < kBrandesBlock / 32; ++w) rt += s_reach[w];
+    contrib[s] += total + 1.0 - static_cast<double>(rt);
+  }
+}
+
+// bw[x] += contrib[b][x] for b = 0 .. batch-1 in that order (sources ascending: a fixed order of additions)
+__global__ void __launch_bounds__(kPathBlock)
+brandes_accumulate_kernel(const double* __restrict__ contrib, int batch, int64_t n, double* __restrict__ bw) {
+  const int64_t x = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (x >= n) return;
+  double acc = bw[x];
+  for (int b = 0; b < batch; ++b) acc += contrib[static_cast<int64_t>(b) * n + x];
+  bw[x] = acc;
+}
+
 struct PathLayout {
   unsigned long long* flags;  // [0] frontier not empty, [1] status
   unsigned long long* best;   // [chunk, n]
@@ -221,6 +373,48 @@ extern "C" int ppg_temporal_closeness(const double* dist, int64_t num_nodes, dou
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (num_nodes == 0) return PPG_OK;
   closeness_kernel<<<static_cast<unsigned>(ceil_div(num_nodes, kPathBlock)), kPathBlock, 0, stream>>>(dist, num_nodes, out);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
+extern "C" size_t ppg_temporal_betweenness_workspace_bytes(int64_t num_events, int64_t num_nodes, int64_t batch_sources) {
+  Workspace ws(nullptr, 0);
+  const size_t B = static_cast<size_t>(batch_sources), m = static_cast<size_t>(num_events), n = static_cast<size_t>(num_nodes);
+  ws.take<int32_t>(B * m);
+  ws.take<double>(B * m);
+  ws.take<double>(B * m);
+  ws.take<double>(B * m);
+  ws.take<int32_t>(B * n);
+  ws.take<double>(B * n);
+  ws.take<double>(B * n);
+  return ws.used + 256;
+}
+
+extern "C" int ppg_temporal_betweenness(const int64_t* edge_index, int64_t num_events, int64_t num_nodes,
+                                        const int32_t* group_off, int64_t num_groups, const int32_t* succ_ptr,
+                                        const int64_t* succ, const int32_t* pred_ptr, const int32_t* pred,
+                                        const int32_t* in_ptr, const int32_t* in_event, const int32_t* sources,
+                                        int64_t batch_sources, void* workspace, size_t workspace_bytes, double* inout_bw,
+                                        void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int64_t m = num_events, n = num_nodes, B = batch_sources;
+  PPG_REQUIRE(m > 0 && m < (1ll << 31) && n > 0 && n < (1ll << 31) && B > 0 && B < (1 << 20) && num_groups > 0 &&
+                  num_groups < (1ll << 31),
+              PPG_ERR_INVALID, "temporal_betweenness: bad sizes (m=%lld, n=%lld, batch=%lld)", (long long)m, (long long)n, (long long)B);
+  Workspace ws(workspace, workspace_bytes);
+  int32_t* dist = ws.take<int32_t>(static_cast<size_t>(B * m));
+  double* sigma = ws.take<double>(static_cast<size_t>(B * m));
+  double* delta = ws.take<double>(static_cast<size_t>(B * m));
+  double* pull = ws.take<double>(static_cast<size_t>(B * m));
+  int32_t* dist_fo = ws.take<int32_t>(static_cast<size_t>(B * n));
+  double* sigma_fo = ws.take<double>(static_cast<size_t>(B * n));
+  double* contrib = ws.take<double>(static_cast<size_t>(B * n));
+  PPG_REQUIRE(ws.fits(), PPG_ERR_WORKSPACE, "temporal_betweenness: workspace of %zu bytes is too small (%zu needed)", workspace_bytes, ws.used);
+  temporal_brandes_kernel<<<static_cast<unsigned>(B), kBrandesBlock, 0, stream>>>(
+      edge_index, edge_index + m, m, n, group_off, static_cast<int>(num_groups), succ_ptr, succ, pred_ptr, pred, in_ptr,
+      in_event, sources, static_cast<int>(B), dist, sigma, delta, pull, dist_fo, sigma_fo, contrib);
+  PPG_LAUNCHED();
+  brandes_accumulate_kernel<<<static_cast<unsigned>(ceil_div(n, kPathBlock)), kPathBlock, 0, stream>>>(contrib, static_cast<int>(B), n, inout_bw);
   PPG_LAUNCHED();
   return PPG_OK;
 }

@@ -713,3 +713,36 @@ def temporal_closeness(dist: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(dev):
         _lib.check(lib.ppg_temporal_closeness(_ptr(dist), n, _ptr(out), _stream(dev)))
     return out
+
+
+def temporal_betweenness(edge_index: torch.Tensor, time: torch.Tensor, event_graph: torch.Tensor, num_nodes: int,
+                         max_workspace_bytes: int = 4 << 30) -> torch.Tensor:
+    """Temporal betweenness of every node (float64 [n]) from the time-sorted events and their event graph: Brandes'
+    dependency accumulation on the event DAG, one CTA per source node, sources in batches."""
+    lib = _lib.load()
+    ei = _edge_index_arg(edge_index)
+    eg = _edge_index_arg(event_graph)
+    dev = _require_cuda(ei, time, eg)
+    m, n = ei.size(1), int(num_nodes)
+    bw = torch.zeros(n, dtype=torch.float64, device=dev)
+    if m == 0 or n == 0:
+        return bw
+    # index plumbing: time groups, CSR / CSC of the event graph, events grouped by target, source list
+    _, counts = torch.unique_consecutive(time, return_counts=True)
+    group_off = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=dev)
+    group_off[1:] = torch.cumsum(counts, 0)
+    succ_ptr = sorted_ids_ptr(eg[0], m)
+    preds = csc_build(eg, m, m)
+    incoming = csc_build(ei, n, n)
+    sources = torch.unique(ei[0]).int()
+    per_source = 28 * m + 20 * n
+    batch_cap = max(1, min(296, max_workspace_bytes // max(per_source, 1)))
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_temporal_betweenness_workspace_bytes(m, n, min(batch_cap, sources.numel())), dev)
+        for b0 in range(0, sources.numel(), batch_cap):
+            batch = sources[b0:b0 + batch_cap].contiguous()
+            _lib.check(lib.ppg_temporal_betweenness(_ptr(ei), m, n, _ptr(group_off), group_off.numel() - 1, _ptr(succ_ptr),
+                                                    _ptr(eg[1].contiguous()), _ptr(preds.colptr), _ptr(preds.src),
+                                                    _ptr(incoming.colptr), _ptr(incoming.eid), _ptr(batch), batch.numel(),
+                                                    _ptr(ws), ws.numel(), _ptr(bw), _stream(dev)))
+    return bw

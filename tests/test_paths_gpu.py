@@ -73,3 +73,27 @@ def test_source_chunks_and_edge_cases(cuda):
     assert pred.cpu().tolist() == [[0, 0, -1], [-1, 1, 1], [-1, -1, 2]]
     with pytest.raises(ValueError):
         ops.temporal_paths(torch.tensor([[0], [7]], device=cuda), None, 3)
+
+
+def test_betweenness_known_answer(cuda):  # reference tests/algorithms/test_centrality.py:45-55
+    g = pp.TemporalGraph.from_edge_list(LONG)
+    bw = pp.algorithms.temporal_betweenness_centrality(g, delta=5)
+    assert [bw[x] for x in "abcdefghi"] == [2.0, 2.0, 4.5, 0, 0, 2.0, 0.5, 0, 0]
+    assert bw["not a node"] == 0.0                                   # defaultdict like the reference's return value
+
+
+@pytest.mark.parametrize("seed,n,m,horizon,delta", [(0, 10, 120, 50, 4), (1, 25, 600, 200, 9), (2, 40, 1500, 60, 2),
+                                                    (3, 16, 400, 400, 50), (4, 60, 2500, 1000, 30)])
+def test_betweenness_vs_oracle_random(cuda, seed, n, m, horizon, delta):
+    gen = torch.Generator().manual_seed(100 + seed)
+    ei = torch.randint(0, n, (2, m), generator=gen)
+    t = torch.sort(torch.randint(0, horizon, (m,), generator=gen)).values
+    want = paths.temporal_betweenness_centrality(ei, t, n, delta)     # the reference's Python loops, restated
+    g = pp.TemporalGraph.from_tensors(ei.to(cuda), t.to(cuda), n)
+    got = pp.algorithms.temporal_betweenness_centrality(g, delta)
+    got = np.array([got[i] for i in range(n)])
+    # float64 sums of fractions in a different (fixed) order than the reference's stack order: 1e-12 relative
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+    eg = ops.lift_order_temporal(ei.to(cuda), t.to(cuda), delta, n)
+    small = ops.temporal_betweenness(ei.to(cuda), t.to(cuda), eg, n, max_workspace_bytes=1)   # one source per launch
+    assert torch.equal(small.cpu(), torch.from_numpy(got))           # batching does not change a single bit

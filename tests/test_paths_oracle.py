@@ -40,3 +40,9 @@ def test_temporal_closeness_known_answer():  # reference tests/algorithms/test_c
     dist, _ = paths.temporal_shortest_paths(ei, t, n, 5)
     want = [12.0, 16.0, 16.0, 14.666666666666666, 14.666666666666666, 24.0, 14.666666666666666, 28.0, 24.0]
     assert paths.temporal_closeness_centrality(dist).tolist() == want
+
+
+def test_temporal_betweenness_known_answer():  # reference tests/algorithms/test_centrality.py:45-55
+    ei, t, n = tensors()
+    bw = paths.temporal_betweenness_centrality(ei, t, n, 5)
+    assert bw.tolist() == [2.0, 2.0, 4.5, 0.0, 0.0, 2.0, 0.5, 0.0, 0.0]
