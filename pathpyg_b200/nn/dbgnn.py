@@ -21,6 +21,15 @@ from torch import nn
 from .. import _lib, _staging, ops
 
 
+_side_streams: dict = {}
+
+
+def _side_stream(dev: torch.device) -> torch.cuda.Stream:
+    if dev not in _side_streams:
+        _side_streams[dev] = torch.cuda.Stream(dev)
+    return _side_streams[dev]
+
+
 def _gcn_forward(x, w, b, graph, act):
     F_in, H = w.size(1), w.size(0)
     if ops.tc_supported(F_in, H):
@@ -174,20 +183,42 @@ class DBGNN(nn.Module):
         """nn/dbgnn.py:121-151.  The three target-grouped views are built without host synchronisation; their id
         checks are collected once, after every kernel of the forward pass has been enqueued."""
         n_fo, n_ho = sizes
-        fo_graph = ops.gcn_prepare(ei, w, n_fo, keep_edge_values=grad, defer_check=True)
-        for layer in self.first_order_layers:
-            if drop:
-                x = F.dropout(x, p=self.p_dropout, training=True)
-            x = layer.forward_prepared(x, fo_graph, _lib.ACT_ELU)
+
+        def first_order(x):
+            fo_graph = ops.gcn_prepare(ei, w, n_fo, keep_edge_values=grad, defer_check=True)
+            for layer in self.first_order_layers:
+                if drop:
+                    x = F.dropout(x, p=self.p_dropout, training=True)
+                x = layer.forward_prepared(x, fo_graph, _lib.ACT_ELU)
+            return x, fo_graph
+
+        # The first-order and the higher-order stack do not depend on each other until the bipartite layer.  Without
+        # autograd the (small, latency-bound) first-order stack runs on a second stream under the higher-order one.
+        fork = not grad and not drop
+        if fork:
+            main = torch.cuda.current_stream(x.device)
+            side = _side_stream(x.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                x, fo_graph = first_order(x)
+                bip_graph = ops.csc_build(bip, n_ho, n_fo, defer_check=True)   # needs the index tensor only
+        else:
+            x, fo_graph = first_order(x)
+            bip_graph = None
         ho_graph = ops.gcn_prepare(ei_h, w_h, n_ho, keep_edge_values=grad, defer_check=True)
         for layer in self.higher_order_layers:
             if drop:
                 x_h = F.dropout(x_h, p=self.p_dropout, training=True)
             x_h = layer.forward_prepared(x_h, ho_graph, _lib.ACT_ELU)
+        if fork:
+            main.wait_stream(side)
+            for t in (x, bip_graph.colptr, bip_graph.src, bip_graph.eid):
+                t.record_stream(main)
         if drop:
             x = F.dropout(x, p=self.p_dropout, training=True)
             x_h = F.dropout(x_h, p=self.p_dropout, training=True)
-        bip_graph = ops.csc_build(bip, n_ho, n_fo, defer_check=True)
+        if bip_graph is None:
+            bip_graph = ops.csc_build(bip, n_ho, n_fo, defer_check=True)
         x = self.bipartite_layer.forward_prepared((x_h, x), bip_graph, _lib.ACT_ELU)
         if drop:
             x = F.dropout(x, p=self.p_dropout, training=True)
