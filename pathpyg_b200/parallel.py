@@ -114,11 +114,29 @@ def all_to_all_rows(rows: torch.Tensor, send_counts: list[int], group=None) -> t
     return out, recv_counts
 
 
-def _by_owner(owner: torch.Tensor, world: int):
-    """Stable order that groups items by owner rank + how many go to each rank."""
-    order = torch.sort(owner, stable=True).indices
-    counts = torch.bincount(owner, minlength=world).tolist()
-    return order, counts
+def _by_owner(owner: torch.Tensor, world: int, local_ops=None):
+    """Stable order that groups items by owner rank + how many go to each rank.  On the GPU the order comes from the
+    library's radix sort over the ceil(log2(world)) significant bits (one digit pass), and the counts from a binary
+    search in the sorted owners (a histogram over `world` bins would be `n` atomics on a handful of addresses)."""
+    if owner.is_cuda and hasattr(local_ops, "sort_pairs_u64") and owner.numel() > 0:
+        keys = owner.clone()
+        order = local_ops.sort_pairs_u64(keys, max(1, (world - 1).bit_length()))[0].long()
+        grouped = keys
+    else:
+        grouped, order = torch.sort(owner, stable=True)
+    bounds = torch.searchsorted(grouped, torch.arange(world + 1, device=owner.device, dtype=owner.dtype))
+    return order, (bounds[1:] - bounds[:-1]).tolist()
+
+
+def _take_rows(rows: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """``rows[index]`` for a [N, k] matrix with a few int64 columns.  torch's row gather launches one CTA per 16-byte
+    row (5 ms for 20M rows on B200); gathering column by column runs at memory speed."""
+    if rows.dim() != 2 or not rows.is_cuda or rows.size(1) > 8:
+        return rows[index]
+    out = torch.empty((index.numel(), rows.size(1)), dtype=rows.dtype, device=rows.device)
+    for c in range(rows.size(1)):
+        out[:, c] = rows[:, c][index]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -221,8 +239,8 @@ class _GlobalIds:
         dev = rows.device
         k = rows.size(1)
         uniq, inv = self.ops.unique_rows(rows) if rows.size(0) else (rows, torch.empty(0, dtype=torch.int64, device=dev))
-        order, counts = _by_owner(self.owner_of(uniq[:, 0]).clamp_(max=self.world - 1), self.world)
-        got, recv_counts = all_to_all_rows(uniq[order], counts, self.group)
+        order, counts = _by_owner(self.owner_of(uniq[:, 0]).clamp_(max=self.world - 1), self.world, self.ops)
+        got, recv_counts = all_to_all_rows(_take_rows(uniq, order), counts, self.group)
         if got.size(0):
             owned, got_inv = self.ops.unique_rows(got)
         else:
@@ -244,7 +262,7 @@ class _GlobalIds:
 def _coalesce_at_owner(gsrc, gdst, w, num_nodes, offsets, ids: _GlobalIds, local_ops):
     """Send every mapped edge to the rank that owns its source row; merge duplicates there."""
     dev = gsrc.device
-    order, counts = _by_owner(ids.owner_of_id(gsrc, offsets), ids.world)
+    order, counts = _by_owner(ids.owner_of_id(gsrc, offsets), ids.world, local_ops)
     payload = torch.stack([gsrc[order], gdst[order], w[order].to(torch.float64).view(torch.int64)], dim=1)
     got, _ = all_to_all_rows(payload, counts, ids.group)
     ei = got[:, :2].t().contiguous()
@@ -293,8 +311,7 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
         # own line-graph edges of this level: columns whose source is an own line-graph node (a prefix, sources ascend)
         own_edges = int(torch.searchsorted(line_index[0].contiguous(), torch.tensor([own_count], device=dev), right=False)) \
             if line_index.size(1) else 0
-        src_rows = node_sequence[line_index[0, :own_edges]]
-        dst_rows = node_sequence[line_index[1, :own_edges]]
+        dst_rows = _take_rows(node_sequence, line_index[1, :own_edges])
         cand = torch.cat([node_sequence[:own_count], dst_rows], dim=0)    # node candidates + look-ups (all are real nodes)
         gid, owned_rows, offset, total = ids.resolve(cand)
         sizes = _all_gather_int([owned_rows.size(0)], dev, group)[:, 0]
@@ -302,7 +319,6 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
         # source k-gram of an own edge = node_sequence row of its source, which is among the first own_count candidates
         gsrc = gid[line_index[0, :own_edges]]
         gdst = gid[own_count:]
-        del src_rows
         ei_k, w_k = _coalesce_at_owner(gsrc, gdst, line_w[:own_edges], total, offsets, ids, local_ops)
         layers[k] = DistributedLayer(k, total, offset, owned_rows, ei_k, w_k)
         if k == max_order:
@@ -310,6 +326,9 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
         # next level on the extended range
         nxt = local_ops.lift_order_edge_index(line_index, num_line_nodes)
         line_w = local_ops.pair_attributes(nxt, line_w, "src") if nxt.size(1) else line_w[:0]
-        node_sequence = torch.cat([node_sequence[line_index[0]], node_sequence[line_index[1]][:, -1:]], dim=1)
+        if hasattr(local_ops, "extend_rows") and node_sequence.is_cuda:
+            node_sequence = local_ops.extend_rows(node_sequence, line_index)
+        else:
+            node_sequence = torch.cat([node_sequence[line_index[0]], node_sequence[line_index[1]][:, -1:]], dim=1)
         num_line_nodes, own_count, line_index = line_index.size(1), own_edges, nxt
     return layers
