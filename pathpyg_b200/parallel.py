@@ -11,13 +11,13 @@ The reference (pathpy/pathpyG) is single-process, single-device: nothing here ha
 * ``shard_walks``                  -- contiguous walk-id ranges balanced by node count.
 * ``distributed_temporal_layers``  -- BASELINE config 5: the time-sorted edge stream is split into contiguous
   ranges; a ghost zone of (K-1)*delta is exchanged once (all-to-all-v); every rank lifts its extended range
-  locally and keeps the causal paths whose FIRST edge it owns (every path is counted exactly once);
-  De Bruijn node ids are made global by range-partitioning the k-gram rows on their first node
-  (all-to-all-v -> local radix sort + unique -> all-gather of counts -> exclusive scan = lexicographic rank)
-  and the mapped edges are exchanged to the owner of their source row and coalesced there.
+  locally and counts the causal paths whose FIRST edge it owns (every path is counted exactly once); per
+  order ONE all-to-all-v carries the line-graph edges to the owner of their source row, where they are merged
+  (local radix sort + run detection); the global index of a merged edge -- all-gather of counts + exclusive
+  scan -- is returned to the senders and IS the De Bruijn node id of the next order.
 
 The local compute goes through ``pathpyg_b200.ops`` (CUDA only).  The CPU tests inject an object with the
-same five functions backed by the oracle, so that the partition / exchange / id-assignment logic is
+same functions backed by the oracle, so that the partition / exchange / id-assignment logic is
 exercised with gloo at world size 2 without a GPU.
 """
 from __future__ import annotations
@@ -223,53 +223,39 @@ def exchange_ghost_zone(edge_index: torch.Tensor, time: torch.Tensor, weight: to
     return ext_ei.contiguous(), ext_t.contiguous(), ext_w
 
 
-class _GlobalIds:
-    """Global lexicographic ranks of k-gram rows, range-partitioned on the first node of the row."""
-
-    def __init__(self, num_first_order_nodes: int, local_ops, group):
-        self.n1, self.ops, self.group = num_first_order_nodes, local_ops, group
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-
-    def owner_of(self, first_node: torch.Tensor) -> torch.Tensor:
-        return (first_node * self.world) // max(self.n1, 1)
-
-    def resolve(self, rows: torch.Tensor):
-        """``rows`` [r, k] (any order, duplicates allowed).  Returns (global id of every row,
-        owned distinct rows sorted, first global id owned, global number of distinct rows)."""
-        dev = rows.device
-        k = rows.size(1)
-        uniq, inv = self.ops.unique_rows(rows) if rows.size(0) else (rows, torch.empty(0, dtype=torch.int64, device=dev))
-        order, counts = _by_owner(self.owner_of(uniq[:, 0]).clamp_(max=self.world - 1), self.world, self.ops)
-        got, recv_counts = all_to_all_rows(_take_rows(uniq, order), counts, self.group)
-        if got.size(0):
-            owned, got_inv = self.ops.unique_rows(got)
-        else:
-            owned, got_inv = got.reshape(0, k), torch.empty(0, dtype=torch.int64, device=dev)
-        sizes = _all_gather_int([owned.size(0)], dev, self.group)[:, 0]
-        offset = int(sizes[:self.rank].sum())
-        total = int(sizes.sum())
-        back, _ = all_to_all_rows((got_inv + offset).unsqueeze(1), recv_counts, self.group)   # ids return to the askers
-        gid_sorted_by_owner = back[:, 0]
-        gid_of_uniq = torch.empty_like(gid_sorted_by_owner)
-        gid_of_uniq[order] = gid_sorted_by_owner
-        return gid_of_uniq[inv], owned, offset, total
-
-    def owner_of_id(self, gid: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
-        """Rank whose owned id range contains ``gid`` (``offsets`` [world+1] cumulative sizes)."""
-        return (torch.searchsorted(offsets.to(gid.device), gid, right=True) - 1).clamp_(0, self.world - 1)
+def _owner_of_id(gid: torch.Tensor, offsets: torch.Tensor, world: int) -> torch.Tensor:
+    """Rank whose owned id range contains ``gid`` (``offsets`` [world+1] cumulative sizes, host tensor)."""
+    return (torch.searchsorted(offsets.to(gid.device), gid, right=True) - 1).clamp_(0, world - 1)
 
 
-def _coalesce_at_owner(gsrc, gdst, w, num_nodes, offsets, ids: _GlobalIds, local_ops):
-    """Send every mapped edge to the rank that owns its source row; merge duplicates there."""
+def _exchange_coalesce(gsrc, gdst, w, last, num_nodes, offsets, local_ops, group):
+    """Send every edge (global node ids) to the rank that owns its source row and merge duplicates there.
+
+    Returns, for the owner: the merged (row, col)-sorted edges, their summed weights and the ``last`` value of every
+    merged edge (identical for all duplicates); for the sender: the GLOBAL index of the merged edge every input edge
+    fell into -- owners hold ascending row ranges, so the concatenation of their merged lists is the global
+    (row, col) order, and an index into it is the id of the next layer's De Bruijn node (the distinct edges of a
+    layer, in (row, col) order, are the k-grams of the next one in lexicographic order); and the cumulative merged
+    edge counts per rank [world + 1] (host)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = gsrc.device
-    order, counts = _by_owner(ids.owner_of_id(gsrc, offsets), ids.world, local_ops)
-    payload = torch.stack([gsrc[order], gdst[order], w[order].to(torch.float64).view(torch.int64)], dim=1)
-    got, _ = all_to_all_rows(payload, counts, ids.group)
+    order, counts = _by_owner(_owner_of_id(gsrc, offsets, world), world, local_ops)
+    payload = torch.stack([gsrc[order], gdst[order], w[order].to(torch.float64).view(torch.int64), last[order]], dim=1)
+    got, recv_counts = all_to_all_rows(payload, counts, group)
     ei = got[:, :2].t().contiguous()
     ww = got[:, 2].view(torch.float64).to(w.dtype)
-    if ei.size(1) == 0:
-        return ei, ww
-    return local_ops.coalesce(ei, None, num_nodes, ww, "sum")
+    if ei.size(1):
+        out_ei, out_w, inv = local_ops.coalesce(ei, None, num_nodes, ww, "sum", return_inverse=True)
+    else:
+        out_ei, out_w, inv = ei, ww, torch.empty(0, dtype=torch.int64, device=dev)
+    out_last = torch.empty(out_ei.size(1), dtype=torch.int64, device=dev)
+    out_last[inv] = got[:, 3]
+    sizes = _all_gather_int([out_ei.size(1)], dev, group)[:, 0]
+    edge_offsets = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(sizes, 0)])
+    back, _ = all_to_all_rows((inv + int(edge_offsets[rank])).unsqueeze(1), recv_counts, group)   # ids return to the senders
+    gid = torch.empty(gsrc.size(0), dtype=torch.int64, device=dev)
+    gid[order] = back[:, 0]
+    return out_ei, out_w, out_last, gid, edge_offsets
 
 
 def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, num_nodes: int, delta, max_order: int,
@@ -277,58 +263,62 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
     """``MultiOrderModel.from_temporal_graph`` over a stream that is split across the ranks.
 
     ``edge_index`` [2, m_local] / ``time`` [m_local]: this rank's CONTIGUOUS range of the globally
-    time-sorted stream (ranges in rank order).  Returns ``{order: DistributedLayer}``."""
+    time-sorted stream (ranges in rank order).  Returns ``{order: DistributedLayer}``.
+
+    Per order there is ONE exchange: the line-graph edges of the extended (own + ghost) range travel to the owner
+    of their source row as (source id, target id, weight, last node) and are merged there; the owner returns the
+    global index of the merged edge, which IS the node id of the next order (see ``_exchange_coalesce``), so no
+    k-gram row ever has to be ranked or sent.  Edges whose path starts with a ghost event are sent with weight 0:
+    they only collect their ids (their owner contributes the weight), every path is counted exactly once."""
     if local_ops is None:
         from . import ops as local_ops
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = edge_index.device
-    ids = _GlobalIds(num_nodes, local_ops, group)
     m_own = edge_index.size(1)
     w_own = edge_weight if edge_weight is not None else torch.ones(m_own, dtype=torch.float32, device=dev)
     layers: dict[int, DistributedLayer] = {}
 
+    # ---- ghost zone once: everything after it is local lifting + one exchange per order
+    if max_order > 1:
+        ext_ei, ext_t, ext_w = exchange_ghost_zone(edge_index, time, w_own, delta * (max_order - 1), group)
+    else:
+        ext_ei, ext_t, ext_w = edge_index, time, w_own
+    counted = ext_w.clone()
+    counted[m_own:] = 0                                  # ghost events: ids only
+
     # ---- order 1: nodes are the first-order nodes themselves, rows owned by node-id range
-    n1_bounds = torch.tensor([-(-num_nodes * p // world) for p in range(world + 1)], dtype=torch.int64)  # ceil: matches owner_of
+    n1_bounds = torch.tensor([-(-num_nodes * p // world) for p in range(world + 1)], dtype=torch.int64)
     lo, hi = int(n1_bounds[rank]), int(n1_bounds[rank + 1])
-    ei1, w1 = _coalesce_at_owner(edge_index[0], edge_index[1], w_own, num_nodes, n1_bounds, ids, local_ops)
-    layers[1] = DistributedLayer(1, num_nodes, lo, torch.arange(lo, hi, device=dev).unsqueeze(1), ei1, w1)
+    ei_k, w_k, last_k, gid_line, offsets = _exchange_coalesce(ext_ei[0], ext_ei[1], counted, ext_ei[1], num_nodes, n1_bounds,
+                                                              local_ops, group)
+    rows_k = torch.arange(lo, hi, device=dev).unsqueeze(1)
+    layers[1] = DistributedLayer(1, num_nodes, lo, rows_k, ei_k, w_k)
     if max_order == 1:
         return layers
 
-    # ---- ghost zone once, then purely local lifts on the extended range
-    horizon = delta * (max_order - 1)
-    ext_ei, ext_t, ext_w = exchange_ghost_zone(edge_index, time, w_own, horizon, group)
-    node_sequence = ext_ei.t().contiguous()           # 2-gram of every (own + ghost) temporal edge
-    own_count = m_own                                 # line-graph nodes whose path starts with an own edge: a prefix
+    # ---- order 2: line-graph nodes are the (own + ghost) events, their ids the merged first-order edges
     try:
         line_index = local_ops.lift_order_temporal(ext_ei, ext_t, delta, num_nodes)
     except (RuntimeError, ValueError):                # no pair in this range (the single-device call fails only if NO rank has one)
         line_index = torch.empty((2, 0), dtype=torch.int64, device=dev)
-    line_w = local_ops.pair_attributes(line_index, ext_w, "src") if line_index.size(1) else ext_w[:0]
+    line_w = local_ops.pair_attributes(line_index, counted, "src") if line_index.size(1) else counted[:0]
+    last_line = ext_ei[1]                             # last first-order node of every line-graph node's k-gram
     num_line_nodes = ext_ei.size(1)
+    row_lo = lo
 
     for k in range(2, max_order + 1):
-        # own line-graph edges of this level: columns whose source is an own line-graph node (a prefix, sources ascend)
-        own_edges = int(torch.searchsorted(line_index[0].contiguous(), torch.tensor([own_count], device=dev), right=False)) \
-            if line_index.size(1) else 0
-        dst_rows = _take_rows(node_sequence, line_index[1, :own_edges])
-        cand = torch.cat([node_sequence[:own_count], dst_rows], dim=0)    # node candidates + look-ups (all are real nodes)
-        gid, owned_rows, offset, total = ids.resolve(cand)
-        sizes = _all_gather_int([owned_rows.size(0)], dev, group)[:, 0]
-        offsets = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(sizes, 0)])
-        # source k-gram of an own edge = node_sequence row of its source, which is among the first own_count candidates
-        gsrc = gid[line_index[0, :own_edges]]
-        gdst = gid[own_count:]
-        ei_k, w_k = _coalesce_at_owner(gsrc, gdst, line_w[:own_edges], total, offsets, ids, local_ops)
-        layers[k] = DistributedLayer(k, total, offset, owned_rows, ei_k, w_k)
+        # rows of the nodes this rank owns at order k = its merged edges of order k - 1
+        prev_rows, prev_lo = rows_k, row_lo
+        rows_k = torch.cat([_take_rows(prev_rows, ei_k[0] - prev_lo), last_k.unsqueeze(1)], dim=1)
+        total, row_lo = int(offsets[-1]), int(offsets[rank])
+        edge_last = last_line[line_index[1]]
+        ei_k, w_k, last_k, gid_next, next_offsets = _exchange_coalesce(gid_line[line_index[0]], gid_line[line_index[1]], line_w,
+                                                                       edge_last, total, offsets, local_ops, group)
+        layers[k] = DistributedLayer(k, total, row_lo, rows_k, ei_k, w_k)
         if k == max_order:
             break
-        # next level on the extended range
         nxt = local_ops.lift_order_edge_index(line_index, num_line_nodes)
         line_w = local_ops.pair_attributes(nxt, line_w, "src") if nxt.size(1) else line_w[:0]
-        if hasattr(local_ops, "extend_rows") and node_sequence.is_cuda:
-            node_sequence = local_ops.extend_rows(node_sequence, line_index)
-        else:
-            node_sequence = torch.cat([node_sequence[line_index[0]], node_sequence[line_index[1]][:, -1:]], dim=1)
-        num_line_nodes, own_count, line_index = line_index.size(1), own_edges, nxt
+        gid_line, last_line, offsets = gid_next, edge_last, next_offsets
+        num_line_nodes, line_index = line_index.size(1), nxt
     return layers

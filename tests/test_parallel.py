@@ -25,12 +25,15 @@ class OracleOps:
         return torch.unique(rows, dim=0, return_inverse=True)
 
     @staticmethod
-    def coalesce(edge_index, remap, num_nodes, edge_weight, reduce="sum"):
+    def coalesce(edge_index, remap, num_nodes, edge_weight, reduce="sum", return_inverse=False):
         ei = edge_index if remap is None else remap[edge_index]
         if ei.numel() and int(ei.max()) >= num_nodes:
             raise ValueError("mapped node id outside [0, num_nodes)")
         out_ei, out_w = pyg.coalesce(ei, edge_weight, num_nodes, reduce)
-        return out_ei, out_w
+        if not return_inverse:
+            return out_ei, out_w
+        inverse = torch.unique(ei[0] * num_nodes + ei[1], return_inverse=True)[1]   # index into the (row, col)-sorted distinct edges
+        return out_ei, out_w, inverse
 
     @staticmethod
     def lift_order_temporal(edge_index, time, delta, num_nodes):
@@ -109,6 +112,12 @@ def _check_temporal(rank, world, seed, n, m, horizon, delta, K, weighted, split)
 ])
 def test_distributed_temporal_layers_world2(seed, n, m, horizon, delta, K, weighted, split):
     _spawn(_check_temporal, 2, seed, n, m, horizon, delta, K, weighted, split)
+
+
+@pytest.mark.parametrize("seed,n,m,horizon,delta,K,weighted", [(7, 9, 260, 35, 2, 5, True), (8, 30, 200, 25, 3, 3, False)])
+def test_distributed_temporal_layers_world3(seed, n, m, horizon, delta, K, weighted):
+    """Three ranks (the middle one's ghost zone spans into the third), orders up to 5."""
+    _spawn(_check_temporal, 3, seed, n, m, horizon, delta, K, weighted, "even")
 
 
 def _check_ghost(rank, world):
