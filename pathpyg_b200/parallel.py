@@ -95,14 +95,17 @@ def _all_gather_int(values: list[int], device, group) -> torch.Tensor:
     return out.cpu()
 
 
-def all_to_all_rows(rows: torch.Tensor, send_counts: list[int], group=None) -> tuple[torch.Tensor, list[int]]:
+def all_to_all_rows(rows: torch.Tensor, send_counts: list[int], group=None,
+                    recv_counts: list[int] | None = None) -> tuple[torch.Tensor, list[int]]:
     """Variable all-to-all of the leading dimension: ``rows`` is ordered by destination rank,
-    ``send_counts[p]`` rows go to rank p.  Returns (received rows ordered by source rank, recv_counts)."""
+    ``send_counts[p]`` rows go to rank p.  Returns (received rows ordered by source rank, recv_counts).
+    ``recv_counts``: pass them when they are already known (the answer to an earlier exchange travels the same
+    routes backwards) -- saves the all-gather of the counts and its host synchronisation."""
     world = dist.get_world_size(group)
     dev = rows.device
-    counts = _all_gather_int(send_counts, dev, group)          # counts[q, p] = rows q sends to p
-    rank = dist.get_rank(group)
-    recv_counts = counts[:, rank].tolist()
+    if recv_counts is None:
+        counts = _all_gather_int(send_counts, dev, group)          # counts[q, p] = rows q sends to p
+        recv_counts = counts[:, dist.get_rank(group)].tolist()
     width = rows.shape[1:]
     out = torch.empty((sum(recv_counts),) + tuple(width), dtype=rows.dtype, device=dev)
     per_row = 1
@@ -240,19 +243,31 @@ def _exchange_coalesce(gsrc, gdst, w, last, num_nodes, offsets, local_ops, group
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = gsrc.device
     order, counts = _by_owner(_owner_of_id(gsrc, offsets, world), world, local_ops)
-    payload = torch.stack([gsrc[order], gdst[order], w[order].to(torch.float64).view(torch.int64), last[order]], dim=1)
-    got, recv_counts = all_to_all_rows(payload, counts, group)
-    ei = got[:, :2].t().contiguous()
-    ww = got[:, 2].view(torch.float64).to(w.dtype)
+    narrow = w.dtype == torch.float32 and num_nodes < (1 << 31)
+    if narrow:
+        # ids and first-order nodes fit 32 bits: (source, target) and (weight bits, last node) travel as two words
+        low = (1 << 32) - 1
+        packed = torch.stack([(gsrc << 32) | gdst, (w.view(torch.int32).to(torch.int64) << 32) | (last & low)], dim=1)
+        got, recv_counts = all_to_all_rows(_take_rows(packed, order), counts, group)
+        ei = torch.stack([got[:, 0] >> 32, got[:, 0] & low])
+        ww = (got[:, 1] >> 32).to(torch.int32).view(torch.float32)
+        got_last = got[:, 1] & low
+    else:
+        payload = torch.stack([gsrc[order], gdst[order], w[order].to(torch.float64).view(torch.int64), last[order]], dim=1)
+        got, recv_counts = all_to_all_rows(payload, counts, group)
+        ei = got[:, :2].t().contiguous()
+        ww = got[:, 2].view(torch.float64).to(w.dtype)
+        got_last = got[:, 3]
     if ei.size(1):
         out_ei, out_w, inv = local_ops.coalesce(ei, None, num_nodes, ww, "sum", return_inverse=True)
     else:
         out_ei, out_w, inv = ei, ww, torch.empty(0, dtype=torch.int64, device=dev)
     out_last = torch.empty(out_ei.size(1), dtype=torch.int64, device=dev)
-    out_last[inv] = got[:, 3]
+    out_last[inv] = got_last
     sizes = _all_gather_int([out_ei.size(1)], dev, group)[:, 0]
     edge_offsets = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(sizes, 0)])
-    back, _ = all_to_all_rows((inv + int(edge_offsets[rank])).unsqueeze(1), recv_counts, group)   # ids return to the senders
+    # ids return to the senders along the same routes: what came from rank q goes back to q
+    back, _ = all_to_all_rows((inv + int(edge_offsets[rank])).unsqueeze(1), recv_counts, group, recv_counts=counts)
     gid = torch.empty(gsrc.size(0), dtype=torch.int64, device=dev)
     gid[order] = back[:, 0]
     return out_ei, out_w, out_last, gid, edge_offsets

@@ -82,6 +82,8 @@ def _stream(seed, n, m, horizon):
 
 def _check_temporal(rank, world, seed, n, m, horizon, delta, K, weighted, split):
     ei, t, w = _stream(seed, n, m, horizon)
+    if weighted == "f64":      # float64 weights travel on the wide (four-word) exchange payload
+        w = w.double()
     want = mom.from_temporal_graph(ei, t, n, delta=delta, max_order=K, edge_weight=w if weighted else None)
     if split == "even":
         lo, hi = parallel.partition_stream(m, rank, world)
@@ -109,6 +111,7 @@ def _check_temporal(rank, world, seed, n, m, horizon, delta, K, weighted, split)
     (1, 15, 400, 50, 2, 3, True, "even"),
     (2, 12, 300, 40, 2, 4, True, "uneven"),
     (3, 40, 500, 30, 4, 2, False, "uneven"),
+    (4, 15, 300, 40, 2, 3, "f64", "even"),
 ])
 def test_distributed_temporal_layers_world2(seed, n, m, horizon, delta, K, weighted, split):
     _spawn(_check_temporal, 2, seed, n, m, horizon, delta, K, weighted, split)
