@@ -107,3 +107,13 @@ def gcn_norm(edge_index: torch.Tensor, edge_weight: torch.Tensor | None, num_nod
     dis = deg.pow(-0.5)
     dis.masked_fill_(dis == float("inf"), 0)
     return edge_index, dis[row] * edge_weight * dis[col]
+
+
+def to_undirected(edge_index: torch.Tensor, edge_attr: torch.Tensor | None, num_nodes: int, reduce: str = "add"):
+    """PyG ``utils.to_undirected`` (call site ``core/graph.py:228-233``): every edge in both directions, the
+    attribute repeated for the reversed copy, then ``coalesce`` with ``reduce``."""
+    row, col = edge_index[0], edge_index[1]
+    both = torch.stack([torch.cat([row, col]), torch.cat([col, row])])
+    if edge_attr is not None:
+        edge_attr = torch.cat([edge_attr, edge_attr])
+    return coalesce(both, edge_attr, num_nodes, reduce)

@@ -308,3 +308,87 @@ def io_module():
                 else:
                     sys.modules[k] = v
     return _cache["io"]
+
+
+# ----------------------------------------------------------------------------------------------
+# containers: the reference's own edge-merging members of Graph / TemporalGraph
+# ----------------------------------------------------------------------------------------------
+class _KwEdgeIndex(torch.Tensor):
+    """Stand-in for torch_geometric.EdgeIndex as the container members use it: ``EdgeIndex(data=, sparse_size=,
+    is_undirected=)``, ``as_tensor()``, ``size``, ``max``, column indexing, ``device``."""
+
+    __torch_function__ = torch._C._disabled_torch_function_impl
+
+    @staticmethod
+    def __new__(cls, data, sparse_size=None, is_undirected=False):
+        out = torch.Tensor._make_subclass(cls, torch.as_tensor(data).as_subclass(torch.Tensor))
+        out.sparse_size_, out.is_undirected = sparse_size, is_undirected
+        return out
+
+    def as_tensor(self):
+        return self.as_subclass(torch.Tensor)
+
+    def __getitem__(self, key):  # PyG keeps the wrapper when columns are selected
+        out = self.as_subclass(torch.Tensor)[key]
+        return _KwEdgeIndex(out, self.sparse_size_, self.is_undirected) if out.dim() == 2 else out
+
+
+class _ContainerSelf:
+    """``self`` of the extracted methods: ``data``, ``mapping``, ``m``, ``node_attrs()``, ``edge_attrs()``."""
+
+    def __init__(self, data):
+        self.data, self.mapping = data, None
+
+    @property
+    def m(self):
+        return self.data.edge_index.size(1)
+
+    def node_attrs(self):  # graph.py:294-309
+        return [k for k in self.data.__dict__ if k != "node_sequence" and k.startswith("node_")]
+
+    def edge_attrs(self):  # graph.py:311-327
+        return [k for k in self.data.__dict__ if k != "edge_index" and k.startswith("edge_")]
+
+
+def container_methods():
+    """``(make_self, methods)``: the reference's ``Graph.to_undirected`` / ``Graph.to_weighted_graph``
+    (core/graph.py:211-270) and ``TemporalGraph.to_static_graph`` (core/temporal_graph.py:191-220), compiled
+    unmodified; PyG's ``to_undirected`` / ``coalesce`` are the restatements of ``oracle/pyg.py`` and ``Graph(...)`` is
+    the holder that applies the constructor's stable row sort."""
+    if "containers" not in _cache:
+        import typing
+
+        class Holder(_Graph):
+            def __init__(self, data, mapping=None):
+                order = torch.sort(data.edge_index.as_subclass(torch.Tensor)[0], stable=True).indices
+                for k, v in list(data.__dict__.items()):
+                    if k == "edge_index":
+                        data.edge_index = v.as_subclass(torch.Tensor)[:, order]
+                    elif k.startswith("edge_") and isinstance(v, torch.Tensor):
+                        data.__dict__[k] = v[order]
+                self.data, self.mapping = data, mapping
+
+            @staticmethod
+            def from_edge_index(edge_index, mapping=None, num_nodes=None):
+                return Holder(_SettableData(edge_index=edge_index, num_nodes=num_nodes), mapping)
+
+        tg = types.SimpleNamespace(utils=types.SimpleNamespace(
+            coalesce=lambda ei, attr=None, num_nodes=None, reduce="sum": pyg.coalesce(
+                ei.as_subclass(torch.Tensor), attr, num_nodes if num_nodes is not None else int(ei.max()) + 1, reduce)))
+        env = dict(torch=torch, torch_geometric=tg, Data=_SettableData, EdgeIndex=_KwEdgeIndex, Graph=Holder,
+                   Optional=typing.Optional, Tuple=typing.Tuple)
+        genv = dict(env)
+        methods = _methods_of("src/pathpyG/core/graph.py", "Graph", ["to_undirected", "to_weighted_graph"], genv)
+        # the method is compiled under the name of the PyG function it calls: rebind the global to the function
+        genv["to_undirected"] = lambda ei, edge_attr=None, num_nodes=None, reduce="add": pyg.to_undirected(
+            ei.as_subclass(torch.Tensor), edge_attr, num_nodes, reduce)
+        methods.update(_methods_of("src/pathpyG/core/temporal_graph.py", "TemporalGraph", ["to_static_graph"], dict(env)))
+
+        def make_self(edge_index, num_nodes=None, **attrs):
+            data = _SettableData(edge_index=_KwEdgeIndex(edge_index, sparse_size=(num_nodes, num_nodes)), **attrs)
+            data.num_nodes = num_nodes
+            data.num_edges = edge_index.size(1)
+            return _ContainerSelf(data)
+
+        _cache["containers"] = (make_self, methods)
+    return _cache["containers"]

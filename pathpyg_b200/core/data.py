@@ -18,7 +18,7 @@ class EdgeIndex(torch.Tensor):
     __torch_function__ = torch._C._disabled_torch_function_impl
 
     @staticmethod
-    def __new__(cls, data, sparse_size=None, sort_order=None, **kwargs):
+    def __new__(cls, data, sparse_size=None, sort_order=None, is_undirected=False, **kwargs):
         t = torch.as_tensor(data, **kwargs)
         if isinstance(t, EdgeIndex):
             t = t.as_subclass(torch.Tensor)
@@ -27,6 +27,7 @@ class EdgeIndex(torch.Tensor):
         out = torch.Tensor._make_subclass(cls, t)
         out._sparse_size = tuple(sparse_size) if sparse_size is not None else (None, None)
         out._sort_order = sort_order
+        out._is_undirected = bool(is_undirected)
         out._cache = {}
         return out
 
@@ -44,6 +45,11 @@ class EdgeIndex(torch.Tensor):
     @property
     def sort_order(self):
         return self._sort_order
+
+    @property
+    def is_undirected(self) -> bool:
+        """The flag the creator set (PyG keeps it as metadata; it is not derived from the edges)."""
+        return self._is_undirected
 
     def validate(self) -> "EdgeIndex":
         t = self.as_tensor()
@@ -67,10 +73,11 @@ class EdgeIndex(torch.Tensor):
         t = self.as_tensor()
         key = t[0] if sort_order == "row" else t[1]
         if key.numel() < 2 or bool((key[1:] >= key[:-1]).all()):
-            out = EdgeIndex(t, sparse_size=self._sparse_size, sort_order=sort_order)
+            out = EdgeIndex(t, sparse_size=self._sparse_size, sort_order=sort_order, is_undirected=self._is_undirected)
             return out, None
         perm = torch.sort(key, stable=True).indices
-        return EdgeIndex(t[:, perm], sparse_size=self._sparse_size, sort_order=sort_order), perm
+        return EdgeIndex(t[:, perm], sparse_size=self._sparse_size, sort_order=sort_order,
+                         is_undirected=self._is_undirected), perm
 
     def _ptr(self, ids: torch.Tensor, n: int) -> torch.Tensor:
         counts = torch.bincount(ids, minlength=n)
@@ -103,13 +110,15 @@ class EdgeIndex(torch.Tensor):
         return self._cache["csc"]
 
     def to(self, *args, **kwargs):  # keep the wrapper across device moves
-        return EdgeIndex(self.as_tensor().to(*args, **kwargs), sparse_size=self._sparse_size, sort_order=self._sort_order)
+        return EdgeIndex(self.as_tensor().to(*args, **kwargs), sparse_size=self._sparse_size, sort_order=self._sort_order,
+                         is_undirected=self._is_undirected)
 
     def __repr__(self):
         return f"EdgeIndex({self.as_tensor().tolist()}, sparse_size={self._sparse_size})"
 
     def __deepcopy__(self, memo):
-        return EdgeIndex(self.as_tensor().clone(), sparse_size=self._sparse_size, sort_order=self._sort_order)
+        return EdgeIndex(self.as_tensor().clone(), sparse_size=self._sparse_size, sort_order=self._sort_order,
+                         is_undirected=self._is_undirected)
 
 
 class Data:
@@ -147,23 +156,48 @@ class Data:
         ei = self.__dict__.get("edge_index")
         return 0 if ei is None else int(ei.size(1))
 
+    def has_self_loops(self) -> bool:
+        ei = self.__dict__.get("edge_index")
+        return bool(ei is not None and ei.numel() and (ei[0] == ei[1]).any())
+
+    def concat(self, other: "Data") -> "Data":
+        """``torch_geometric.data.Data.concat``: tensors of both objects joined along their cat dimension
+        (last for ``*index*`` keys, first otherwise), numpy arrays along axis 0; other values are kept from ``self``."""
+        import numpy as np
+
+        out = copy.copy(self)
+        for k, v in self.__dict__.items():
+            w = other.__dict__.get(k)
+            if isinstance(v, torch.Tensor) and isinstance(w, torch.Tensor):
+                a, b = v.as_subclass(torch.Tensor), w.as_subclass(torch.Tensor)
+                out.__dict__[k] = torch.cat([a, b], dim=-1 if "index" in k else 0)
+            elif isinstance(v, np.ndarray) and isinstance(w, np.ndarray):
+                out.__dict__[k] = np.concatenate([v, w])
+        return out
+
     def edge_attrs(self):
-        """Keys holding one entry per edge (PyG: name contains 'edge', or leading dim == num_edges)."""
+        """Keys holding one entry per edge (PyG: name contains 'edge', or leading dim == num_edges); tensors and
+        numpy arrays (the reference keeps string attributes as numpy arrays, io/pandas.py:91-92)."""
+        import numpy as np
+
         m = self.num_edges
         out = []
         for k, v in self.__dict__.items():
-            if not isinstance(v, torch.Tensor):
-                continue
-            if k == "edge_index" or (k.startswith("edge_") and v.dim() >= 1 and v.size(0) == m):
-                out.append(k)
-            elif k == "time" and v.dim() >= 1 and v.size(0) == m:
+            if isinstance(v, torch.Tensor):
+                if k == "edge_index" or ((k.startswith("edge_") or k == "time") and v.dim() >= 1 and v.size(0) == m):
+                    out.append(k)
+            elif isinstance(v, np.ndarray) and k.startswith("edge_") and v.ndim >= 1 and v.shape[0] == m:
                 out.append(k)
         return out
 
     def node_attrs(self):
+        import numpy as np
+
         n = self.__dict__.get("num_nodes")
         return [k for k, v in self.__dict__.items()
-                if isinstance(v, torch.Tensor) and k.startswith("node_") and v.dim() >= 1 and v.size(0) == n]
+                if k.startswith("node_") and k != "node_sequence" and (
+                    (isinstance(v, torch.Tensor) and v.dim() >= 1 and v.size(0) == n)
+                    or (isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == n))]
 
     # ---- time order (TemporalGraph input, multi_order_model.py:148-151)
     def is_sorted_by_time(self) -> bool:

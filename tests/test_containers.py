@@ -1,0 +1,210 @@
+"""Graph / TemporalGraph container surface: the known answers of the reference's own tests
+(``tests/core/test_graph.py``, ``tests/core/test_temporal_graph.py``) for the members that are index plumbing and
+therefore run wherever the tensors live.  The members that merge edges run on the CUDA path only and are covered
+in ``tests/test_containers_gpu.py``."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import pathpyg_b200 as pp
+from pathpyg_b200 import Graph, IndexMap, TemporalGraph
+
+LONG = [("a", "b", 1), ("b", "c", 5), ("c", "d", 9), ("c", "e", 9), ("c", "f", 11), ("f", "a", 13), ("a", "g", 18),
+        ("b", "f", 21), ("a", "g", 26), ("c", "f", 27), ("h", "f", 27), ("g", "h", 28), ("a", "c", 30), ("a", "b", 31),
+        ("c", "h", 32), ("f", "h", 33), ("b", "i", 42), ("i", "b", 42), ("c", "i", 47), ("h", "i", 50)]  # tests/core/conftest.py:50-74
+
+
+@pytest.fixture
+def simple_graph():  # tests/core/conftest.py:12-15
+    return Graph.from_edge_list([("a", "b"), ("b", "c"), ("a", "c")])
+
+
+@pytest.fixture
+def long_temporal_graph():
+    return TemporalGraph.from_edge_list(LONG)
+
+
+def test_from_edge_list_id_order():  # test_graph.py:59-99
+    g = Graph.from_edge_list([("a", "b"), ("c", "a"), ("b", "c")])
+    assert [g.mapping.to_idx(v) for v in "abc"] == [0, 1, 2]
+    assert torch.equal(g.data.edge_index, pp.EdgeIndex([[0, 1, 2], [1, 2, 0]]))
+    g = Graph.from_edge_list([(1, 12), (2, 1)])
+    assert [g.mapping.to_idx(v) for v in (1, 2, 12)] == [0, 1, 2]
+    g = Graph.from_edge_list([("1", "12"), ("2", "1"), ("21", "3")])
+    assert [g.mapping.to_idx(v) for v in ("1", "2", "3", "12", "21")] == [0, 1, 2, 3, 4]
+
+
+def test_undirected_flag_and_edge_count():  # test_graph.py:102-115, graph.py:646-662
+    g = Graph.from_edge_list([("a", "b"), ("b", "a"), ("b", "c"), ("c", "b"), ("c", "a"), ("a", "c")], is_undirected=True)
+    assert g.is_undirected() and not g.is_directed()
+    assert g.m == 3
+    assert str(g).startswith("Undirected graph with 3 nodes and 3 edges")
+    loops = Graph(pp.Data(edge_index=pp.EdgeIndex([[0, 0, 1], [0, 1, 0]], sparse_size=(2, 2), is_undirected=True), num_nodes=2))
+    assert loops.m == 2 and loops.has_self_loops()
+
+
+def test_attr_name_lists(simple_graph):  # test_graph.py:131-148
+    assert simple_graph.node_attrs() == [] and simple_graph.edge_attrs() == []
+    simple_graph.data["node_class"] = torch.tensor([[1], [2], [3]])
+    simple_graph.data["edge_weight"] = torch.tensor([[1], [1], [2]])
+    assert simple_graph.node_attrs() == ["node_class"] and simple_graph.edge_attrs() == ["edge_weight"]
+
+
+def test_nodes_edges_neighbours(simple_graph):  # test_graph.py:151-189
+    assert simple_graph.nodes == ["a", "b", "c"]
+    assert [tuple(e) for e in simple_graph.edges] == [("a", "b"), ("a", "c"), ("b", "c")]
+    assert simple_graph.successors("a") == ["b", "c"] and simple_graph.successors("c") == []
+    assert simple_graph.predecessors("b") == ["a"] and simple_graph.predecessors("a") == []
+    for v, w in (("a", "b"), ("a", "c"), ("b", "c")):
+        assert simple_graph.is_edge(v, w) and not simple_graph.is_edge(w, v)
+    plain = Graph.from_edge_index(torch.tensor([[0, 0, 1], [1, 2, 2]]))
+    assert plain.successors(0) == [1, 2] and plain.predecessors(2) == [0, 1]
+    assert plain.get_successors(7).numel() == 0
+
+
+def test_sparse_adj_matrix(simple_graph):  # test_graph.py:192-215
+    adj = simple_graph.sparse_adj_matrix()
+    assert adj.shape == (3, 3) and adj.nnz == 3
+    simple_graph.data["edge_weight"] = torch.tensor([[1], [1], [2]])
+    weighted = simple_graph.sparse_adj_matrix("edge_weight")
+    assert isinstance(weighted, sp.coo_matrix) and weighted.shape == (3, 3)
+    assert weighted.data.tolist() == [1, 1, 2]
+    g = Graph.from_edge_index(torch.tensor([[0], [1]]), num_nodes=5)
+    assert g.sparse_adj_matrix().shape == (5, 5) and g.sparse_adj_matrix().nnz == 1
+    g.data.edge_attr = torch.tensor([[1]])
+    assert g.sparse_adj_matrix("edge_attr").nnz == 1
+
+
+def test_laplacian(simple_graph):  # test_graph.py:266-276
+    lap = simple_graph.laplacian()
+    assert isinstance(lap, sp.coo_matrix) and lap.shape == (3, 3) and lap.nnz == 6
+    assert lap.data.tolist() == [-1, -1, -1, 2, 1, 0]
+    sym = simple_graph.laplacian(normalization="sym").toarray()
+    # a -> b, a -> c, b -> c: out-degrees (2, 1, 0); D^-1/2 A D^-1/2 with inf -> 0
+    want = np.eye(3)
+    want[0, 1] = -1 / np.sqrt(2)
+    assert np.allclose(sym, want)
+    rw = simple_graph.laplacian(normalization="rw").toarray()
+    assert np.allclose(rw, [[1, -0.5, -0.5], [0, 1, -1], [0, 0, 1]])
+    simple_graph.data["edge_weight"] = torch.tensor([1.0, 3.0, 2.0])
+    assert simple_graph.laplacian(edge_attr="edge_weight").data.tolist() == [-1, -3, -2, 4, 2, 0]
+
+
+def test_add_without_ids():  # test_graph.py:279-291
+    g1 = Graph.from_edge_index(torch.IntTensor([[0, 1, 1], [1, 2, 3]]), num_nodes=4)
+    g2 = Graph.from_edge_index(torch.IntTensor([[0, 1, 1], [1, 2, 3]]), num_nodes=4)
+    g = g1 + g2
+    assert g.n == 4 and g.m == 6
+    assert torch.equal(g.data.edge_index, torch.tensor([[0, 0, 1, 1, 1, 1], [1, 1, 2, 3, 2, 3]]))
+    g3 = Graph.from_edge_index(torch.IntTensor([[0, 2, 3], [2, 3, 4]]), num_nodes=5)
+    g = g1 + g2 + g3
+    assert g.n == 5 and g.m == 9
+    assert torch.equal(g.data.edge_index, torch.tensor([[0, 0, 0, 1, 1, 1, 1, 2, 3], [1, 1, 2, 2, 3, 2, 3, 3, 4]]))
+
+
+@pytest.mark.parametrize("ids2, n, want", [
+    (["a", "b", "c", "d"], 4, [[0, 0, 1, 1, 1, 1], [1, 1, 2, 3, 2, 3]]),    # test_graph.py:294-301
+    (["e", "f", "g", "h"], 8, [[0, 1, 1, 4, 5, 5], [1, 2, 3, 5, 6, 7]]),    # :304-311
+    (["a", "b", "g", "h"], 6, [[0, 0, 1, 1, 1, 1], [1, 1, 2, 3, 4, 5]]),    # :314-321
+])
+def test_add_with_ids(ids2, n, want):
+    g1 = Graph.from_edge_index(torch.IntTensor([[0, 1, 1], [1, 2, 3]]), mapping=IndexMap(["a", "b", "c", "d"]))
+    g2 = Graph.from_edge_index(torch.IntTensor([[0, 1, 1], [1, 2, 3]]), mapping=IndexMap(ids2))
+    g = g1 + g2
+    assert g.n == n and g.m == 6
+    assert torch.equal(g.data.edge_index, torch.tensor(want))
+
+
+def test_add_with_attributes():  # test_graph.py:324-357
+    g1 = Graph.from_edge_index(torch.IntTensor([[0, 1, 1], [1, 2, 3]]), mapping=IndexMap(["a", "b", "c", "d"]))
+    g2 = Graph.from_edge_index(torch.IntTensor([[0, 1, 1], [1, 2, 3]]), mapping=IndexMap(["a", "b", "g", "h"]))
+    g1["node_class"], g2["node_class"] = torch.tensor([[1], [2], [3], [4]]), torch.tensor([[5], [6], [7], [8]])
+    g1["edge_weight"], g2["edge_weight"] = torch.tensor([[1], [2], [3]]), torch.tensor([[4], [5], [6]])
+    g = g1 + g2
+    assert torch.equal(g["node_class"], torch.tensor([[6], [8], [3], [4], [7], [8]]))
+    assert torch.equal(g["edge_weight"], torch.tensor([[1], [4], [2], [3], [5], [6]]))
+    assert torch.equal(g1.__add__(g2, reduce="max")["node_class"], torch.tensor([[5], [6], [3], [4], [7], [8]]))
+    assert torch.equal(g1.__add__(g2, reduce="mul")["node_class"], torch.tensor([[5], [12], [3], [4], [7], [8]]))
+
+
+def test_get_and_set_attributes(simple_graph):  # test_graph.py:371-449
+    simple_graph["node_class"] = torch.tensor([[1], [2], [3]])
+    assert [simple_graph["node_class", v].item() for v in "abc"] == [1, 2, 3]
+    simple_graph["node_class", "a"] = 42
+    assert simple_graph["node_class", "a"].item() == 42
+    with pytest.raises(KeyError):
+        simple_graph["node_class", "d"]
+    with pytest.raises(KeyError):
+        simple_graph["node_class_1", "a"]
+    with pytest.raises(KeyError):
+        simple_graph["node_class", "d"] = 42
+    with pytest.raises(KeyError):
+        simple_graph["node_class_1", "a"] = 42
+    simple_graph["edge_weight"] = torch.tensor([[1], [1], [2]])
+    assert simple_graph["edge_weight", "a", "b"].item() == 1 and simple_graph["edge_weight", "b", "c"].item() == 2
+    simple_graph["edge_weight", "a", "b"] = 42
+    assert simple_graph["edge_weight", "a", "b"].item() == 42
+    with pytest.raises(KeyError):
+        simple_graph["edge_weight", "a", "d"]
+    with pytest.raises(KeyError):
+        simple_graph["edge_weight_1", "a", "b"] = 42
+    with pytest.raises(ValueError):
+        simple_graph["node_short"] = torch.tensor([1])
+    simple_graph["graph_feature"] = torch.tensor([42])
+    assert simple_graph["graph_feature"].item() == 42
+    with pytest.raises(KeyError):
+        simple_graph["graph_feature", "a"] = 42
+    with pytest.raises(KeyError):
+        simple_graph["nothing"]
+
+
+def test_graph_str_lists_attributes(simple_graph):  # graph.py:772-805 (docstring of to_undirected, :222-223)
+    assert str(simple_graph) == ("Directed graph with 3 nodes and 3 edges\n"
+                                 "{'Edge Attributes': {}, 'Graph Attributes': {'num_nodes': \"<class 'int'>\"}, 'Node Attributes': {}}")
+
+
+# ---- TemporalGraph (tests/core/test_temporal_graph.py) ----------------------------------------------------------
+def test_temporal_sizes_and_span(long_temporal_graph):  # :42-54
+    g = long_temporal_graph
+    assert (g.n, g.m, g.start_time, g.end_time, g.order) == (9, 20, 1, 50, 1)
+    assert g.temporal_edges[:2] == [("a", "b", 1), ("b", "c", 5)]
+    assert str(g).startswith("Temporal Graph with 9 nodes, 17 unique edges and 20 events in [1, 50]")
+
+
+def test_temporal_static_and_undirected(long_temporal_graph):  # :57-85
+    g = long_temporal_graph
+    s = g.to_static_graph()
+    assert (s.n, s.m) == (9, 20)
+    w = g.to_static_graph(time_window=(9, 12))
+    assert w.m == 3
+    u = g.to_undirected()
+    assert (u.n, u.m) == (9, 40) and u.data.is_sorted_by_time()
+    g.shuffle_time()
+    assert (g.n, g.m) == (9, 20) and g.to_static_graph().m == 20
+    assert not g.time_is_known_sorted()
+
+
+def test_temporal_batch_and_window(long_temporal_graph):  # :88-116
+    g = long_temporal_graph
+    assert (g.get_batch(1, 9).n, g.get_batch(1, 9).m) == (9, 8)
+    assert (g.get_batch(9, 13).n, g.get_batch(9, 13).m) == (9, 4)
+    assert g.get_window(1, 10).m == 4 and g.get_window(10, 14).m == 2
+    g.data.edge_tensor = torch.arange(g.m)
+    g.data.edge_array = np.arange(g.m)
+    b = g.get_batch(1, 9)
+    assert b.data.edge_tensor.tolist() == list(range(1, 9)) and b.data.edge_array.tolist() == list(range(1, 9))
+    w = g.get_window(2, 10)
+    assert w.data.edge_tensor.tolist() == [1, 2, 3] and w.data.edge_array.tolist() == [1, 2, 3]
+    assert w.mapping is g.mapping
+    assert g["edge_tensor", "a", "b"].item() == 13 and g["edge_tensor", "a", "b", 1].item() == 0  # last event / exact event
+    with pytest.raises(KeyError):
+        g["edge_other", "a", "b"]
+
+
+def test_temporal_ctor_orders_numpy_edge_attributes():
+    d = pp.Data(edge_index=torch.tensor([[0, 1, 2], [1, 2, 0]]), time=torch.tensor([5, 1, 3]), num_nodes=3,
+                edge_label=np.array(["x", "y", "z"]), edge_w=torch.tensor([1.0, 2.0, 3.0]))
+    g = TemporalGraph(d)
+    assert g.data.time.tolist() == [1, 3, 5] and g.data.edge_label.tolist() == ["y", "z", "x"]
+    assert g.data.edge_w.tolist() == [2.0, 3.0, 1.0]
