@@ -22,6 +22,7 @@ import pandas as pd
 import torch
 
 from ..core.data import Data
+from ..core.graph import Graph
 from ..core.index_map import IndexMap
 from ..core.path_data import PathData
 from ..core.temporal_graph import TemporalGraph
@@ -29,7 +30,7 @@ from ..core.temporal_graph import TemporalGraph
 logger = logging.getLogger("root")
 
 # the reference's column classifiers (io/pandas.py:22-25)
-_iterable_re = re.compile(r"^\s*[\[\(\{].*[\]\)\}]\s*$")
+_iterable_re = re.compile(r"^\s*[\[\(].*[\]\)]\s*$")
 _number_re = re.compile(r"^\s*[+-]?(\d+(\.\d*)?|\.\d+)([eE][+-]?\d+)?\s*$")
 _integer_re = re.compile(r"^\s*[+-]?\d+\s*$")
 
@@ -74,6 +75,81 @@ def _parse_df_column(df: pd.DataFrame, data: Data, attr: str, idx=None, prefix: 
         data[prefix + attr] = torch.tensor(col.values[idx], device=dev)
 
 
+def df_to_graph(df: pd.DataFrame, is_undirected: bool = False, multiedges: bool = False, num_nodes: int | None = None,
+                device=None) -> Graph:
+    """io/pandas.py:109-180: columns ``v``, ``w`` (or the first two of a header-less frame) are the edges, every other
+    column an edge attribute.  ``device`` (extension): where the index tensors are created."""
+    if all(isinstance(x, int) for x in df.columns.values.tolist()):
+        df.columns = ["v", "w"] + [f"edge_attr_{i - 2}" for i in range(2, len(df.columns))]
+    if not multiedges and df[["v", "w"]].duplicated().any():
+        logger.debug("Data frame contains multiple edges, but multiedges is set to False. Removing duplicates.")
+        df = df.drop_duplicates(subset=["v", "w"])
+    # sorted distinct ids like IndexMap(np.unique(...)) (:154); the inverse IS mapping.to_idxs of the end points
+    node_ids, inverse = np.unique(df[["v", "w"]].values, return_inverse=True)
+    mapping = IndexMap(node_ids)
+    edge_index = torch.from_numpy(np.ascontiguousarray(inverse.reshape(-1, 2).T.astype(np.int64)))
+    if device is not None:
+        edge_index = edge_index.to(device)
+    data = Data(edge_index=edge_index, num_nodes=num_nodes if num_nodes is not None else int(node_ids.shape[0]))
+    for col in [c for c in df.columns if c not in ("v", "w")]:
+        _parse_df_column(df=df, data=data, attr=col, prefix="" if col.startswith("edge_") else "edge_")
+    g = Graph(data=data, mapping=mapping)
+    return g.to_undirected() if is_undirected else g
+
+
+def add_node_attributes(df: pd.DataFrame, g: Graph) -> None:
+    """io/pandas.py:183-234: rows are nodes named in column ``v`` (ids) or ``index`` (indices); every other column
+    becomes ``node_<column>``, stored in node order."""
+    if "v" in df:
+        named = list(df["v"])
+    elif "index" in df:
+        named = list(df["index"])
+    else:
+        raise ValueError("DataFrame must either have `index` or `v` column")
+    if len(set(named)) < len(named):
+        raise ValueError("DataFrame cannot contain multiple attribute values for single node")
+    if set(named) != (set(g.nodes) if "v" in df else set(range(g.n))):
+        raise ValueError("Mismatch between nodes in DataFrame and nodes in graph")
+    node_idx = g.mapping.to_idxs(named).tolist() if "v" in df else named
+    for attr in [c for c in df.columns if c not in ("v", "index")]:
+        _parse_df_column(df=df, data=g.data, idx=node_idx, attr=attr, prefix="" if attr.startswith("node_") else "node_")
+
+
+def add_edge_attributes(df: pd.DataFrame, g: Graph, time_attr: str | None = None) -> None:
+    """io/pandas.py:237-315: rows are edges ``v``, ``w`` (plus the time stamp column ``time_attr`` for a temporal
+    graph); every other column becomes ``edge_<column>``, taken in the order the rows are listed."""
+    if "v" not in df or "w" not in df:
+        raise ValueError("Data frame must have columns `v` and `w` for source and target nodes")
+    node_ids = set(df["v"]).union(set(df["w"]))
+    known = set(g.nodes)
+    if not node_ids.issubset(known):
+        raise ValueError(f"DataFrame contains nodes {node_ids - known} that do not exist in the graph. "
+                         "Please ensure all nodes in the DataFrame are present in the graph.")
+    if g.m != len(df):
+        raise ValueError(f"DataFrame contains {len(df)} edges, but the graph has {g.m} edges. "
+                         "Please ensure the DataFrame matches the number of edges in the graph.")
+    src = g.mapping.to_idxs(df["v"].tolist()).tolist()
+    tgt = g.mapping.to_idxs(df["w"].tolist()).tolist()
+    edge_attrs = [c for c in df.columns if c not in ("v", "w")]
+    if time_attr is not None:
+        if time_attr not in df:
+            raise ValueError(f"Data frame must have column {time_attr} for time stamps")
+        edge_attrs.remove(time_attr)
+        lut, keys = g.tedge_to_index, list(zip(src, tgt, df[time_attr].values.tolist()))
+    else:
+        lut, keys = g.edge_to_index, list(zip(src, tgt))
+    edge_idx = []
+    for key in keys:
+        at = lut.get(key)
+        if at is None:
+            raise ValueError(f"Edge ({key[0]}, {key[1]}) does not exist" + (f" at time {key[2]}" if time_attr else "")
+                             + " in the graph.")
+        edge_idx.append(at)
+    picked = df.iloc[edge_idx]
+    for attr in edge_attrs:
+        _parse_df_column(df=picked, data=g.data, attr=attr, prefix="" if attr.startswith("edge_") else "edge_")
+
+
 def df_to_temporal_graph(df: pd.DataFrame, multiedges: bool = False, timestamp_format="%Y-%m-%d %H:%M:%S", time_rescale=1,
                          num_nodes: int | None = None, device=None) -> TemporalGraph:
     """io/pandas.py:318-396.  ``device`` (extension): where the index tensors are created; with a CUDA device the
@@ -104,6 +180,33 @@ def read_csv_temporal_graph(filename: str, sep: str = ",", header: bool = True, 
     return df_to_temporal_graph(df, timestamp_format=timestamp_format, time_rescale=time_rescale, **kwargs)
 
 
+def _attr_list(val):
+    return val.cpu().numpy().tolist() if isinstance(val, torch.Tensor) else val.tolist()
+
+
+def graph_to_df(graph: Graph, node_indices: bool = False) -> pd.DataFrame:
+    """io/pandas.py:399-428: one row per edge, edge attributes as extra columns."""
+    ei = graph.data.edge_index.as_tensor().cpu().numpy()
+    v, w = (ei[0], ei[1]) if node_indices else (graph.mapping.to_ids(ei[0]), graph.mapping.to_ids(ei[1]))
+    return pd.DataFrame({"v": v, "w": w, **{a: _attr_list(graph.data[a]) for a in graph.edge_attrs()}})
+
+
+def read_csv_graph(filename: str, sep: str = ",", header: bool = True, is_undirected: bool = False,
+                   multiedges: bool = False, **kwargs: Any) -> Graph:
+    """io/pandas.py:472-508."""
+    df = pd.read_csv(filename, header=0 if header else None, sep=sep)
+    return df_to_graph(df, is_undirected=is_undirected, multiedges=multiedges, **kwargs)
+
+
+def write_csv(graph, node_indices: bool = False, path_or_buf: Any = None, **pdargs: Any) -> None:
+    """io/pandas.py:548-569: the edge table of a graph or temporal graph as csv."""
+    if isinstance(graph, TemporalGraph):
+        frame = temporal_graph_to_df(graph=graph, node_indices=node_indices)
+    else:
+        frame = graph_to_df(graph=graph, node_indices=node_indices)
+    frame.to_csv(index=False, path_or_buf=path_or_buf, **pdargs)
+
+
 def temporal_graph_to_df(graph: TemporalGraph, node_indices: bool = False) -> pd.DataFrame:
     """io/pandas.py:437-471: one row per time-stamped edge, edge attributes as extra columns."""
     ei = graph.data.edge_index.as_tensor().cpu().numpy()
@@ -113,10 +216,7 @@ def temporal_graph_to_df(graph: TemporalGraph, node_indices: bool = False) -> pd
         v, w = graph.mapping.to_ids(ei[0]), graph.mapping.to_ids(ei[1])
     df = pd.DataFrame({"v": v, "w": w, "t": graph.data.time.cpu().numpy()})
     for attr in graph.edge_attrs():
-        if attr in ("edge_index", "time"):
-            continue
-        val = graph.data[attr]
-        df[attr] = val.cpu().numpy().tolist() if isinstance(val, torch.Tensor) else list(val)
+        df[attr] = _attr_list(graph.data[attr])
     return df
 
 

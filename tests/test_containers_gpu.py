@@ -101,3 +101,19 @@ def test_window_views_on_device(cuda):
     u = tg.to_undirected()
     assert (u.n, u.m) == (9, 40) and u.data.is_sorted_by_time()
     assert tg.to_static_graph(weighted=True, time_window=(9, 12)).data.edge_weight.tolist() == [1.0, 1.0, 1.0]
+
+
+def test_df_to_graph_undirected(cuda):  # reference tests/io/test_pandas.py:203-210
+    import pandas as pd
+
+    from pathpyg_b200.io import df_to_graph
+
+    df = pd.DataFrame({"v": ["a", "b", "c"], "w": ["b", "c", "a"], "edge_weight": ["a", "b", "c"]})
+    g = df_to_graph(df, is_undirected=True)
+    assert (g.n, g.m) == (3, 3) and g.is_undirected()
+    assert g.data.edge_index.as_tensor().tolist() == [[0, 0, 1, 1, 2, 2], [1, 2, 0, 2, 0, 1]]
+    assert g.data.edge_weight.tolist() == ["a", "c", "a", "b", "c", "b"]     # text attributes (numpy) follow the edges
+    on_gpu = df_to_graph(pd.DataFrame({"v": [0, 1, 2, 0], "w": [1, 2, 0, 1], "x": [1.0, 2.0, 3.0, 4.0]}), multiedges=True,
+                         is_undirected=True, device=cuda)
+    assert on_gpu.data.edge_index.is_cuda and on_gpu.m == 3
+    assert on_gpu.data.edge_x.tolist() == [1.0, 3.0, 1.0, 2.0, 3.0, 2.0]      # merged (0,1) pair keeps the attribute of its first edge
