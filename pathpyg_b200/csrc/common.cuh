@@ -90,6 +90,17 @@ __device__ __forceinline__ unsigned long long state_load(const unsigned long lon
   return w;
 }
 
+// 32-bit variant for per-tile digit counts (<= 4096): code << 24 | count
+__device__ __forceinline__ void tile_state_store(uint32_t* p, unsigned code, uint32_t value) {
+  const uint32_t w = (code << 24) | (value & 0xffffffu);
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t tile_state_load(const uint32_t* p) {
+  uint32_t w;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(w) : "l"(p) : "memory");
+  return w;
+}
+
 // ---------------------------------------------------------------- warp helpers
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 __device__ __forceinline__ unsigned lanemask_lt() {

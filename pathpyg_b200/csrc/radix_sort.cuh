@@ -14,7 +14,10 @@
 // every digit's run is written out as one contiguous (coalesced) segment.
 //
 // Look-back: thread d owns digit d.  Two levels (tiles inside a group of 16, then groups), every walk with
-// kLookBatch independent loads in flight consumed in order -- see the comment in the kernel.
+// kLookBatch independent loads in flight consumed in order -- see the comment in the kernel.  A tile counts its
+// digits with shared-memory atomics and publishes them BEFORE it ranks its keys: when it looks back after the
+// ranking, its predecessors' counts have long been published and the walk does not poll (B200, 64M (u64, u32)
+// pairs: 559 us per pass against 650 us when the counts were published after the ranking).
 //
 // Tile size: 256 threads x 16 keys (the per-tile fixed costs -- look-back, digit scans, counter reset -- are
 // amortised over 4096 keys); 256 x 8 up to 512K keys, where more tiles fill more SMs.
@@ -47,7 +50,7 @@ constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kSortBlock = 256;  // == kRadix: thread d owns digit d in the per-digit phases
 constexpr int kMaxPasses = 8;
-constexpr int kLookBatch = 8;
+constexpr int kLookBatch = 8;   // look-back words in flight per thread
 constexpr int kLookGroup = 16;  // tiles per look-back group
 constexpr int64_t kSmallSortLimit = 512ll << 10;
 
@@ -162,14 +165,14 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);
   // [NW][256] per-warp digit counts: a warp holds at most 32 * ITEMS <= 512 keys of one digit, a tile 4096: 16 bits
   uint16_t* s_whist = reinterpret_cast<uint16_t*>(s_vals + (HAS_VALUES ? TILE : 0));
-  uint32_t* s_binstart = reinterpret_cast<uint32_t*>(s_whist + NW * kRadix);  // [256] first slot of a digit in the tile
-  long long* s_gbase = reinterpret_cast<long long*>(s_binstart + kRadix);   // [256] global slot of tile slot 0 of a digit
+  long long* s_gbase = reinterpret_cast<long long*>(s_whist + NW * kRadix);  // [256] global slot of tile slot 0 of a digit
   // [NW][2][256] per-warp peer masks of the ranking rounds: they are dead before the tile is reordered, so they
   // live in the buffer the reorder fills (TILE * 8 bytes >= NW * 2 * 256 * 4 for every ITEMS >= 4)
   uint32_t* s_wmask = reinterpret_cast<uint32_t*>(smem_raw);
   __shared__ unsigned s_tile;
   __shared__ unsigned long long s_scan[2 * NW];
   __shared__ unsigned s_next[kRadix];  // digit counts of this tile for the NEXT pass
+  __shared__ unsigned s_cnt[kRadix];   // digit counts of this tile for THIS pass, taken before the ranking
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -181,6 +184,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   }
   for (int i = tid; i < NW * kRadix / 2; i += kSortBlock) reinterpret_cast<uint32_t*>(s_whist)[i] = 0;
   s_next[tid] = 0;
+  s_cnt[tid] = 0;
   if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
   __syncthreads();
   const unsigned tile = s_tile;
@@ -198,26 +202,74 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
     key[i] = idx < n ? ld_stream(keys_in + idx) : static_cast<KeyT>(~static_cast<KeyT>(0));
   }
 
-  // ---- digit counts for the next pass, taken while the keys are in registers: the sort reads its keys once per
-  // pass and never for a histogram of its own (only digit 0 is counted up front).  High digits of small-range keys
-  // are often identical across a warp: one shared-memory atomic instead of 32.
+  // ---- digit counts, taken while the keys are in registers (one shared-memory atomic per key and digit; lanes
+  // that share a digit hit one address, which the shared-memory atomic unit combines -- measured on B200, a
+  // warp-uniformity vote in front of the atomic costs more on random digits than it saves on uniform ones):
+  //  * the NEXT pass's digits -> ghist_next: the sort reads its keys once per pass and never for a histogram of
+  //    its own (only digit 0 is counted up front);
+  //  * THIS pass's digits of the tile -> published BEFORE the ranking.  The ranking yields the same counts, but
+  //    2-3 us later; published early, the counts of a tile's predecessors are long out when it looks back after its
+  //    own ranking, so the look-back no longer polls (the polls were a quarter of the kernel's instructions).
   if (ghist_next != nullptr) {
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
-      const bool valid = warp_base + i * 32 + lane < n;
       const unsigned d1 = static_cast<unsigned>(key[i] >> (shift + kRadixBits)) & (kRadix - 1);
-      const unsigned live = __ballot_sync(kFullMask, valid);
-      if (live == 0) continue;
-      const unsigned d0 = __shfl_sync(kFullMask, d1, __ffs(live) - 1);
-      if (__all_sync(kFullMask, !valid || d1 == d0)) {
-        if (lane == static_cast<unsigned>(__ffs(live) - 1)) atomicAdd(&s_next[d1], static_cast<unsigned>(__popc(live)));
-      } else if (valid) {
-        atomicAdd(&s_next[d1], 1u);
-      }
+      if (warp_base + i * 32 + lane < n) atomicAdd(&s_next[d1], 1u);
     }
   }
+  {
+    const bool full_tile = valid_in_tile == TILE;
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+      const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
+      if (full_tile || warp_base + i * 32 + lane < n) atomicAdd(&s_cnt[d], 1u);
+    }
+  }
+  __syncthreads();
 
-  PPG_TRACE(tile, 1);  // (issue point only: the loads complete at their first use)
+  // ---- two-level decoupled look-back, part 1: publish (thread d owns digit d)
+  // Tiles are grouped by kLookGroup.  A tile sums the partial counts of the earlier tiles of its own group
+  // (all loads independent), the last tile of a group publishes the group aggregate, and the prefix over
+  // earlier groups comes from a look-back over the group words (aggregate -> inclusive, as in single-level
+  // decoupled look-back).  When all tiles of a sort start together (n up to a few million keys: tiles ~ SM
+  // slots) a single-level walk is a dependent chain of ~tiles/16 L2 round trips and reads ~tiles^2/4 words;
+  // here it is <= 2 + groups/8 round trips and <= (kLookGroup + groups) words per tile and digit.
+  const unsigned grp_id = tile / kLookGroup;
+  const bool closes_group = tile % kLookGroup == kLookGroup - 1;
+  unsigned long long* my_group = gstate + static_cast<size_t>(grp_id) * kRadix + tid;
+  const unsigned long long count = s_cnt[tid];  // valid keys of the tile with digit `tid`
+  state_store(state + static_cast<size_t>(tile) * kRadix + tid, code_partial, count);
+  auto sum_group_predecessors = [&]() {  // keys with this digit in the earlier tiles of this group
+    unsigned long long sum = 0;
+    int64_t q = static_cast<int64_t>(tile) - 1;
+    const int64_t stop = static_cast<int64_t>(grp_id) * kLookGroup;
+    while (q >= stop) {
+      unsigned long long w[kLookBatch];
+#pragma unroll
+      for (int j = 0; j < kLookBatch; ++j) {
+        const int64_t qq = q - j;
+        w[j] = qq >= stop ? state_load(state + static_cast<size_t>(qq) * kRadix + tid) : 0ull;
+      }
+      int consumed = 0;
+#pragma unroll
+      for (int j = 0; j < kLookBatch; ++j) {
+        if (consumed == j && q - j >= stop && static_cast<unsigned>(w[j] >> 56) == code_partial) {
+          sum += w[j] & kStateValueMask;
+          consumed = j + 1;
+        }
+      }
+      q -= consumed;  // unpublished words are polled again
+    }
+    return sum;
+  };
+  unsigned long long within = 0;
+  if (closes_group) {
+    // the tile that closes a group sums the group right away, so that the group's aggregate is out early too
+    within = sum_group_predecessors();
+    state_store(my_group, grp_id == 0 ? code_inclusive : code_partial, within + count);
+  }
+
+  PPG_TRACE(tile, 1);
   // ---- stable rank inside the warp, digit counts per warp
   // Lanes holding the same digit find each other through shared memory: every lane ORs its lane bit into the
   // warp's mask word of its digit, the warp synchronises, and the word read back IS the peer set (one RED.OR +
@@ -251,8 +303,8 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
     const unsigned c = s_next[tid];
     if (c) atomicAdd(&ghist_next[tid], static_cast<unsigned long long>(c));
   }
-  // ---- per digit (thread d): exclusive over warps, tile count, publish, look back
-  unsigned long long count = 0;
+  // ---- per digit (thread d): exclusive over warps (the out-of-range slots of the last tile carry all-ones keys:
+  // they sit at the very end of the top digit's run, after every valid slot, and are never written out)
   {
     uint32_t sum = 0;
 #pragma unroll
@@ -261,50 +313,11 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
       s_whist[w * kRadix + tid] = static_cast<uint16_t>(sum);
       sum += t;
     }
-    // out-of-range slots of the last tile were given all-ones keys: they sit at the very end of the
-    // top digit's run (stable order), so dropping them from that count leaves every valid slot intact
-    if (tid == kRadix - 1) sum -= static_cast<uint32_t>(TILE - valid_in_tile);
-    count = sum;
   }
-  // ---- two-level decoupled look-back (thread d owns digit d)
-  // Tiles are grouped by kLookGroup.  A tile sums the partial counts of the earlier tiles of its own group
-  // (all loads independent), the last tile of a group publishes the group aggregate, and the prefix over
-  // earlier groups comes from a look-back over the group words (aggregate -> inclusive, as in single-level
-  // decoupled look-back).  When all tiles of a sort start together (n up to a few million keys: tiles ~ SM
-  // slots) a single-level walk is a dependent chain of ~tiles/16 L2 round trips and reads ~tiles^2/4 words;
-  // here it is <= 2 + groups/8 round trips and <= (kLookGroup + groups) words per tile and digit.
-  const unsigned grp_id = tile / kLookGroup;
-  const unsigned in_grp = tile % kLookGroup;
-  state_store(state + static_cast<size_t>(tile) * kRadix + tid, code_partial, count);
-  unsigned long long within = 0;  // keys with this digit in the earlier tiles of this group
-  {
-    int64_t q = static_cast<int64_t>(tile) - 1;
-    const int64_t stop = static_cast<int64_t>(grp_id) * kLookGroup;
-    while (q >= stop) {
-      unsigned long long w[kLookBatch];
-#pragma unroll
-      for (int j = 0; j < kLookBatch; ++j) {
-        const int64_t qq = q - j;
-        w[j] = qq >= stop ? state_load(state + static_cast<size_t>(qq) * kRadix + tid) : 0ull;
-      }
-      int consumed = 0;
-#pragma unroll
-      for (int j = 0; j < kLookBatch; ++j) {
-        if (consumed == j && q - j >= stop && static_cast<unsigned>(w[j] >> 56) == code_partial) {
-          within += w[j] & kStateValueMask;
-          consumed = j + 1;
-        }
-      }
-      q -= consumed;  // unpublished words are polled again
-    }
-  }
-  const bool closes_group = in_grp == kLookGroup - 1;
-  unsigned long long* my_group = gstate + static_cast<size_t>(grp_id) * kRadix + tid;
+  // ---- look-back, part 2: the predecessors' counts have been out since before their ranking
+  if (!closes_group) within = sum_group_predecessors();
   unsigned long long before_group = 0;  // keys with this digit in earlier groups
-  if (grp_id == 0) {
-    if (closes_group) state_store(my_group, code_inclusive, within + count);
-  } else {
-    if (closes_group) state_store(my_group, code_partial, within + count);
+  if (grp_id != 0) {
     int64_t q = static_cast<int64_t>(grp_id) - 1;
     bool done = false;
     while (!done) {
@@ -355,7 +368,9 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
     }
     const unsigned long long bin_start = oa + a - count;
     const unsigned long long out_start = ob + b - g;
-    s_binstart[tid] = static_cast<uint32_t>(bin_start);
+    // the digit's first slot goes into the per-warp offsets: one look-up per key in the reorder instead of two
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s_whist[w * kRadix + tid] = static_cast<uint16_t>(s_whist[w * kRadix + tid] + bin_start);
     s_gbase[tid] = static_cast<long long>(out_start + prev) - static_cast<long long>(bin_start);
   }
   __syncthreads();
@@ -366,7 +381,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   for (int i = 0; i < ITEMS; ++i) {
     const unsigned d = static_cast<unsigned>(key[i] >> shift) & (kRadix - 1);
     const uint32_t r = (i & 1) ? (rank2[i >> 1] >> 16) : (rank2[i >> 1] & 0xffffu);
-    const uint32_t pos = s_binstart[d] + my_hist[d] + r;
+    const uint32_t pos = my_hist[d] + r;
     rank2[i >> 1] = (i & 1) ? ((rank2[i >> 1] & 0xffffu) | (pos << 16)) : ((rank2[i >> 1] & 0xffff0000u) | pos);
     s_keys[pos] = key[i];
   }
@@ -396,7 +411,7 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
 template <typename KeyT, bool HAS_VALUES, int ITEMS>
 constexpr size_t onesweep_smem_bytes() {
   return static_cast<size_t>(kSortBlock * ITEMS) * sizeof(KeyT) + (HAS_VALUES ? kSortBlock * ITEMS * sizeof(uint32_t) : 0) +
-         (kSortBlock / 32) * kRadix * sizeof(uint16_t) + kRadix * sizeof(uint32_t) + kRadix * sizeof(long long);
+         (kSortBlock / 32) * kRadix * sizeof(uint16_t) + kRadix * sizeof(long long);
 }
 
 template <typename KeyT, bool HAS_VALUES, bool IOTA, int ITEMS>

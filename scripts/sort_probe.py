@@ -15,7 +15,10 @@ def main():
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     g = torch.Generator().manual_seed(0)
     for n in sizes:
-        base = torch.randint(0, 1 << bits, (n,), generator=g).to(dev)
+        base = torch.randint(0, 1 << bits, (n,), generator=g)
+        if os.environ.get("PROBE_SORTED"):  # already ordered input: the high digits are uniform across a warp
+            base = torch.sort(base).values
+        base = base.to(dev)
         per = []
         for it in range(6):
             keys = base.clone()
