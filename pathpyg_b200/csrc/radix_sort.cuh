@@ -150,6 +150,15 @@ struct SortMinCtas {
   static constexpr int value = ITEMS >= 16 ? PPG_SORT_CTAS16 : 4;
 };
 
+// bytes of the buffer the tile is reordered through; the peer-mask words of the ranking ([NW][2][256] u32) live in
+// it before that, so it is at least as large as they are (only a keys-only sort of small 32-bit tiles is smaller)
+template <typename KeyT, bool HAS_VALUES, int ITEMS>
+constexpr size_t onesweep_reorder_bytes() {
+  constexpr size_t tile = static_cast<size_t>(kSortBlock * ITEMS) * (sizeof(KeyT) + (HAS_VALUES ? sizeof(uint32_t) : 0));
+  constexpr size_t masks = static_cast<size_t>(kSortBlock / 32) * 2 * kRadix * sizeof(uint32_t);
+  return tile > masks ? tile : masks;
+}
+
 template <typename KeyT, bool HAS_VALUES, bool IOTA, int ITEMS, int MIN_CTAS>
 __global__ void __launch_bounds__(kSortBlock, MIN_CTAS)
 onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
@@ -164,10 +173,10 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
   KeyT* s_keys = reinterpret_cast<KeyT*>(smem_raw);
   uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + TILE);
   // [NW][256] per-warp digit counts: a warp holds at most 32 * ITEMS <= 512 keys of one digit, a tile 4096: 16 bits
-  uint16_t* s_whist = reinterpret_cast<uint16_t*>(s_vals + (HAS_VALUES ? TILE : 0));
+  uint16_t* s_whist = reinterpret_cast<uint16_t*>(smem_raw + onesweep_reorder_bytes<KeyT, HAS_VALUES, ITEMS>());
   long long* s_gbase = reinterpret_cast<long long*>(s_whist + NW * kRadix);  // [256] global slot of tile slot 0 of a digit
   // [NW][2][256] per-warp peer masks of the ranking rounds: they are dead before the tile is reordered, so they
-  // live in the buffer the reorder fills (TILE * 8 bytes >= NW * 2 * 256 * 4 for every ITEMS >= 4)
+  // live in the buffer the reorder fills (onesweep_reorder_bytes is never smaller than they are)
   uint32_t* s_wmask = reinterpret_cast<uint32_t*>(smem_raw);
   __shared__ unsigned s_tile;
   __shared__ unsigned long long s_scan[2 * NW];
@@ -410,8 +419,8 @@ onesweep_pass_kernel(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_o
 
 template <typename KeyT, bool HAS_VALUES, int ITEMS>
 constexpr size_t onesweep_smem_bytes() {
-  return static_cast<size_t>(kSortBlock * ITEMS) * sizeof(KeyT) + (HAS_VALUES ? kSortBlock * ITEMS * sizeof(uint32_t) : 0) +
-         (kSortBlock / 32) * kRadix * sizeof(uint16_t) + kRadix * sizeof(long long);
+  return onesweep_reorder_bytes<KeyT, HAS_VALUES, ITEMS>() + (kSortBlock / 32) * kRadix * sizeof(uint16_t) +
+         kRadix * sizeof(long long);
 }
 
 template <typename KeyT, bool HAS_VALUES, bool IOTA, int ITEMS>
