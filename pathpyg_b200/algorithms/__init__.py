@@ -4,7 +4,9 @@ from .lift_order import (
     lift_order_edge_index,
     lift_order_edge_index_weighted,
 )
-from .centrality import temporal_betweenness_centrality, temporal_closeness_centrality
+from .centrality import (map_to_nodes, path_node_traversals, path_visitation_probabilities,
+                         temporal_betweenness_centrality, temporal_closeness_centrality)
+from .rolling_time_window import RollingTimeWindow
 from .temporal import lift_order_temporal, temporal_shortest_paths
 
 __all__ = [
@@ -16,4 +18,8 @@ __all__ = [
     "temporal_shortest_paths",
     "temporal_closeness_centrality",
     "temporal_betweenness_centrality",
+    "path_node_traversals",
+    "path_visitation_probabilities",
+    "map_to_nodes",
+    "RollingTimeWindow",
 ]

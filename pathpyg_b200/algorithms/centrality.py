@@ -3,7 +3,27 @@ the shortest time-respecting path distances, and ``temporal_betweenness_centrali
 dependency accumulation over the event DAG."""
 from __future__ import annotations
 
+import torch
+
 from .. import _staging, ops
+
+
+def path_node_traversals(paths) -> dict:
+    """How often the walks of a ``PathData`` object pass each node (centrality.py:50-57): ``{node id: visits}``."""
+    nodes, visits = torch.unique(paths.data.node_sequence, return_counts=True)
+    return {paths.mapping.to_id(v): c for v, c in zip(nodes.tolist(), visits.tolist())}
+
+
+def path_visitation_probabilities(paths) -> dict:
+    """Share of all node visits that falls on each node (centrality.py:134-161)."""
+    visits = path_node_traversals(paths)
+    total = float(sum(visits.values()))
+    return {v: c / total for v, c in visits.items()}
+
+
+def map_to_nodes(graph, centralities: dict) -> dict:
+    """Re-key ``{node index: value}`` by node id (centrality.py:60-76)."""
+    return {graph.mapping.to_id(i): centralities[i] for i in centralities}
 
 
 def temporal_closeness_centrality(graph, delta: int) -> dict:

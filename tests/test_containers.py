@@ -208,3 +208,24 @@ def test_temporal_ctor_orders_numpy_edge_attributes():
     g = TemporalGraph(d)
     assert g.data.time.tolist() == [1, 3, 5] and g.data.edge_label.tolist() == ["y", "z", "x"]
     assert g.data.edge_w.tolist() == [2.0, 3.0, 1.0]
+
+
+# ---- callers of the containers ----------------------------------------------------------------------------------
+def test_rolling_time_window(long_temporal_graph):  # tests/algorithms/test_rolling_time_window.py:6-20
+    # (unweighted snapshots: the weighted ones merge edges on the GPU; no window of this fixture repeats an edge)
+    r = pp.algorithms.RollingTimeWindow(long_temporal_graph, 10, 10, False, weighted=False)
+    assert [(g.n, g.m) for g in r] == [(5, 4), (7, 3), (8, 6), (8, 3), (9, 4)]
+    r = pp.algorithms.RollingTimeWindow(long_temporal_graph, 10, 20, return_window=True, weighted=False)
+    assert [w for _, w in r] == [(1, 11), (21, 31), (41, 51)]
+
+
+def test_path_visit_statistics():  # tests/algorithms/test_centrality.py:22-42 with tests/algorithms/conftest.py:49-55
+    paths = pp.PathData(mapping=IndexMap(["A", "B", "C", "D", "E", "F"]))
+    for walk in (("C", "B", "D", "F"), ("A", "B", "D"), ("D", "E")):
+        paths.append_walk(walk, weight=1.0)
+    assert pp.algorithms.path_node_traversals(paths) == {"A": 1, "B": 2, "C": 1, "D": 3, "E": 1, "F": 1}
+    prob = pp.algorithms.path_visitation_probabilities(paths)
+    assert prob == {"A": 1 / 9, "B": 2 / 9, "C": 1 / 9, "D": 3 / 9, "E": 1 / 9, "F": 1 / 9}
+    g = Graph.from_edge_list([("a", "b"), ("b", "c")])
+    assert pp.algorithms.map_to_nodes(g, {0: 0.5, 2: 0.3}) == {"a": 0.5, "c": 0.3}
+    assert pp.utils.to_numpy(g.data.edge_index).tolist() == [[0, 1], [1, 2]] and pp.utils.to_numpy([1, 2]).tolist() == [1, 2]
