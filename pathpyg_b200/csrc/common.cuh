@@ -146,4 +146,20 @@ inline int grid_for(int64_t work_items, int per_block, int max_blocks = kNumSMsB
   return static_cast<int>(g);
 }
 
+// development aid: per-tile phase time stamps (globaltimer, ns) of the onesweep digit passes and of the fused
+// GCN layer; enabled with -DPPG_SORT_TRACE (make trace), read with scripts/sort_trace.py / scripts/gcn_trace.py
+#ifdef PPG_SORT_TRACE
+extern __device__ unsigned long long* g_sort_trace;  // [tiles][8]
+__device__ __forceinline__ void sort_trace(unsigned tile, int slot) {
+  if (threadIdx.x == 0 && g_sort_trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_sort_trace[static_cast<size_t>(tile) * 8 + slot] = t;
+  }
+}
+#define PPG_TRACE(tile, slot) sort_trace(tile, slot)
+#else
+#define PPG_TRACE(tile, slot)
+#endif
+
 }  // namespace ppg

@@ -198,6 +198,7 @@ gcn_tc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ sr
   const int64_t num_tiles = ceil_div(n, kTcTile);
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * kTcTile;
+    PPG_TRACE(static_cast<unsigned>(tile), 0);
 
     // ---------------- phase 1: segment-reduce the incoming rows of 128 target nodes (see gcn_fused.cu)
     if (tid <= kTcTile) {
@@ -296,6 +297,7 @@ gcn_tc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ sr
     // generic-proxy writes of the operands -> visible to the tensor core (async proxy)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    PPG_TRACE(static_cast<unsigned>(tile), 1);  // rows gathered
 
     // ---------------- phase 2: D[128 x H] (TMEM) = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T, one issuing thread
     if (tid == 0) {
@@ -317,6 +319,7 @@ gcn_tc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ sr
     mbar_wait(mbar, parity);
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    PPG_TRACE(static_cast<unsigned>(tile), 2);  // product in TMEM
 
     // ---------------- epilogue: TMEM -> registers (thread = one row, CPT consecutive columns) -> bias + act ->
     // shared memory (the operand buffers are idle once the MMAs have completed) -> coalesced 16-byte stores
@@ -349,6 +352,7 @@ gcn_tc_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ sr
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();  // TMEM tile and operand buffers are free for the next tile
+    PPG_TRACE(static_cast<unsigned>(tile), 3);  // tile written
   }
 
   if (warp == 0) {

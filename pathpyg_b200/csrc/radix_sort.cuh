@@ -31,21 +31,6 @@
 
 namespace ppg {
 
-// development aid: per-tile phase time stamps (globaltimer, ns) of the digit passes; enabled with -DPPG_SORT_TRACE
-#ifdef PPG_SORT_TRACE
-extern __device__ unsigned long long* g_sort_trace;  // [tiles][8]
-__device__ __forceinline__ void sort_trace(unsigned tile, int slot) {
-  if (threadIdx.x == 0 && g_sort_trace != nullptr) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_sort_trace[static_cast<size_t>(tile) * 8 + slot] = t;
-  }
-}
-#define PPG_TRACE(tile, slot) sort_trace(tile, slot)
-#else
-#define PPG_TRACE(tile, slot)
-#endif
-
 constexpr int kRadixBits = 8;
 constexpr int kRadix = 1 << kRadixBits;
 constexpr int kSortBlock = 256;  // == kRadix: thread d owns digit d in the per-digit phases
