@@ -229,3 +229,23 @@ def test_path_visit_statistics():  # tests/algorithms/test_centrality.py:22-42 w
     g = Graph.from_edge_list([("a", "b"), ("b", "c")])
     assert pp.algorithms.map_to_nodes(g, {0: 0.5, 2: 0.3}) == {"a": 0.5, "c": 0.3}
     assert pp.utils.to_numpy(g.data.edge_index).tolist() == [[0, 1], [1, 2]] and pp.utils.to_numpy([1, 2]).tolist() == [1, 2]
+
+
+def test_add_higher_order_graphs():  # tests/core/test_graph.py:360-368 (layers built by hand: the lift itself needs the GPU)
+    base = IndexMap(["A", "B", "C", "D", "E"])
+    ns = torch.tensor([[0, 2], [1, 2], [2, 3], [2, 4]])   # order-2 nodes of the walks A-C-D, B-C-E
+
+    def layer(weight):
+        d = pp.Data(edge_index=torch.tensor([[0, 1], [2, 3]]), num_nodes=4, node_sequence=ns.clone(),
+                    edge_weight=torch.tensor(weight), inverse_idx=torch.tensor([0, 2, 0, 2, 1, 3, 1, 3]))
+        return Graph(d, mapping=pp.HigherOrderIndexMap(base, ns))
+
+    g1, g2 = layer([2.0, 2.0]), layer([4.0, 4.0])
+    g = g1 + g2
+    assert (g.n, g.m, g.order) == (4, 4, 2)
+    assert g.nodes == [("A", "C"), ("B", "C"), ("C", "D"), ("C", "E")]
+    half = g1.data.inverse_idx.size(0)
+    assert (g.mapping.to_ids(g.data.inverse_idx[:half]) == g1.mapping.to_ids(g1.data.inverse_idx)).all()
+    assert (g.mapping.to_ids(g.data.inverse_idx[half:]) == g2.mapping.to_ids(g2.data.inverse_idx)).all()
+    assert g.data.edge_weight.tolist() == [2.0, 4.0, 2.0, 4.0]
+    assert g.successors(("A", "C")) == [("C", "D"), ("C", "D")]
