@@ -6,6 +6,8 @@ from .lift_order import (
 )
 from .centrality import (map_to_nodes, path_node_traversals, path_visitation_probabilities,
                          temporal_betweenness_centrality, temporal_closeness_centrality)
+from . import centrality, shortest_paths
+from .components import connected_components, largest_connected_component
 from .rolling_time_window import RollingTimeWindow
 from .temporal import lift_order_temporal, temporal_shortest_paths
 
@@ -22,4 +24,8 @@ __all__ = [
     "path_visitation_probabilities",
     "map_to_nodes",
     "RollingTimeWindow",
+    "centrality",
+    "shortest_paths",
+    "connected_components",
+    "largest_connected_component",
 ]

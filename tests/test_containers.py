@@ -249,3 +249,44 @@ def test_add_higher_order_graphs():  # tests/core/test_graph.py:360-368 (layers 
     assert (g.mapping.to_ids(g.data.inverse_idx[half:]) == g2.mapping.to_ids(g2.data.inverse_idx)).all()
     assert g.data.edge_weight.tolist() == [2.0, 4.0, 2.0, 4.0]
     assert g.successors(("A", "C")) == [("C", "D"), ("C", "D")]
+
+
+def _both_ways(edges):
+    return Graph.from_edge_list(edges + [(w, v) for v, w in edges], is_undirected=True)   # = to_undirected() without the GPU
+
+
+TWO_PARTS = [("a", "b"), ("b", "c"), ("c", "a"), ("d", "e"), ("e", "f"), ("f", "g"), ("g", "d"), ("d", "f")]
+
+
+def test_static_hop_distances():  # tests/algorithms/test_shortest_paths.py:8-24
+    from pathpyg_b200.algorithms.shortest_paths import avg_path_length, diameter, shortest_paths_dijkstra
+
+    g = _both_ways([("a", "b"), ("b", "c"), ("c", "e"), ("b", "d"), ("d", "e")])
+    dist, pred = shortest_paths_dijkstra(g)
+    assert dist.tolist() == [[0, 1, 2, 2, 3], [1, 0, 1, 1, 2], [2, 1, 0, 2, 1], [2, 1, 2, 0, 1], [3, 2, 1, 1, 0]]
+    for i in range(5):
+        for j in range(5):
+            if i != j:
+                assert dist[i, j] == dist[i, pred[i, j]] + 1
+    assert diameter(g) == 3 and avg_path_length(g) == 1.6
+
+
+def test_connected_components():  # tests/algorithms/test_components.py:9-95
+    from pathpyg_b200.algorithms import connected_components, largest_connected_component
+
+    count, labels = connected_components(_both_ways(TWO_PARTS))
+    assert count == 2 and labels.tolist() == [0, 0, 0, 1, 1, 1, 1]
+    lcc = largest_connected_component(_both_ways(TWO_PARTS))
+    assert lcc.n == 4 and set(lcc.mapping.node_ids) == {"d", "e", "f", "g"} and lcc.is_undirected()
+    bridged = TWO_PARTS + [("c", "d")]
+    count, labels = connected_components(_both_ways(bridged))
+    assert count == 1 and labels.tolist() == [0] * 7
+    g = Graph.from_edge_list(bridged)
+    assert connected_components(g, connection="weak")[0] == 1
+    count, labels = connected_components(g, connection="strong")
+    assert count == 2 and labels.tolist() == [1, 1, 1, 0, 0, 0, 0]
+    assert largest_connected_component(g, connection="weak").n == 7
+    strong = largest_connected_component(g, connection="strong")
+    assert strong.n == 4 and set(strong.mapping.node_ids) == {"d", "e", "f", "g"}
+    count, labels = connected_components(Graph.from_edge_list(TWO_PARTS), connection="weak")
+    assert count == 2 and labels.tolist() == [0, 0, 0, 1, 1, 1, 1]
