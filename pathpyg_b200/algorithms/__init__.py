@@ -4,7 +4,7 @@ from .lift_order import (
     lift_order_edge_index,
     lift_order_edge_index_weighted,
 )
-from .centrality import (map_to_nodes, path_node_traversals, path_visitation_probabilities,
+from .centrality import (betweenness_centrality, map_to_nodes, path_node_traversals, path_visitation_probabilities,
                          temporal_betweenness_centrality, temporal_closeness_centrality)
 from . import centrality, shortest_paths
 from .components import connected_components, largest_connected_component
@@ -23,6 +23,7 @@ __all__ = [
     "path_node_traversals",
     "path_visitation_probabilities",
     "map_to_nodes",
+    "betweenness_centrality",
     "RollingTimeWindow",
     "centrality",
     "shortest_paths",

@@ -21,6 +21,83 @@ def path_visitation_probabilities(paths) -> dict:
     return {v: c / total for v, c in visits.items()}
 
 
+def betweenness_centrality(graph, sources: list | None = None) -> dict:
+    """Unnormalised betweenness of a static graph over shortest (hop) paths, Brandes' accumulation as the reference
+    states it (centrality.py:79-131; parallel edges count as separate paths, and a node's dependency is weighted by
+    its number of shortest-path predecessor edges).
+    Level-synchronous on the host: every BFS level and every dependency step is one sparse matrix-vector product.
+    Nodes that no source reaches are absent from the returned ``defaultdict`` (they read 0.0)."""
+    from collections import defaultdict
+
+    import numpy as np
+
+    n = graph.n
+    adj = graph.sparse_adj_matrix().tocsr()          # duplicates summed: entry = number of parallel edges
+    adj_t = adj.T.tocsr()
+    total = np.zeros(n)
+    touched = np.zeros(n, dtype=bool)
+    for s in (range(n) if sources is None else [graph.mapping.to_idx(v) for v in sources]):
+        level = np.full(n, -1)
+        sigma = np.zeros(n)
+        level[s], sigma[s] = 0, 1.0
+        frontier, depth = np.zeros(n), 0
+        frontier[s] = 1.0
+        while True:
+            reach = adj_t @ frontier                   # path counts handed to the next level
+            new = (reach > 0) & (level < 0)
+            if not new.any():
+                break
+            depth += 1
+            level[new] = depth
+            sigma[new] = reach[new]
+            frontier = np.where(new, sigma, 0.0)
+        delta = np.zeros(n)
+        for d in range(depth - 1, -1, -1):
+            carry = np.where(level == d + 1, (1.0 + delta) / np.where(sigma > 0, sigma, 1.0), 0.0)
+            here = level == d
+            delta[here] = sigma[here] * (adj @ carry)[here]
+        reached = level > 0
+        # the reference adds a node's dependency once per predecessor EDGE on a shortest path (the update sits inside
+        # its loop over the predecessor list, centrality.py:126-129), not once per source as in Brandes' paper
+        pred_edges = np.zeros(n)
+        for d in range(1, depth + 1):
+            here = level == d
+            pred_edges[here] = (adj_t @ (level == d - 1).astype(float))[here]
+        total[reached] += delta[reached] * pred_edges[reached]
+        touched |= reached
+    out = defaultdict(lambda: 0.0)
+    for i in np.flatnonzero(touched):
+        out[graph.mapping.to_id(int(i))] = float(total[i])
+    return out
+
+
+def __getattr__(name: str):
+    """Any other ``*centrality*`` function is networkx's, applied to the graph's edges and re-keyed by node id
+    (centrality.py:327-356)."""
+    if name.startswith("__"):
+        raise AttributeError(name)
+
+    def delegate(*args, **kwargs):
+        import networkx as nx
+
+        from ..core.graph import Graph
+        from ..core.temporal_graph import TemporalGraph
+
+        if len(args) == 0:
+            raise RuntimeError(f"Did not find method {name} with no arguments")
+        if isinstance(args[0], TemporalGraph):
+            raise NotImplementedError(f"Missing implementation of {name} for temporal graphs")
+        if not isinstance(args[0], Graph):
+            raise RuntimeError(f"Did not find method {name} that accepts first argument of type {type(args[0])}")
+        g = nx.DiGraph()
+        g.add_nodes_from(range(args[0].n))
+        g.add_edges_from(args[0].data.edge_index.as_tensor().t().cpu().tolist())
+        result = getattr(nx.algorithms.centrality, name)(g, *args[1:], **kwargs)
+        return map_to_nodes(args[0], result) if "centrality" in name and isinstance(result, dict) else result
+
+    return delegate
+
+
 def map_to_nodes(graph, centralities: dict) -> dict:
     """Re-key ``{node index: value}`` by node id (centrality.py:60-76)."""
     return {graph.mapping.to_id(i): centralities[i] for i in centralities}

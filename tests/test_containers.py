@@ -290,3 +290,48 @@ def test_connected_components():  # tests/algorithms/test_components.py:9-95
     assert strong.n == 4 and set(strong.mapping.node_ids) == {"d", "e", "f", "g"}
     count, labels = connected_components(Graph.from_edge_list(TWO_PARTS), connection="weak")
     assert count == 2 and labels.tolist() == [0, 0, 0, 1, 1, 1, 1]
+
+
+def _reference_betweenness(g):
+    """Restatement of the reference's loop (algorithms/centrality.py:100-131) for the check below."""
+    from collections import defaultdict
+
+    bw = defaultdict(float)
+    for s in range(g.n):
+        order, preds, sigma, dist, queue = [], defaultdict(list), defaultdict(int), defaultdict(lambda: -1), [s]
+        sigma[s], dist[s] = 1, 0
+        while queue:
+            v = queue.pop(0)
+            order.append(v)
+            for w in g.get_successors(v).tolist():
+                if dist[w] < 0:
+                    queue.append(w)
+                    dist[w] = dist[v] + 1
+                if dist[w] == dist[v] + 1:
+                    sigma[w] += sigma[v]
+                    preds[w].append(v)
+        delta = defaultdict(float)
+        while order:
+            w = order.pop()
+            for v in preds[w]:
+                delta[v] += sigma[v] / sigma[w] * (1 + delta[w])
+                bw[w] = bw[w] + delta[w]
+    return bw
+
+
+def test_static_centralities():  # tests/algorithms/test_centrality.py:12-19
+    from pathpyg_b200.algorithms import centrality
+
+    triangle = _both_ways([("a", "b"), ("b", "c"), ("a", "c")])
+    assert centrality.betweenness_centrality(triangle) == {"a": 0.0, "b": 0.0, "c": 0.0}
+    assert centrality.closeness_centrality(triangle) == {"a": 1.0, "b": 1.0, "c": 1.0}       # networkx, re-keyed by node id
+    with pytest.raises(NotImplementedError):
+        centrality.closeness_centrality(TemporalGraph.from_edge_list(LONG))
+    for seed, (n, e) in enumerate([(30, 120), (50, 100), (12, 80)]):     # multigraphs with self-loops
+        gen = torch.Generator().manual_seed(seed)
+        g = Graph.from_edge_index(torch.randint(0, n, (2, e), generator=gen), num_nodes=n)
+        want, got = _reference_betweenness(g), centrality.betweenness_centrality(g)
+        assert set(want) == set(got)
+        assert all(abs(want[k] - got[k]) <= 1e-9 * max(1.0, abs(want[k])) for k in want)
+    line = Graph.from_edge_list([("a", "b"), ("b", "c"), ("c", "d")])
+    assert centrality.betweenness_centrality(line, sources=["a"]) == {"b": 2.0, "c": 1.0, "d": 0.0}
