@@ -209,7 +209,10 @@ class Data:
         out = copy.copy(self)
         for k in self.edge_attrs():
             v = self.__dict__[k]
-            out.__dict__[k] = v[:, perm] if k == "edge_index" else v[perm]
+            if k == "edge_index":
+                out.__dict__[k] = v[:, perm]
+            else:
+                out.__dict__[k] = v[perm] if isinstance(v, torch.Tensor) else v[perm.cpu().numpy()]
         return out
 
     # ---- device
