@@ -9,6 +9,7 @@ from .centrality import (betweenness_centrality, map_to_nodes, path_node_travers
 from . import centrality, shortest_paths
 from .components import connected_components, largest_connected_component
 from .rolling_time_window import RollingTimeWindow
+from .weisfeiler_leman import WeisfeilerLeman_test
 from .temporal import lift_order_temporal, temporal_shortest_paths
 
 __all__ = [
@@ -29,4 +30,5 @@ __all__ = [
     "shortest_paths",
     "connected_components",
     "largest_connected_component",
+    "WeisfeilerLeman_test",
 ]

@@ -335,3 +335,55 @@ def test_static_centralities():  # tests/algorithms/test_centrality.py:12-19
         assert all(abs(want[k] - got[k]) <= 1e-9 * max(1.0, abs(want[k])) for k in want)
     line = Graph.from_edge_list([("a", "b"), ("b", "c"), ("c", "d")])
     assert centrality.betweenness_centrality(line, sources=["a"]) == {"b": 2.0, "c": 1.0, "d": 0.0}
+
+
+def test_weisfeiler_leman():  # tests/algorithms/test_wl.py:7-66
+    from pathpyg_b200.algorithms import WeisfeilerLeman_test
+
+    same, c1, c2 = WeisfeilerLeman_test(Graph.from_edge_list([("a", "b"), ("b", "c")]), Graph.from_edge_list([("y", "z"), ("x", "y")]))
+    assert same is True and c1 == c2
+    same, c1, c2 = WeisfeilerLeman_test(Graph.from_edge_list([("a", "b"), ("b", "c")]), Graph.from_edge_list([("y", "z"), ("x", "z")]))
+    assert same is False and c1 != c2
+    cube_a = _both_ways([("a", "g"), ("a", "h"), ("a", "i"), ("b", "g"), ("b", "h"), ("b", "j"), ("c", "g"), ("c", "i"), ("c", "j"),
+                         ("d", "h"), ("d", "i"), ("d", "j")])
+    cube_b = _both_ways([("1", "2"), ("1", "5"), ("1", "4"), ("2", "6"), ("2", "3"), ("3", "7"), ("3", "4"), ("4", "8"), ("5", "6"),
+                         ("6", "7"), ("7", "8"), ("8", "5")])
+    same, c1, c2 = WeisfeilerLeman_test(cube_a, cube_b)
+    assert same is True and c1 == c2
+    with pytest.raises(Exception, match="must not overlap"):
+        WeisfeilerLeman_test(cube_a, cube_a)
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).available(), reason="/root/reference not mounted")
+def test_weisfeiler_leman_matches_reference_source():
+    """The reference's own weisfeiler_leman.py, executed on these containers, returns the same triple."""
+    import importlib.util
+    import sys
+    import types
+
+    from oracle import ref_loader
+    from pathpyg_b200.algorithms import WeisfeilerLeman_test
+
+    stubs = {"pathpyG": types.ModuleType("pathpyG"), "pathpyG.core": types.ModuleType("pathpyG.core"),
+             "pathpyG.core.graph": types.ModuleType("pathpyG.core.graph")}
+    stubs["pathpyG.core.graph"].Graph = Graph
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location(
+            "_ref_wl", ref_loader.REFERENCE_ROOT + "/src/pathpyG/algorithms/weisfeiler_leman.py")
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    for seed in range(12):
+        gen = torch.Generator().manual_seed(seed)
+        e1 = torch.randint(0, 8, (2, 14), generator=gen)
+        e2 = torch.randperm(8, generator=gen)[e1] if seed % 2 == 0 else torch.randint(0, 8, (2, 14), generator=gen)
+        g1 = Graph.from_edge_index(e1, mapping=IndexMap([f"a{i}" for i in range(8)]), num_nodes=8)
+        g2 = Graph.from_edge_index(e2, mapping=IndexMap([f"b{i}" for i in range(8)]), num_nodes=8)
+        assert ref.WeisfeilerLeman_test(g1, g2) == WeisfeilerLeman_test(g1, g2)
