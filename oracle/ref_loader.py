@@ -392,3 +392,47 @@ def container_methods():
 
         _cache["containers"] = (make_self, methods)
     return _cache["containers"]
+
+
+# ----------------------------------------------------------------------------------------------
+# drop-in check: reference modules that only need the containers, executed ON this package's containers
+# ----------------------------------------------------------------------------------------------
+def reference_module_on(package, rel_path: str, name: str):
+    """Execute one of the reference's own modules (``rel_path`` under ``src/pathpyG/``) with ``pathpyG.*`` imports
+    resolved to ``package`` (= ``pathpyg_b200``): the module's functions then run on this package's ``Graph`` /
+    ``TemporalGraph`` / ``PathData``.  Third-party imports the module makes but the compared functions do not need
+    (``torch_geometric``, ``tqdm``) are stubbed."""
+    stubs = {}
+
+    def mod(modname, **attrs):
+        m = types.ModuleType(modname)
+        m.__dict__.update(attrs)
+        stubs[modname] = m
+        return m
+
+    mod("pathpyG", Graph=package.Graph, TemporalGraph=package.TemporalGraph, PathData=package.PathData, IndexMap=package.IndexMap)
+    mod("pathpyG.core")
+    mod("pathpyG.core.graph", Graph=package.Graph)
+    mod("pathpyG.core.temporal_graph", TemporalGraph=package.TemporalGraph)
+    mod("pathpyG.core.path_data", PathData=package.PathData)
+    mod("pathpyG.core.index_map", IndexMap=package.IndexMap)
+    mod("pathpyG.utils", to_numpy=package.utils.to_numpy)
+    mod("pathpyG.algorithms")
+    mod("pathpyG.algorithms.temporal", lift_order_temporal=package.algorithms.lift_order_temporal,
+        temporal_shortest_paths=package.algorithms.temporal_shortest_paths)
+    mod("torch_geometric")
+    mod("torch_geometric.utils", to_networkx=None, degree=pyg.degree)
+    mod("tqdm", tqdm=lambda it, *a, **k: it)
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REFERENCE_ROOT, "src/pathpyG", rel_path))
+        module = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(module)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return module
