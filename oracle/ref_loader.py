@@ -417,6 +417,8 @@ def reference_module_on(package, rel_path: str, name: str):
     mod("pathpyG.core.path_data", PathData=package.PathData)
     mod("pathpyG.core.index_map", IndexMap=package.IndexMap)
     mod("pathpyG.utils", to_numpy=package.utils.to_numpy)
+    mod("pathpyG.utils.convert", to_numpy=package.utils.to_numpy)
+    mod("torch_geometric.data", Data=package.Data)
     mod("pathpyG.algorithms")
     mod("pathpyG.algorithms.temporal", lift_order_temporal=package.algorithms.lift_order_temporal,
         temporal_shortest_paths=package.algorithms.temporal_shortest_paths)

@@ -70,3 +70,53 @@ def test_rolling_time_window_unweighted():
     assert len(want) == len(got) == 10
     for (a, wa), (b, wb) in zip(want, got):
         assert wa == wb and torch.equal(a.data.edge_index.as_tensor(), b.data.edge_index.as_tensor())
+
+
+def _same_graph(a, b):
+    assert a.n == b.n and a.m == b.m and a.mapping == b.mapping
+    assert torch.equal(a.data.edge_index.as_tensor(), b.data.edge_index.as_tensor())
+    assert sorted(a.edge_attrs()) == sorted(b.edge_attrs()) and sorted(a.node_attrs()) == sorted(b.node_attrs())
+    for k in a.edge_attrs() + a.node_attrs():
+        x, y = a.data[k], b.data[k]
+        assert type(x) is type(y)
+        assert torch.equal(x, y) if isinstance(x, torch.Tensor) else np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("strings, multi", [(True, False), (False, True), (True, True)])
+def test_reference_io_module_on_containers(strings, multi, tmp_path):
+    """The reference's io/pandas.py building THIS package's Graph / TemporalGraph, against this package's io functions."""
+    import pandas as pd
+
+    ref = ref_loader.reference_module_on(pp, "io/pandas.py", "_ref_io_on_containers")
+    rng = np.random.default_rng(11)
+    v, w = rng.integers(0, 25, 300), rng.integers(0, 25, 300)
+    if strings:
+        v, w = np.array([f"n{x:02d}" for x in v]), np.array([f"n{x:02d}" for x in w])
+    df = pd.DataFrame({"v": v, "w": w, "weight": rng.integers(1, 9, 300).astype(float), "edge_tag": rng.integers(0, 5, 300),
+                       "label": [f"l{x}" for x in rng.integers(0, 4, 300)], "vec": [str([int(x), int(x) + 1]) for x in rng.integers(0, 9, 300)]})
+    want, got = ref.df_to_graph(df.copy(), multiedges=multi), pp.io.df_to_graph(df.copy(), multiedges=multi)
+    _same_graph(want, got)
+    assert ref.graph_to_df(want).equals(pp.io.graph_to_df(got))
+    assert ref.graph_to_df(want, node_indices=True).equals(pp.io.graph_to_df(got, node_indices=True))
+    nodes = pd.DataFrame({"v": list(got.nodes), "score": rng.random(got.n), "node_kind": rng.integers(0, 3, got.n)}).sample(frac=1.0, random_state=1)
+    ref.add_node_attributes(nodes.copy(), want)
+    pp.io.add_node_attributes(nodes.copy(), got)
+    _same_graph(want, got)
+    if not multi:
+        edges = ref.graph_to_df(want)[["v", "w"]].copy()
+        edges["flow"] = rng.random(len(edges))
+        ref.add_edge_attributes(edges.copy(), want)
+        pp.io.add_edge_attributes(edges.copy(), got)
+        _same_graph(want, got)
+    ref.write_csv(want, path_or_buf=tmp_path / "a.csv")
+    pp.io.write_csv(got, path_or_buf=tmp_path / "b.csv")
+    assert (tmp_path / "a.csv").read_text() == (tmp_path / "b.csv").read_text()
+    if strings:
+        _same_graph(ref.read_csv_graph(str(tmp_path / "a.csv"), multiedges=multi), pp.io.read_csv_graph(str(tmp_path / "b.csv"), multiedges=multi))
+    # temporal side: events with ties in time (both constructors use this package's stable time ordering)
+    t = rng.integers(0, 40, 300)
+    tdf = pd.DataFrame({"v": v, "w": w, "t": t, "weight": rng.integers(1, 9, 300).astype(float)})
+    twant, tgot = ref.df_to_temporal_graph(tdf.copy(), multiedges=multi), pp.io.df_to_temporal_graph(tdf.copy(), multiedges=multi)
+    _same_graph(twant, tgot)
+    assert torch.equal(twant.data.time, tgot.data.time)
+    assert ref.temporal_graph_to_df(twant).equals(pp.io.temporal_graph_to_df(tgot))
