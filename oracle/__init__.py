@@ -23,6 +23,10 @@ What is restated here (reference paths are relative to ``/root/reference``):
 * ``oracle/paths.py``    ``temporal_shortest_paths`` (``algorithms/temporal.py:57-107``),
   ``temporal_closeness_centrality`` and ``temporal_betweenness_centrality`` (``algorithms/centrality.py:164-324``).
 
+* ``oracle/containers.py`` the edge-merging members of ``Graph`` / ``TemporalGraph``; ``oracle/ref_loader.py`` also runs the
+  reference's own algorithm / io modules ON this package's containers (``reference_module_on``), and ``oracle/ref_suite.py``
+  runs the reference's own TEST FILES against this package under an import alias.
+
 Pinning status
 --------------
 * lift / indexing (a1-a9): PINNED.  ``tests/golden/make_golden.py`` executes the

@@ -40,7 +40,14 @@ class EdgeIndex(torch.Tensor):
         return self._sparse_size
 
     def get_sparse_size(self, dim: int | None = None):
-        return self._sparse_size if dim is None else self._sparse_size[dim]
+        """Like PyG: a dimension that was not declared is the largest index of that row + 1."""
+        if dim is None:
+            return (self.get_sparse_size(0), self.get_sparse_size(1))
+        size = self._sparse_size[dim]
+        if size is None:
+            row = self.as_tensor()[dim]
+            size = int(row.max()) + 1 if row.numel() else 0
+        return size
 
     @property
     def sort_order(self):

@@ -19,7 +19,7 @@ class TemporalGraph(Graph):
         self.data = data
         if data.num_nodes is None:
             # PyG infers a missing num_nodes from the EdgeIndex's sparse size, else from the largest index
-            size = data.edge_index.get_sparse_size(0) if isinstance(data.edge_index, EdgeIndex) else None
+            size = data.edge_index.sparse_size[0] if isinstance(data.edge_index, EdgeIndex) else None
             data.num_nodes = size if size is not None else (int(data.edge_index.max()) + 1 if data.edge_index.numel() else 0)
         if not isinstance(data.edge_index, EdgeIndex):
             data.edge_index = EdgeIndex(data.edge_index.contiguous(), sparse_size=(data.num_nodes, data.num_nodes))
