@@ -85,9 +85,11 @@ int ppg_lift_order_fill(const void* workspace, int64_t num_edges, int64_t num_no
 /* ---------------------------------------------------------------------------------------------
  * a3  aggregate_node_attributes        reference: src/pathpyG/algorithms/lift_order.py:10-45
  *   out[j] = rule(attr[edge_index[0][j]], attr[edge_index[1][j]])
+ *   ids outside [0, num_attr) read attr[0] and set bit 0 of *status_word (device uint32, zeroed by the caller,
+ *   may be NULL when the caller knows the ids are in range); the reference raises IndexError there.
  * ------------------------------------------------------------------------------------------- */
 int ppg_pair_attributes(const int64_t* edge_index, int64_t num_edges, const void* attr, int64_t num_attr, int dtype,
-                        int rule, void* out, void* stream);
+                        int rule, void* out, void* status_word, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a1  lift_order_temporal              reference: src/pathpyG/algorithms/temporal.py:17-54

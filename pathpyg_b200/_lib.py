@@ -38,7 +38,7 @@ PROTOTYPES = {
     "ppg_lift_order_workspace_bytes": (c_size_t, [_i64, _i64]),
     "ppg_lift_order_count": (c_int, [_p, _i64, _i64, _p, c_size_t, _ph_i64, _p]),
     "ppg_lift_order_fill": (c_int, [_p, _i64, _i64, _i64, _p, _p]),
-    "ppg_pair_attributes": (c_int, [_p, _i64, _p, _i64, c_int, c_int, _p, _p]),
+    "ppg_pair_attributes": (c_int, [_p, _i64, _p, _i64, c_int, c_int, _p, _p, _p]),
     "ppg_lift_temporal_workspace_bytes": (c_size_t, [_i64, _i64]),
     "ppg_lift_temporal_group": (c_int, [_p, _i64, _i64, _p, c_size_t, _p]),
     "ppg_lift_temporal_count": (c_int, [_p, _p, _i64, _i64, c_int, _i64, c_double, _p, c_size_t, _ph_i64, _p]),

@@ -40,7 +40,7 @@ def lift_order_edge_index_weighted(edge_index: torch.Tensor, edge_weight: torch.
     if num_nodes is None:
         num_nodes = int(edge_index.max()) + 1 if edge_index.numel() else 0
     ho_index = ops.lift_order_edge_index(_staging.up(edge_index, dev), int(num_nodes))
-    ho_weight = ops.pair_attributes(ho_index, _staging.up(edge_weight, dev), aggr)
+    ho_weight = ops.pair_attributes(ho_index, _staging.up(edge_weight, dev), aggr, index_bound=int(edge_index.size(1)))
     return _staging.down(ho_index, to_host), _staging.down(ho_weight, to_host)
 
 

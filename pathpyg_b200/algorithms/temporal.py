@@ -18,7 +18,8 @@ def lift_order_temporal(g, delta: float | int = 1) -> torch.Tensor:
     num_nodes = g.data.num_nodes
     if num_nodes is None:
         num_nodes = int(edge_index.max()) + 1 if edge_index.numel() else 0
-    out = ops.lift_order_temporal(_staging.up(edge_index, dev), _staging.up(time, dev), delta, int(num_nodes))
+    known = getattr(g, "time_is_known_sorted", lambda: False)()
+    out = ops.lift_order_temporal(_staging.up(edge_index, dev), _staging.up(time, dev), delta, int(num_nodes), assume_sorted=known)
     return _staging.down(out, to_host)
 
 

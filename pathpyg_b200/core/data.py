@@ -182,29 +182,35 @@ class Data:
                 out.__dict__[k] = np.concatenate([v, w])
         return out
 
-    def edge_attrs(self):
-        """Keys holding one entry per edge (PyG: name contains 'edge', or leading dim == num_edges); tensors and
-        numpy arrays (the reference keeps string attributes as numpy arrays, io/pandas.py:91-92)."""
+    def _per_item(self, k, v, count) -> bool:
+        """PyG's shape test (``BaseStorage.is_node_attr`` / ``is_edge_attr``): a tensor or numpy array with at least
+        one dimension whose concatenation dimension (last for ``*index*`` keys, first otherwise) has ``count`` entries."""
         import numpy as np
 
-        m = self.num_edges
+        if not isinstance(v, (torch.Tensor, np.ndarray)) or v.ndim == 0 or count is None:
+            return False
+        return v.shape[-1 if "index" in k else 0] == count
+
+    def edge_attrs(self):
+        """Keys holding one entry per edge, by PyG's rule (``GlobalStorage.is_edge_attr``, used by the reference through
+        ``data.edge_attrs()``): the size along the concatenation dimension equals ``num_edges``; when ``num_nodes ==
+        num_edges`` makes that ambiguous, the name decides ('edge' in the key; ``time`` is per event by definition).
+        Numpy arrays count too (the reference keeps string attributes as numpy arrays, io/pandas.py:91-92)."""
+        m, n = self.num_edges, self.__dict__.get("num_nodes")
         out = []
         for k, v in self.__dict__.items():
-            if isinstance(v, torch.Tensor):
-                if k == "edge_index" or ((k.startswith("edge_") or k == "time") and v.dim() >= 1 and v.size(0) == m):
-                    out.append(k)
-            elif isinstance(v, np.ndarray) and k.startswith("edge_") and v.ndim >= 1 and v.shape[0] == m:
+            if k == "edge_index":
+                out.append(k)
+            elif self._per_item(k, v, m) and (n != m or "edge" in k or k == "time"):
                 out.append(k)
         return out
 
     def node_attrs(self):
-        import numpy as np
-
-        n = self.__dict__.get("num_nodes")
+        """Keys holding one entry per node (``GlobalStorage.is_node_attr``): size ``num_nodes`` along the concatenation
+        dimension; with ``num_nodes == num_edges`` keys naming an edge are excluded."""
+        m, n = self.num_edges, self.__dict__.get("num_nodes")
         return [k for k, v in self.__dict__.items()
-                if k.startswith("node_") and k != "node_sequence" and (
-                    (isinstance(v, torch.Tensor) and v.dim() >= 1 and v.size(0) == n)
-                    or (isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[0] == n))]
+                if k != "edge_index" and self._per_item(k, v, n) and (n != m or ("edge" not in k and k != "time"))]
 
     # ---- time order (TemporalGraph input, multi_order_model.py:148-151)
     def is_sorted_by_time(self) -> bool:

@@ -59,7 +59,7 @@ def _lift_step(edge_index, node_sequence, edge_weight, aggr, save):
     n_prev = int(node_sequence.size(0))
     ho_index = ops.lift_order_edge_index(edge_index, n_prev)
     if edge_weight is not None:
-        edge_weight = ops.pair_attributes(ho_index, edge_weight, aggr)
+        edge_weight = ops.pair_attributes(ho_index, edge_weight, aggr, index_bound=int(edge_index.size(1)))
     node_sequence = _extend_node_sequence(node_sequence, edge_index)
     gk = _aggregate(ho_index, node_sequence, edge_weight) if save else None
     return ho_index, node_sequence, edge_weight, gk
@@ -216,13 +216,15 @@ class MultiOrderModel:
                     return ops.lift_order_temporal_begin(src_ei, time_dev, delta, n, grouped_ws=grouped_ws)
             else:
                 src_t = _staging.up(data.time if data is g.data else g.data.time, dev)
-                pending = ops.lift_order_temporal_begin(src_ei, src_t, delta, n)   # count pass runs with the layer-1 sort
+                # count pass runs with the layer-1 sort; a shuffled g.data takes the order-independent route
+                pending = ops.lift_order_temporal_begin(src_ei, src_t, delta, n, assume_sorted=data is g.data)
         ids = torch.arange(n, device=dev)
         chain.first_layer(edge_index, None, n, ids.unsqueeze(1), ids, edge_weight, overlap=pending)
         if max_order > 1:
             line_index = chain.overlapped if event_graph is None else _plain(_staging.up(event_graph, dev)).long()
             if edge_weight is not None:
-                edge_weight = ops.pair_attributes(line_index, edge_weight, "src")
+                edge_weight = ops.pair_attributes(line_index, edge_weight, "src",
+                                                  index_bound=int(edge_index.size(1)) if event_graph is None else None)
             num_line_nodes = edge_index.size(1)
             for k in range(2, max_order + 1):
                 pending = ops.lift_order_edge_index_begin(line_index, num_line_nodes) if k < max_order else None
@@ -230,7 +232,7 @@ class MultiOrderModel:
                 if k < max_order:
                     nxt = chain.overlapped
                     if edge_weight is not None:
-                        edge_weight = ops.pair_attributes(nxt, edge_weight, "src")
+                        edge_weight = ops.pair_attributes(nxt, edge_weight, "src", index_bound=int(line_index.size(1)))
                     num_line_nodes, line_index = line_index.size(1), nxt
         m._finish(g.mapping, to_host)
         return m
@@ -263,7 +265,7 @@ class MultiOrderModel:
         line_index, num_line_nodes = edge_index, node_sequence.size(0)
         for _ in range(2, max_order + 1):
             nxt = ops.lift_order_edge_index(line_index, num_line_nodes)
-            edge_weight = ops.pair_attributes(nxt, edge_weight, aggr)
+            edge_weight = ops.pair_attributes(nxt, edge_weight, aggr, index_bound=int(line_index.size(1)))
             num_line_nodes, line_index = line_index.size(1), nxt
             chain.next_layer(line_index, edge_weight)
         m._finish(path_data.mapping, to_host)

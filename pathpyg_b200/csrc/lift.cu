@@ -362,39 +362,48 @@ static int temporal_count_scan(const TemporalLayout& L, const int64_t* edge_inde
 }
 
 // ------------------------------------------------------------------ a3: per-edge attribute from its end points
+// ids outside [0, num_attr) read slot 0 and raise the status bit (the reference fails with an IndexError there)
 template <typename T, int RULE>
 __global__ void __launch_bounds__(256)
-pair_attributes_kernel(const int64_t* __restrict__ ei, int64_t E, const T* __restrict__ attr, T* __restrict__ out) {
+pair_attributes_kernel(const int64_t* __restrict__ ei, int64_t E, const T* __restrict__ attr, int64_t num_attr,
+                       T* __restrict__ out, unsigned* __restrict__ status) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  bool bad = false;
+  auto fetch = [&](int64_t id) {
+    const bool ok = id >= 0 && id < num_attr;
+    bad |= !ok;
+    return attr[ok ? id : 0];
+  };
   for (int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; j < E; j += stride) {
     T r;
     if (RULE == PPG_PAIR_SRC) {
-      r = attr[ld_stream(ei + j)];
+      r = fetch(ld_stream(ei + j));
     } else if (RULE == PPG_PAIR_DST) {
-      r = attr[ld_stream(ei + E + j)];
+      r = fetch(ld_stream(ei + E + j));
     } else {
-      const T a = attr[ld_stream(ei + j)];
-      const T b = attr[ld_stream(ei + E + j)];
+      const T a = fetch(ld_stream(ei + j));
+      const T b = fetch(ld_stream(ei + E + j));
       if (RULE == PPG_PAIR_MAX) r = a > b ? a : (b > a ? b : (a == a ? a : b)); // torch.maximum propagates NaN
       else if (RULE == PPG_PAIR_MUL) r = a * b;
       else r = a + b;
     }
     st_stream(out + j, r);
   }
+  if (bad && status != nullptr) atomicOr(status, kStatusIdOutOfRange);
 }
 
 template <typename T>
-static int pair_attributes_dispatch(const int64_t* ei, int64_t E, const void* attr, int rule, void* out,
-                                    cudaStream_t stream) {
+static int pair_attributes_dispatch(const int64_t* ei, int64_t E, const void* attr, int64_t num_attr, int rule, void* out,
+                                    unsigned* status, cudaStream_t stream) {
   const int grid = grid_for(E, 256 * 4);
   const T* a = static_cast<const T*>(attr);
   T* o = static_cast<T*>(out);
   switch (rule) {
-    case PPG_PAIR_SRC: pair_attributes_kernel<T, PPG_PAIR_SRC><<<grid, 256, 0, stream>>>(ei, E, a, o); break;
-    case PPG_PAIR_DST: pair_attributes_kernel<T, PPG_PAIR_DST><<<grid, 256, 0, stream>>>(ei, E, a, o); break;
-    case PPG_PAIR_MAX: pair_attributes_kernel<T, PPG_PAIR_MAX><<<grid, 256, 0, stream>>>(ei, E, a, o); break;
-    case PPG_PAIR_MUL: pair_attributes_kernel<T, PPG_PAIR_MUL><<<grid, 256, 0, stream>>>(ei, E, a, o); break;
-    case PPG_PAIR_ADD: pair_attributes_kernel<T, PPG_PAIR_ADD><<<grid, 256, 0, stream>>>(ei, E, a, o); break;
+    case PPG_PAIR_SRC: pair_attributes_kernel<T, PPG_PAIR_SRC><<<grid, 256, 0, stream>>>(ei, E, a, num_attr, o, status); break;
+    case PPG_PAIR_DST: pair_attributes_kernel<T, PPG_PAIR_DST><<<grid, 256, 0, stream>>>(ei, E, a, num_attr, o, status); break;
+    case PPG_PAIR_MAX: pair_attributes_kernel<T, PPG_PAIR_MAX><<<grid, 256, 0, stream>>>(ei, E, a, num_attr, o, status); break;
+    case PPG_PAIR_MUL: pair_attributes_kernel<T, PPG_PAIR_MUL><<<grid, 256, 0, stream>>>(ei, E, a, num_attr, o, status); break;
+    case PPG_PAIR_ADD: pair_attributes_kernel<T, PPG_PAIR_ADD><<<grid, 256, 0, stream>>>(ei, E, a, num_attr, o, status); break;
     default: PPG_REQUIRE(false, PPG_ERR_INVALID, "Unknown aggregation method %d", rule);
   }
   PPG_LAUNCHED();
@@ -455,16 +464,17 @@ extern "C" int ppg_lift_order_fill(const void* workspace, int64_t E, int64_t N, 
 
 // =================================================================== a3
 extern "C" int ppg_pair_attributes(const int64_t* edge_index, int64_t E, const void* attr, int64_t num_attr, int dtype,
-                                   int rule, void* out, void* stream_) {
+                                   int rule, void* out, void* status_word, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  (void)num_attr;
+  unsigned* status = static_cast<unsigned*>(status_word);
   PPG_REQUIRE(rule >= PPG_PAIR_SRC && rule <= PPG_PAIR_ADD, PPG_ERR_INVALID, "Unknown aggregation method %d", rule);
   if (E == 0) return PPG_OK;
+  PPG_REQUIRE(num_attr > 0, PPG_ERR_INVALID, "pair_attributes: edges present but the attribute tensor is empty");
   switch (dtype) {
-    case PPG_F32: return pair_attributes_dispatch<float>(edge_index, E, attr, rule, out, stream);
-    case PPG_F64: return pair_attributes_dispatch<double>(edge_index, E, attr, rule, out, stream);
-    case PPG_I64: return pair_attributes_dispatch<long long>(edge_index, E, attr, rule, out, stream);
-    case PPG_I32: return pair_attributes_dispatch<int>(edge_index, E, attr, rule, out, stream);
+    case PPG_F32: return pair_attributes_dispatch<float>(edge_index, E, attr, num_attr, rule, out, status, stream);
+    case PPG_F64: return pair_attributes_dispatch<double>(edge_index, E, attr, num_attr, rule, out, status, stream);
+    case PPG_I64: return pair_attributes_dispatch<long long>(edge_index, E, attr, num_attr, rule, out, status, stream);
+    case PPG_I32: return pair_attributes_dispatch<int>(edge_index, E, attr, num_attr, rule, out, status, stream);
     default: PPG_REQUIRE(false, PPG_ERR_INVALID, "pair_attributes: unsupported dtype code %d", dtype);
   }
   return PPG_OK;

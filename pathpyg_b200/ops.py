@@ -96,7 +96,12 @@ def lift_order_edge_index(edge_index: torch.Tensor, num_nodes: int) -> torch.Ten
 
 
 # --------------------------------------------------------------------------------------- a3
-def pair_attributes(edge_index: torch.Tensor, node_attribute: torch.Tensor, aggr: str) -> torch.Tensor:
+def pair_attributes(edge_index: torch.Tensor, node_attribute: torch.Tensor, aggr: str,
+                    index_bound: int | None = None) -> torch.Tensor:
+    """``index_bound``: exclusive upper bound of the ids the caller vouches for (ids produced by this library's own
+    lift are below the number of lifted-from edges); it is compared with ``len(node_attribute)`` on the host.  Without
+    it the kernel reports ids outside the attribute tensor through a status word that is read back (one
+    synchronisation) and raised as IndexError, like the reference's indexing (lift_order.py:31-45)."""
     if aggr not in _lib.PAIR_RULES:
         raise ValueError(f"Unknown aggregation method {aggr}")
     lib = _lib.load()
@@ -107,9 +112,18 @@ def pair_attributes(edge_index: torch.Tensor, node_attribute: torch.Tensor, aggr
         raise TypeError(f"node_attribute must be a 1-D float32/float64/int64/int32 tensor, got {attr.dtype} {tuple(attr.shape)}")
     E = ei.size(1)
     out = torch.empty(E, dtype=attr.dtype, device=dev)
+    if E == 0:
+        return out
+    if index_bound is not None and index_bound > attr.numel():
+        raise IndexError(f"index {index_bound - 1} is out of bounds for dimension 0 with size {attr.numel()}")
+    if attr.numel() == 0:
+        raise IndexError("index is out of bounds for dimension 0 with size 0")
+    status = None if index_bound is not None else torch.zeros(1, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.ppg_pair_attributes(_ptr(ei), E, _ptr(attr), attr.numel(), _DTYPE_CODES[attr.dtype],
-                                           _lib.PAIR_RULES[aggr], _ptr(out), _stream(dev)))
+                                           _lib.PAIR_RULES[aggr], _ptr(out), _ptr(status), _stream(dev)))
+    if status is not None and int(status.item()) & 1:
+        raise IndexError(f"index out of range in self: edge_index holds an id outside [0, {attr.numel()})")
     return out
 
 
@@ -171,8 +185,34 @@ def lift_order_temporal_group(edge_index: torch.Tensor, num_nodes: int) -> torch
     return ws
 
 
+class PendingUnsortedTemporalLift:
+    """Temporal lift of a stream whose time stamps are NOT in ascending order (``TemporalGraph.shuffle_time()``
+    followed by a lift, as the reference's DBGNN tutorial does).  The reference's loop (temporal.py:33-53) does not
+    care about the order of the events: it emits the pairs by ascending source time stamp, then ascending source
+    POSITION, then ascending target POSITION.  The kernels need a time-ordered stream (binary searches over the
+    time-ordered out-edges of a node), so the stream is put in order with a stable sort, lifted, and the pairs are
+    mapped back to the caller's positions: the source order (time, position) is already the kernel's output order,
+    the targets of one source are re-ordered by position with one radix sort over (source rank, target position)."""
+
+    def __init__(self, ei, time, mode, delta_i, delta_f, num_nodes):
+        self.perm = stable_argsort(time)
+        self.inner = PendingTemporalLift(ei[:, self.perm].contiguous(), time[self.perm].contiguous(), mode, delta_i, delta_f,
+                                         num_nodes)
+
+    def finish(self) -> torch.Tensor:
+        pairs = self.inner.finish()
+        m = self.perm.numel()
+        bits = max(1, (m - 1).bit_length())
+        keys = (pairs[0] << bits) | self.perm[pairs[1]]
+        del pairs
+        sort_pairs_u64(keys, 2 * bits)
+        return torch.stack([self.perm[keys >> bits], keys & ((1 << bits) - 1)])
+
+
 def lift_order_temporal_begin(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int,
-                              grouped_ws: torch.Tensor | None = None) -> PendingTemporalLift:
+                              grouped_ws: torch.Tensor | None = None, assume_sorted: bool = False):
+    """``assume_sorted``: the caller knows that ``time`` ascends (a ``TemporalGraph`` whose constructor put it in
+    order); otherwise one device pass checks it, and an unordered stream takes ``PendingUnsortedTemporalLift``."""
     ei = _edge_index_arg(edge_index)
     _require_cuda(ei, time)
     time, mode, delta_i, delta_f = _time_mode(time.contiguous(), delta)
@@ -180,11 +220,14 @@ def lift_order_temporal_begin(edge_index: torch.Tensor, time: torch.Tensor, delt
         raise ValueError("time and edge_index disagree on the number of edges")
     if ei.size(1) == 0 or num_nodes <= 0:
         raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors (lift_order_temporal: empty input)")
+    if not assume_sorted and grouped_ws is None and time.numel() > 1 and not bool((time[1:] >= time[:-1]).all()):
+        return PendingUnsortedTemporalLift(ei, time, mode, delta_i, delta_f, int(num_nodes))
     return PendingTemporalLift(ei, time, mode, delta_i, delta_f, int(num_nodes), grouped_ws)
 
 
-def lift_order_temporal(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int) -> torch.Tensor:
-    return lift_order_temporal_begin(edge_index, time, delta, num_nodes).finish()
+def lift_order_temporal(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int,
+                        assume_sorted: bool = False) -> torch.Tensor:
+    return lift_order_temporal_begin(edge_index, time, delta, num_nodes, assume_sorted=assume_sorted).finish()
 
 
 # --------------------------------------------------------------------------------------- a4
