@@ -70,6 +70,12 @@ int ppg_result_read(const void* workspace, int64_t* h_total, int* h_status_bits,
 const char* ppg_last_error(void);
 /* number of kernels this library has launched in this process (monotonic; for bench accounting) */
 unsigned long long ppg_launch_count(void);
+/* Opt-in timing of the radix digit passes (the dominant kernel of the lift) with CUDA events on the launching
+ * stream: between _begin and _end every pass of every sort is bracketed by an event pair (at most 512 passes);
+ * _end synchronises the device and returns, per pass, its duration, the number of (key, payload) pairs and the
+ * algorithmic bytes per pair (read + write of key and payload).  Benchmark instrumentation; off by default. */
+int ppg_profile_begin(void);
+int ppg_profile_end(float* h_ms, int64_t* h_items, int* h_bytes_per_item, int capacity, int* h_count);
 
 /* ---------------------------------------------------------------------------------------------
  * a2  lift_order_edge_index            reference: src/pathpyG/algorithms/lift_order.py:48-79
@@ -107,6 +113,51 @@ int ppg_lift_temporal_count(const int64_t* edge_index, const void* time, int64_t
                             int64_t* h_num_pairs, void* stream);
 int ppg_lift_temporal_fill(const void* workspace, int64_t num_edges, int64_t num_nodes, int64_t num_pairs,
                            int64_t* out_index, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * e   cross-partition exchange of lifted edges (the reference is single-device, there is no
+ *     counterpart in /root/reference: the gathered result must equal MultiOrderModel.from_temporal_graph,
+ *     src/pathpyG/core/multi_order_model.py:124-192, bit for bit)
+ *
+ *   ppg_lift_limit        after ppg_lift_order_count (temporal = 0) / ppg_lift_temporal_count (temporal = 1): make
+ *                         the pending count the number of columns whose source is < limit_sources (a prefix of the
+ *                         output, which is ascending in the source); fill with that count writes exactly that prefix.
+ *   ppg_route_count       line_index [2,E] of one level; node_info [line nodes] u64 = id << 32 | last first-order node
+ *                         (NULL on the first level: id = the value itself); offsets [world + 1] (device) = first row
+ *                         owned by every rank.  out_counts [world] (device int64) = records per destination.
+ *   ppg_route_pack        stable partition by destination: out_records [E] 16-byte records {id(target), id(source),
+ *                         last node of target, float32 weight bits} grouped by destination rank in edge order;
+ *                         sources (first level: positions) >= own_prefix carry weight 0; out_slot [E] = record index;
+ *                         out_last [E] = last first-order node of the edge's path.
+ *   ppg_route_unpack      back [E] = merged-edge index returned by the owner for every record (record order);
+ *                         edge_offsets [world + 1] (device) = global index of every owner's first merged edge;
+ *                         out_node_info [E] = the node_info of the NEXT level.
+ *   ppg_merge_records_*   owner side: rows [row_lo, row_lo + rows_owned), columns < total_nodes (<= 2^32);
+ *                         sort leaves {merged count, status} at the head of the workspace (ppg_result_read) and
+ *                         out_inverse [R] = merged-edge index (local) of every record; fill writes the merged edges
+ *                         (global ids, (row, col)-sorted), their weights summed in arrival order and their last node.
+ *   ppg_extend_owned_rows out_rows [n, width + 1] = prev_rows[src_ids - prev_row_lo] ++ last
+ * ------------------------------------------------------------------------------------------- */
+#define PPG_ROUTE_MAX_RANKS 16
+int ppg_lift_limit(void* workspace, int temporal, int64_t num_sources, int64_t num_nodes, int64_t limit_sources,
+                   void* stream);
+size_t ppg_route_workspace_bytes(int64_t num_edges);
+int ppg_route_count(const int64_t* line_index, int64_t num_edges, const void* node_info, const int64_t* offsets,
+                    int world, void* workspace, size_t workspace_bytes, int64_t* out_counts, void* stream);
+int ppg_route_pack(const int64_t* line_index, int64_t num_edges, const void* node_info, const float* weights,
+                   int64_t own_prefix, const int64_t* offsets, int world, const void* workspace, void* out_records,
+                   uint32_t* out_slot, uint32_t* out_last, void* stream);
+int ppg_route_unpack(const void* workspace, int64_t num_edges, const uint32_t* back, const uint32_t* slot,
+                     const uint32_t* last, const int64_t* edge_offsets, int world, void* out_node_info, void* stream);
+size_t ppg_merge_records_workspace_bytes(int64_t num_records, int64_t rows_owned, int64_t total_nodes);
+int ppg_merge_records_sort(const void* records, int64_t num_records, int64_t row_lo, int64_t rows_owned,
+                           int64_t total_nodes, void* workspace, size_t workspace_bytes, uint32_t* out_inverse,
+                           void* stream);
+int ppg_merge_records_fill(const void* workspace, const void* records, int64_t num_records, int64_t row_lo,
+                           int64_t rows_owned, int64_t total_nodes, int64_t num_out, int64_t* out_edge_index,
+                           float* out_weights, int64_t* out_last, void* stream);
+int ppg_extend_owned_rows(const int64_t* prev_rows, int64_t width, int64_t prev_row_lo, const int64_t* src_ids,
+                          const int64_t* last, int64_t n, int64_t* out_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a4  aggregate_edge_index             reference: src/pathpyG/algorithms/lift_order.py:109-152

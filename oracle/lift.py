@@ -98,7 +98,8 @@ def aggregate_edge_index(edge_index, node_sequence, edge_weight=None, aggr: str 
     return Layer(agg_index[:, order], int(unique_nodes.size(0)), unique_nodes, agg_weight[order], inverse_idx)
 
 
-def lift_order_temporal(edge_index: torch.Tensor, timestamps: torch.Tensor, delta=1) -> torch.Tensor:
+def lift_order_temporal(edge_index: torch.Tensor, timestamps: torch.Tensor, delta=1, *, max_source_stamps: int | None = None,
+                        budget_s: float | None = None, stats: dict | None = None) -> torch.Tensor:
     """temporal.py:17-54 in the reference's own order of operations.
 
     (e -> f) iff dst(e) == src(f) and t_e < t_f <= t_e + delta.  The loop over the
@@ -106,17 +107,31 @@ def lift_order_temporal(edge_index: torch.Tensor, timestamps: torch.Tensor, delt
     (temporal.py:37-51); torch's type promotion of ``t + delta`` is therefore
     inherited, including float32 for int64 times with a float delta.
     Raises RuntimeError when no pair exists (``torch.cat`` of an empty list, :53).
+
+    ``max_source_stamps`` / ``budget_s`` (bench.py's bounded CPU sample only): stop the loop after that many
+    distinct source time stamps / seconds -- every iteration still runs against the FULL stream, so the
+    per-time-stamp cost is the full run's; ``stats`` receives ``stamps`` (done) and ``of_stamps`` (all).
     """
+    import time as _time
+
     delta_t = torch.tensor(delta)                                    # :30
     positions = torch.arange(0, edge_index.size(1))                  # :31
     pieces = []
-    for t in torch.unique(timestamps, sorted=True):                  # :33,37
+    stamps = torch.unique(timestamps, sorted=True)                   # :33
+    done, t0 = 0, _time.perf_counter()
+    for t in stamps:                                                 # :37
         heads = positions[timestamps == t]                           # :39-40
         tails = positions[(timestamps > t) & (timestamps <= t + delta_t)]  # :43-44
         if heads.numel() and tails.numel():                          # :46
             pairs = torch.cartesian_prod(heads, tails)               # :49
             keep = edge_index[1, pairs[:, 0]] == edge_index[0, pairs[:, 1]]  # :50
             pieces.append(pairs[keep])
+        done += 1
+        if (max_source_stamps is not None and done >= max_source_stamps) or \
+                (budget_s is not None and _time.perf_counter() - t0 > budget_s):
+            break
+    if stats is not None:
+        stats["stamps"], stats["of_stamps"] = done, int(stamps.numel())
     return torch.cat(pieces, dim=0).t().contiguous()                 # :53
 
 

@@ -34,6 +34,8 @@ PROTOTYPES = {
     "ppg_abi_version": (c_int, []),
     "ppg_last_error": (c_char_p, []),
     "ppg_launch_count": (ctypes.c_uint64, []),
+    "ppg_profile_begin": (c_int, []),
+    "ppg_profile_end": (c_int, [POINTER(ctypes.c_float), _ph_i64, _ph_int, c_int, _ph_int]),
     "ppg_result_read": (c_int, [_p, _ph_i64, _ph_int, _p]),
     "ppg_lift_order_workspace_bytes": (c_size_t, [_i64, _i64]),
     "ppg_lift_order_count": (c_int, [_p, _i64, _i64, _p, c_size_t, _ph_i64, _p]),
@@ -52,6 +54,15 @@ PROTOTYPES = {
     "ppg_coalesce_sort": (c_int, [_p, _i64, _p, _i64, _i64, _p, c_size_t, _p, _ph_i64, _p]),
     "ppg_extend_rows": (c_int, [_p, _i64, _i64, _p, _i64, _p, _p]),
     "ppg_coalesce_fill": (c_int, [_p, _i64, _i64, _i64, _p, c_int, c_int, _p, _p, _p]),
+    "ppg_lift_limit": (c_int, [_p, c_int, _i64, _i64, _i64, _p]),
+    "ppg_route_workspace_bytes": (c_size_t, [_i64]),
+    "ppg_route_count": (c_int, [_p, _i64, _p, _p, c_int, _p, c_size_t, _p, _p]),
+    "ppg_route_pack": (c_int, [_p, _i64, _p, _p, _i64, _p, c_int, _p, _p, _p, _p, _p]),
+    "ppg_route_unpack": (c_int, [_p, _i64, _p, _p, _p, _p, c_int, _p, _p]),
+    "ppg_merge_records_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
+    "ppg_merge_records_sort": (c_int, [_p, _i64, _i64, _i64, _i64, _p, c_size_t, _p, _p]),
+    "ppg_merge_records_fill": (c_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p]),
+    "ppg_extend_owned_rows": (c_int, [_p, _i64, _i64, _p, _p, _i64, _p, _p]),
     "ppg_sort_pairs_workspace_bytes": (c_size_t, [_i64, c_int]),
     "ppg_sort_pairs_u64": (c_int, [_p, _p, _i64, c_int, _p, c_size_t, POINTER(ctypes.c_float), _p]),
     "ppg_csc_workspace_bytes": (c_size_t, [_i64, _i64]),
@@ -102,7 +113,7 @@ _lib = None
 
 def build(verbose: bool = False) -> str:
     """Compile the CUDA sources for sm_100a with nvcc (cross-compiles without a GPU)."""
-    proc = subprocess.run(["make", "-C", CSRC_DIR], capture_output=True, text=True)
+    proc = subprocess.run(["make", "-j", str(min(8, os.cpu_count() or 1)), "-C", CSRC_DIR], capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("building libpathpyg_b200.so failed:\n" + proc.stdout + proc.stderr)
     if verbose:

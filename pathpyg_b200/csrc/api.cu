@@ -15,6 +15,37 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace ppg
 
+namespace ppg { PassProfile g_pass_profile; }
+
+extern "C" int ppg_profile_begin(void) {
+  ppg::PassProfile& p = ppg::g_pass_profile;
+  if (!p.created) {
+    for (int i = 0; i < ppg::PassProfile::kCapacity; ++i) {
+      PPG_CUDA_TRY(cudaEventCreate(&p.start[i]));
+      PPG_CUDA_TRY(cudaEventCreate(&p.stop[i]));
+    }
+    p.created = true;
+  }
+  p.count = 0;
+  p.enabled = true;
+  return PPG_OK;
+}
+
+extern "C" int ppg_profile_end(float* h_ms, int64_t* h_items, int* h_bytes_per_item, int capacity, int* h_count) {
+  ppg::PassProfile& p = ppg::g_pass_profile;
+  p.enabled = false;
+  PPG_CUDA_TRY(cudaDeviceSynchronize());
+  const int n = p.count < capacity ? p.count : capacity;
+  for (int i = 0; i < n; ++i) {
+    PPG_CUDA_TRY(cudaEventElapsedTime(&h_ms[i], p.start[i], p.stop[i]));
+    h_items[i] = p.items[i];
+    h_bytes_per_item[i] = p.bytes_per_item[i];
+  }
+  *h_count = n;
+  p.count = 0;
+  return PPG_OK;
+}
+
 extern "C" int ppg_abi_version(void) { return PPG_ABI_VERSION; }
 extern "C" const char* ppg_last_error(void) { return ppg::g_last_error; }
 extern "C" unsigned long long ppg_launch_count(void) { return ppg::g_launch_count; }

@@ -33,6 +33,32 @@ extern unsigned long long g_launch_count;
     ++::ppg::g_launch_count;                                                             \
   } while (0)
 
+// opt-in timing of every radix digit pass with CUDA events on the launching stream (ppg_profile_begin / _end):
+// the benchmark reads the durations of the passes that ran INSIDE a real step instead of probing a synthetic sort
+struct PassProfile {
+  static constexpr int kCapacity = 512;
+  bool enabled = false;
+  int count = 0;
+  cudaEvent_t start[kCapacity], stop[kCapacity];
+  long long items[kCapacity];
+  int bytes_per_item[kCapacity];
+  bool created = false;
+};
+extern PassProfile g_pass_profile;
+inline void profile_pass_begin(cudaStream_t stream) {
+  PassProfile& p = g_pass_profile;
+  if (p.enabled && p.count < PassProfile::kCapacity) cudaEventRecord(p.start[p.count], stream);
+}
+inline void profile_pass_end(cudaStream_t stream, long long items, int bytes_per_item) {
+  PassProfile& p = g_pass_profile;
+  if (p.enabled && p.count < PassProfile::kCapacity) {
+    cudaEventRecord(p.stop[p.count], stream);
+    p.items[p.count] = items;
+    p.bytes_per_item[p.count] = bytes_per_item;
+    ++p.count;
+  }
+}
+
 #define PPG_REQUIRE(cond, code, ...)                                                     \
   do {                                                                                   \
     if (!(cond)) {                                                                       \

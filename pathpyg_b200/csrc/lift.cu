@@ -557,6 +557,36 @@ extern "C" int ppg_lift_temporal_fill(const void* workspace, int64_t m, int64_t 
   return launch_expand(L.off, m, num_pairs, out_index, TemporalTail{L.first, L.grouped()}, stream);
 }
 
+// =================================================================== prefix-limited lifts
+// The columns of a lift are ascending in the source, so "the lift of the first `limit` sources only" is a prefix of the
+// full output: off[limit] columns.  The distributed lift (exchange.cu) needs only the paths that start before a cut.
+__global__ void lift_limit_kernel(const unsigned long long* __restrict__ off, int64_t limit, ppg::ResultWords* result) {
+  result->total = off[limit];
+}
+
+extern "C" int ppg_lift_limit(void* workspace, int temporal, int64_t num_sources, int64_t num_nodes, int64_t limit_sources,
+                              void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(limit_sources >= 0 && limit_sources <= num_sources, PPG_ERR_INVALID, "lift_limit: %lld outside [0, %lld]",
+              (long long)limit_sources, (long long)num_sources);
+  if (num_sources == 0) return PPG_OK;
+  Workspace ws(workspace, ~static_cast<size_t>(0));
+  ResultWords* result;
+  const unsigned long long* off;
+  if (temporal) {
+    TemporalLayout L(ws, num_sources, num_nodes);
+    result = L.result;
+    off = L.off;
+  } else {
+    LiftLayout L(ws, num_sources, num_nodes);
+    result = L.result;
+    off = L.off;
+  }
+  lift_limit_kernel<<<1, 1, 0, stream>>>(off, limit_sources, result);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
 // =================================================================== deferred count read-back
 // Every workspace of a count -> fill pair starts with {total, status}.  A *_count / *_sort call with a NULL
 // host pointer only enqueues its kernels; several such calls can be in flight on the stream before the

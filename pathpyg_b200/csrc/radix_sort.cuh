@@ -477,6 +477,7 @@ inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32
     const unsigned long long* h = ghist + static_cast<size_t>(p) * kRadix;
     unsigned long long* hn = p + 1 < P ? ghist + static_cast<size_t>(p + 1) * kRadix : nullptr;
     const int shift = p * kRadixBits;
+    profile_pass_begin(stream);
     if (!has_values) {
       PPG_TRY((launch_onesweep_pass<KeyT, false, false>(kin, kout, nullptr, nullptr, n, shift, h, hn, counter, state, gstate, p, stream)));
     } else if (p == 0 && iota_payload) {
@@ -488,6 +489,7 @@ inline int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32
     uint32_t* tv = (p == 0 && iota_payload) ? vals_a : vin;
     vin = vout; vout = tv;
     *in_b ^= 1;
+    profile_pass_end(stream, n, 2 * static_cast<int>(sizeof(KeyT) + (has_values ? sizeof(uint32_t) : 0)));
     if (h_pass_ms != nullptr) PPG_CUDA_TRY(cudaEventRecord(ev[p + 1], stream));
   }
   if (h_pass_ms != nullptr) {

@@ -63,6 +63,11 @@ def _read_result(ws: torch.Tensor, dev: torch.device, what: str) -> int:
     return total.value
 
 
+def _lift_limit(ws: torch.Tensor, temporal: int, num_sources: int, num_nodes: int, limit: int, dev: torch.device) -> None:
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().ppg_lift_limit(_ptr(ws), temporal, num_sources, num_nodes, max(int(limit), 0), _stream(dev)))
+
+
 # --------------------------------------------------------------------------------------- a2
 class PendingLift:
     """lift_order_edge_index whose count pass is enqueued; ``finish()`` reads the size, allocates and fills."""
@@ -76,7 +81,10 @@ class PendingLift:
                 self.ws = _workspace(lib.ppg_lift_order_workspace_bytes(self.E, num_nodes), self.dev)
                 _lib.check(lib.ppg_lift_order_count(_ptr(ei), self.E, num_nodes, _ptr(self.ws), self.ws.numel(), None, _stream(self.dev)))
 
-    def finish(self) -> torch.Tensor:
+    def finish(self, limit_sources: int | None = None) -> torch.Tensor:
+        """``limit_sources``: only the columns whose source edge is < limit_sources (a prefix of the full lift)."""
+        if self.E and limit_sources is not None and limit_sources < self.E:
+            _lift_limit(self.ws, 0, self.E, self.num_nodes, limit_sources, self.dev)
         total = _read_result(self.ws, self.dev, "lift_order_edge_index") if self.E else 0
         out = torch.empty((2, total), dtype=torch.int64, device=self.dev)
         if total:
@@ -91,8 +99,8 @@ def lift_order_edge_index_begin(edge_index: torch.Tensor, num_nodes: int) -> Pen
     return PendingLift(ei, int(num_nodes))
 
 
-def lift_order_edge_index(edge_index: torch.Tensor, num_nodes: int) -> torch.Tensor:
-    return lift_order_edge_index_begin(edge_index, num_nodes).finish()
+def lift_order_edge_index(edge_index: torch.Tensor, num_nodes: int, limit_sources: int | None = None) -> torch.Tensor:
+    return lift_order_edge_index_begin(edge_index, num_nodes).finish(limit_sources)
 
 
 # --------------------------------------------------------------------------------------- a3
@@ -158,8 +166,14 @@ class PendingTemporalLift:
             _lib.check(lib.ppg_lift_temporal_count(_ptr(ei), _ptr(time), self.m, num_nodes, mode, delta_i, delta_f, _ptr(self.ws),
                                                    self.ws.numel(), None, _stream(self.dev)))
 
-    def finish(self) -> torch.Tensor:
+    def finish(self, limit_sources: int | None = None, allow_empty: bool = False) -> torch.Tensor:
+        """``limit_sources``: only the pairs whose source event is < limit_sources (a prefix of the full output);
+        ``allow_empty``: return a [2, 0] tensor instead of raising when no pair exists (one rank's slice of a stream)."""
+        if limit_sources is not None and limit_sources < self.m:
+            _lift_limit(self.ws, 1, self.m, self.num_nodes, limit_sources, self.dev)
         total = _read_result(self.ws, self.dev, "lift_order_temporal")
+        if total == 0 and allow_empty:
+            return torch.empty((2, 0), dtype=torch.int64, device=self.dev)
         if total == 0:
             raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors "
                                       "(lift_order_temporal: no time-respecting pair for this delta)")
@@ -226,8 +240,11 @@ def lift_order_temporal_begin(edge_index: torch.Tensor, time: torch.Tensor, delt
 
 
 def lift_order_temporal(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int,
-                        assume_sorted: bool = False) -> torch.Tensor:
-    return lift_order_temporal_begin(edge_index, time, delta, num_nodes, assume_sorted=assume_sorted).finish()
+                        assume_sorted: bool = False, limit_sources: int | None = None, allow_empty: bool = False) -> torch.Tensor:
+    pending = lift_order_temporal_begin(edge_index, time, delta, num_nodes, assume_sorted=assume_sorted)
+    if limit_sources is None and not allow_empty:
+        return pending.finish()
+    return pending.finish(limit_sources, allow_empty)
 
 
 # --------------------------------------------------------------------------------------- a4
@@ -417,6 +434,102 @@ def stable_argsort(values: torch.Tensor) -> torch.Tensor:
         raise TypeError(f"stable_argsort supports int64 and float64 (got {v.dtype})")
     perm, _ = sort_pairs_u64(keys, end_bit)  # keys is a fresh tensor in every branch (sorted in place)
     return perm.long()
+
+
+# --------------------------------------------------------------------------------------- e: cross-partition exchange
+class RoutePlan:
+    """Stable partition of the line-graph edges of one level by the rank that owns their source row
+    (``csrc/exchange.cu``).  ``counts`` [world] (device int64) is available right after construction."""
+
+    def __init__(self, line_index: torch.Tensor, node_info: torch.Tensor | None, offsets: torch.Tensor, world: int):
+        lib = _lib.load()
+        self.li = _edge_index_arg(line_index)
+        self.dev = _require_cuda(self.li, node_info, offsets)
+        self.E, self.world = self.li.size(1), int(world)
+        self.node_info = None if node_info is None else node_info.contiguous()
+        self.offsets = offsets.contiguous()
+        if self.offsets.dtype != torch.int64 or self.offsets.numel() != world + 1:
+            raise ValueError("offsets must be int64 with world + 1 entries")
+        self.counts = torch.empty(world, dtype=torch.int64, device=self.dev)
+        self.slot = self.last = None
+        with torch.cuda.device(self.dev):
+            self.ws = _workspace(lib.ppg_route_workspace_bytes(self.E), self.dev)
+            _lib.check(lib.ppg_route_count(_ptr(self.li), self.E, _ptr(self.node_info), _ptr(self.offsets), self.world,
+                                           _ptr(self.ws), self.ws.numel(), _ptr(self.counts), _stream(self.dev)))
+
+    def pack(self, weights: torch.Tensor | None, own_prefix: int) -> torch.Tensor:
+        """Records [E, 2] int64 (16 bytes each) grouped by destination rank, edge order inside a destination."""
+        if weights is not None:
+            weights = weights.contiguous()
+            if weights.dtype != torch.float32 or weights.numel() != self.E:
+                raise TypeError("route weights must be float32 with one entry per edge")
+        records = torch.empty((self.E, 2), dtype=torch.int64, device=self.dev)
+        self.slot = torch.empty(self.E, dtype=torch.int32, device=self.dev)
+        self.last = torch.empty(self.E, dtype=torch.int32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.load().ppg_route_pack(_ptr(self.li), self.E, _ptr(self.node_info), _ptr(weights), int(own_prefix),
+                                                  _ptr(self.offsets), self.world, _ptr(self.ws), _ptr(records), _ptr(self.slot),
+                                                  _ptr(self.last), _stream(self.dev)))
+        return records
+
+    def unpack(self, back: torch.Tensor, edge_offsets: torch.Tensor) -> torch.Tensor:
+        """``back`` [E] int32: merged-edge index of every record as returned by its owner; ``edge_offsets`` [world + 1]
+        device int64.  Result [E] int64: ``global merged-edge id << 32 | last node`` per edge = next level's node_info."""
+        out = torch.empty(self.E, dtype=torch.int64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.load().ppg_route_unpack(_ptr(self.ws), self.E, _ptr(back), _ptr(self.slot), _ptr(self.last),
+                                                    _ptr(edge_offsets.contiguous()), self.world, _ptr(out), _stream(self.dev)))
+        return out
+
+
+def route_plan(line_index, node_info, offsets, world) -> RoutePlan:
+    return RoutePlan(line_index, node_info, offsets, world)
+
+
+class PendingMerge:
+    """Owner side of the exchange: merge the received records of the rows [row_lo, row_lo + rows_owned).
+    ``result_words`` (device int64 [2]: merged count, status bits) is valid once the stream has run;
+    ``inverse`` [R] int32 = merged-edge index of every record."""
+
+    def __init__(self, records: torch.Tensor, row_lo: int, rows_owned: int, total_nodes: int):
+        lib = _lib.load()
+        self.records = records.contiguous()
+        self.dev = _require_cuda(self.records)
+        self.R = self.records.size(0)
+        self.row_lo, self.rows_owned, self.total_nodes = int(row_lo), int(rows_owned), int(total_nodes)
+        self.inverse = torch.empty(self.R, dtype=torch.int32, device=self.dev)
+        with torch.cuda.device(self.dev):
+            self.ws = _workspace(lib.ppg_merge_records_workspace_bytes(self.R, self.rows_owned, self.total_nodes), self.dev)
+            _lib.check(lib.ppg_merge_records_sort(_ptr(self.records), self.R, self.row_lo, self.rows_owned, self.total_nodes,
+                                                  _ptr(self.ws), self.ws.numel(), _ptr(self.inverse), _stream(self.dev)))
+        self.result_words = self.ws[:16].view(torch.int64)
+
+    def finish(self, num_out: int):
+        """(edge_index [2, num_out] global ids, edge_weight float32, last node int64) of the merged edges."""
+        out_ei = torch.empty((2, num_out), dtype=torch.int64, device=self.dev)
+        out_w = torch.empty(num_out, dtype=torch.float32, device=self.dev)
+        out_last = torch.empty(num_out, dtype=torch.int64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.load().ppg_merge_records_fill(_ptr(self.ws), _ptr(self.records), self.R, self.row_lo, self.rows_owned,
+                                                          self.total_nodes, int(num_out), _ptr(out_ei), _ptr(out_w), _ptr(out_last),
+                                                          _stream(self.dev)))
+        return out_ei, out_w, out_last
+
+
+def merge_records_begin(records, row_lo, rows_owned, total_nodes) -> PendingMerge:
+    return PendingMerge(records, row_lo, rows_owned, total_nodes)
+
+
+def extend_owned_rows(prev_rows: torch.Tensor, prev_row_lo: int, src_ids: torch.Tensor, last: torch.Tensor) -> torch.Tensor:
+    """``cat([prev_rows[src_ids - prev_row_lo], last[:, None]], 1)`` in one kernel."""
+    prev = prev_rows.contiguous()
+    dev = _require_cuda(prev, src_ids, last)
+    n, w = src_ids.numel(), prev.size(1)
+    out = torch.empty((n, w + 1), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().ppg_extend_owned_rows(_ptr(prev), w, int(prev_row_lo), _ptr(src_ids.contiguous()), _ptr(last.contiguous()),
+                                                     n, _ptr(out), _stream(dev)))
+    return out
 
 
 # --------------------------------------------------------------------------------------- a10 / a11

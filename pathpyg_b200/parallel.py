@@ -11,14 +11,16 @@ The reference (pathpy/pathpyG) is single-process, single-device: nothing here ha
 * ``shard_walks``                  -- contiguous walk-id ranges balanced by node count.
 * ``distributed_temporal_layers``  -- BASELINE config 5: the time-sorted edge stream is split into contiguous
   ranges; a ghost zone of (K-1)*delta is exchanged once (all-to-all-v); every rank lifts its extended range
-  locally and counts the causal paths whose FIRST edge it owns (every path is counted exactly once); per
-  order ONE all-to-all-v carries the line-graph edges to the owner of their source row, where they are merged
-  (local radix sort + run detection); the global index of a merged edge -- all-gather of counts + exclusive
-  scan -- is returned to the senders and IS the De Bruijn node id of the next order.
+  locally -- only the prefix of every line graph that later orders still need -- and counts the causal paths
+  whose FIRST edge it owns (every path is counted exactly once); per order ONE all-to-all-v carries the
+  line-graph edges as 16-byte records to the owner of their source row (stable partition by owner, ``csrc/
+  exchange.cu``), where they are merged (radix sort + run detection); the global index of a merged edge --
+  all-gather of the merged counts + exclusive scan -- returns to the senders as 4 bytes per edge and IS the
+  De Bruijn node id of the next order.  The local lift of the next order runs while the records are in flight.
 
 The local compute goes through ``pathpyg_b200.ops`` (CUDA only).  The CPU tests inject an object with the
-same functions backed by the oracle, so that the partition / exchange / id-assignment logic is
-exercised with gloo at world size 2 without a GPU.
+same functions written in torch, so that the partition / exchange / id-assignment / pruning logic is
+exercised with gloo at world size 2 and 3 without a GPU.
 """
 from __future__ import annotations
 
@@ -26,6 +28,8 @@ from dataclasses import dataclass
 
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 # ------------------------------------------------------------------------------------------------
@@ -117,31 +121,6 @@ def all_to_all_rows(rows: torch.Tensor, send_counts: list[int], group=None,
     return out, recv_counts
 
 
-def _by_owner(owner: torch.Tensor, world: int, local_ops=None):
-    """Stable order that groups items by owner rank + how many go to each rank.  On the GPU the order comes from the
-    library's radix sort over the ceil(log2(world)) significant bits (one digit pass), and the counts from a binary
-    search in the sorted owners (a histogram over `world` bins would be `n` atomics on a handful of addresses)."""
-    if owner.is_cuda and hasattr(local_ops, "sort_pairs_u64") and owner.numel() > 0:
-        keys = owner.clone()
-        order = local_ops.sort_pairs_u64(keys, max(1, (world - 1).bit_length()))[0].long()
-        grouped = keys
-    else:
-        grouped, order = torch.sort(owner, stable=True)
-    bounds = torch.searchsorted(grouped, torch.arange(world + 1, device=owner.device, dtype=owner.dtype))
-    return order, (bounds[1:] - bounds[:-1]).tolist()
-
-
-def _take_rows(rows: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
-    """``rows[index]`` for a [N, k] matrix with a few int64 columns.  torch's row gather launches one CTA per 16-byte
-    row (5 ms for 20M rows on B200); gathering column by column runs at memory speed."""
-    if rows.dim() != 2 or not rows.is_cuda or rows.size(1) > 8:
-        return rows[index]
-    out = torch.empty((index.numel(), rows.size(1)), dtype=rows.dtype, device=rows.device)
-    for c in range(rows.size(1)):
-        out[:, c] = rows[:, c][index]
-    return out
-
-
 # ------------------------------------------------------------------------------------------------
 # distributed temporal lift (BASELINE config 5)
 # ------------------------------------------------------------------------------------------------
@@ -157,13 +136,55 @@ class DistributedLayer:
     node_sequence: torch.Tensor  # [owned, k] first-order node ids
     edge_index: torch.Tensor     # [2, owned edges] GLOBAL node ids, (row, col)-sorted, rows in the owned range
     edge_weight: torch.Tensor
+    edge_offset: int = 0         # global index of the first owned edge (= id of the next order's first owned node)
+    num_edges: int = 0           # global
+
+    def digest(self) -> torch.Tensor:
+        """This rank's part of ``layer_digest`` (sum over the ranks = digest of the whole layer)."""
+        return layer_digest(self.edge_index, self.edge_weight, self.node_sequence, self.edge_offset, self.row_offset)
 
     def gather(self, group=None) -> "DistributedLayer":
         """The full layer on every rank (tests / small graphs)."""
         ns = _all_gather_var(self.node_sequence, group)
         ei = _all_gather_var(self.edge_index.t().contiguous(), group).t().contiguous()
         w = _all_gather_var(self.edge_weight, group)
-        return DistributedLayer(self.order, self.num_nodes, 0, ns, ei, w)
+        return DistributedLayer(self.order, self.num_nodes, 0, ns, ei, w, 0, self.num_edges)
+
+
+# ------------------------------------------------------------------------------------------------
+# order-sensitive 64-bit digests: a distributed build is checked against a single-device one without gathering it
+# ------------------------------------------------------------------------------------------------
+_DIGEST_CHUNK = 1 << 25
+_DIGEST_MULS = (0x2545F4914F6CDD1D, -0x61C8864680B583EB, 0x1B873593CC9E2D51, -0x3A39CE76F1A9D8B5, 0x27D4EB2F165667C5,
+                -0x00B1A2C3D4E5F607, 0x5851F42D4C957F2D)
+
+
+def _mix_sum(first_position: int, columns) -> torch.Tensor:
+    """sum_i mix(first_position + i, columns[0][i], columns[1][i], ...) in wrapping int64 arithmetic: depends on the
+    position of every element, and partial sums over disjoint position ranges add up to the sum over their union."""
+    n, dev = columns[0].numel(), columns[0].device
+    total = torch.zeros((), dtype=torch.int64, device=dev)
+    for a in range(0, n, _DIGEST_CHUNK):
+        b = min(n, a + _DIGEST_CHUNK)
+        h = (torch.arange(a, b, device=dev, dtype=torch.int64) + (first_position + 1)) * _DIGEST_MULS[0]
+        for j, col in enumerate(columns):
+            h = (h ^ col[a:b]) * _DIGEST_MULS[1 + j % (len(_DIGEST_MULS) - 1)]
+            h ^= h >> 29
+        total += h.sum()
+    return total
+
+
+def layer_digest(edge_index, edge_weight, node_sequence, edge_offset: int = 0, row_offset: int = 0) -> torch.Tensor:
+    """[2] int64 (edges, nodes) of the rows / edges held here, at their GLOBAL positions.  The digests of the parts of a
+    ``DistributedLayer`` summed over the ranks (wrapping) equal the digest of the single-device layer iff -- up to
+    64-bit hash collisions -- edge index, weights and node sequences agree element by element."""
+    ei = edge_index.as_subclass(torch.Tensor)
+    w = edge_weight.contiguous()
+    wbits = w.view(torch.int32).long() if w.dtype == torch.float32 else w.to(torch.float64).view(torch.int64)
+    edges = _mix_sum(edge_offset, [ei[0], ei[1], wbits])
+    ns = node_sequence.as_subclass(torch.Tensor)
+    nodes = _mix_sum(row_offset, [ns[:, c] for c in range(ns.size(1))])
+    return torch.stack([edges, nodes])
 
 
 def _all_gather_var(t: torch.Tensor, group) -> torch.Tensor:
@@ -226,51 +247,60 @@ def exchange_ghost_zone(edge_index: torch.Tensor, time: torch.Tensor, weight: to
     return ext_ei.contiguous(), ext_t.contiguous(), ext_w
 
 
-def _owner_of_id(gid: torch.Tensor, offsets: torch.Tensor, world: int) -> torch.Tensor:
-    """Rank whose owned id range contains ``gid`` (``offsets`` [world+1] cumulative sizes, host tensor)."""
-    return (torch.searchsorted(offsets.to(gid.device), gid, right=True) - 1).clamp_(0, world - 1)
+def _gather_counts(mine: torch.Tensor, group) -> torch.Tensor:
+    """All ranks' copies of a small device vector -> [world, len] on the host (the one synchronisation of a step)."""
+    world = dist.get_world_size(group)
+    mine = mine.reshape(1, -1).contiguous()
+    out = torch.empty((world, mine.size(1)), dtype=mine.dtype, device=mine.device)
+    if mine.is_cuda:
+        dist.all_gather_into_tensor(out, mine, group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), mine[0], group=group)
+    return out.cpu()
 
 
-def _exchange_coalesce(gsrc, gdst, w, last, num_nodes, offsets, local_ops, group):
-    """Send every edge (global node ids) to the rank that owns its source row and merge duplicates there.
+def _exchange_merge(line_index, node_info, weights, own_prefix, offsets, offsets_dev, total_nodes, local_ops, group,
+                    between=None):
+    """One level of the exchange.  Every line-graph edge travels as a 16-byte record to the rank that owns its source
+    row (``offsets``: first row of every rank), is merged there with its duplicates, and the owner returns the index of
+    the merged edge.  Owners hold ascending row ranges, so the concatenation of their merged lists is the global
+    (row, col) order and an index into it is the id of the next layer's De Bruijn node (the distinct edges of a layer in
+    (row, col) order are the k-grams of the next one in lexicographic order).
 
-    Returns, for the owner: the merged (row, col)-sorted edges, their summed weights and the ``last`` value of every
-    merged edge (identical for all duplicates); for the sender: the GLOBAL index of the merged edge every input edge
-    fell into -- owners hold ascending row ranges, so the concatenation of their merged lists is the global
-    (row, col) order, and an index into it is the id of the next layer's De Bruijn node (the distinct edges of a
-    layer, in (row, col) order, are the k-grams of the next one in lexicographic order); and the cumulative merged
-    edge counts per rank [world + 1] (host)."""
+    Returns (merged edge_index (global ids), weights, last nodes) of the owned rows; the ``node_info`` of the next
+    level (one word per input edge: merged id << 32 | last node); the cumulative merged counts [world + 1] as a host
+    list and as a device tensor.  ``between``: callable run while the records are in flight (local work of the next level)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    dev = gsrc.device
-    order, counts = _by_owner(_owner_of_id(gsrc, offsets, world), world, local_ops)
-    narrow = w.dtype == torch.float32 and num_nodes < (1 << 31)
-    if narrow:
-        # ids and first-order nodes fit 32 bits: (source, target) and (weight bits, last node) travel as two words
-        low = (1 << 32) - 1
-        packed = torch.stack([(gsrc << 32) | gdst, (w.view(torch.int32).to(torch.int64) << 32) | (last & low)], dim=1)
-        got, recv_counts = all_to_all_rows(_take_rows(packed, order), counts, group)
-        ei = torch.stack([got[:, 0] >> 32, got[:, 0] & low])
-        ww = (got[:, 1] >> 32).to(torch.int32).view(torch.float32)
-        got_last = got[:, 1] & low
-    else:
-        payload = torch.stack([gsrc[order], gdst[order], w[order].to(torch.float64).view(torch.int64), last[order]], dim=1)
-        got, recv_counts = all_to_all_rows(payload, counts, group)
-        ei = got[:, :2].t().contiguous()
-        ww = got[:, 2].view(torch.float64).to(w.dtype)
-        got_last = got[:, 3]
-    if ei.size(1):
-        out_ei, out_w, inv = local_ops.coalesce(ei, None, num_nodes, ww, "sum", return_inverse=True)
-    else:
-        out_ei, out_w, inv = ei, ww, torch.empty(0, dtype=torch.int64, device=dev)
-    out_last = torch.empty(out_ei.size(1), dtype=torch.int64, device=dev)
-    out_last[inv] = got_last
-    sizes = _all_gather_int([out_ei.size(1)], dev, group)[:, 0]
-    edge_offsets = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(sizes, 0)])
-    # ids return to the senders along the same routes: what came from rank q goes back to q
-    back, _ = all_to_all_rows((inv + int(edge_offsets[rank])).unsqueeze(1), recv_counts, group, recv_counts=counts)
-    gid = torch.empty(gsrc.size(0), dtype=torch.int64, device=dev)
-    gid[order] = back[:, 0]
-    return out_ei, out_w, out_last, gid, edge_offsets
+    dev = line_index.device
+    plan = local_ops.route_plan(line_index, node_info, offsets_dev, world)
+    counts = _gather_counts(plan.counts, group)                      # counts[q, p] = records q sends to p   (sync 1)
+    send, recv = counts[rank].tolist(), counts[:, rank].tolist()
+    records = plan.pack(weights, own_prefix)
+    received = torch.empty((sum(recv), 2), dtype=torch.int64, device=dev)
+    work = dist.all_to_all_single(received.view(-1), records.view(-1), [2 * c for c in recv], [2 * c for c in send],
+                                  group=group, async_op=True)
+    carried = between() if between is not None else None             # overlaps the transfer
+    work.wait()
+    del records
+    row_lo, rows_owned = int(offsets[rank]), int(offsets[rank + 1] - offsets[rank])
+    merge = local_ops.merge_records_begin(received, row_lo, rows_owned, total_nodes)
+    # the merged-edge indices go back along the same routes while the owner writes its merged edges
+    back = torch.empty(plan.E, dtype=torch.int32, device=dev)
+    work = dist.all_to_all_single(back, merge.inverse, send, recv, group=group, async_op=True)
+    results = _gather_counts(merge.result_words, group)              # [world, 2]: merged count, status   (sync 2)
+    if int(results[:, 1].max()) & 1:
+        raise ValueError("distributed lift: a node id outside its layer reached an owner (inconsistent inputs)")
+    sizes = results[:, 0]
+    edge_offsets = [0]
+    for c in sizes.tolist():
+        edge_offsets.append(edge_offsets[-1] + int(c))
+    if edge_offsets[-1] > (1 << 32):
+        raise ValueError(f"distributed lift: {edge_offsets[-1]} merged edges exceed the 32-bit record fields")
+    edge_offsets_dev = torch.tensor(edge_offsets, dtype=torch.int64, device=dev)
+    out_ei, out_w, out_last = merge.finish(int(sizes[rank]))
+    work.wait()
+    next_info = plan.unpack(back, edge_offsets_dev)
+    return out_ei, out_w, out_last, next_info, edge_offsets, edge_offsets_dev, carried
 
 
 def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, num_nodes: int, delta, max_order: int,
@@ -280,60 +310,101 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
     ``edge_index`` [2, m_local] / ``time`` [m_local]: this rank's CONTIGUOUS range of the globally
     time-sorted stream (ranges in rank order).  Returns ``{order: DistributedLayer}``.
 
-    Per order there is ONE exchange: the line-graph edges of the extended (own + ghost) range travel to the owner
-    of their source row as (source id, target id, weight, last node) and are merged there; the owner returns the
-    global index of the merged edge, which IS the node id of the next order (see ``_exchange_coalesce``), so no
-    k-gram row ever has to be ranked or sent.  Edges whose path starts with a ghost event are sent with weight 0:
-    they only collect their ids (their owner contributes the weight), every path is counted exactly once."""
+    Per order there is ONE exchange (``_exchange_merge``): the line-graph edges of the extended (own + ghost) range
+    travel to the owner of their source row as (source id, target id, weight, last node) and are merged there; the
+    owner returns the global index of the merged edge, which IS the node id of the next order, so no k-gram row ever
+    has to be ranked or sent.  Paths that start with a ghost event travel with weight 0: they only collect their ids
+    (the rank that owns their first event contributes the weight), so every path is counted exactly once.
+
+    Only what later orders need is lifted: at order j a path is needed if it starts no later than
+    ``t_last(own) + (K - j) delta`` (its id is the target of a path one order up), and such paths are a PREFIX of the
+    line graph, whose columns are ascending in the source (``limit_sources``).
+
+    Limits: float32 weights; fewer than 2^32 nodes per layer (32-bit record fields)."""
     if local_ops is None:
         from . import ops as local_ops
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = edge_index.device
+    K = int(max_order)
     m_own = edge_index.size(1)
-    w_own = edge_weight if edge_weight is not None else torch.ones(m_own, dtype=torch.float32, device=dev)
+    if edge_weight is not None and edge_weight.dtype != torch.float32:
+        raise TypeError("distributed_temporal_layers: edge weights must be float32")
+    if num_nodes > (1 << 32):
+        raise ValueError("distributed_temporal_layers: more than 2^32 first-order nodes")
     layers: dict[int, DistributedLayer] = {}
 
     # ---- ghost zone once: everything after it is local lifting + one exchange per order
-    if max_order > 1:
-        ext_ei, ext_t, ext_w = exchange_ghost_zone(edge_index, time, w_own, delta * (max_order - 1), group)
+    if K > 1:
+        ext_ei, ext_t, ext_w = exchange_ghost_zone(edge_index, time, edge_weight, delta * (K - 1), group)
     else:
-        ext_ei, ext_t, ext_w = edge_index, time, w_own
-    counted = ext_w.clone()
-    counted[m_own:] = 0                                  # ghost events: ids only
+        ext_ei, ext_t, ext_w = edge_index.contiguous(), time, edge_weight
+    m_ext = ext_ei.size(1)
+
+    # ---- cuts: events that may START a path needed at order j (see above); exact for integer time stamps, no pruning otherwise
+    exact = (not time.is_floating_point()) and isinstance(delta, int)
+    cuts = {K: m_own}
+    if 1 < K:
+        if exact and m_own > 0:
+            limits = torch.tensor([(K - j) * delta for j in range(2, K)], dtype=time.dtype, device=dev) + time[-1]
+            found = torch.searchsorted(ext_t, limits, right=True).tolist() if K > 2 else []
+        else:
+            found = [m_ext if m_own > 0 else 0] * (K - 2)
+        for j, c in zip(range(2, K), found):
+            cuts[j] = int(c)
 
     # ---- order 1: nodes are the first-order nodes themselves, rows owned by node-id range
-    n1_bounds = torch.tensor([-(-num_nodes * p // world) for p in range(world + 1)], dtype=torch.int64)
-    lo, hi = int(n1_bounds[rank]), int(n1_bounds[rank + 1])
-    ei_k, w_k, last_k, gid_line, offsets = _exchange_coalesce(ext_ei[0], ext_ei[1], counted, ext_ei[1], num_nodes, n1_bounds,
-                                                              local_ops, group)
+    n1_bounds = [-(-num_nodes * p // world) for p in range(world + 1)]
+    n1_dev = torch.tensor(n1_bounds, dtype=torch.int64, device=dev)
+    lo, hi = n1_bounds[rank], n1_bounds[rank + 1]
+
+    def first_lift():
+        if K == 1 or m_ext == 0:
+            return torch.empty((2, 0), dtype=torch.int64, device=dev)
+        return local_ops.lift_order_temporal(ext_ei, ext_t, delta, num_nodes, assume_sorted=True, limit_sources=cuts[2],
+                                             allow_empty=True)
+
+    ei_k, w_k, last_k, info, offsets, offsets_dev, line_index = _exchange_merge(
+        ext_ei, None, ext_w, m_own, n1_bounds, n1_dev, num_nodes, local_ops, group, between=first_lift)
     rows_k = torch.arange(lo, hi, device=dev).unsqueeze(1)
-    layers[1] = DistributedLayer(1, num_nodes, lo, rows_k, ei_k, w_k)
-    if max_order == 1:
+    layers[1] = DistributedLayer(1, num_nodes, lo, rows_k, ei_k, w_k, offsets[rank], offsets[-1])
+    if K == 1:
         return layers
 
-    # ---- order 2: line-graph nodes are the (own + ghost) events, their ids the merged first-order edges
-    try:
-        line_index = local_ops.lift_order_temporal(ext_ei, ext_t, delta, num_nodes)
-    except (RuntimeError, ValueError):                # no pair in this range (the single-device call fails only if NO rank has one)
-        line_index = torch.empty((2, 0), dtype=torch.int64, device=dev)
-    line_w = local_ops.pair_attributes(line_index, counted, "src") if line_index.size(1) else counted[:0]
-    last_line = ext_ei[1]                             # last first-order node of every line-graph node's k-gram
-    num_line_nodes = ext_ei.size(1)
+    # ---- orders 2..K: the line-graph nodes of level k are the edges of level k - 1 (level 1: the events)
+    line_w = None
+    if ext_w is not None:
+        line_w = local_ops.pair_attributes(line_index, ext_w, "src", index_bound=m_ext) if line_index.size(1) else ext_w[:0]
+    num_line_nodes = m_ext
+    # prefix[j] = number of level-k line-graph NODES that start before cut j (level 2: the events themselves)
+    prefix = dict(cuts)
     row_lo = lo
-
-    for k in range(2, max_order + 1):
-        # rows of the nodes this rank owns at order k = its merged edges of order k - 1
+    for k in range(2, K + 1):
+        # number of level-k EDGES (= level-(k+1) nodes) that start before every later cut
+        later = [j for j in range(k + 1, K + 1)]
+        if later and line_index.size(1):
+            at = torch.tensor([prefix[j] for j in later], dtype=torch.int64, device=dev)
+            nxt_prefix = dict(zip(later, torch.searchsorted(line_index[0].contiguous(), at, right=False).tolist()))
+        else:
+            nxt_prefix = {j: 0 for j in later}
+        own_edges_from = prefix[K]                           # sources >= this start with a ghost event: weight 0
         prev_rows, prev_lo = rows_k, row_lo
-        rows_k = torch.cat([_take_rows(prev_rows, ei_k[0] - prev_lo), last_k.unsqueeze(1)], dim=1)
-        total, row_lo = int(offsets[-1]), int(offsets[rank])
-        edge_last = last_line[line_index[1]]
-        ei_k, w_k, last_k, gid_next, next_offsets = _exchange_coalesce(gid_line[line_index[0]], gid_line[line_index[1]], line_w,
-                                                                       edge_last, total, offsets, local_ops, group)
-        layers[k] = DistributedLayer(k, total, row_lo, rows_k, ei_k, w_k)
-        if k == max_order:
+        rows_k = local_ops.extend_owned_rows(prev_rows, prev_lo, ei_k[0], last_k)
+        total, row_lo = offsets[-1], offsets[rank]
+
+        def next_lift(k=k, line_index=line_index, num_line_nodes=num_line_nodes, nxt_prefix=nxt_prefix):
+            if k == K or line_index.size(1) == 0:
+                return torch.empty((2, 0), dtype=torch.int64, device=dev)
+            return local_ops.lift_order_edge_index(line_index, num_line_nodes, limit_sources=nxt_prefix[k + 1])
+
+        ei_k, w_k, last_k, info, offsets, offsets_dev, nxt = _exchange_merge(
+            line_index, info, line_w, own_edges_from, offsets, offsets_dev, total, local_ops, group, between=next_lift)
+        if k == 2 and offsets[-1] == 0:
+            # no time-respecting pair on ANY rank: the single-device build fails in lift_order_temporal (temporal.py:53)
+            raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors (distributed lift: no time-respecting pair)")
+        layers[k] = DistributedLayer(k, total, row_lo, rows_k, ei_k, w_k, offsets[rank], offsets[-1])
+        if k == K:
             break
-        nxt = local_ops.lift_order_edge_index(line_index, num_line_nodes)
-        line_w = local_ops.pair_attributes(nxt, line_w, "src") if nxt.size(1) else line_w[:0]
-        gid_line, last_line, offsets = gid_next, edge_last, next_offsets
-        num_line_nodes, line_index = line_index.size(1), nxt
+        if line_w is not None:
+            line_w = local_ops.pair_attributes(nxt, line_w, "src", index_bound=line_index.size(1)) if nxt.size(1) else line_w[:0]
+        num_line_nodes, line_index, prefix = line_index.size(1), nxt, nxt_prefix
     return layers

@@ -141,6 +141,54 @@ def test_temporal_float_promotions(cuda):
         assert torch.equal(lift_order_temporal(TG(ei.to(cuda), tf.to(cuda), 30), delta).cpu(), want)
 
 
+@pytest.mark.parametrize("seed,n,m,horizon,delta,as_float", [(0, 12, 400, 40, 3, False), (1, 300, 20_000, 500, 9, False),
+                                                             (2, 20, 600, 30, 2.5, True)])
+def test_temporal_lift_of_shuffled_time_stamps(cuda, seed, n, m, horizon, delta, as_float):
+    """The reference's lift does not need a time-ordered event list (temporal.py:33-53: masks per distinct time
+    stamp); its DBGNN tutorial lifts right after TemporalGraph.shuffle_time().  Pairs come out by ascending source
+    time stamp, source position, target position."""
+    g = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, n, (2, m), generator=g)
+    t = torch.randint(0, horizon, (m,), generator=g)        # NOT sorted
+    if as_float:
+        t = t.double() / 2
+    want = lift.lift_order_temporal(ei, t, delta)
+    got = lift_order_temporal(TG(ei.to(cuda), t.to(cuda), n), delta)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_model_from_a_graph_with_shuffled_time_stamps(cuda):
+    """TemporalGraph.shuffle_time() then from_temporal_graph (the reference's DBGNN tutorial): the event graph is taken
+    over the SHUFFLED positions of g.data, node sequences and weights from the re-sorted events
+    (multi_order_model.py:148-170).  Distinct time stamps, so that the re-sorting has no ties to break."""
+    from oracle import mom
+
+    g = torch.Generator().manual_seed(4)
+    n, m = 15, 500
+    ei = torch.randint(0, n, (2, m), generator=g)
+    tg = pp.TemporalGraph.from_tensors(ei.to(cuda), torch.arange(m, device=cuda), n)
+    tg.shuffle_time()
+    shuffled = tg.data.time.cpu()
+    model = pp.MultiOrderModel.from_temporal_graph(tg, delta=25, max_order=3)
+    order = torch.sort(shuffled, stable=True).indices
+    ref = mom.from_temporal_graph(ei[:, order], shuffled[order], n, delta=25, max_order=3,
+                                  event_graph=lift.lift_order_temporal(ei, shuffled, 25))
+    for k in (1, 2, 3):
+        assert torch.equal(model.layers[k].data.edge_index.as_tensor().cpu(), ref[k].edge_index), k
+        assert torch.equal(model.layers[k].data.edge_weight.cpu(), ref[k].edge_weight), k
+        assert torch.equal(model.layers[k].data.node_sequence.cpu(), ref[k].node_sequence), k
+
+
+def test_pair_attributes_rejects_ids_outside_the_attribute(cuda):
+    ei = torch.tensor([[0, 1, 5], [1, 2, 0]], device=cuda)
+    with pytest.raises(IndexError):
+        aggregate_node_attributes(ei, torch.ones(4, device=cuda), "src")
+    with pytest.raises(IndexError):
+        aggregate_node_attributes(torch.tensor([[0, -1], [1, 0]], device=cuda), torch.ones(4, device=cuda), "add")
+    with pytest.raises(IndexError):  # weights shorter than the edge list they belong to
+        lift_order_edge_index_weighted(torch.tensor([[0, 1], [1, 0]], device=cuda), torch.ones(1, device=cuda), 2)
+
+
 def test_temporal_rejects_bad_ids(cuda):
     ei = torch.tensor([[0, 9], [1, 2]], device=cuda)
     with pytest.raises(ValueError):

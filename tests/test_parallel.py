@@ -1,10 +1,10 @@
 """Host logic of the multi-GPU path (pathpyg_b200/parallel.py) with gloo at world size 2 on CPU.
 
-The local compute is injected: an object with the five functions of ``pathpyg_b200.ops`` that the
-distributed lift calls, backed by the oracle (tests may use the oracle; the product path cannot, and on
-the GPU box the default ``local_ops`` is the CUDA library).  What is tested here is the partitioning, the
-ghost-zone exchange, the global k-gram ranks and the owner-side coalesce: the gathered result must be
-IDENTICAL to the single-process oracle model."""
+The local compute is injected: an object with the functions of ``pathpyg_b200.ops`` that the distributed lift calls,
+written in plain torch + the oracle's lift (tests may use the oracle; the product path cannot, and on the GPU box
+the default ``local_ops`` is the CUDA library).  What is tested here is the partitioning, the ghost-zone exchange,
+the pruning of the line graphs to what later orders need, the record routing and the global ids: the gathered
+result must be IDENTICAL to the single-process oracle model."""
 import os
 import socket
 
@@ -13,41 +13,9 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from oracle import lift, mom, pyg
+from oracle import mom
 from pathpyg_b200 import parallel
-
-
-class OracleOps:
-    """CPU stand-in for pathpyg_b200.ops (same call signatures)."""
-
-    @staticmethod
-    def unique_rows(rows):
-        return torch.unique(rows, dim=0, return_inverse=True)
-
-    @staticmethod
-    def coalesce(edge_index, remap, num_nodes, edge_weight, reduce="sum", return_inverse=False):
-        ei = edge_index if remap is None else remap[edge_index]
-        if ei.numel() and int(ei.max()) >= num_nodes:
-            raise ValueError("mapped node id outside [0, num_nodes)")
-        out_ei, out_w = pyg.coalesce(ei, edge_weight, num_nodes, reduce)
-        if not return_inverse:
-            return out_ei, out_w
-        inverse = torch.unique(ei[0] * num_nodes + ei[1], return_inverse=True)[1]   # index into the (row, col)-sorted distinct edges
-        return out_ei, out_w, inverse
-
-    @staticmethod
-    def lift_order_temporal(edge_index, time, delta, num_nodes):
-        return lift.lift_order_temporal(edge_index, time, delta)
-
-    @staticmethod
-    def lift_order_edge_index(edge_index, num_nodes):
-        if edge_index.size(1) == 0:
-            return edge_index.new_empty((2, 0))
-        return lift.lift_order_edge_index(edge_index, num_nodes)
-
-    @staticmethod
-    def pair_attributes(edge_index, attr, rule):
-        return lift.aggregate_node_attributes(edge_index, attr, rule)
+from torch_local_ops import TorchOps
 
 
 def _free_port():
@@ -82,8 +50,6 @@ def _stream(seed, n, m, horizon):
 
 def _check_temporal(rank, world, seed, n, m, horizon, delta, K, weighted, split):
     ei, t, w = _stream(seed, n, m, horizon)
-    if weighted == "f64":      # float64 weights travel on the wide (four-word) exchange payload
-        w = w.double()
     want = mom.from_temporal_graph(ei, t, n, delta=delta, max_order=K, edge_weight=w if weighted else None)
     if split == "even":
         lo, hi = parallel.partition_stream(m, rank, world)
@@ -91,7 +57,7 @@ def _check_temporal(rank, world, seed, n, m, horizon, delta, K, weighted, split)
         cuts = [0, m // 5, m] if world == 2 else [0] + [m] * world
         lo, hi = cuts[rank], cuts[rank + 1]
     got = parallel.distributed_temporal_layers(ei[:, lo:hi].contiguous(), t[lo:hi].contiguous(), n, delta, K,
-                                               edge_weight=w[lo:hi].contiguous() if weighted else None, local_ops=OracleOps)
+                                               edge_weight=w[lo:hi].contiguous() if weighted else None, local_ops=TorchOps)
     assert sorted(got) == sorted(want)
     for k, layer in want.items():
         full = got[k].gather()
@@ -111,7 +77,7 @@ def _check_temporal(rank, world, seed, n, m, horizon, delta, K, weighted, split)
     (1, 15, 400, 50, 2, 3, True, "even"),
     (2, 12, 300, 40, 2, 4, True, "uneven"),
     (3, 40, 500, 30, 4, 2, False, "uneven"),
-    (4, 15, 300, 40, 2, 3, "f64", "even"),
+    (4, 15, 300, 40, 2, 5, True, "even"),
 ])
 def test_distributed_temporal_layers_world2(seed, n, m, horizon, delta, K, weighted, split):
     _spawn(_check_temporal, 2, seed, n, m, horizon, delta, K, weighted, split)
