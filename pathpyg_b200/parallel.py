@@ -247,6 +247,43 @@ def exchange_ghost_zone(edge_index: torch.Tensor, time: torch.Tensor, weight: to
     return ext_ei.contiguous(), ext_t.contiguous(), ext_w
 
 
+class _Trace:
+    """NVTX range per phase (always; free without a profiler) and, with ``PPG_DIST_TRACE=1``, CUDA-event time stamps
+    of the phases of one call: ``parallel.last_trace`` then holds [(label, ms since the start of the call)]."""
+
+    def __init__(self, dev):
+        import os
+        self.timed = os.environ.get("PPG_DIST_TRACE", "0") == "1" and dev.type == "cuda"
+        self.cuda = dev.type == "cuda"
+        self.marks = []
+        self.open = False
+        self.mark("start")
+
+    def mark(self, label):
+        if self.cuda:
+            if self.open:
+                torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_push(label)
+            self.open = True
+        if self.timed:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((label, ev))
+
+    def close(self):
+        global last_trace
+        if self.cuda and self.open:
+            torch.cuda.nvtx.range_pop()
+            self.open = False
+        if self.timed:
+            torch.cuda.synchronize()
+            t0 = self.marks[0][1]
+            last_trace = [(label, t0.elapsed_time(ev)) for label, ev in self.marks]
+
+
+last_trace = None
+
+
 def _gather_counts(mine: torch.Tensor, group) -> torch.Tensor:
     """All ranks' copies of a small device vector -> [world, len] on the host (the one synchronisation of a step)."""
     world = dist.get_world_size(group)
@@ -260,7 +297,7 @@ def _gather_counts(mine: torch.Tensor, group) -> torch.Tensor:
 
 
 def _exchange_merge(line_index, node_info, weights, own_prefix, offsets, offsets_dev, total_nodes, local_ops, group,
-                    between=None):
+                    between=None, trace=None, level=0):
     """One level of the exchange.  Every line-graph edge travels as a 16-byte record to the rank that owns its source
     row (``offsets``: first row of every rank), is merged there with its duplicates, and the owner returns the index of
     the merged edge.  Owners hold ascending row ranges, so the concatenation of their merged lists is the global
@@ -272,21 +309,28 @@ def _exchange_merge(line_index, node_info, weights, own_prefix, offsets, offsets
     list and as a device tensor.  ``between``: callable run while the records are in flight (local work of the next level)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = line_index.device
+    mark = trace.mark if trace is not None else (lambda label: None)
+    mark(f"route_count[{level}]")
     plan = local_ops.route_plan(line_index, node_info, offsets_dev, world)
     counts = _gather_counts(plan.counts, group)                      # counts[q, p] = records q sends to p   (sync 1)
     send, recv = counts[rank].tolist(), counts[:, rank].tolist()
+    mark(f"route_pack[{level}]")
     records = plan.pack(weights, own_prefix)
     received = torch.empty((sum(recv), 2), dtype=torch.int64, device=dev)
     work = dist.all_to_all_single(received.view(-1), records.view(-1), [2 * c for c in recv], [2 * c for c in send],
                                   group=group, async_op=True)
+    mark(f"lift_next[{level}]")
     carried = between() if between is not None else None             # overlaps the transfer
+    mark(f"records_wait[{level}]")
     work.wait()
     del records
+    mark(f"merge_sort[{level}]")
     row_lo, rows_owned = int(offsets[rank]), int(offsets[rank + 1] - offsets[rank])
     merge = local_ops.merge_records_begin(received, row_lo, rows_owned, total_nodes)
     # the merged-edge indices go back along the same routes while the owner writes its merged edges
     back = torch.empty(plan.E, dtype=torch.int32, device=dev)
     work = dist.all_to_all_single(back, merge.inverse, send, recv, group=group, async_op=True)
+    mark(f"merge_sync[{level}]")
     results = _gather_counts(merge.result_words, group)              # [world, 2]: merged count, status   (sync 2)
     if int(results[:, 1].max()) & 1:
         raise ValueError("distributed lift: a node id outside its layer reached an owner (inconsistent inputs)")
@@ -297,8 +341,11 @@ def _exchange_merge(line_index, node_info, weights, own_prefix, offsets, offsets
     if edge_offsets[-1] > (1 << 32):
         raise ValueError(f"distributed lift: {edge_offsets[-1]} merged edges exceed the 32-bit record fields")
     edge_offsets_dev = torch.tensor(edge_offsets, dtype=torch.int64, device=dev)
+    mark(f"merge_fill[{level}]")
     out_ei, out_w, out_last = merge.finish(int(sizes[rank]))
+    mark(f"ids_wait[{level}]")
     work.wait()
+    mark(f"route_unpack[{level}]")
     next_info = plan.unpack(back, edge_offsets_dev)
     return out_ei, out_w, out_last, next_info, edge_offsets, edge_offsets_dev, carried
 
@@ -332,6 +379,8 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
     if num_nodes > (1 << 32):
         raise ValueError("distributed_temporal_layers: more than 2^32 first-order nodes")
     layers: dict[int, DistributedLayer] = {}
+    trace = _Trace(dev)
+    trace.mark("ghost_zone")
 
     # ---- ghost zone once: everything after it is local lifting + one exchange per order
     if K > 1:
@@ -364,10 +413,11 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
                                              allow_empty=True)
 
     ei_k, w_k, last_k, info, offsets, offsets_dev, line_index = _exchange_merge(
-        ext_ei, None, ext_w, m_own, n1_bounds, n1_dev, num_nodes, local_ops, group, between=first_lift)
+        ext_ei, None, ext_w, m_own, n1_bounds, n1_dev, num_nodes, local_ops, group, between=first_lift, trace=trace, level=1)
     rows_k = torch.arange(lo, hi, device=dev).unsqueeze(1)
     layers[1] = DistributedLayer(1, num_nodes, lo, rows_k, ei_k, w_k, offsets[rank], offsets[-1])
     if K == 1:
+        trace.close()
         return layers
 
     # ---- orders 2..K: the line-graph nodes of level k are the edges of level k - 1 (level 1: the events)
@@ -388,6 +438,7 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
             nxt_prefix = {j: 0 for j in later}
         own_edges_from = prefix[K]                           # sources >= this start with a ghost event: weight 0
         prev_rows, prev_lo = rows_k, row_lo
+        trace.mark(f"rows[{k}]")
         rows_k = local_ops.extend_owned_rows(prev_rows, prev_lo, ei_k[0], last_k)
         total, row_lo = offsets[-1], offsets[rank]
 
@@ -397,7 +448,8 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
             return local_ops.lift_order_edge_index(line_index, num_line_nodes, limit_sources=nxt_prefix[k + 1])
 
         ei_k, w_k, last_k, info, offsets, offsets_dev, nxt = _exchange_merge(
-            line_index, info, line_w, own_edges_from, offsets, offsets_dev, total, local_ops, group, between=next_lift)
+            line_index, info, line_w, own_edges_from, offsets, offsets_dev, total, local_ops, group, between=next_lift,
+            trace=trace, level=k)
         if k == 2 and offsets[-1] == 0:
             # no time-respecting pair on ANY rank: the single-device build fails in lift_order_temporal (temporal.py:53)
             raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors (distributed lift: no time-respecting pair)")
@@ -407,4 +459,5 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
         if line_w is not None:
             line_w = local_ops.pair_attributes(nxt, line_w, "src", index_bound=line_index.size(1)) if nxt.size(1) else line_w[:0]
         num_line_nodes, line_index, prefix = line_index.size(1), nxt, nxt_prefix
+    trace.close()
     return layers

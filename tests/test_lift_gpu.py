@@ -160,7 +160,10 @@ def test_temporal_lift_of_shuffled_time_stamps(cuda, seed, n, m, horizon, delta,
 def test_model_from_a_graph_with_shuffled_time_stamps(cuda):
     """TemporalGraph.shuffle_time() then from_temporal_graph (the reference's DBGNN tutorial): the event graph is taken
     over the SHUFFLED positions of g.data, node sequences and weights from the re-sorted events
-    (multi_order_model.py:148-170).  Distinct time stamps, so that the re-sorting has no ties to break."""
+    (multi_order_model.py:148-170).  Distinct time stamps, so that the re-sorting has no ties to break.  Orders 1
+    and 2 only: beyond, the reference hands this event graph -- no longer sorted by its source row -- to
+    lift_order_edge_index, whose precondition (lift_order.py:56, "sorted edge index") it violates; what comes out
+    there is not a defined result."""
     from oracle import mom
 
     g = torch.Generator().manual_seed(4)
@@ -169,11 +172,11 @@ def test_model_from_a_graph_with_shuffled_time_stamps(cuda):
     tg = pp.TemporalGraph.from_tensors(ei.to(cuda), torch.arange(m, device=cuda), n)
     tg.shuffle_time()
     shuffled = tg.data.time.cpu()
-    model = pp.MultiOrderModel.from_temporal_graph(tg, delta=25, max_order=3)
+    model = pp.MultiOrderModel.from_temporal_graph(tg, delta=25, max_order=2)
     order = torch.sort(shuffled, stable=True).indices
-    ref = mom.from_temporal_graph(ei[:, order], shuffled[order], n, delta=25, max_order=3,
+    ref = mom.from_temporal_graph(ei[:, order], shuffled[order], n, delta=25, max_order=2,
                                   event_graph=lift.lift_order_temporal(ei, shuffled, 25))
-    for k in (1, 2, 3):
+    for k in (1, 2):
         assert torch.equal(model.layers[k].data.edge_index.as_tensor().cpu(), ref[k].edge_index), k
         assert torch.equal(model.layers[k].data.edge_weight.cpu(), ref[k].edge_weight), k
         assert torch.equal(model.layers[k].data.node_sequence.cpu(), ref[k].node_sequence), k
