@@ -70,6 +70,16 @@ def static_config(name: str, world: int) -> dict:
     return out
 
 
+def ghost_overhead(cfg, world):
+    """Estimated extra work of a rank that has a ghost zone (all but the last): at order j it also lifts the paths that
+    start up to (K - j) delta after its own range; orders weighted by their line-graph sizes E_j ~ c^(j-2),
+    c = (m / n)(delta / T).  The last rank gets 1 + g times the others' share of the stream."""
+    K, c = cfg["order"], cfg["m"] / cfg["n"] * cfg["delta"] / cfg["T"]
+    weights = [c ** (j - 2) for j in range(2, K + 1)]
+    extra = sum(w * (K - j) for w, j in zip(weights, range(2, K + 1))) / sum(weights)
+    return extra * cfg["delta"] * world / cfg["T"]
+
+
 def make_stream(cfg, seed):
     g = torch.Generator().manual_seed(seed)
     ei = torch.randint(0, cfg["n"], (2, cfg["m"]), generator=g)
@@ -468,7 +478,7 @@ def run_dist(args, name, rank, world, local_rank, as_extra=False):
     steps = args.steps if not as_extra else max(3, min(args.steps, 5))
     warmup = args.warmup if not as_extra else 3
     ei_h, t_h = make_stream(cfg, seed=0)                      # every rank draws the SAME stream and keeps its time range
-    lo, hi = parallel.partition_stream(cfg["m"], rank, world)
+    lo, hi = parallel.partition_stream(cfg["m"], rank, world, last_share=1.0 + ghost_overhead(cfg, world))
     ei_pin, t_pin = ei_h[:, lo:hi].contiguous().pin_memory(), t_h[lo:hi].contiguous().pin_memory()
     ei_l, t_l = ei_pin.to(dev), t_pin.to(dev)
     stream = torch.cuda.current_stream(dev)

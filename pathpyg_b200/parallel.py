@@ -198,9 +198,15 @@ def _all_gather_var(t: torch.Tensor, group) -> torch.Tensor:
     return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
 
 
-def partition_stream(num_edges: int, rank: int, world: int) -> tuple[int, int]:
-    """Contiguous range of positions of the time-sorted stream owned by ``rank``."""
-    return num_edges * rank // world, num_edges * (rank + 1) // world
+def partition_stream(num_edges: int, rank: int, world: int, last_share: float = 1.0) -> tuple[int, int]:
+    """Contiguous range of positions of the time-sorted stream owned by ``rank``.  ``last_share``: size of the LAST
+    rank's range relative to the others -- it has no ghost zone (nothing follows it), so it can own ``1 + g`` times as
+    many events as a rank whose ghost paths cost it a fraction ``g`` of extra work."""
+    if world == 1:
+        return 0, num_edges
+    unit = num_edges / (world - 1 + last_share)
+    cuts = [min(num_edges, int(round(unit * r))) for r in range(world)] + [num_edges]
+    return cuts[rank], cuts[rank + 1]
 
 
 def exchange_ghost_zone(edge_index: torch.Tensor, time: torch.Tensor, weight: torch.Tensor | None, horizon,
@@ -327,11 +333,12 @@ def _exchange_merge(line_index, node_info, weights, own_prefix, offsets, offsets
     mark(f"merge_sort[{level}]")
     row_lo, rows_owned = int(offsets[rank]), int(offsets[rank + 1] - offsets[rank])
     merge = local_ops.merge_records_begin(received, row_lo, rows_owned, total_nodes)
+    mark(f"merge_sync[{level}]")
+    # (collectives of one communicator run in issue order: the small all-gather goes first, the bulk transfer after it)
+    results = _gather_counts(merge.result_words, group)              # [world, 2]: merged count, status   (sync 2)
     # the merged-edge indices go back along the same routes while the owner writes its merged edges
     back = torch.empty(plan.E, dtype=torch.int32, device=dev)
     work = dist.all_to_all_single(back, merge.inverse, send, recv, group=group, async_op=True)
-    mark(f"merge_sync[{level}]")
-    results = _gather_counts(merge.result_words, group)              # [world, 2]: merged count, status   (sync 2)
     if int(results[:, 1].max()) & 1:
         raise ValueError("distributed lift: a node id outside its layer reached an owner (inconsistent inputs)")
     sizes = results[:, 0]

@@ -34,7 +34,7 @@ def main():
     os.environ.setdefault("MASTER_PORT", "29512")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     ei, t = bench.make_stream(cfg, seed=0)
-    lo, hi = parallel.partition_stream(cfg["m"], rank, world)
+    lo, hi = parallel.partition_stream(cfg["m"], rank, world, last_share=1.0 + bench.ghost_overhead(cfg, world))
     ei_l, t_l = ei[:, lo:hi].contiguous().to(dev), t[lo:hi].contiguous().to(dev)
     del ei, t
     K = cfg["order"]
