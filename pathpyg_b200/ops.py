@@ -70,9 +70,12 @@ def _lift_limit(ws: torch.Tensor, temporal: int, num_sources: int, num_nodes: in
 
 # --------------------------------------------------------------------------------------- a2
 class PendingLift:
-    """lift_order_edge_index whose count pass is enqueued; ``finish()`` reads the size, allocates and fills."""
+    """lift_order_edge_index whose count pass is enqueued; ``finish()`` reads the size, allocates and fills.
+    ``limit_sources``: only the columns whose source edge is < limit_sources (a prefix of the full lift).
+    ``result_words`` (device int64 [2]: column count, status bits) lets a caller collect the count together with other
+    pending results in ONE synchronisation and hand it to ``finish(total=..., status=...)``."""
 
-    def __init__(self, ei, num_nodes):
+    def __init__(self, ei, num_nodes, limit_sources=None):
         self.ei, self.num_nodes, self.dev, self.E = ei, num_nodes, ei.device, ei.size(1)
         self.ws = None
         if self.E:
@@ -80,12 +83,17 @@ class PendingLift:
             with torch.cuda.device(self.dev):
                 self.ws = _workspace(lib.ppg_lift_order_workspace_bytes(self.E, num_nodes), self.dev)
                 _lib.check(lib.ppg_lift_order_count(_ptr(ei), self.E, num_nodes, _ptr(self.ws), self.ws.numel(), None, _stream(self.dev)))
+            if limit_sources is not None and limit_sources < self.E:
+                _lift_limit(self.ws, 0, self.E, self.num_nodes, limit_sources, self.dev)
+            self.result_words = self.ws[:16].view(torch.int64)
+        else:
+            self.result_words = torch.zeros(2, dtype=torch.int64, device=self.dev)
 
-    def finish(self, limit_sources: int | None = None) -> torch.Tensor:
-        """``limit_sources``: only the columns whose source edge is < limit_sources (a prefix of the full lift)."""
-        if self.E and limit_sources is not None and limit_sources < self.E:
-            _lift_limit(self.ws, 0, self.E, self.num_nodes, limit_sources, self.dev)
-        total = _read_result(self.ws, self.dev, "lift_order_edge_index") if self.E else 0
+    def finish(self, total: int | None = None, status: int = 0, allow_empty: bool = True) -> torch.Tensor:
+        if total is None:
+            total = _read_result(self.ws, self.dev, "lift_order_edge_index") if self.E else 0
+        elif status & 1:
+            raise ValueError("lift_order_edge_index: node id outside [0, num_nodes)")
         out = torch.empty((2, total), dtype=torch.int64, device=self.dev)
         if total:
             with torch.cuda.device(self.dev):
@@ -93,14 +101,14 @@ class PendingLift:
         return out
 
 
-def lift_order_edge_index_begin(edge_index: torch.Tensor, num_nodes: int) -> PendingLift:
+def lift_order_edge_index_begin(edge_index: torch.Tensor, num_nodes: int, limit_sources: int | None = None) -> PendingLift:
     ei = _edge_index_arg(edge_index)
     _require_cuda(ei)
-    return PendingLift(ei, int(num_nodes))
+    return PendingLift(ei, int(num_nodes), limit_sources)
 
 
 def lift_order_edge_index(edge_index: torch.Tensor, num_nodes: int, limit_sources: int | None = None) -> torch.Tensor:
-    return lift_order_edge_index_begin(edge_index, num_nodes).finish(limit_sources)
+    return lift_order_edge_index_begin(edge_index, num_nodes, limit_sources).finish()
 
 
 # --------------------------------------------------------------------------------------- a3
@@ -154,7 +162,10 @@ def _time_mode(time: torch.Tensor, delta):
 
 
 class PendingTemporalLift:
-    def __init__(self, ei, time, mode, delta_i, delta_f, num_nodes, grouped_ws=None):
+    """``limit_sources``: only the pairs whose source event is < limit_sources (a prefix of the full output);
+    ``result_words``: see ``PendingLift``."""
+
+    def __init__(self, ei, time, mode, delta_i, delta_f, num_nodes, grouped_ws=None, limit_sources=None):
         self.dev, self.m, self.num_nodes = ei.device, ei.size(1), num_nodes
         self.keep = (ei, time)  # inputs stay alive until the kernels have run
         lib = _lib.load()
@@ -165,13 +176,16 @@ class PendingTemporalLift:
                 self.ws, mode = grouped_ws, mode | _lib.TIME_GROUPED
             _lib.check(lib.ppg_lift_temporal_count(_ptr(ei), _ptr(time), self.m, num_nodes, mode, delta_i, delta_f, _ptr(self.ws),
                                                    self.ws.numel(), None, _stream(self.dev)))
-
-    def finish(self, limit_sources: int | None = None, allow_empty: bool = False) -> torch.Tensor:
-        """``limit_sources``: only the pairs whose source event is < limit_sources (a prefix of the full output);
-        ``allow_empty``: return a [2, 0] tensor instead of raising when no pair exists (one rank's slice of a stream)."""
         if limit_sources is not None and limit_sources < self.m:
             _lift_limit(self.ws, 1, self.m, self.num_nodes, limit_sources, self.dev)
-        total = _read_result(self.ws, self.dev, "lift_order_temporal")
+        self.result_words = self.ws[:16].view(torch.int64)
+
+    def finish(self, total: int | None = None, status: int = 0, allow_empty: bool = False) -> torch.Tensor:
+        """``allow_empty``: return a [2, 0] tensor instead of raising when no pair exists (one rank's slice of a stream)."""
+        if total is None:
+            total = _read_result(self.ws, self.dev, "lift_order_temporal")
+        elif status & 1:
+            raise ValueError("lift_order_temporal: node id outside [0, num_nodes)")
         if total == 0 and allow_empty:
             return torch.empty((2, 0), dtype=torch.int64, device=self.dev)
         if total == 0:
@@ -224,7 +238,8 @@ class PendingUnsortedTemporalLift:
 
 
 def lift_order_temporal_begin(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int,
-                              grouped_ws: torch.Tensor | None = None, assume_sorted: bool = False):
+                              grouped_ws: torch.Tensor | None = None, assume_sorted: bool = False,
+                              limit_sources: int | None = None):
     """``assume_sorted``: the caller knows that ``time`` ascends (a ``TemporalGraph`` whose constructor put it in
     order); otherwise one device pass checks it, and an unordered stream takes ``PendingUnsortedTemporalLift``."""
     ei = _edge_index_arg(edge_index)
@@ -236,15 +251,14 @@ def lift_order_temporal_begin(edge_index: torch.Tensor, time: torch.Tensor, delt
         raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors (lift_order_temporal: empty input)")
     if not assume_sorted and grouped_ws is None and time.numel() > 1 and not bool((time[1:] >= time[:-1]).all()):
         return PendingUnsortedTemporalLift(ei, time, mode, delta_i, delta_f, int(num_nodes))
-    return PendingTemporalLift(ei, time, mode, delta_i, delta_f, int(num_nodes), grouped_ws)
+    return PendingTemporalLift(ei, time, mode, delta_i, delta_f, int(num_nodes), grouped_ws, limit_sources)
 
 
 def lift_order_temporal(edge_index: torch.Tensor, time: torch.Tensor, delta, num_nodes: int,
                         assume_sorted: bool = False, limit_sources: int | None = None, allow_empty: bool = False) -> torch.Tensor:
-    pending = lift_order_temporal_begin(edge_index, time, delta, num_nodes, assume_sorted=assume_sorted)
-    if limit_sources is None and not allow_empty:
-        return pending.finish()
-    return pending.finish(limit_sources, allow_empty)
+    pending = lift_order_temporal_begin(edge_index, time, delta, num_nodes, assume_sorted=assume_sorted,
+                                        limit_sources=limit_sources)
+    return pending.finish(allow_empty=allow_empty) if isinstance(pending, PendingTemporalLift) else pending.finish()
 
 
 # --------------------------------------------------------------------------------------- a4

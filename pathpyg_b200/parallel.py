@@ -99,28 +99,6 @@ def _all_gather_int(values: list[int], device, group) -> torch.Tensor:
     return out.cpu()
 
 
-def all_to_all_rows(rows: torch.Tensor, send_counts: list[int], group=None,
-                    recv_counts: list[int] | None = None) -> tuple[torch.Tensor, list[int]]:
-    """Variable all-to-all of the leading dimension: ``rows`` is ordered by destination rank,
-    ``send_counts[p]`` rows go to rank p.  Returns (received rows ordered by source rank, recv_counts).
-    ``recv_counts``: pass them when they are already known (the answer to an earlier exchange travels the same
-    routes backwards) -- saves the all-gather of the counts and its host synchronisation."""
-    world = dist.get_world_size(group)
-    dev = rows.device
-    if recv_counts is None:
-        counts = _all_gather_int(send_counts, dev, group)          # counts[q, p] = rows q sends to p
-        recv_counts = counts[:, dist.get_rank(group)].tolist()
-    width = rows.shape[1:]
-    out = torch.empty((sum(recv_counts),) + tuple(width), dtype=rows.dtype, device=dev)
-    per_row = 1
-    for w in width:
-        per_row *= w
-    dist.all_to_all_single(out.reshape(-1), rows.contiguous().reshape(-1),
-                           [c * per_row for c in recv_counts], [c * per_row for c in send_counts], group=group)
-    assert len(recv_counts) == world
-    return out, recv_counts
-
-
 # ------------------------------------------------------------------------------------------------
 # distributed temporal lift (BASELINE config 5)
 # ------------------------------------------------------------------------------------------------
@@ -216,40 +194,42 @@ def exchange_ghost_zone(edge_index: torch.Tensor, time: torch.Tensor, weight: to
     Every rank holds a contiguous range of the globally time-sorted stream, so what rank q needs is a
     prefix of the concatenation of the later ranks' ranges; rank r > q sends the prefix of its range with
     ``t <= t_last(q) + horizon`` (empty ranges in between contribute nothing).  Returns the extended
-    (edge_index, time, weight) -- own edges first, then the ghosts in stream order."""
+    (edge_index, time, weight) -- own edges first, then the ghosts in stream order.
+
+    Two host synchronisations: the ranks' last time stamps, then the matrix of prefix lengths."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = time.device
     m = time.numel()
     is_float = time.is_floating_point()
-    # last own time stamp per rank (ranks with an empty range: "nothing needed")
-    last = torch.zeros(world, dtype=torch.float64 if is_float else torch.int64, device=dev)
-    has = torch.zeros(world, dtype=torch.int64, device=dev)
+    # last own time stamp per rank (ranks with an empty range need nothing), as raw 64-bit words
+    mine = torch.zeros(2, dtype=torch.int64, device=dev)
     if m > 0:
-        last[rank] = time[-1].to(last.dtype)
-        has[rank] = 1
-    dist.all_reduce(last, group=group)
-    dist.all_reduce(has, group=group)
-    send_counts = [0] * world
-    for q in range(rank):
-        if has[q].item() and m > 0:
-            limit = (last[q] + horizon).to(time.dtype) if not is_float else last[q] + horizon
-            send_counts[q] = int(torch.searchsorted(time, limit.reshape(1).to(time.dtype), right=True))
-    # rows are ordered by destination rank: prefix for rank 0, prefix for rank 1, ...
-    packed = torch.cat([time.to(torch.float64).view(torch.int64) if is_float else time,
-                        edge_index[0], edge_index[1]]).reshape(3, m).t().contiguous() if m else \
-        torch.empty((0, 3), dtype=torch.int64, device=dev)
-    cols = [packed]
-    if weight is not None:
-        cols.append(weight.to(torch.float64).view(torch.int64).unsqueeze(1))
-    packed = torch.cat(cols, dim=1)
-    to_send = torch.cat([packed[:send_counts[q]] for q in range(world)], dim=0)
-    got, recv_counts = all_to_all_rows(to_send, send_counts, group)
+        mine[0] = time[-1].to(torch.float64).view(torch.int64) if is_float else time[-1].to(torch.int64)
+        mine[1] = 1
+    lasts = _gather_counts(mine, group)
+    last = lasts[:, 0].view(torch.float64) if is_float else lasts[:, 0]
+    has = lasts[:, 1].tolist()
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    earlier = [q for q in range(rank) if has[q] and m > 0]
+    if earlier:
+        limits = (last[earlier] + horizon).to(time.dtype).to(dev)
+        counts[earlier] = torch.searchsorted(time, limits, right=True)
+    matrix = _gather_counts(counts, group)                      # matrix[r, q] = events r sends to q
+    send_counts, recv_counts = matrix[rank].tolist(), matrix[:, rank].tolist()
+
+    def prefixes(column: torch.Tensor) -> torch.Tensor:
+        """column[:c_0] ++ column[:c_1] ++ ...  -> what arrives, ordered by source rank"""
+        out = torch.empty(sum(recv_counts), dtype=column.dtype, device=dev)
+        parts = [column[:c] for c in send_counts if c]
+        inp = torch.cat(parts) if parts else column[:0]
+        dist.all_to_all_single(out, inp.contiguous(), recv_counts, send_counts, group=group)
+        return out
+
     # a later rank's prefix is only usable if all ranks in between were sent COMPLETELY; by construction
     # (sorted stream, same limit) they were, unless they are empty.
-    ghost_t = got[:, 0].view(torch.float64).to(time.dtype) if is_float else got[:, 0]
-    ext_ei = torch.cat([edge_index, got[:, 1:3].t()], dim=1)
-    ext_t = torch.cat([time, ghost_t])
-    ext_w = torch.cat([weight, got[:, 3].view(torch.float64).to(weight.dtype)]) if weight is not None else None
+    ext_ei = torch.cat([edge_index, torch.stack([prefixes(edge_index[0]), prefixes(edge_index[1])])], dim=1)
+    ext_t = torch.cat([time, prefixes(time)])
+    ext_w = torch.cat([weight, prefixes(weight)]) if weight is not None else None
     return ext_ei.contiguous(), ext_t.contiguous(), ext_w
 
 
@@ -302,31 +282,52 @@ def _gather_counts(mine: torch.Tensor, group) -> torch.Tensor:
     return out.cpu()
 
 
+class _PendingIds:
+    """The merged-edge ids of one level on their way back to the senders."""
+
+    def __init__(self, plan, back, work, edge_offsets_dev, mark, level):
+        self.plan, self.back, self.work, self.edge_offsets_dev, self.mark, self.level = plan, back, work, edge_offsets_dev, mark, level
+
+    def finish(self) -> torch.Tensor:
+        """node_info of the next level: one word per input edge, merged id << 32 | last node."""
+        self.mark(f"ids_wait[{self.level}]")
+        self.work.wait()
+        self.mark(f"route_unpack[{self.level}]")
+        return self.plan.unpack(self.back, self.edge_offsets_dev)
+
+
 def _exchange_merge(line_index, node_info, weights, own_prefix, offsets, offsets_dev, total_nodes, local_ops, group,
-                    between=None, trace=None, level=0):
+                    lift_begin=None, trace=None, level=0):
     """One level of the exchange.  Every line-graph edge travels as a 16-byte record to the rank that owns its source
     row (``offsets``: first row of every rank), is merged there with its duplicates, and the owner returns the index of
     the merged edge.  Owners hold ascending row ranges, so the concatenation of their merged lists is the global
     (row, col) order and an index into it is the id of the next layer's De Bruijn node (the distinct edges of a layer in
     (row, col) order are the k-grams of the next one in lexicographic order).
 
-    Returns (merged edge_index (global ids), weights, last nodes) of the owned rows; the ``node_info`` of the next
-    level (one word per input edge: merged id << 32 | last node); the cumulative merged counts [world + 1] as a host
-    list and as a device tensor.  ``between``: callable run while the records are in flight (local work of the next level)."""
+    ``lift_begin``: callable that enqueues the count pass of the NEXT level's local lift; its column count is collected
+    in the same synchronisation as the record counts, and its fill pass runs while the records are in flight.
+
+    Returns (merged edge_index (global ids), weights, last nodes) of the owned rows; a ``_PendingIds`` whose
+    ``finish()`` gives the ``node_info`` of the next level; the cumulative merged counts [world + 1] as a host list and
+    as a device tensor; the next level's line graph (or None).  Two host synchronisations."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = line_index.device
     mark = trace.mark if trace is not None else (lambda label: None)
     mark(f"route_count[{level}]")
     plan = local_ops.route_plan(line_index, node_info, offsets_dev, world)
-    counts = _gather_counts(plan.counts, group)                      # counts[q, p] = records q sends to p   (sync 1)
-    send, recv = counts[rank].tolist(), counts[:, rank].tolist()
+    pending = lift_begin() if lift_begin is not None else None
+    payload = plan.counts if pending is None else torch.cat([plan.counts, pending.result_words])
+    gathered = _gather_counts(payload, group)                        # [q, p] = records q sends to p (+ lift count)  (sync 1)
+    send, recv = gathered[rank, :world].tolist(), gathered[:, rank].tolist()
     mark(f"route_pack[{level}]")
     records = plan.pack(weights, own_prefix)
     received = torch.empty((sum(recv), 2), dtype=torch.int64, device=dev)
     work = dist.all_to_all_single(received.view(-1), records.view(-1), [2 * c for c in recv], [2 * c for c in send],
                                   group=group, async_op=True)
     mark(f"lift_next[{level}]")
-    carried = between() if between is not None else None             # overlaps the transfer
+    carried = None
+    if pending is not None:                                          # overlaps the transfer
+        carried = pending.finish(total=int(gathered[rank, world]), status=int(gathered[rank, world + 1]), allow_empty=True)
     mark(f"records_wait[{level}]")
     work.wait()
     del records
@@ -350,11 +351,8 @@ def _exchange_merge(line_index, node_info, weights, own_prefix, offsets, offsets
     edge_offsets_dev = torch.tensor(edge_offsets, dtype=torch.int64, device=dev)
     mark(f"merge_fill[{level}]")
     out_ei, out_w, out_last = merge.finish(int(sizes[rank]))
-    mark(f"ids_wait[{level}]")
-    work.wait()
-    mark(f"route_unpack[{level}]")
-    next_info = plan.unpack(back, edge_offsets_dev)
-    return out_ei, out_w, out_last, next_info, edge_offsets, edge_offsets_dev, carried
+    ids = _PendingIds(plan, back, work, edge_offsets_dev, mark, level)
+    return out_ei, out_w, out_last, ids, edge_offsets, edge_offsets_dev, carried
 
 
 def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, num_nodes: int, delta, max_order: int,
@@ -411,21 +409,23 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
     # ---- order 1: nodes are the first-order nodes themselves, rows owned by node-id range
     n1_bounds = [-(-num_nodes * p // world) for p in range(world + 1)]
     n1_dev = torch.tensor(n1_bounds, dtype=torch.int64, device=dev)
-    lo, hi = n1_bounds[rank], n1_bounds[rank + 1]
+    lo = n1_bounds[rank]
 
     def first_lift():
-        if K == 1 or m_ext == 0:
-            return torch.empty((2, 0), dtype=torch.int64, device=dev)
-        return local_ops.lift_order_temporal(ext_ei, ext_t, delta, num_nodes, assume_sorted=True, limit_sources=cuts[2],
-                                             allow_empty=True)
+        if m_ext == 0:
+            return None
+        return local_ops.lift_order_temporal_begin(ext_ei, ext_t, delta, num_nodes, assume_sorted=True, limit_sources=cuts[2])
 
-    ei_k, w_k, last_k, info, offsets, offsets_dev, line_index = _exchange_merge(
-        ext_ei, None, ext_w, m_own, n1_bounds, n1_dev, num_nodes, local_ops, group, between=first_lift, trace=trace, level=1)
-    rows_k = torch.arange(lo, hi, device=dev).unsqueeze(1)
+    ei_k, w_k, last_k, ids, offsets, offsets_dev, line_index = _exchange_merge(
+        ext_ei, None, ext_w, m_own, n1_bounds, n1_dev, num_nodes, local_ops, group,
+        lift_begin=first_lift if K > 1 and m_ext > 0 else None, trace=trace, level=1)
+    rows_k, row_lo = torch.arange(lo, n1_bounds[rank + 1], device=dev).unsqueeze(1), lo
     layers[1] = DistributedLayer(1, num_nodes, lo, rows_k, ei_k, w_k, offsets[rank], offsets[-1])
     if K == 1:
         trace.close()
         return layers
+    if line_index is None:
+        line_index = torch.empty((2, 0), dtype=torch.int64, device=dev)
 
     # ---- orders 2..K: the line-graph nodes of level k are the edges of level k - 1 (level 1: the events)
     line_w = None
@@ -434,8 +434,12 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
     num_line_nodes = m_ext
     # prefix[j] = number of level-k line-graph NODES that start before cut j (level 2: the events themselves)
     prefix = dict(cuts)
-    row_lo = lo
     for k in range(2, K + 1):
+        # the owned rows of layer k = the merged edges of layer k - 1 (local work while the ids of level k - 1 travel)
+        trace.mark(f"rows[{k}]")
+        rows_k = local_ops.extend_owned_rows(rows_k, row_lo, ei_k[0], last_k)
+        total, row_lo = offsets[-1], offsets[rank]
+        info = ids.finish()
         # number of level-k EDGES (= level-(k+1) nodes) that start before every later cut
         later = [j for j in range(k + 1, K + 1)]
         if later and line_index.size(1):
@@ -443,26 +447,21 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
             nxt_prefix = dict(zip(later, torch.searchsorted(line_index[0].contiguous(), at, right=False).tolist()))
         else:
             nxt_prefix = {j: 0 for j in later}
-        own_edges_from = prefix[K]                           # sources >= this start with a ghost event: weight 0
-        prev_rows, prev_lo = rows_k, row_lo
-        trace.mark(f"rows[{k}]")
-        rows_k = local_ops.extend_owned_rows(prev_rows, prev_lo, ei_k[0], last_k)
-        total, row_lo = offsets[-1], offsets[rank]
 
-        def next_lift(k=k, line_index=line_index, num_line_nodes=num_line_nodes, nxt_prefix=nxt_prefix):
-            if k == K or line_index.size(1) == 0:
-                return torch.empty((2, 0), dtype=torch.int64, device=dev)
-            return local_ops.lift_order_edge_index(line_index, num_line_nodes, limit_sources=nxt_prefix[k + 1])
+        def next_lift(line_index=line_index, num_line_nodes=num_line_nodes, limit=nxt_prefix.get(k + 1, 0)):
+            return local_ops.lift_order_edge_index_begin(line_index, num_line_nodes, limit_sources=limit)
 
-        ei_k, w_k, last_k, info, offsets, offsets_dev, nxt = _exchange_merge(
-            line_index, info, line_w, own_edges_from, offsets, offsets_dev, total, local_ops, group, between=next_lift,
-            trace=trace, level=k)
+        ei_k, w_k, last_k, ids, offsets, offsets_dev, nxt = _exchange_merge(
+            line_index, info, line_w, prefix[K], offsets, offsets_dev, total, local_ops, group,
+            lift_begin=next_lift if k < K and line_index.size(1) else None, trace=trace, level=k)
         if k == 2 and offsets[-1] == 0:
             # no time-respecting pair on ANY rank: the single-device build fails in lift_order_temporal (temporal.py:53)
             raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors (distributed lift: no time-respecting pair)")
         layers[k] = DistributedLayer(k, total, row_lo, rows_k, ei_k, w_k, offsets[rank], offsets[-1])
         if k == K:
             break
+        if nxt is None:
+            nxt = torch.empty((2, 0), dtype=torch.int64, device=dev)
         if line_w is not None:
             line_w = local_ops.pair_attributes(nxt, line_w, "src", index_bound=line_index.size(1)) if nxt.size(1) else line_w[:0]
         num_line_nodes, line_index, prefix = line_index.size(1), nxt, nxt_prefix

@@ -59,26 +59,36 @@ class _TorchMerge:
         return ei, w, last
 
 
+class _TorchPendingLift:
+    def __init__(self, out):
+        self.out = out
+        self.result_words = torch.tensor([out.size(1), 0], dtype=torch.int64, device=out.device)
+
+    def finish(self, total=None, status=0, allow_empty=False):
+        assert total is None or total == self.out.size(1)
+        if self.out.size(1) == 0 and not allow_empty:
+            raise RuntimeError("torch.cat(): expected a non-empty list of Tensors")
+        return self.out
+
+
 class TorchOps:
     """CPU stand-in (plain torch + the oracle's lift) for the functions of pathpyg_b200.ops that the distributed lift
     calls, with the same call signatures and record format."""
 
     @staticmethod
-    def lift_order_temporal(edge_index, time, delta, num_nodes, assume_sorted=True, limit_sources=None, allow_empty=False):
+    def lift_order_temporal_begin(edge_index, time, delta, num_nodes, assume_sorted=True, limit_sources=None):
         try:
             out = lift.lift_order_temporal(edge_index, time, delta)
         except (RuntimeError, ValueError):
-            if not allow_empty:
-                raise
             out = edge_index.new_empty((2, 0))
-        return out if limit_sources is None else out[:, out[0] < limit_sources].contiguous()
+        return _TorchPendingLift(out if limit_sources is None else out[:, out[0] < limit_sources].contiguous())
 
     @staticmethod
-    def lift_order_edge_index(edge_index, num_nodes, limit_sources=None):
+    def lift_order_edge_index_begin(edge_index, num_nodes, limit_sources=None):
         if edge_index.size(1) == 0:
-            return edge_index.new_empty((2, 0))
+            return _TorchPendingLift(edge_index.new_empty((2, 0)))
         out = lift.lift_order_edge_index(edge_index, num_nodes)
-        return out if limit_sources is None else out[:, out[0] < limit_sources].contiguous()
+        return _TorchPendingLift(out if limit_sources is None else out[:, out[0] < limit_sources].contiguous())
 
     @staticmethod
     def pair_attributes(edge_index, attr, rule, index_bound=None):
@@ -90,5 +100,3 @@ class TorchOps:
     @staticmethod
     def extend_owned_rows(prev_rows, prev_row_lo, src_ids, last):
         return torch.cat([prev_rows[src_ids - prev_row_lo], last.unsqueeze(1)], dim=1)
-
-
