@@ -127,6 +127,9 @@ int ppg_lift_temporal_fill(const void* workspace, int64_t num_edges, int64_t num
  *                         owned by every rank.  out_counts [world] (device int64) = records per destination.
  *   ppg_route_pack        stable partition by destination: out_records [E] 16-byte records {id(target), id(source),
  *                         last node of target, float32 weight bits} grouped by destination rank in edge order;
+ *                         instead of out_records, h_peer_records (HOST array of `world` DEVICE pointers) names, per
+ *                         destination rank, the first slot reserved for this sender in that rank's receive buffer
+ *                         (peer memory mapped over NVLink): the kernel then stores into the owners' memory directly;
  *                         sources (first level: positions) >= own_prefix carry weight 0; out_slot [E] = record index;
  *                         out_last [E] = last first-order node of the edge's path.
  *   ppg_route_unpack      back [E] = merged-edge index returned by the owner for every record (record order);
@@ -146,7 +149,7 @@ int ppg_route_count(const int64_t* line_index, int64_t num_edges, const void* no
                     int world, void* workspace, size_t workspace_bytes, int64_t* out_counts, void* stream);
 int ppg_route_pack(const int64_t* line_index, int64_t num_edges, const void* node_info, const float* weights,
                    int64_t own_prefix, const int64_t* offsets, int world, const void* workspace, void* out_records,
-                   uint32_t* out_slot, uint32_t* out_last, void* stream);
+                   void* const* h_peer_records, uint32_t* out_slot, uint32_t* out_last, void* stream);
 int ppg_route_unpack(const void* workspace, int64_t num_edges, const uint32_t* back, const uint32_t* slot,
                      const uint32_t* last, const int64_t* edge_offsets, int world, void* out_node_info, void* stream);
 size_t ppg_merge_records_workspace_bytes(int64_t num_records, int64_t rows_owned, int64_t total_nodes);

@@ -57,7 +57,7 @@ PROTOTYPES = {
     "ppg_lift_limit": (c_int, [_p, c_int, _i64, _i64, _i64, _p]),
     "ppg_route_workspace_bytes": (c_size_t, [_i64]),
     "ppg_route_count": (c_int, [_p, _i64, _p, _p, c_int, _p, c_size_t, _p, _p]),
-    "ppg_route_pack": (c_int, [_p, _i64, _p, _p, _i64, _p, c_int, _p, _p, _p, _p, _p]),
+    "ppg_route_pack": (c_int, [_p, _i64, _p, _p, _i64, _p, c_int, _p, _p, POINTER(c_void_p), _p, _p, _p]),
     "ppg_route_unpack": (c_int, [_p, _i64, _p, _p, _p, _p, c_int, _p, _p]),
     "ppg_merge_records_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
     "ppg_merge_records_sort": (c_int, [_p, _i64, _i64, _i64, _i64, _p, c_size_t, _p, _p]),

@@ -133,20 +133,32 @@ route_scan_kernel(const uint32_t* __restrict__ counts, int chunks, int world, ui
   }
 }
 
+// Where the records of every destination go.  local != nullptr: one send buffer on this device, destination d at
+// segment[d] (the collective moves it).  Otherwise peer[d] is rank d's receive buffer mapped into this process (NVLink
+// peer memory), already advanced to the first slot reserved for this sender: the partition kernel stores straight
+// into the owners' memory, so the transfer IS the kernel's write stream and needs no collective and no staging copy.
+struct RouteTargets {
+  uint4* local;
+  uint4* peer[kRouteMaxRanks];
+};
+
 __global__ void __launch_bounds__(kRouteBlock)
 route_pack_kernel(RouteInput in, const uint32_t* __restrict__ base, const long long* __restrict__ segment,
-                  uint4* __restrict__ send, uint32_t* __restrict__ slot, uint32_t* __restrict__ last_next) {
+                  RouteTargets targets, uint32_t* __restrict__ slot, uint32_t* __restrict__ last_next) {
   constexpr int NW = kRouteBlock / 32;
   __shared__ long long s_off[kRouteMaxRanks + 1];
   __shared__ unsigned s_cursor[kRouteMaxRanks];
   __shared__ unsigned s_wcount[NW][kRouteMaxRanks];
   __shared__ unsigned s_wbase[NW][kRouteMaxRanks];
+  __shared__ uint4* s_target[kRouteMaxRanks];   // s_target[d] + record index = where the record goes
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const unsigned lane = lane_id();
   if (tid <= in.world) s_off[tid] = in.offsets[tid];
-  if (tid < kRouteMaxRanks)
+  if (tid < kRouteMaxRanks) {
     s_cursor[tid] = base[static_cast<size_t>(blockIdx.x) * kRouteMaxRanks + tid] + static_cast<unsigned>(segment[tid]);
+    s_target[tid] = targets.local != nullptr ? targets.local : targets.peer[tid] - segment[tid];
+  }
   const int64_t begin = static_cast<int64_t>(blockIdx.x) * in.chunk_edges;
   const int64_t end = begin + in.chunk_edges < in.E ? begin + in.chunk_edges : in.E;
   for (int64_t tile = begin; tile < end; tile += kRouteTile) {
@@ -210,7 +222,7 @@ route_pack_kernel(RouteInput in, const uint32_t* __restrict__ base, const long l
     for (int i = 0; i < kRouteItems; ++i) {
       if (pos[i] < end) {
         const unsigned at = s_wbase[warp][dest[i]] + rank[i];
-        send[at] = rec[i];
+        s_target[dest[i]][at] = rec[i];
         st_stream(slot + pos[i], at);
         st_stream(last_next + pos[i], rec[i].z);
       }
@@ -394,15 +406,21 @@ extern "C" int ppg_route_count(const int64_t* line_index, int64_t E, const void*
 
 extern "C" int ppg_route_pack(const int64_t* line_index, int64_t E, const void* node_info, const float* weights,
                               int64_t own_prefix, const int64_t* offsets, int world, const void* workspace,
-                              void* out_records, uint32_t* out_slot, uint32_t* out_last, void* stream_) {
+                              void* out_records, void* const* h_peer_records, uint32_t* out_slot, uint32_t* out_last,
+                              void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (E == 0) return PPG_OK;
   RouteInput in;
   PPG_TRY(route_input(in, line_index, E, node_info, weights, own_prefix, offsets, world));
+  PPG_REQUIRE((out_records != nullptr) != (h_peer_records != nullptr), PPG_ERR_INVALID,
+              "route_pack: give either a local record buffer or the peers' receive buffers");
   Workspace ws(const_cast<void*>(workspace), ~static_cast<size_t>(0));
   RouteLayout L(ws, E);
-  route_pack_kernel<<<route_geometry(E).chunks, kRouteBlock, 0, stream>>>(in, L.base, L.segment, static_cast<uint4*>(out_records),
-                                                                          out_slot, out_last);
+  RouteTargets targets = {};
+  targets.local = static_cast<uint4*>(out_records);
+  if (h_peer_records != nullptr)
+    for (int d = 0; d < world; ++d) targets.peer[d] = static_cast<uint4*>(h_peer_records[d]);
+  route_pack_kernel<<<route_geometry(E).chunks, kRouteBlock, 0, stream>>>(in, L.base, L.segment, targets, out_slot, out_last);
   PPG_LAUNCHED();
   return PPG_OK;
 }

@@ -471,19 +471,23 @@ class RoutePlan:
             _lib.check(lib.ppg_route_count(_ptr(self.li), self.E, _ptr(self.node_info), _ptr(self.offsets), self.world,
                                            _ptr(self.ws), self.ws.numel(), _ptr(self.counts), _stream(self.dev)))
 
-    def pack(self, weights: torch.Tensor | None, own_prefix: int) -> torch.Tensor:
-        """Records [E, 2] int64 (16 bytes each) grouped by destination rank, edge order inside a destination."""
+    def pack(self, weights: torch.Tensor | None, own_prefix: int, peer_slots: list[int] | None = None):
+        """Records [E, 2] int64 (16 bytes each) grouped by destination rank, edge order inside a destination.
+        ``peer_slots``: per destination rank the DEVICE address (mapped peer memory) of the first record slot reserved
+        for this sender in that rank's receive buffer -- the kernel then stores straight into the owners' memory and
+        nothing is returned."""
         if weights is not None:
             weights = weights.contiguous()
             if weights.dtype != torch.float32 or weights.numel() != self.E:
                 raise TypeError("route weights must be float32 with one entry per edge")
-        records = torch.empty((self.E, 2), dtype=torch.int64, device=self.dev)
+        records = torch.empty((self.E, 2), dtype=torch.int64, device=self.dev) if peer_slots is None else None
+        peers = None if peer_slots is None else (ctypes.c_void_p * self.world)(*[ctypes.c_void_p(int(p)) for p in peer_slots])
         self.slot = torch.empty(self.E, dtype=torch.int32, device=self.dev)
         self.last = torch.empty(self.E, dtype=torch.int32, device=self.dev)
         with torch.cuda.device(self.dev):
             _lib.check(_lib.load().ppg_route_pack(_ptr(self.li), self.E, _ptr(self.node_info), _ptr(weights), int(own_prefix),
-                                                  _ptr(self.offsets), self.world, _ptr(self.ws), _ptr(records), _ptr(self.slot),
-                                                  _ptr(self.last), _stream(self.dev)))
+                                                  _ptr(self.offsets), self.world, _ptr(self.ws), _ptr(records), peers,
+                                                  _ptr(self.slot), _ptr(self.last), _stream(self.dev)))
         return records
 
     def unpack(self, back: torch.Tensor, edge_offsets: torch.Tensor) -> torch.Tensor:

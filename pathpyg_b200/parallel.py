@@ -282,6 +282,63 @@ def _gather_counts(mine: torch.Tensor, group) -> torch.Tensor:
     return out.cpu()
 
 
+class _PeerArenas:
+    """Two symmetric receive buffers per (process, device), mapped into every peer (``torch.distributed.
+    _symmetric_memory``: CUDA virtual-memory handles exchanged once, NVLink peer access).  The pack kernel of a sender
+    stores its records straight into the owner's buffer; a device-side barrier over the buffers' signal pads tells the
+    owner that all senders are done.  Levels alternate between the two buffers: the barrier of level k + 1 is behind
+    every rank's reads of level k's records in stream order, so level k + 2 may overwrite them."""
+
+    _cache: dict = {}
+    disabled = None   # None: not tried yet
+
+    def __init__(self, group, dev):
+        self.group, self.dev, self.capacity = group, dev, 0
+        self.buffers, self.handles = [None, None], [None, None]
+
+    @classmethod
+    def get(cls, group, dev):
+        key = (id(group) if group is not None else 0, dev.index)
+        if key not in cls._cache:
+            cls._cache[key] = cls(group, dev)
+        return cls._cache[key]
+
+    @classmethod
+    def available(cls, dev) -> bool:
+        import os
+        if cls.disabled is None:
+            cls.disabled = os.environ.get("PPG_DIST_P2P", "1") == "0" or dev.type != "cuda"
+            if not cls.disabled:
+                try:
+                    import torch.distributed._symmetric_memory  # noqa: F401
+                except Exception:
+                    cls.disabled = True
+        return not cls.disabled
+
+    def ensure(self, records: int) -> None:
+        """Collective when it grows: every rank passes the same number (the largest receive count of the level)."""
+        if records <= self.capacity:
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+        capacity = (int(records * 1.02) + 4096) // 1024 * 1024
+        group = self.group if self.group is not None else dist.group.WORLD
+        for i in range(2):
+            self.handles[i] = self.buffers[i] = None                # release the old mapping first
+        for i in range(2):
+            self.buffers[i] = symm_mem.empty(capacity * 2, dtype=torch.int64, device=self.dev)
+            self.handles[i] = symm_mem.rendezvous(self.buffers[i], group)
+        self.capacity = capacity
+
+    def peer_slot(self, which: int, rank: int, record_offset: int) -> int:
+        return int(self.handles[which].buffer_ptrs[rank]) + 16 * int(record_offset)
+
+    def barrier(self, which: int) -> None:
+        self.handles[which].barrier(channel=0)
+
+    def received(self, which: int, count: int) -> torch.Tensor:
+        return self.buffers[which][:2 * count].view(count, 2)
+
+
 class _PendingIds:
     """The merged-edge ids of one level on their way back to the senders."""
 
@@ -318,19 +375,33 @@ def _exchange_merge(line_index, node_info, weights, own_prefix, offsets, offsets
     pending = lift_begin() if lift_begin is not None else None
     payload = plan.counts if pending is None else torch.cat([plan.counts, pending.result_words])
     gathered = _gather_counts(payload, group)                        # [q, p] = records q sends to p (+ lift count)  (sync 1)
-    send, recv = gathered[rank, :world].tolist(), gathered[:, rank].tolist()
+    matrix = gathered[:, :world]
+    send, recv = matrix[rank].tolist(), matrix[:, rank].tolist()
     mark(f"route_pack[{level}]")
-    records = plan.pack(weights, own_prefix)
-    received = torch.empty((sum(recv), 2), dtype=torch.int64, device=dev)
-    work = dist.all_to_all_single(received.view(-1), records.view(-1), [2 * c for c in recv], [2 * c for c in send],
-                                  group=group, async_op=True)
+    peer_to_peer = world > 1 and _PeerArenas.available(dev)
+    if peer_to_peer:
+        # fused partition + transfer: the pack kernel stores every record into its owner's receive buffer over NVLink
+        arenas = _PeerArenas.get(group, dev)
+        arenas.ensure(int(matrix.sum(0).max()))
+        which = level & 1
+        ahead = matrix[:rank].sum(0).tolist()                        # records of the lower ranks in every owner's buffer
+        plan.pack(weights, own_prefix, peer_slots=[arenas.peer_slot(which, d, ahead[d]) for d in range(world)])
+    else:
+        records = plan.pack(weights, own_prefix)
+        received = torch.empty((sum(recv), 2), dtype=torch.int64, device=dev)
+        work = dist.all_to_all_single(received.view(-1), records.view(-1), [2 * c for c in recv], [2 * c for c in send],
+                                      group=group, async_op=True)
     mark(f"lift_next[{level}]")
     carried = None
-    if pending is not None:                                          # overlaps the transfer
+    if pending is not None:                                          # overlaps the transfer / absorbs the ranks' skew
         carried = pending.finish(total=int(gathered[rank, world]), status=int(gathered[rank, world + 1]), allow_empty=True)
     mark(f"records_wait[{level}]")
-    work.wait()
-    del records
+    if peer_to_peer:
+        arenas.barrier(which)                                        # every sender's records have landed
+        received = arenas.received(which, sum(recv))
+    else:
+        work.wait()
+        del records
     mark(f"merge_sort[{level}]")
     row_lo, rows_owned = int(offsets[rank]), int(offsets[rank + 1] - offsets[rank])
     merge = local_ops.merge_records_begin(received, row_lo, rows_owned, total_nodes)
