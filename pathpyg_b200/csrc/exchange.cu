@@ -151,6 +151,11 @@ route_pack_kernel(RouteInput in, const uint32_t* __restrict__ base, const long l
   __shared__ unsigned s_wcount[NW][kRouteMaxRanks];
   __shared__ unsigned s_wbase[NW][kRouteMaxRanks];
   __shared__ uint4* s_target[kRouteMaxRanks];   // s_target[d] + record index = where the record goes
+  // the tile's records grouped by destination: they leave as contiguous runs (coalesced 512-byte warp stores; over
+  // NVLink that is the difference between 64-byte fragments and full packets)
+  __shared__ __align__(16) uint4 s_rec[kRouteTile];
+  __shared__ unsigned s_tfirst[kRouteMaxRanks];      // record index (in the destination's stream) of the tile's first record
+  __shared__ unsigned s_dstart[kRouteMaxRanks + 1];  // first slot of every destination in s_rec
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const unsigned lane = lane_id();
@@ -208,24 +213,42 @@ route_pack_kernel(RouteInput in, const uint32_t* __restrict__ base, const long l
       __syncwarp();
     }
     __syncthreads();
-    if (tid < in.world) {
+    if (tid < kRouteMaxRanks) {
       unsigned run = s_cursor[tid];
+      s_tfirst[tid] = run;
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
         s_wbase[w][tid] = run;
-        run += s_wcount[w][tid];
+        run += tid < in.world ? s_wcount[w][tid] : 0u;
       }
       s_cursor[tid] = run;
+      // exclusive scan of the tile's per-destination counts over the (<= 16) destinations
+      const unsigned cnt = run - s_tfirst[tid];
+      unsigned inc = cnt;
+#pragma unroll
+      for (int d = 1; d < kRouteMaxRanks; d <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffu, inc, d, kRouteMaxRanks);
+        if (tid >= d) inc += y;
+      }
+      s_dstart[tid] = inc - cnt;
+      if (tid == kRouteMaxRanks - 1) s_dstart[kRouteMaxRanks] = inc;
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kRouteItems; ++i) {
       if (pos[i] < end) {
         const unsigned at = s_wbase[warp][dest[i]] + rank[i];
-        s_target[dest[i]][at] = rec[i];
+        s_rec[s_dstart[dest[i]] + (at - s_tfirst[dest[i]])] = rec[i];
         st_stream(slot + pos[i], at);
         st_stream(last_next + pos[i], rec[i].z);
       }
+    }
+    __syncthreads();
+    const unsigned in_tile = s_dstart[kRouteMaxRanks];
+    for (unsigned j = tid; j < in_tile; j += kRouteBlock) {
+      int d = 0;
+      for (int q = 1; q < in.world; ++q) d += j >= s_dstart[q] ? 1 : 0;
+      s_target[d][s_tfirst[d] + (j - s_dstart[d])] = s_rec[j];
     }
   }
 }

@@ -217,19 +217,27 @@ def exchange_ghost_zone(edge_index: torch.Tensor, time: torch.Tensor, weight: to
     matrix = _gather_counts(counts, group)                      # matrix[r, q] = events r sends to q
     send_counts, recv_counts = matrix[rank].tolist(), matrix[:, rank].tolist()
 
-    def prefixes(column: torch.Tensor) -> torch.Tensor:
-        """column[:c_0] ++ column[:c_1] ++ ...  -> what arrives, ordered by source rank"""
-        out = torch.empty(sum(recv_counts), dtype=column.dtype, device=dev)
-        parts = [column[:c] for c in send_counts if c]
-        inp = torch.cat(parts) if parts else column[:0]
-        dist.all_to_all_single(out, inp.contiguous(), recv_counts, send_counts, group=group)
-        return out
-
+    # one transfer: per destination the prefix of every column (source row, target row, time, weight) as 64-bit words
+    columns = [edge_index[0], edge_index[1], time.view(torch.int64) if time.dtype in (torch.int64, torch.float64) else time.to(torch.int64)]
+    if weight is not None:
+        columns.append(weight.to(torch.float64).view(torch.int64))
+    ncol = len(columns)
+    parts = [col[:c] for c in send_counts if c for col in columns]
+    to_send = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device=dev)
+    got = torch.empty(ncol * sum(recv_counts), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(got, to_send, [ncol * c for c in recv_counts], [ncol * c for c in send_counts], group=group)
     # a later rank's prefix is only usable if all ranks in between were sent COMPLETELY; by construction
     # (sorted stream, same limit) they were, unless they are empty.
-    ext_ei = torch.cat([edge_index, torch.stack([prefixes(edge_index[0]), prefixes(edge_index[1])])], dim=1)
-    ext_t = torch.cat([time, prefixes(time)])
-    ext_w = torch.cat([weight, prefixes(weight)]) if weight is not None else None
+    blocks, at = [], 0
+    for c in recv_counts:
+        if c:
+            blocks.append(got[at:at + ncol * c].view(ncol, c))
+            at += ncol * c
+    ghosts = torch.cat(blocks, dim=1) if blocks else torch.empty((ncol, 0), dtype=torch.int64, device=dev)
+    ext_ei = torch.cat([edge_index, ghosts[:2]], dim=1)
+    ghost_t = ghosts[2].view(time.dtype) if time.dtype in (torch.int64, torch.float64) else ghosts[2].to(time.dtype)
+    ext_t = torch.cat([time, ghost_t])
+    ext_w = torch.cat([weight, ghosts[3].view(torch.float64).to(weight.dtype)]) if weight is not None else None
     return ext_ei.contiguous(), ext_t.contiguous(), ext_w
 
 
