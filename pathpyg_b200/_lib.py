@@ -45,6 +45,19 @@ PROTOTYPES = {
     "ppg_lift_temporal_group": (c_int, [_p, _i64, _i64, _p, c_size_t, _p]),
     "ppg_lift_temporal_count": (c_int, [_p, _p, _i64, _i64, c_int, _i64, c_double, _p, c_size_t, _ph_i64, _p]),
     "ppg_lift_temporal_fill": (c_int, [_p, _i64, _i64, _i64, _p, _p]),
+    "ppg_lift_temporal_views": (c_int, [_p, _i64, _i64, POINTER(c_void_p)]),
+    "ppg_chain_heavy_default": (c_int, []),
+    "ppg_chain_tile_slots": (c_int, []),
+    "ppg_chain_scan_workspace_bytes": (c_size_t, [_i64]),
+    "ppg_chain_first_tiles": (c_int, [_p, _i64, _i64, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ppg_chain_count": (c_int, [_p, _p, _i64, _p, c_size_t, _p, _p, _p, _p]),
+    "ppg_chain_count_sorted": (c_int, [_p, _i64, _p, _p, _p, _i64, _p, c_size_t, _p, _p, _p, _p, _p, _p]),
+    "ppg_chain_tiles": (c_int, [_i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ppg_chain_heads": (c_int, [_p, _p, _p, _i64, _p, c_size_t, _p, _p, _p, _p, _p]),
+    "ppg_chain_heavy_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
+    "ppg_chain_heavy_fix": (c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, c_size_t, _p]),
+    "ppg_chain_fill": (c_int, [_p, _p, _p, _p, _i64, _p, _p, _p]),
+    "ppg_chain_widen": (c_int, [_p, _i64, _p, _p]),
     "ppg_rows_minmax_workspace_bytes": (c_size_t, [_i64]),
     "ppg_rows_minmax": (c_int, [_p, _i64, _i64, _p, c_size_t, _ph_i64, _ph_i64, _ph_int, _p]),
     "ppg_unique_rows_workspace_bytes": (c_size_t, [_i64, c_int]),

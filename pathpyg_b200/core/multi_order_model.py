@@ -128,6 +128,43 @@ class _LayerChain:
         self.inverse_next = res[2] if more else None
 
 
+def _sort_free_ok(edge_index, edge_weight, n, event_graph, same_data, dev) -> bool:
+    """The generation-order chain covers the standard call: a device build from the graph's own time-sorted events with
+    unit or float32 weights.  Everything else (a caller-supplied event graph, shuffled time stamps, other weight dtypes)
+    takes the sort-per-order chain.  ``PPG_CHAIN=0`` switches it off (A/B measurements)."""
+    import os
+    if os.environ.get("PPG_CHAIN", "1") == "0" or event_graph is not None or not same_data or dev.type != "cuda":
+        return False
+    if edge_index.dtype != torch.int64 or not 0 < edge_index.size(1) < (1 << 31) or not 0 < n < (1 << 31):
+        return False
+    return edge_weight is None or (edge_weight.dtype == torch.float32 and edge_weight.dim() == 1)
+
+
+def _sort_free_layers(model, edge_index, time, delta, n, max_order, edge_weight, cached, grouped_ws, before_time) -> None:
+    from ..chain import TemporalChain
+
+    dev = edge_index.device
+    ids = torch.arange(n, device=dev)
+    state = {"ns": ids.unsqueeze(1), "ei": None}
+
+    def store(order, agg_index, agg_weight, num_nodes, inverse):
+        if order == 1:
+            node_sequence, inverse = state["ns"], ids
+        elif order == 2:
+            node_sequence = state["ei"].t().contiguous()
+        else:
+            node_sequence = ops.extend_rows(state["ns"], state["ei"])
+        state["ns"], state["ei"] = node_sequence, agg_index
+        if cached or order == max_order:
+            data = Data(edge_index=EdgeIndex(agg_index, sparse_size=(num_nodes, num_nodes), sort_order="row"), num_nodes=num_nodes,
+                        node_sequence=node_sequence, edge_weight=agg_weight, inverse_idx=inverse)
+            model.layers[order] = Graph._from_sorted(data)
+
+    if edge_weight is not None:
+        edge_weight = edge_weight.contiguous()
+    TemporalChain(edge_index.contiguous(), n, edge_weight, max_order).run(time, delta, store, grouped_ws, before_time, cached)
+
+
 class MultiOrderModel:
     """Higher-order De Bruijn graph layers keyed by order (``layers: dict[int, Graph]``)."""
 
@@ -202,6 +239,14 @@ class MultiOrderModel:
             else:
                 edge_index = _plain(_staging.up(data.edge_index, dev)).long()
         edge_weight = _staging.up(data[weight], dev) if weight in data else None  # None == ones(m), :154-157
+
+        if _sort_free_ok(edge_index, edge_weight, n, event_graph, data is g.data, dev):
+            # one device, time-sorted stream: the layers are generated in their final order (csrc/chain.cu)
+            _sort_free_layers(m, edge_index, _staging.up(data.time, dev) if time_ready is None else time_dev, delta, n, max_order,
+                              edge_weight, cached, grouped_ws,
+                              (lambda: (main.wait_event(time_ready), time_dev.record_stream(main))) if time_ready is not None else None)
+            m._finish(g.mapping, to_host)
+            return m
 
         chain = _LayerChain(m, cached, max_order)
         pending = None

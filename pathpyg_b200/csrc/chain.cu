@@ -1,0 +1,805 @@
+// a4-a6 without a global sort per order: the De Bruijn layers of consecutive orders built by EXPANDING the line graph
+// in the merged order of its source nodes.
+//
+// The reference (lift_order.py:109-152 called from multi_order_model.py:124-192) lifts the line graph L_k of order k
+// (one column per pair (e, f) of consecutive level-(k-1) items, ascending in (e, f)), maps both ends through the
+// inverse index of layer k-1 and coalesces: a sort of E_k keys (row, col) = (id(e), id(f)).  aggregate.cu does that
+// with an LSD radix sort: ceil(2 bits(n_k) / 8) passes of 24 B per pair and direction.
+//
+// Here the sort is replaced by the ORDER OF GENERATION.  Layer k-1 was produced in (row, col) order, so the stable order
+// P of the level-(k-1) items by their merged id id(e) is known (it is the order in which they were written).  Expanding
+// the items in THAT order -- for s = 0, 1, ...: e = P[s], emit (e, f) for the continuations f of e -- yields the pairs
+// grouped by row id(e), rows ascending, and inside a row in ascending (e, f): exactly the state of a stable sort by
+// row.  What is left is a stable sort by col INSIDE every row, and rows are short (out-degree x multiplicity): a CTA
+// stages a tile of whole rows in shared memory and ranks every pair among the pairs of its row by counting
+// (rank = #{j in row: (col_j, j) < (col_i, i)}), which needs no key bits, no passes and no global traffic.  Rows longer
+// than `heavy` pairs (hubs) are left in generation order, listed, and put in order afterwards by ONE radix sort over
+// only those pairs (ppg_chain_heavy_fix).
+//
+//   level k-1 -> k:  count (item order)  : deg[e] = #continuations, ptr_k = exclusive scan            (lift.cu for k = 2)
+//                    count (P order)     : offP = exclusive scan of deg[P[s]]; tile boundaries
+//                    tiles               : expand + rank inside rows -> (row, col, label) in final order; tail of every pair
+//                    heads               : run heads -> merged id of every pair (by slot and by label), run starts
+//                    fill                : merged edges + weights (sum of a run in slot order = stream order)
+//
+// Labels: a pair keeps the index it has in the reference's line graph (label = ptr_k[e] + j), so `inverse_idx` of the
+// next layer is the id array itself, and ties inside a run are in label order = the summation order of the reference's
+// coalesce (stable sort + scatter_add).
+//
+// Algorithmic bytes per pair and level (c = continuation factor E_k / E_{k-1}): reads 4/c (P) + 16/c (first, ptr pair) +
+// 8/c + 4 (id of the continuation) , writes 12 (row, col, label) + 4 (tail) + 8 (ids) -- about 40-50 B against
+// 48 * passes of the sort it replaces.
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace ppg {
+
+constexpr int kChainBlock = 256;
+constexpr int kChainTile = 1024;                         // nominal slots (pairs) per tile
+constexpr int kChainHeavyMax = 256;                      // rows above this never take the in-tile ranking
+constexpr int kChainCap = kChainTile + kChainHeavyMax;   // slots staged per chunk: every non-heavy row of a tile fits
+constexpr int kChainPerThread = kChainCap / kChainBlock; // 5
+static_assert(kChainCap % kChainBlock == 0 && kChainCap < 65535, "chunk geometry");
+
+// result words of one level (device int64[8], zeroed by the caller)
+enum { kResHeads = 0, kResStatus = 1, kResHeavySlots = 2, kResHeavyRows = 3 };
+constexpr unsigned long long kChainStatusIdOutOfRange = 1ull;
+
+// ------------------------------------------------------------------ count in item order (levels >= 3)
+struct ChainCountProducer {
+  const uint32_t* tail;                  // [E] continuation node (a level-(k-1) item) of every level-k item
+  const unsigned long long* ptr_prev;    // [E_prev + 1] first level-k item of every level-(k-1) item
+  uint32_t* first;                       // out [E]
+  __device__ unsigned long long operator()(int64_t q) const {
+    const uint32_t t = ld_stream(tail + q);
+    const unsigned long long a = ptr_prev[t];
+    first[q] = static_cast<uint32_t>(a);
+    return ptr_prev[t + 1] - a;
+  }
+};
+struct ChainOffsetConsumer {
+  unsigned long long* off;
+  int64_t n;
+  __device__ void operator()(int64_t i, unsigned long long v, unsigned long long prefix) const {
+    off[i] = prefix;
+    if (i == n - 1) off[n] = prefix + v;
+  }
+};
+
+// ------------------------------------------------------------------ count in merged (P) order
+struct ChainSortedProducer {
+  const uint32_t* P;                     // [n] item at every position of the merged order
+  const uint32_t* first;                 // [n] by item
+  const unsigned long long* ptr_next;    // [n + 1] by item
+  const float* w_item;                   // [n] by item or nullptr
+  int64_t limit;                         // items >= limit are not expanded
+  uint32_t* firstP;
+  uint32_t* lblP;
+  float* wP;
+  __device__ unsigned long long operator()(int64_t s) const {
+    const uint32_t q = ld_stream(P + s);
+    const unsigned long long a = ptr_next[q];
+    const unsigned long long b = ptr_next[q + 1];
+    firstP[s] = first[q];
+    lblP[s] = static_cast<uint32_t>(a);
+    if (wP != nullptr) wP[s] = w_item[q];
+    return static_cast<int64_t>(q) < limit ? b - a : 0ull;
+  }
+};
+struct ChainSortedConsumer {
+  unsigned long long* offP;  // [n + 1]
+  uint32_t* srcbound;        // [tiles]: the source that holds slot t * kChainTile
+  int64_t n;
+  __device__ void operator()(int64_t s, unsigned long long v, unsigned long long prefix) const {
+    offP[s] = prefix;
+    if (s == n - 1) offP[n] = prefix + v;
+    if (v) {
+      for (unsigned long long t = (prefix + kChainTile - 1) / kChainTile; t * kChainTile < prefix + v; ++t)
+        srcbound[t] = static_cast<uint32_t>(s);
+    }
+  }
+};
+
+// ------------------------------------------------------------------ tiles
+struct ChainTileArgs {
+  // sources (items of the previous level) in merged order
+  const unsigned long long* offP;  // [n_sources + 1] first slot                       (FIRST: identity)
+  const uint32_t* firstP;          // [n_sources] first continuation                   (FIRST: identity)
+  const uint32_t* lblP;            // [n_sources] label of the first slot              (FIRST: event at the position)
+  const float* wP;                 // [n_sources] weight of the source or nullptr      (FIRST: by event)
+  const uint32_t* run_start;       // [n_rows + 1] first source of every row
+  const uint32_t* rowid;           // [n_sources] row of every source
+  const uint32_t* colsrc;          // merged id of an item                             (FIRST: unused)
+  const uint32_t* via;             // continuation position -> item (temporal level) or nullptr
+  const int64_t* dst;              // FIRST: target node of every event
+  const uint32_t* srcbound;        // [tiles]                                          (FIRST: unused)
+  int64_t n_sources, n_rows, n_slots, num_cols;
+  int heavy;
+  uint32_t *rowS, *colS, *labS;
+  float* wS;
+  uint32_t* tail_out;              // [n_slots] by label or nullptr
+  float* w_item_out;               // [n_slots] by label or nullptr
+  uint2* heavy_list;
+  unsigned long long* result;
+  // run heads, fused: valid when no row of the level is heavy (otherwise ppg_chain_heavy_fix + ppg_chain_heads redo them)
+  unsigned long long* tile_state;  // [tiles] zeroed
+  unsigned code_partial, code_inclusive;
+  uint32_t *idS, *id_item, *run_start_out;
+};
+
+// largest s in [lo, hi) with off[s] <= target; requires off[lo] <= target
+__device__ __forceinline__ int64_t warp_search_range(const unsigned long long* __restrict__ off, int64_t lo, int64_t hi,
+                                                     unsigned long long target) {
+  const unsigned lane = lane_id();
+  while (hi - lo > 1) {
+    const int64_t step = ceil_div(hi - lo, 32);
+    const int64_t p = lo + static_cast<int64_t>(lane) * step;
+    const bool le = p < hi && off[p] <= target;
+    const int cnt = __popc(__ballot_sync(kFullMask, le));
+    const int64_t nlo = lo + static_cast<int64_t>(cnt - 1) * step;
+    const int64_t nhi = lo + static_cast<int64_t>(cnt) * step;
+    lo = nlo;
+    hi = nhi < hi ? nhi : hi;
+  }
+  return lo;
+}
+
+// One look-back step shared by all tiles of a launch: the number of run heads (merged edges) in the tiles before this one.
+// Tiles are taken in blockIdx order (CTAs are dispatched in that order, so a tile only waits for tiles that are running
+// or done); the words carry a code per call like the scan's (common.cuh).
+__device__ __forceinline__ unsigned long long chain_tile_prefix(unsigned long long* __restrict__ state, unsigned tile,
+                                                                unsigned long long total, unsigned code_partial,
+                                                                unsigned code_inclusive) {
+  // called by warp 0
+  const unsigned lane = lane_id();
+  if (tile == 0) {
+    if (lane == 0) state_store(&state[0], code_inclusive, total);
+    return 0;
+  }
+  if (lane == 0) state_store(&state[tile], code_partial, total);
+  unsigned long long acc = 0;
+  int64_t newest = static_cast<int64_t>(tile) - 1;
+  while (true) {
+    const int64_t q = newest - lane;
+    unsigned code = code_inclusive;
+    unsigned long long val = 0;
+    if (q >= 0) {
+      unsigned long long w;
+      do {
+        w = state_load(&state[q]);
+        code = static_cast<unsigned>(w >> 56);
+      } while (code != code_partial && code != code_inclusive);
+      val = w & kStateValueMask;
+    }
+    const unsigned incl = __ballot_sync(kFullMask, code == code_inclusive);
+    if (incl) {
+      const unsigned first = __ffs(incl) - 1;
+      acc += warp_sum(lane <= first ? val : 0ull);
+      break;
+    }
+    acc += warp_sum(val);
+    newest -= 32;
+  }
+  if (lane == 0) state_store(&state[tile], code_inclusive, acc + total);
+  return acc;
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kChainBlock)
+chain_tile_kernel(ChainTileArgs a) {
+  extern __shared__ __align__(16) uint32_t chain_smem[];
+  uint32_t* s_mark = chain_smem;                                   // (row's first slot + 1) << 16 | (source's first slot + 1)
+  uint32_t* s_col = s_mark + kChainCap;
+  int32_t* s_soff = reinterpret_cast<int32_t*>(s_col + kChainCap);  // at a source's first slot: its first slot - chunk base (may be < 0)
+  uint32_t* s_first = reinterpret_cast<uint32_t*>(s_soff + kChainCap);
+  uint32_t* s_lbl = s_first + kChainCap;
+  float* s_w = reinterpret_cast<float*>(s_lbl + kChainCap);
+  uint32_t* s_row = reinterpret_cast<uint32_t*>(s_w + kChainCap);   // at a row's first slot: the row
+  uint32_t* s_len = s_row + kChainCap;                              // at a row's first slot: its length; later: run index of every slot
+  uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_len + kChainCap);
+  __shared__ int64_t s_geo[4];
+  __shared__ int64_t s_bound[2];
+  __shared__ uint32_t s_warp_max[kChainBlock / 32];
+  __shared__ uint32_t s_warp_cnt[kChainBlock / 32];
+  __shared__ unsigned long long s_base_id;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const unsigned lane = lane_id();
+  auto off = [&](int64_t s) -> int64_t { return FIRST ? s : static_cast<int64_t>(a.offP[s]); };
+
+  // ---- tile geometry: the rows whose first slot lies in [t T, (t + 1) T).  Four dependent loads: the source that holds
+  // slot t T -> its row -> first source of that row and of the next -> their first slots.
+  if (tid < 2) {
+    const int64_t target = (static_cast<int64_t>(blockIdx.x) + tid) * kChainTile;
+    int64_t src = a.n_sources, slot = a.n_slots;
+    if (target < a.n_slots) {
+      const int64_t s0 = FIRST ? target : static_cast<int64_t>(a.srcbound[blockIdx.x + tid]);
+      const int64_t r0 = a.rowid[s0];
+      const int64_t rs0 = a.run_start[r0], rs1 = a.run_start[r0 + 1];
+      const int64_t o0 = off(rs0), o1 = off(rs1);
+      src = o0 == target ? rs0 : rs1;
+      slot = o0 == target ? o0 : o1;
+    }
+    s_geo[tid] = src;
+    s_geo[2 + tid] = slot;
+  }
+  __syncthreads();
+  const int64_t sa = s_geo[0], sb = s_geo[1];
+  const int64_t base = s_geo[2], end = s_geo[3];
+  const int64_t n = end - base;
+  const bool last_tile = blockIdx.x == gridDim.x - 1;
+
+  if (n == 0) {  // a row of an earlier tile covers this window: nothing to do but to keep the look-back chain whole
+    if (warp == 0) {
+      const unsigned long long before = chain_tile_prefix(a.tile_state, blockIdx.x, 0ull, a.code_partial, a.code_inclusive);
+      if (last_tile && lane == 0) {
+        a.result[kResHeads] = before;
+        a.run_start_out[before] = static_cast<uint32_t>(a.n_slots);
+      }
+    }
+    return;
+  }
+
+  for (int64_t c0 = 0; c0 < n; c0 += kChainCap) {
+    const int64_t cb = base + c0;
+    const int cn = static_cast<int>(n - c0 < kChainCap ? n - c0 : kChainCap);
+    for (int i = tid; i < kChainCap; i += kChainBlock) {
+      s_mark[i] = 0;
+      s_row[i] = 0;
+    }
+    // sources of this chunk: all of the tile's, unless the tile is longer than a chunk (then its last row is heavy)
+    if (n <= kChainCap) {
+      if (tid == 0) {
+        s_bound[0] = sa;
+        s_bound[1] = sb - 1;
+      }
+    } else if (FIRST) {
+      if (tid == 0) {
+        s_bound[0] = cb;
+        s_bound[1] = cb + cn - 1;
+      }
+    } else if (warp < 2) {
+      const unsigned long long target = static_cast<unsigned long long>(warp == 0 ? cb : cb + cn - 1);
+      const int64_t r = (warp == 0 && c0 == 0) ? sa : warp_search_range(a.offP, sa, sb, target);
+      if (lane == 0) s_bound[warp] = r;
+    }
+    __syncthreads();
+    const int64_t s_lo = s_bound[0], s_hi = s_bound[1];
+    for (int64_t s = s_lo + tid; s <= s_hi; s += kChainBlock) {
+      const int64_t o0 = off(s), o1 = off(s + 1);
+      const uint32_t rid = a.rowid[s];
+      const int64_t x = o0 - cb;
+      if (c0 == 0 && x < cn && (s == 0 || a.rowid[s - 1] != rid)) {
+        // first source of a row: the row's slots (if it has any) start here; of several empty rows and one that owns
+        // the slot, the last (largest) is the owner
+        atomicOr(&s_mark[x], static_cast<uint32_t>(x + 1) << 16);
+        atomicMax(&s_row[x], rid);
+      }
+      if (o1 > o0 && o1 > cb && x < cn) {
+        const int f0 = x > 0 ? static_cast<int>(x) : 0;
+        s_soff[f0] = static_cast<int32_t>(x);
+        s_first[f0] = FIRST ? static_cast<uint32_t>(s) : a.firstP[s];
+        const uint32_t lbl = a.lblP[s];
+        s_lbl[f0] = lbl;
+        if (a.wS != nullptr) s_w[f0] = FIRST ? a.wP[lbl] : a.wP[s];
+        uint32_t mark = static_cast<uint32_t>(f0 + 1);
+        if (c0 > 0 && f0 == 0) {  // chunks after the first hold only the tile's last (heavy) row
+          mark |= 1u << 16;
+          s_row[0] = rid;
+        }
+        atomicOr(&s_mark[f0], mark);
+      }
+    }
+    __syncthreads();
+
+    // ---- both marks spread to the right: inclusive max-scan on the two 16-bit halves
+    {
+      uint32_t m[kChainPerThread];
+#pragma unroll
+      for (int i = 0; i < kChainPerThread; ++i) m[i] = s_mark[tid * kChainPerThread + i];
+#pragma unroll
+      for (int i = 1; i < kChainPerThread; ++i) m[i] = __vmaxu2(m[i], m[i - 1]);
+      uint32_t inc = m[kChainPerThread - 1];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(kFullMask, inc, d);
+        if (lane >= static_cast<unsigned>(d)) inc = __vmaxu2(inc, y);
+      }
+      uint32_t before = __shfl_up_sync(kFullMask, inc, 1);
+      if (lane == 0) before = 0;
+      if (lane == 31) s_warp_max[warp] = inc;
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < kChainBlock / 32; ++w)
+        if (w < warp) before = __vmaxu2(before, s_warp_max[w]);
+#pragma unroll
+      for (int i = 0; i < kChainPerThread; ++i) s_mark[tid * kChainPerThread + i] = __vmaxu2(m[i], before);
+    }
+    __syncthreads();
+
+    // ---- every slot: its continuation, the continuation's merged id (the column), its tail; the last slot of a row
+    // records the row's length
+#pragma unroll
+    for (int k = 0; k < kChainPerThread; ++k) {
+      const int i = k * kChainBlock + tid;
+      if (i < cn) {
+        const uint32_t mk = s_mark[i];
+        const int f0 = static_cast<int>(mk & 0xffffu) - 1;
+        const int g0 = static_cast<int>(mk >> 16) - 1;
+        const int64_t jj = static_cast<int64_t>(i) - s_soff[f0];
+        const uint32_t label = s_lbl[f0] + static_cast<uint32_t>(jj);
+        uint32_t col;
+        if (FIRST) {
+          const int64_t v = a.dst[label];
+          col = static_cast<uint32_t>(v);
+          if (v < 0 || v >= a.num_cols) {
+            atomicOr(a.result + kResStatus, kChainStatusIdOutOfRange);
+            col = 0;
+          }
+        } else {
+          const uint32_t g = s_first[f0] + static_cast<uint32_t>(jj);
+          const uint32_t item = a.via != nullptr ? a.via[g] : g;
+          col = a.colsrc[item];
+          if (a.tail_out != nullptr) a.tail_out[label] = item;
+          if (a.w_item_out != nullptr) a.w_item_out[label] = s_w[f0];
+        }
+        s_col[i] = col;
+        if (i == cn - 1 || static_cast<int>(s_mark[i + 1] >> 16) - 1 != g0) {
+          int64_t len = static_cast<int64_t>(i) + 1 - g0;
+          if (i == cn - 1 && c0 + cn < n) len = (n - c0) - g0;   // the tile's last row runs on into the next chunk
+          if (c0 > 0 && g0 == 0) {
+            len = 0xffffffffll;                                  // ... and this is one of its later chunks
+          } else if (len > a.heavy) {
+            const unsigned long long at = atomicAdd(a.result + kResHeavyRows, 1ull);
+            atomicAdd(a.result + kResHeavySlots, static_cast<unsigned long long>(len));
+            a.heavy_list[at] = make_uint2(static_cast<uint32_t>(cb + g0), static_cast<uint32_t>(len));
+          }
+          s_len[g0] = len > 0xffffffffll ? 0xffffffffu : static_cast<uint32_t>(len);
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- stable rank of every slot among the slots of its row (rows above `heavy` keep their order)
+#pragma unroll
+    for (int k = 0; k < kChainPerThread; ++k) {
+      const int i = k * kChainBlock + tid;
+      if (i < cn) {
+        const int g0 = static_cast<int>(s_mark[i] >> 16) - 1;
+        const uint32_t len = s_len[g0];
+        int at = i;
+        if (len > 1 && len <= static_cast<uint32_t>(a.heavy)) {
+          const uint32_t key = s_col[i];
+          int rank = 0;
+          const int g1 = g0 + static_cast<int>(len);
+          for (int j = g0; j < g1; ++j) {
+            const uint32_t c = s_col[j];
+            rank += (c < key || (c == key && j < i)) ? 1 : 0;
+          }
+          at = g0 + rank;
+        }
+        s_perm[at] = static_cast<uint16_t>(i);
+      }
+    }
+    __syncthreads();
+
+    // ---- run heads of the chunk in its final order (a tile starts with a row, so its first slot is a head): every
+    // slot gets the index of its run inside the chunk
+    {
+      const int p0 = tid * kChainPerThread;
+      uint32_t prev_row = 0xffffffffu, prev_col = 0;
+      if (p0 > 0 && p0 <= cn) {
+        prev_row = s_mark[p0 - 1] >> 16;
+        prev_col = s_col[s_perm[p0 - 1]];
+      }
+      uint32_t run[kChainPerThread];
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int k = 0; k < kChainPerThread; ++k) {
+        const int p = p0 + k;
+        if (p < cn) {
+          const uint32_t row = s_mark[p] >> 16;
+          const uint32_t col = s_col[s_perm[p]];
+          cnt += (row != prev_row || col != prev_col) ? 1u : 0u;
+          prev_row = row;
+          prev_col = col;
+        }
+        run[k] = cnt;
+      }
+      const uint32_t inc = warp_inclusive_sum(cnt);
+      if (lane == 31) s_warp_cnt[warp] = inc;
+      __syncthreads();   // also: every thread has read s_len for the ranking
+      uint32_t before = inc - cnt;
+      uint32_t total = 0;
+#pragma unroll
+      for (int w = 0; w < kChainBlock / 32; ++w) {
+        if (w < warp) before += s_warp_cnt[w];
+        total += s_warp_cnt[w];
+      }
+#pragma unroll
+      for (int k = 0; k < kChainPerThread; ++k)
+        if (p0 + k < cn) s_len[p0 + k] = before + run[k] - 1;
+      if (c0 == 0 && warp == 0) {
+        const unsigned long long prefix = chain_tile_prefix(a.tile_state, blockIdx.x, total, a.code_partial, a.code_inclusive);
+        if (lane == 0) {
+          s_base_id = prefix;
+          if (last_tile) {
+            a.result[kResHeads] = prefix + total;
+            a.run_start_out[prefix + total] = static_cast<uint32_t>(a.n_slots);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned long long base_id = s_base_id;
+
+    // ---- write the chunk in its final order
+#pragma unroll
+    for (int k = 0; k < kChainPerThread; ++k) {
+      const int p = k * kChainBlock + tid;
+      if (p < cn) {
+        const int i = s_perm[p];
+        const int g0 = static_cast<int>(s_mark[p] >> 16) - 1;
+        const int f0 = static_cast<int>(s_mark[i] & 0xffffu) - 1;
+        const int64_t jj = static_cast<int64_t>(i) - s_soff[f0];
+        const uint32_t label = s_lbl[f0] + static_cast<uint32_t>(jj);
+        const uint32_t run = s_len[p];
+        const uint32_t id = static_cast<uint32_t>(base_id + run);
+        st_stream(a.rowS + cb + p, s_row[g0]);
+        st_stream(a.colS + cb + p, s_col[i]);
+        st_stream(a.labS + cb + p, label);
+        if (a.wS != nullptr) st_stream(a.wS + cb + p, s_w[f0]);
+        if (a.idS != nullptr) st_stream(a.idS + cb + p, id);
+        if (a.id_item != nullptr) a.id_item[label] = id;
+        if (p == 0 || s_len[p - 1] != run) a.run_start_out[id] = static_cast<uint32_t>(cb + p);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+constexpr size_t kChainTileSmem = static_cast<size_t>(kChainCap) * (8 * 4 + 2);
+
+// ------------------------------------------------------------------ heads
+struct ChainHeadProducer {
+  const uint32_t* rowS;
+  const uint32_t* colS;
+  __device__ unsigned long long operator()(int64_t i) const {
+    if (i == 0) return 1ull;
+    return (rowS[i] != rowS[i - 1] || colS[i] != colS[i - 1]) ? 1ull : 0ull;
+  }
+};
+struct ChainHeadConsumer {
+  const uint32_t* labS;
+  uint32_t* idS;        // merged id of every slot (nullable)
+  uint32_t* id_item;    // merged id of every item, by label (nullable)
+  uint32_t* run_start;  // [heads + 1]
+  int64_t n;
+  __device__ void operator()(int64_t i, unsigned long long head, unsigned long long prefix) const {
+    const uint32_t id = static_cast<uint32_t>(prefix + head - 1);
+    if (head) run_start[prefix] = static_cast<uint32_t>(i);
+    if (i == n - 1) run_start[prefix + head] = static_cast<uint32_t>(n);
+    if (idS != nullptr) idS[i] = id;
+    if (id_item != nullptr) id_item[ld_stream(labS + i)] = id;
+  }
+};
+
+// ------------------------------------------------------------------ fill
+__global__ void __launch_bounds__(256)
+chain_fill_kernel(const uint32_t* __restrict__ rowS, const uint32_t* __restrict__ colS, const float* __restrict__ wS,
+                  const uint32_t* __restrict__ run_start, int64_t num_out, int64_t* __restrict__ out_ei,
+                  float* __restrict__ out_w) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < num_out; r += stride) {
+    const uint32_t a = run_start[r];
+    const uint32_t b = run_start[r + 1];
+    st_stream(out_ei + r, static_cast<int64_t>(rowS[a]));
+    st_stream(out_ei + num_out + r, static_cast<int64_t>(colS[a]));
+    float acc;
+    if (wS == nullptr) {
+      acc = static_cast<float>(b - a);  // unit weights: the sum of b - a ones is exact in fp32 up to 2^24 and rounds like it above
+      if (b - a > (1u << 24)) {
+        acc = 0.f;
+        for (uint32_t i = a; i < b; ++i) acc += 1.f;
+      }
+    } else {
+      acc = wS[a];
+      for (uint32_t i = a + 1; i < b; ++i) acc += wS[i];  // slot order = label order = stream order
+    }
+    st_stream(out_w + r, acc);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+chain_widen_kernel(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    st_stream(out + i, static_cast<int64_t>(ld_stream(in + i)));
+}
+
+// ------------------------------------------------------------------ heavy rows
+struct HeavyLayout {
+  unsigned long long* scan_ws;
+  unsigned long long* sort_ws;
+  size_t zero_bytes;
+  unsigned long long* hoff;  // [rows + 1]
+  unsigned long long *keys_a, *keys_b;
+  uint32_t *vals_a, *vals_b;
+  uint32_t* t_lab;
+  float* t_w;
+  uint32_t* t_dest;
+  int bits;
+  HeavyLayout(Workspace& ws, int64_t slots, int64_t rows, int64_t n_slots) {
+    bits = 32 + bits_for(n_slots > 0 ? static_cast<uint64_t>(n_slots - 1) : 0);
+    scan_ws = ws.take<unsigned long long>(scan_state_words(rows));
+    sort_ws = ws.take<unsigned long long>(sort_state_words(slots, bits));
+    zero_bytes = ws.used;
+    hoff = ws.take<unsigned long long>(static_cast<size_t>(rows) + 1);
+    keys_a = ws.take<unsigned long long>(static_cast<size_t>(slots));
+    keys_b = ws.take<unsigned long long>(static_cast<size_t>(slots));
+    vals_a = ws.take<uint32_t>(static_cast<size_t>(slots));
+    vals_b = ws.take<uint32_t>(static_cast<size_t>(slots));
+    t_lab = ws.take<uint32_t>(static_cast<size_t>(slots));
+    t_w = ws.take<float>(static_cast<size_t>(slots));
+    t_dest = ws.take<uint32_t>(static_cast<size_t>(slots));
+  }
+};
+struct HeavyLenProducer {
+  const uint2* list;
+  __device__ unsigned long long operator()(int64_t k) const { return list[k].y; }
+};
+
+// compact index c -> (heavy row k, offset): key = first slot of the row << 32 | col, payload = the slot
+__global__ void __launch_bounds__(256)
+heavy_compact_kernel(const uint2* __restrict__ list, const unsigned long long* __restrict__ hoff, int64_t rows, int64_t slots,
+                     const uint32_t* __restrict__ colS, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < slots; c += stride) {
+    int64_t lo = 0, hi = rows;  // last k with hoff[k] <= c
+    while (hi - lo > 1) {
+      const int64_t mid = lo + ((hi - lo) >> 1);
+      if (hoff[mid] <= static_cast<unsigned long long>(c)) lo = mid; else hi = mid;
+    }
+    const uint2 row = list[lo];
+    const uint32_t slot = row.x + static_cast<uint32_t>(c - static_cast<int64_t>(hoff[lo]));
+    keys[c] = (static_cast<unsigned long long>(row.x) << 32) | colS[slot];
+    vals[c] = slot;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+heavy_gather_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t slots,
+                    const uint32_t* __restrict__ labS, const float* __restrict__ wS, uint32_t* __restrict__ t_lab,
+                    float* __restrict__ t_w, uint32_t* __restrict__ t_dest) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slots; i += stride) {
+    const unsigned long long k = keys[i];
+    const unsigned long long row_key = k & 0xffffffff00000000ull;
+    int64_t lo = -1, hi = i;  // first index with key >= row_key
+    while (hi - lo > 1) {
+      const int64_t mid = lo + ((hi - lo) >> 1);
+      if (keys[mid] >= row_key) hi = mid; else lo = mid;
+    }
+    const uint32_t src = vals[i];
+    t_dest[i] = static_cast<uint32_t>(k >> 32) + static_cast<uint32_t>(i - hi);
+    t_lab[i] = labS[src];
+    if (wS != nullptr) t_w[i] = wS[src];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+heavy_write_kernel(const unsigned long long* __restrict__ keys, int64_t slots, const uint32_t* __restrict__ t_lab,
+                   const float* __restrict__ t_w, const uint32_t* __restrict__ t_dest, uint32_t* __restrict__ colS,
+                   uint32_t* __restrict__ labS, float* __restrict__ wS) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slots; i += stride) {
+    const uint32_t d = t_dest[i];
+    colS[d] = static_cast<uint32_t>(keys[i]);
+    labS[d] = t_lab[i];
+    if (wS != nullptr) wS[d] = t_w[i];
+  }
+}
+
+static int launch_tiles(ChainTileArgs& a, bool first, cudaStream_t stream) {
+  if (a.n_slots == 0) return PPG_OK;
+  a.code_partial = 1;
+  a.code_inclusive = 2;
+  PPG_REQUIRE(a.tile_state != nullptr && a.run_start_out != nullptr, PPG_ERR_INVALID, "chain: tile state and run_start are required");
+  const int64_t tiles = ceil_div(a.n_slots, kChainTile);
+  PPG_REQUIRE(tiles < (1ll << 31), PPG_ERR_INVALID, "chain: %lld pairs are too many", (long long)a.n_slots);
+  PPG_CUDA_TRY(cudaMemsetAsync(a.tile_state, 0, static_cast<size_t>(tiles) * sizeof(unsigned long long), stream));
+  if (first) {
+    chain_tile_kernel<true><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
+  } else {
+    chain_tile_kernel<false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
+  }
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
+}  // namespace ppg
+
+using namespace ppg;
+
+extern "C" int ppg_chain_heavy_default(void) { return kChainHeavyMax; }
+extern "C" int ppg_chain_tile_slots(void) { return kChainTile; }
+
+// Level 1: rows = first-order nodes, items = events grouped by source node (arrays of ppg_lift_temporal_group).
+extern "C" int ppg_chain_first_tiles(const int64_t* edge_index, int64_t m, int64_t N, const uint32_t* ptr1,
+                                     const uint32_t* grouped, const uint32_t* sorted_src, const float* weights, int heavy,
+                                     uint32_t* rowS, uint32_t* colS, uint32_t* labS, float* wS, uint32_t* idS,
+                                     uint32_t* id_item, uint32_t* run_start, void* tile_state, void* heavy_list,
+                                     int64_t* result, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(m > 0 && N > 0 && m < (1ll << 31) && N < (1ll << 31), PPG_ERR_INVALID, "chain: sizes m=%lld N=%lld outside (0, 2^31)",
+              (long long)m, (long long)N);
+  PPG_REQUIRE(heavy >= 1 && heavy <= kChainHeavyMax, PPG_ERR_INVALID, "chain: heavy threshold %d outside [1, %d]", heavy, kChainHeavyMax);
+  PPG_REQUIRE((weights == nullptr) == (wS == nullptr), PPG_ERR_INVALID, "chain: weights in and out must come together");
+  ChainTileArgs a = {};
+  a.lblP = grouped;
+  a.wP = weights;
+  a.run_start = ptr1;
+  a.rowid = sorted_src;
+  a.dst = edge_index + m;
+  a.n_sources = m;
+  a.n_rows = N;
+  a.n_slots = m;
+  a.num_cols = N;
+  a.heavy = heavy;
+  a.rowS = rowS;
+  a.colS = colS;
+  a.labS = labS;
+  a.wS = wS;
+  a.heavy_list = static_cast<uint2*>(heavy_list);
+  a.result = reinterpret_cast<unsigned long long*>(result);
+  a.idS = idS;
+  a.id_item = id_item;
+  a.run_start_out = run_start;
+  a.tile_state = static_cast<unsigned long long*>(tile_state);
+  return launch_tiles(a, true, stream);
+}
+
+extern "C" size_t ppg_chain_scan_workspace_bytes(int64_t n) { return (scan_state_words(n < 0 ? 0 : n) + 4) * sizeof(unsigned long long); }
+
+// Run heads of the slots in final order -> merged ids; result[kResHeads] = number of merged edges.
+extern "C" int ppg_chain_heads(const uint32_t* rowS, const uint32_t* colS, const uint32_t* labS, int64_t n, void* workspace,
+                               size_t workspace_bytes, uint32_t* idS, uint32_t* id_item, uint32_t* run_start, int64_t* result,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(n >= 0 && n < (1ll << 31), PPG_ERR_INVALID, "chain: %lld slots outside [0, 2^31)", (long long)n);
+  const size_t need = ppg_chain_scan_workspace_bytes(n);
+  PPG_REQUIRE(workspace_bytes >= need, PPG_ERR_WORKSPACE, "chain_heads: workspace %zu < %zu bytes", workspace_bytes, need);
+  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, stream));
+  if (n == 0) {
+    PPG_CUDA_TRY(cudaMemsetAsync(result + kResHeads, 0, sizeof(int64_t), stream));
+    PPG_CUDA_TRY(cudaMemsetAsync(run_start, 0, sizeof(uint32_t), stream));
+    return PPG_OK;
+  }
+  return launch_scan(ChainHeadProducer{rowS, colS}, ChainHeadConsumer{labS, idS, id_item, run_start, n}, n,
+                     static_cast<unsigned long long*>(workspace), reinterpret_cast<unsigned long long*>(result) + kResHeads, stream);
+}
+
+extern "C" int ppg_chain_fill(const uint32_t* rowS, const uint32_t* colS, const float* wS, const uint32_t* run_start,
+                              int64_t num_out, int64_t* out_edge_index, float* out_weights, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (num_out == 0) return PPG_OK;
+  chain_fill_kernel<<<grid_for(num_out, 256), 256, 0, stream>>>(rowS, colS, wS, run_start, num_out, out_edge_index, out_weights);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
+extern "C" int ppg_chain_widen(const uint32_t* in, int64_t n, int64_t* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n == 0) return PPG_OK;
+  chain_widen_kernel<<<grid_for(n, 256 * 4), 256, 0, stream>>>(in, n, out);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
+// Count pass of level k + 1 in item order (k >= 2): first continuation and row pointer of every level-k item.
+// total[0] = number of level-(k+1) items.
+extern "C" int ppg_chain_count(const uint32_t* tail, const void* ptr_prev, int64_t E, void* workspace, size_t workspace_bytes,
+                               uint32_t* first, void* ptr_next, int64_t* total, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(E >= 0 && E < (1ll << 31), PPG_ERR_INVALID, "chain: %lld items outside [0, 2^31)", (long long)E);
+  const size_t need = ppg_chain_scan_workspace_bytes(E);
+  PPG_REQUIRE(workspace_bytes >= need, PPG_ERR_WORKSPACE, "chain_count: workspace %zu < %zu bytes", workspace_bytes, need);
+  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, stream));
+  if (E == 0) {
+    PPG_CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(int64_t), stream));
+    PPG_CUDA_TRY(cudaMemsetAsync(ptr_next, 0, sizeof(unsigned long long), stream));
+    return PPG_OK;
+  }
+  return launch_scan(ChainCountProducer{tail, static_cast<const unsigned long long*>(ptr_prev), first},
+                     ChainOffsetConsumer{static_cast<unsigned long long*>(ptr_next), E}, E,
+                     static_cast<unsigned long long*>(workspace), reinterpret_cast<unsigned long long*>(total), stream);
+}
+
+// Count pass in merged order: slot offsets of the expansion, per-source data in that order, tile boundaries.
+extern "C" int ppg_chain_count_sorted(const uint32_t* P, int64_t n, const uint32_t* first, const void* ptr_next,
+                                      const float* w_item, int64_t limit, void* workspace, size_t workspace_bytes, void* offP,
+                                      uint32_t* firstP, uint32_t* lblP, float* wP, uint32_t* srcbound, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(n > 0 && n < (1ll << 31), PPG_ERR_INVALID, "chain: %lld sources outside (0, 2^31)", (long long)n);
+  const size_t need = ppg_chain_scan_workspace_bytes(n);
+  PPG_REQUIRE(workspace_bytes >= need, PPG_ERR_WORKSPACE, "chain_count_sorted: workspace %zu < %zu bytes", workspace_bytes, need);
+  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, stream));
+  return launch_scan(ChainSortedProducer{P, first, static_cast<const unsigned long long*>(ptr_next), w_item, limit, firstP, lblP, wP},
+                     ChainSortedConsumer{static_cast<unsigned long long*>(offP), srcbound, n}, n,
+                     static_cast<unsigned long long*>(workspace), nullptr, stream);
+}
+
+// Tiles of level k >= 2: `via` maps a continuation position to its item (temporal level: the events grouped by source).
+extern "C" int ppg_chain_tiles(int64_t n_sources, int64_t n_rows, int64_t n_slots, const void* offP, const uint32_t* firstP,
+                               const uint32_t* lblP, const float* wP, const uint32_t* run_start, const uint32_t* rowid,
+                               const uint32_t* colsrc, const uint32_t* via, const uint32_t* srcbound, int heavy, uint32_t* rowS,
+                               uint32_t* colS, uint32_t* labS, float* wS, uint32_t* tail_out, float* w_item_out,
+                               uint32_t* idS, uint32_t* id_item, uint32_t* run_start_out, void* tile_state,
+                               void* heavy_list, int64_t* result, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(n_sources > 0 && n_sources < (1ll << 31) && n_slots >= 0 && n_slots < (1ll << 31) && n_rows > 0, PPG_ERR_INVALID,
+              "chain: sizes outside [0, 2^31)");
+  PPG_REQUIRE(heavy >= 1 && heavy <= kChainHeavyMax, PPG_ERR_INVALID, "chain: heavy threshold %d outside [1, %d]", heavy, kChainHeavyMax);
+  PPG_REQUIRE((wP == nullptr) == (wS == nullptr), PPG_ERR_INVALID, "chain: weights in and out must come together");
+  ChainTileArgs a = {};
+  a.offP = static_cast<const unsigned long long*>(offP);
+  a.firstP = firstP;
+  a.lblP = lblP;
+  a.wP = wP;
+  a.run_start = run_start;
+  a.rowid = rowid;
+  a.colsrc = colsrc;
+  a.via = via;
+  a.srcbound = srcbound;
+  a.n_sources = n_sources;
+  a.n_rows = n_rows;
+  a.n_slots = n_slots;
+  a.heavy = heavy;
+  a.rowS = rowS;
+  a.colS = colS;
+  a.labS = labS;
+  a.wS = wS;
+  a.tail_out = tail_out;
+  a.w_item_out = w_item_out;
+  a.heavy_list = static_cast<uint2*>(heavy_list);
+  a.result = reinterpret_cast<unsigned long long*>(result);
+  a.idS = idS;
+  a.id_item = id_item;
+  a.run_start_out = run_start_out;
+  a.tile_state = static_cast<unsigned long long*>(tile_state);
+  return launch_tiles(a, false, stream);
+}
+
+extern "C" size_t ppg_chain_heavy_workspace_bytes(int64_t heavy_slots, int64_t heavy_rows, int64_t n_slots) {
+  Workspace ws(nullptr, 0);
+  HeavyLayout L(ws, heavy_slots, heavy_rows, n_slots);
+  return ws.used + 256;
+}
+
+// Rows the tiles left in generation order: one stable radix sort over their pairs only, written back in place.
+extern "C" int ppg_chain_heavy_fix(const void* heavy_list, int64_t heavy_rows, int64_t heavy_slots, int64_t n_slots,
+                                   uint32_t* colS, uint32_t* labS, float* wS, void* workspace, size_t workspace_bytes,
+                                   void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (heavy_rows == 0 || heavy_slots == 0) return PPG_OK;
+  Workspace ws(workspace, workspace_bytes);
+  HeavyLayout L(ws, heavy_slots, heavy_rows, n_slots);
+  PPG_REQUIRE(ws.fits(), PPG_ERR_WORKSPACE, "chain_heavy_fix: workspace %zu < %zu bytes", workspace_bytes, ws.used);
+  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, L.zero_bytes, stream));
+  const uint2* list = static_cast<const uint2*>(heavy_list);
+  PPG_TRY(launch_scan(HeavyLenProducer{list}, ChainOffsetConsumer{L.hoff, heavy_rows}, heavy_rows, L.scan_ws, nullptr, stream));
+  heavy_compact_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(list, L.hoff, heavy_rows, heavy_slots, colS, L.keys_a, L.vals_a);
+  PPG_LAUNCHED();
+  int in_b = 0;
+  PPG_TRY(radix_sort_pairs<unsigned long long>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, false, heavy_slots, L.bits, L.sort_ws,
+                                               &in_b, stream));
+  const unsigned long long* keys = in_b ? L.keys_b : L.keys_a;
+  const uint32_t* vals = in_b ? L.vals_b : L.vals_a;
+  heavy_gather_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(keys, vals, heavy_slots, labS, wS, L.t_lab, L.t_w, L.t_dest);
+  PPG_LAUNCHED();
+  heavy_write_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(keys, heavy_slots, L.t_lab, L.t_w, L.t_dest, colS, labS, wS);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}

@@ -557,6 +557,23 @@ extern "C" int ppg_lift_temporal_fill(const void* workspace, int64_t m, int64_t 
   return launch_expand(L.off, m, num_pairs, out_index, TemporalTail{L.first, L.grouped()}, stream);
 }
 
+// Device arrays a grouped / counted temporal workspace holds, for the layer chain (chain.cu):
+// out[0] ptr u32 [N + 1] (CSR over the source node), out[1] grouped u32 [m] (event at every grouped position),
+// out[2] source node of every grouped position u32 [m], out[3] first u32 [m] (grouped position of an event's first
+// continuation), out[4] off u64 [m + 1] (row pointer of the event graph), out[5] {total, status}
+extern "C" int ppg_lift_temporal_views(const void* workspace, int64_t m, int64_t N, const void** out) {
+  Workspace ws(const_cast<void*>(workspace), ~static_cast<size_t>(0));
+  TemporalLayout L(ws, m, N);
+  const bool odd = (sort_num_passes(L.sort_bits) & 1) != 0;
+  out[0] = L.ptr;
+  out[1] = L.grouped();
+  out[2] = odd ? L.keys_b : L.keys_a;
+  out[3] = L.first;
+  out[4] = L.off;
+  out[5] = L.result;
+  return PPG_OK;
+}
+
 // =================================================================== prefix-limited lifts
 // The columns of a lift are ascending in the source, so "the lift of the first `limit` sources only" is a prefix of the
 // full output: off[limit] columns.  The distributed lift (exchange.cu) needs only the paths that start before a cut.
