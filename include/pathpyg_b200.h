@@ -139,7 +139,8 @@ int ppg_lift_temporal_views(const void* workspace, int64_t num_edges, int64_t nu
  *   ppg_chain_first_tiles   level 1: rows = source nodes; ptr1 / grouped / sorted_src from ppg_lift_temporal_views
  *   ppg_chain_count         k >= 2: continuation count of every level-k item in label order -> first, ptr_next u64 [E+1]
  *   ppg_chain_count_sorted  the same counts in merged order P (items >= limit are not expanded): offP u64 [n+1], firstP,
- *                           lblP, wP [n], srcbound [ceil(pairs / ppg_chain_tile_slots())]
+ *                           lblP, wP [n], srcbound [ceil(pairs / ppg_chain_tile_slots())][2] (rowid / run_start: the
+ *                           previous level's idS / run_start)
  *   ppg_chain_tiles         expand + rank: `via` maps a continuation position to its item (temporal level: `grouped`);
  *                           the run heads are found in the same kernel (tile_state: 8 bytes per tile of
  *                           ppg_chain_tile_slots() pairs) -> idS, id_item (nullable), run_start, result[0]: final unless
@@ -158,8 +159,9 @@ int ppg_chain_first_tiles(const int64_t* edge_index, int64_t num_edges, int64_t 
 int ppg_chain_count(const uint32_t* tail, const void* ptr_prev, int64_t num_items, void* workspace, size_t workspace_bytes,
                     uint32_t* first, void* ptr_next, int64_t* total, void* stream);
 int ppg_chain_count_sorted(const uint32_t* P, int64_t num_items, const uint32_t* first, const void* ptr_next,
-                           const float* w_item, int64_t limit, void* workspace, size_t workspace_bytes, void* offP,
-                           uint32_t* firstP, uint32_t* lblP, float* wP, uint32_t* srcbound, void* stream);
+                           const float* w_item, int64_t limit, const uint32_t* rowid, const uint32_t* run_start,
+                           void* workspace, size_t workspace_bytes, void* offP, uint32_t* firstP, uint32_t* lblP, float* wP,
+                           uint32_t* srcbound, void* stream);
 int ppg_chain_tiles(int64_t num_sources, int64_t num_rows, int64_t num_slots, const void* offP, const uint32_t* firstP,
                     const uint32_t* lblP, const float* wP, const uint32_t* run_start, const uint32_t* rowid,
                     const uint32_t* colsrc, const uint32_t* via, const uint32_t* srcbound, int heavy, uint32_t* rowS,

@@ -51,7 +51,7 @@ PROTOTYPES = {
     "ppg_chain_scan_workspace_bytes": (c_size_t, [_i64]),
     "ppg_chain_first_tiles": (c_int, [_p, _i64, _i64, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ppg_chain_count": (c_int, [_p, _p, _i64, _p, c_size_t, _p, _p, _p, _p]),
-    "ppg_chain_count_sorted": (c_int, [_p, _i64, _p, _p, _p, _i64, _p, c_size_t, _p, _p, _p, _p, _p, _p]),
+    "ppg_chain_count_sorted": (c_int, [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, c_size_t, _p, _p, _p, _p, _p, _p]),
     "ppg_chain_tiles": (c_int, [_i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ppg_chain_heads": (c_int, [_p, _p, _p, _i64, _p, c_size_t, _p, _p, _p, _p, _p]),
     "ppg_chain_heavy_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),

@@ -160,9 +160,10 @@ class TemporalChain:
                 firstP = torch.empty(ns, dtype=_u32, device=dev)
                 lblP = torch.empty(ns, dtype=_u32, device=dev)
                 wP = torch.empty(ns, dtype=torch.float32, device=dev) if self.weighted else None
-                srcbound = torch.empty(-(-pairs // self.tile), dtype=_u32, device=dev)
+                srcbound = torch.empty((-(-pairs // self.tile), 2), dtype=_u32, device=dev)
                 ws = self._scan_ws(ns)
-                _lib.check(lib.ppg_chain_count_sorted(_ptr(prev.labS), ns, first, ptr_next, _ptr(w_item), ns, _ptr(ws), ws.numel(),
+                _lib.check(lib.ppg_chain_count_sorted(_ptr(prev.labS), ns, first, ptr_next, _ptr(w_item), ns, _ptr(prev.idS),
+                                                      _ptr(prev.run_start), _ptr(ws), ws.numel(),
                                                       _ptr(offP), _ptr(firstP), _ptr(lblP), _ptr(wP), _ptr(srcbound), stream))
                 if more:
                     cur.tail = torch.empty(pairs, dtype=_u32, device=dev)

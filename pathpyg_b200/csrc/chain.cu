@@ -89,14 +89,20 @@ struct ChainSortedProducer {
 };
 struct ChainSortedConsumer {
   unsigned long long* offP;  // [n + 1]
-  uint32_t* srcbound;        // [tiles]: the source that holds slot t * kChainTile
+  uint2* srcbound;           // [tiles]: first source of the row that holds slot t * kChainTile, and of the next row
+  const uint32_t* rowid;     // [n] row of every source
+  const uint32_t* run_start; // [rows + 1]
   int64_t n;
   __device__ void operator()(int64_t s, unsigned long long v, unsigned long long prefix) const {
     offP[s] = prefix;
     if (s == n - 1) offP[n] = prefix + v;
     if (v) {
-      for (unsigned long long t = (prefix + kChainTile - 1) / kChainTile; t * kChainTile < prefix + v; ++t)
-        srcbound[t] = static_cast<uint32_t>(s);
+      const unsigned long long t0 = (prefix + kChainTile - 1) / kChainTile;
+      if (t0 * kChainTile < prefix + v) {
+        const uint32_t r0 = rowid[s];
+        const uint2 b = make_uint2(run_start[r0], run_start[r0 + 1]);
+        for (unsigned long long t = t0; t * kChainTile < prefix + v; ++t) srcbound[t] = b;
+      }
     }
   }
 };
@@ -113,7 +119,7 @@ struct ChainTileArgs {
   const uint32_t* colsrc;          // merged id of an item                             (FIRST: unused)
   const uint32_t* via;             // continuation position -> item (temporal level) or nullptr
   const int64_t* dst;              // FIRST: target node of every event
-  const uint32_t* srcbound;        // [tiles]                                          (FIRST: unused)
+  const uint32_t* srcbound;        // [tiles][2] (see ChainSortedConsumer)              (FIRST: unused)
   int64_t n_sources, n_rows, n_slots, num_cols;
   int heavy;
   uint32_t *rowS, *colS, *labS;
@@ -145,19 +151,20 @@ __device__ __forceinline__ int64_t warp_search_range(const unsigned long long* _
   return lo;
 }
 
-// One look-back step shared by all tiles of a launch: the number of run heads (merged edges) in the tiles before this one.
-// Tiles are taken in blockIdx order (CTAs are dispatched in that order, so a tile only waits for tiles that are running
-// or done); the words carry a code per call like the scan's (common.cuh).
+// Look-back over the tiles of a launch: the number of run heads (merged edges) in the tiles before this one.  Tiles are
+// taken in blockIdx order (CTAs are dispatched in that order, so a tile only waits for tiles that are running or done);
+// the words carry a code per call like the scan's (common.cuh).  A tile publishes its count as soon as it has it and
+// resolves its prefix after it has written everything that does not need it.
+__device__ __forceinline__ void chain_tile_publish(unsigned long long* __restrict__ state, unsigned tile, unsigned long long total,
+                                                   unsigned code_partial, unsigned code_inclusive) {
+  state_store(&state[tile], tile == 0 ? code_inclusive : code_partial, total);
+}
+// called by warp 0, some time after chain_tile_publish: by then the predecessors' words are usually out
 __device__ __forceinline__ unsigned long long chain_tile_prefix(unsigned long long* __restrict__ state, unsigned tile,
                                                                 unsigned long long total, unsigned code_partial,
                                                                 unsigned code_inclusive) {
-  // called by warp 0
   const unsigned lane = lane_id();
-  if (tile == 0) {
-    if (lane == 0) state_store(&state[0], code_inclusive, total);
-    return 0;
-  }
-  if (lane == 0) state_store(&state[tile], code_partial, total);
+  if (tile == 0) return 0;
   unsigned long long acc = 0;
   int64_t newest = static_cast<int64_t>(tile) - 1;
   while (true) {
@@ -203,21 +210,31 @@ chain_tile_kernel(ChainTileArgs a) {
   __shared__ uint32_t s_warp_max[kChainBlock / 32];
   __shared__ uint32_t s_warp_cnt[kChainBlock / 32];
   __shared__ unsigned long long s_base_id;
+  __shared__ unsigned long long s_total;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const unsigned lane = lane_id();
   auto off = [&](int64_t s) -> int64_t { return FIRST ? s : static_cast<int64_t>(a.offP[s]); };
 
-  // ---- tile geometry: the rows whose first slot lies in [t T, (t + 1) T).  Four dependent loads: the source that holds
-  // slot t T -> its row -> first source of that row and of the next -> their first slots.
+  // ---- tile geometry: the rows whose first slot lies in [t T, (t + 1) T).  The source that holds slot t T belongs to row
+  // r0; the tile starts with r0 if that row starts exactly at t T, else with the next row (the count pass left the
+  // first sources of both rows in srcbound: two dependent loads here).
   if (tid < 2) {
-    const int64_t target = (static_cast<int64_t>(blockIdx.x) + tid) * kChainTile;
+    const int64_t t = static_cast<int64_t>(blockIdx.x) + tid;
+    const int64_t target = t * kChainTile;
     int64_t src = a.n_sources, slot = a.n_slots;
     if (target < a.n_slots) {
-      const int64_t s0 = FIRST ? target : static_cast<int64_t>(a.srcbound[blockIdx.x + tid]);
-      const int64_t r0 = a.rowid[s0];
-      const int64_t rs0 = a.run_start[r0], rs1 = a.run_start[r0 + 1];
+      int64_t rs0, rs1;
+      if (FIRST) {
+        const int64_t r0 = a.rowid[target];
+        rs0 = a.run_start[r0];
+        rs1 = a.run_start[r0 + 1];
+      } else {
+        const uint2 b = reinterpret_cast<const uint2*>(a.srcbound)[t];
+        rs0 = b.x;
+        rs1 = b.y;
+      }
       const int64_t o0 = off(rs0), o1 = off(rs1);
       src = o0 == target ? rs0 : rs1;
       slot = o0 == target ? o0 : o1;
@@ -233,6 +250,7 @@ chain_tile_kernel(ChainTileArgs a) {
 
   if (n == 0) {  // a row of an earlier tile covers this window: nothing to do but to keep the look-back chain whole
     if (warp == 0) {
+      if (lane == 0) chain_tile_publish(a.tile_state, blockIdx.x, 0ull, a.code_partial, a.code_inclusive);
       const unsigned long long before = chain_tile_prefix(a.tile_state, blockIdx.x, 0ull, a.code_partial, a.code_inclusive);
       if (last_tile && lane == 0) {
         a.result[kResHeads] = before;
@@ -421,21 +439,15 @@ chain_tile_kernel(ChainTileArgs a) {
 #pragma unroll
       for (int k = 0; k < kChainPerThread; ++k)
         if (p0 + k < cn) s_len[p0 + k] = before + run[k] - 1;
-      if (c0 == 0 && warp == 0) {
-        const unsigned long long prefix = chain_tile_prefix(a.tile_state, blockIdx.x, total, a.code_partial, a.code_inclusive);
-        if (lane == 0) {
-          s_base_id = prefix;
-          if (last_tile) {
-            a.result[kResHeads] = prefix + total;
-            a.run_start_out[prefix + total] = static_cast<uint32_t>(a.n_slots);
-          }
-        }
+      if (c0 == 0 && tid == 0) {
+        s_total = total;
+        chain_tile_publish(a.tile_state, blockIdx.x, total, a.code_partial, a.code_inclusive);
       }
     }
     __syncthreads();
-    const unsigned long long base_id = s_base_id;
 
-    // ---- write the chunk in its final order
+    // ---- write the chunk in its final order: first what does not depend on the tiles before this one ...
+    uint32_t label[kChainPerThread];
 #pragma unroll
     for (int k = 0; k < kChainPerThread; ++k) {
       const int p = k * kChainBlock + tid;
@@ -444,15 +456,35 @@ chain_tile_kernel(ChainTileArgs a) {
         const int g0 = static_cast<int>(s_mark[p] >> 16) - 1;
         const int f0 = static_cast<int>(s_mark[i] & 0xffffu) - 1;
         const int64_t jj = static_cast<int64_t>(i) - s_soff[f0];
-        const uint32_t label = s_lbl[f0] + static_cast<uint32_t>(jj);
-        const uint32_t run = s_len[p];
-        const uint32_t id = static_cast<uint32_t>(base_id + run);
+        label[k] = s_lbl[f0] + static_cast<uint32_t>(jj);
         st_stream(a.rowS + cb + p, s_row[g0]);
         st_stream(a.colS + cb + p, s_col[i]);
-        st_stream(a.labS + cb + p, label);
+        st_stream(a.labS + cb + p, label[k]);
         if (a.wS != nullptr) st_stream(a.wS + cb + p, s_w[f0]);
+      }
+    }
+    // ... then the merged ids, once the number of run heads before this tile is known
+    if (c0 == 0 && warp == 0) {
+      const unsigned long long total = s_total;
+      const unsigned long long prefix = chain_tile_prefix(a.tile_state, blockIdx.x, total, a.code_partial, a.code_inclusive);
+      if (lane == 0) {
+        s_base_id = prefix;
+        if (last_tile) {
+          a.result[kResHeads] = prefix + total;
+          a.run_start_out[prefix + total] = static_cast<uint32_t>(a.n_slots);
+        }
+      }
+    }
+    __syncthreads();
+    const unsigned long long base_id = s_base_id;
+#pragma unroll
+    for (int k = 0; k < kChainPerThread; ++k) {
+      const int p = k * kChainBlock + tid;
+      if (p < cn) {
+        const uint32_t run = s_len[p];
+        const uint32_t id = static_cast<uint32_t>(base_id + run);
         if (a.idS != nullptr) st_stream(a.idS + cb + p, id);
-        if (a.id_item != nullptr) a.id_item[label] = id;
+        if (a.id_item != nullptr) a.id_item[label[k]] = id;
         if (p == 0 || s_len[p - 1] != run) a.run_start_out[id] = static_cast<uint32_t>(cb + p);
       }
     }
@@ -719,15 +751,16 @@ extern "C" int ppg_chain_count(const uint32_t* tail, const void* ptr_prev, int64
 
 // Count pass in merged order: slot offsets of the expansion, per-source data in that order, tile boundaries.
 extern "C" int ppg_chain_count_sorted(const uint32_t* P, int64_t n, const uint32_t* first, const void* ptr_next,
-                                      const float* w_item, int64_t limit, void* workspace, size_t workspace_bytes, void* offP,
-                                      uint32_t* firstP, uint32_t* lblP, float* wP, uint32_t* srcbound, void* stream_) {
+                                      const float* w_item, int64_t limit, const uint32_t* rowid, const uint32_t* run_start,
+                                      void* workspace, size_t workspace_bytes, void* offP, uint32_t* firstP, uint32_t* lblP,
+                                      float* wP, uint32_t* srcbound, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PPG_REQUIRE(n > 0 && n < (1ll << 31), PPG_ERR_INVALID, "chain: %lld sources outside (0, 2^31)", (long long)n);
   const size_t need = ppg_chain_scan_workspace_bytes(n);
   PPG_REQUIRE(workspace_bytes >= need, PPG_ERR_WORKSPACE, "chain_count_sorted: workspace %zu < %zu bytes", workspace_bytes, need);
   PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, stream));
   return launch_scan(ChainSortedProducer{P, first, static_cast<const unsigned long long*>(ptr_next), w_item, limit, firstP, lblP, wP},
-                     ChainSortedConsumer{static_cast<unsigned long long*>(offP), srcbound, n}, n,
+                     ChainSortedConsumer{static_cast<unsigned long long*>(offP), reinterpret_cast<uint2*>(srcbound), rowid, run_start, n}, n,
                      static_cast<unsigned long long*>(workspace), nullptr, stream);
 }
 
