@@ -173,10 +173,41 @@ int ppg_chain_heads(const uint32_t* rowS, const uint32_t* colS, const uint32_t* 
                     void* stream);
 size_t ppg_chain_heavy_workspace_bytes(int64_t heavy_slots, int64_t heavy_rows, int64_t num_slots);
 int ppg_chain_heavy_fix(const void* heavy_list, int64_t heavy_rows, int64_t heavy_slots, int64_t num_slots, uint32_t* colS,
-                        uint32_t* labS, float* wS, void* workspace, size_t workspace_bytes, void* stream);
+                        uint32_t* labS, float* wS, uint32_t* extraS, void* workspace, size_t workspace_bytes, void* stream);
 int ppg_chain_fill(const uint32_t* rowS, const uint32_t* colS, const float* wS, const uint32_t* run_start, int64_t num_out,
                    int64_t* out_edge_index, float* out_weights, void* stream);
 int ppg_chain_widen(const uint32_t* in, int64_t n, int64_t* out, void* stream);
+
+/* The same chain on a rank of a distributed build (no counterpart in /root/reference).  A rank expands its
+ * items in the order of their GLOBAL merged ids, so its pairs are sorted by (row, col) in global ids and the pairs of one
+ * owner (owners hold ascending row ranges) are one contiguous slot range; an owner merges one sorted run per sender.
+ *   ppg_chain_tiles_dist    as ppg_chain_tiles with `info` by item (global id << 32 | last node) for colsrc, LOCAL rows
+ *                           (rowid / run_start / row_value from ppg_chain_unpack), lastS out; rowS receives global ids
+ *   ppg_chain_dest_bounds   first slot of every destination rank: dstart [world + 1], counts [world] (device int64)
+ *   ppg_chain_pack          slots -> 16-byte records {col, row, last node, weight} into a local buffer or the owners'
+ *                           receive buffers (peer memory), slot order
+ *   ppg_merge_sorted        owner: merge the runs in shared-memory tiles of whole row ranges -> compact merged arrays +
+ *                           the merged edge of every record; result[1] & 2: a tile overflowed, use ppg_merge_records_*
+ *   ppg_chain_unpack        sender: returned indices -> global ids, local rows of the next level, info word of every item */
+int ppg_chain_tiles_dist(int64_t num_sources, int64_t num_rows, int64_t num_slots, const void* offP, const uint32_t* firstP,
+                         const uint32_t* lblP, const float* wP, const uint32_t* run_start, const uint32_t* rowid,
+                         const uint32_t* row_value, const void* info, const uint32_t* via, const uint32_t* srcbound, int heavy,
+                         uint32_t* rowS, uint32_t* colS, uint32_t* labS, float* wS, uint32_t* lastS, uint32_t* tail_out,
+                         float* w_item_out, uint32_t* run_start_scratch, void* tile_state, void* heavy_list, int64_t* result,
+                         void* stream);
+int ppg_chain_dest_bounds(const uint32_t* rowS, int64_t num_slots, const int64_t* offsets, int world, int64_t* dstart,
+                          int64_t* counts, void* stream);
+int ppg_chain_pack(const uint32_t* rowS, const uint32_t* colS, const uint32_t* lastS, const float* wS, int64_t num_slots,
+                   const int64_t* dstart, int world, void* out_records, void* const* h_peer_records, void* stream);
+int ppg_chain_unpack(const uint32_t* back, int64_t num_slots, const int64_t* dstart, const int64_t* edge_offsets, int world,
+                     const uint32_t* labS, const uint32_t* lastS, void* workspace, size_t workspace_bytes, uint32_t* rowid,
+                     uint32_t* run_start, uint32_t* row_value, void* info_item, int64_t* result, void* stream);
+int64_t ppg_merge_sorted_tiles(int64_t num_records);
+int ppg_merge_sorted(const void* records, int64_t num_records, const int64_t* seg, int world, int64_t row_lo, int64_t rows_owned,
+                     int64_t total_nodes, uint32_t* bounds, void* tile_state, uint32_t* out_inverse, uint32_t* row_m,
+                     uint32_t* col_m, float* w_m, uint32_t* last_m, int64_t* result, void* stream);
+int ppg_merge_sorted_fill(const uint32_t* row_m, const uint32_t* col_m, const float* w_m, const uint32_t* last_m,
+                          int64_t num_out, int64_t* out_edge_index, float* out_weights, int64_t* out_last, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * e   cross-partition exchange of lifted edges (the reference is single-device, there is no

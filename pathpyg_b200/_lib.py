@@ -55,7 +55,15 @@ PROTOTYPES = {
     "ppg_chain_tiles": (c_int, [_i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ppg_chain_heads": (c_int, [_p, _p, _p, _i64, _p, c_size_t, _p, _p, _p, _p, _p]),
     "ppg_chain_heavy_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
-    "ppg_chain_heavy_fix": (c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, c_size_t, _p]),
+    "ppg_chain_heavy_fix": (c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, c_size_t, _p]),
+    "ppg_chain_tiles_dist": (c_int, [_i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                     _p, _p]),
+    "ppg_chain_dest_bounds": (c_int, [_p, _i64, _p, c_int, _p, _p, _p]),
+    "ppg_chain_pack": (c_int, [_p, _p, _p, _p, _i64, _p, c_int, _p, POINTER(c_void_p), _p]),
+    "ppg_chain_unpack": (c_int, [_p, _i64, _p, _p, c_int, _p, _p, _p, c_size_t, _p, _p, _p, _p, _p, _p]),
+    "ppg_merge_sorted_tiles": (_i64, [_i64]),
+    "ppg_merge_sorted": (c_int, [_p, _i64, _p, c_int, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ppg_merge_sorted_fill": (c_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "ppg_chain_fill": (c_int, [_p, _p, _p, _p, _i64, _p, _p, _p]),
     "ppg_chain_widen": (c_int, [_p, _i64, _p, _p]),
     "ppg_rows_minmax_workspace_bytes": (c_size_t, [_i64]),

@@ -82,7 +82,7 @@ class TemporalChain:
         """Order the rows the tiles skipped, redo the run heads; returns the merged count (one more synchronisation)."""
         ws = torch.empty(self.lib.ppg_chain_heavy_workspace_bytes(slots, rows, level.items), dtype=torch.uint8, device=self.dev)
         _lib.check(self.lib.ppg_chain_heavy_fix(_ptr(level.heavy_list), rows, slots, level.items, _ptr(level.colS), _ptr(level.labS),
-                                                _ptr(level.wS), _ptr(ws), ws.numel(), _stream(self.dev)))
+                                                _ptr(level.wS), None, _ptr(ws), ws.numel(), _stream(self.dev)))
         self._heads(level, k)
         return int(self.res[k, _RES_HEADS].item())
 

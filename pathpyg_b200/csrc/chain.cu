@@ -132,6 +132,10 @@ struct ChainTileArgs {
   unsigned long long* tile_state;  // [tiles] zeroed
   unsigned code_partial, code_inclusive;
   uint32_t *idS, *id_item, *run_start_out;
+  // distributed build (DIST): ids are global, rows are local
+  const unsigned long long* info;  // by item: global id << 32 | last first-order node (replaces colsrc)
+  const uint32_t* row_value;       // by local row: its global id (what rowS receives)
+  uint32_t* lastS;                 // out: last node of every slot's pair
 };
 
 // largest s in [lo, hi) with off[s] <= target; requires off[lo] <= target
@@ -192,7 +196,7 @@ __device__ __forceinline__ unsigned long long chain_tile_prefix(unsigned long lo
   return acc;
 }
 
-template <bool FIRST>
+template <bool FIRST, bool DIST>
 __global__ void __launch_bounds__(kChainBlock)
 chain_tile_kernel(ChainTileArgs a) {
   extern __shared__ __align__(16) uint32_t chain_smem[];
@@ -205,6 +209,7 @@ chain_tile_kernel(ChainTileArgs a) {
   uint32_t* s_row = reinterpret_cast<uint32_t*>(s_w + kChainCap);   // at a row's first slot: the row
   uint32_t* s_len = s_row + kChainCap;                              // at a row's first slot: its length; later: run index of every slot
   uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_len + kChainCap);
+  uint32_t* s_last = reinterpret_cast<uint32_t*>(s_perm + kChainCap);  // DIST only: last first-order node of every slot's pair
   __shared__ int64_t s_geo[4];
   __shared__ int64_t s_bound[2];
   __shared__ uint32_t s_warp_max[kChainBlock / 32];
@@ -254,7 +259,7 @@ chain_tile_kernel(ChainTileArgs a) {
       const unsigned long long before = chain_tile_prefix(a.tile_state, blockIdx.x, 0ull, a.code_partial, a.code_inclusive);
       if (last_tile && lane == 0) {
         a.result[kResHeads] = before;
-        a.run_start_out[before] = static_cast<uint32_t>(a.n_slots);
+        if (a.run_start_out != nullptr) a.run_start_out[before] = static_cast<uint32_t>(a.n_slots);
       }
     }
     return;
@@ -359,7 +364,13 @@ chain_tile_kernel(ChainTileArgs a) {
         } else {
           const uint32_t g = s_first[f0] + static_cast<uint32_t>(jj);
           const uint32_t item = a.via != nullptr ? a.via[g] : g;
-          col = a.colsrc[item];
+          if (DIST) {  // global id << 32 | last node of the continuation
+            const unsigned long long info = a.info[item];
+            col = static_cast<uint32_t>(info >> 32);
+            s_last[i] = static_cast<uint32_t>(info);
+          } else {
+            col = a.colsrc[item];
+          }
           if (a.tail_out != nullptr) a.tail_out[label] = item;
           if (a.w_item_out != nullptr) a.w_item_out[label] = s_w[f0];
         }
@@ -457,8 +468,9 @@ chain_tile_kernel(ChainTileArgs a) {
         const int f0 = static_cast<int>(s_mark[i] & 0xffffu) - 1;
         const int64_t jj = static_cast<int64_t>(i) - s_soff[f0];
         label[k] = s_lbl[f0] + static_cast<uint32_t>(jj);
-        st_stream(a.rowS + cb + p, s_row[g0]);
+        st_stream(a.rowS + cb + p, DIST ? a.row_value[s_row[g0]] : s_row[g0]);
         st_stream(a.colS + cb + p, s_col[i]);
+        if (DIST) st_stream(a.lastS + cb + p, s_last[i]);
         st_stream(a.labS + cb + p, label[k]);
         if (a.wS != nullptr) st_stream(a.wS + cb + p, s_w[f0]);
       }
@@ -471,7 +483,7 @@ chain_tile_kernel(ChainTileArgs a) {
         s_base_id = prefix;
         if (last_tile) {
           a.result[kResHeads] = prefix + total;
-          a.run_start_out[prefix + total] = static_cast<uint32_t>(a.n_slots);
+          if (a.run_start_out != nullptr) a.run_start_out[prefix + total] = static_cast<uint32_t>(a.n_slots);
         }
       }
     }
@@ -485,7 +497,7 @@ chain_tile_kernel(ChainTileArgs a) {
         const uint32_t id = static_cast<uint32_t>(base_id + run);
         if (a.idS != nullptr) st_stream(a.idS + cb + p, id);
         if (a.id_item != nullptr) a.id_item[label[k]] = id;
-        if (p == 0 || s_len[p - 1] != run) a.run_start_out[id] = static_cast<uint32_t>(cb + p);
+        if (a.run_start_out != nullptr && (p == 0 || s_len[p - 1] != run)) a.run_start_out[id] = static_cast<uint32_t>(cb + p);
       }
     }
     __syncthreads();
@@ -493,6 +505,7 @@ chain_tile_kernel(ChainTileArgs a) {
 }
 
 constexpr size_t kChainTileSmem = static_cast<size_t>(kChainCap) * (8 * 4 + 2);
+constexpr size_t kChainTileSmemDist = kChainTileSmem + static_cast<size_t>(kChainCap) * 4;
 
 // ------------------------------------------------------------------ heads
 struct ChainHeadProducer {
@@ -560,6 +573,7 @@ struct HeavyLayout {
   unsigned long long *keys_a, *keys_b;
   uint32_t *vals_a, *vals_b;
   uint32_t* t_lab;
+  uint32_t* t_extra;
   float* t_w;
   uint32_t* t_dest;
   int bits;
@@ -574,6 +588,7 @@ struct HeavyLayout {
     vals_a = ws.take<uint32_t>(static_cast<size_t>(slots));
     vals_b = ws.take<uint32_t>(static_cast<size_t>(slots));
     t_lab = ws.take<uint32_t>(static_cast<size_t>(slots));
+    t_extra = ws.take<uint32_t>(static_cast<size_t>(slots));
     t_w = ws.take<float>(static_cast<size_t>(slots));
     t_dest = ws.take<uint32_t>(static_cast<size_t>(slots));
   }
@@ -603,8 +618,9 @@ heavy_compact_kernel(const uint2* __restrict__ list, const unsigned long long* _
 
 __global__ void __launch_bounds__(256)
 heavy_gather_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t slots,
-                    const uint32_t* __restrict__ labS, const float* __restrict__ wS, uint32_t* __restrict__ t_lab,
-                    float* __restrict__ t_w, uint32_t* __restrict__ t_dest) {
+                    const uint32_t* __restrict__ labS, const float* __restrict__ wS, const uint32_t* __restrict__ extraS,
+                    uint32_t* __restrict__ t_lab, float* __restrict__ t_w, uint32_t* __restrict__ t_extra,
+                    uint32_t* __restrict__ t_dest) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slots; i += stride) {
     const unsigned long long k = keys[i];
@@ -618,19 +634,308 @@ heavy_gather_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
     t_dest[i] = static_cast<uint32_t>(k >> 32) + static_cast<uint32_t>(i - hi);
     t_lab[i] = labS[src];
     if (wS != nullptr) t_w[i] = wS[src];
+    if (extraS != nullptr) t_extra[i] = extraS[src];
   }
 }
 
 __global__ void __launch_bounds__(256)
 heavy_write_kernel(const unsigned long long* __restrict__ keys, int64_t slots, const uint32_t* __restrict__ t_lab,
-                   const float* __restrict__ t_w, const uint32_t* __restrict__ t_dest, uint32_t* __restrict__ colS,
-                   uint32_t* __restrict__ labS, float* __restrict__ wS) {
+                   const float* __restrict__ t_w, const uint32_t* __restrict__ t_extra, const uint32_t* __restrict__ t_dest,
+                   uint32_t* __restrict__ colS, uint32_t* __restrict__ labS, float* __restrict__ wS, uint32_t* __restrict__ extraS) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slots; i += stride) {
     const uint32_t d = t_dest[i];
     colS[d] = static_cast<uint32_t>(keys[i]);
     labS[d] = t_lab[i];
     if (wS != nullptr) wS[d] = t_w[i];
+    if (extraS != nullptr) extraS[d] = t_extra[i];
+  }
+}
+
+// ================================================================== distributed build
+// Every rank expands ITS items in the order of their GLOBAL merged ids, so its pairs come out sorted by (row, col) with
+// global ids, ties in stream order; the owners hold ascending row ranges, hence the pairs of one owner are one
+// contiguous range of slots: no partition pass.  An owner receives one sorted run per sender and merges the runs in
+// shared-memory tiles of whole row ranges (rank of a record = its index in its own run + binary searches in the other
+// runs: senders in rank order = stream order, so equal keys stay in the single-device summation order).
+constexpr int kMergeBlock = 256;
+constexpr int kMergeTile = 1024;  // records a tile is sized for
+constexpr int kMergeCap = 2048;   // records a tile can hold (uniform row ranges: load varies)
+constexpr int kMergePerThread = kMergeCap / kMergeBlock;
+constexpr int kMaxRanks = PPG_ROUTE_MAX_RANKS;
+constexpr unsigned long long kMergeStatusOverflow = 2ull;
+
+// first slot of every destination: rows are ascending, owners hold ascending row ranges
+__global__ void chain_dest_bounds_kernel(const uint32_t* __restrict__ rowS, int64_t n, const int64_t* __restrict__ offsets,
+                                         int world, int64_t* __restrict__ dstart, int64_t* __restrict__ counts) {
+  __shared__ int64_t s_start[kMaxRanks + 1];
+  const int d = threadIdx.x;
+  if (d <= world) {
+    int64_t lo = 0, hi = n;  // first slot whose row is >= offsets[d]
+    if (d == world) lo = n;
+    const int64_t target = offsets[d];
+    while (lo < hi) {
+      const int64_t mid = lo + ((hi - lo) >> 1);
+      if (static_cast<int64_t>(rowS[mid]) >= target) hi = mid; else lo = mid + 1;
+    }
+    if (d == 0) lo = 0;
+    s_start[d] = lo;
+    dstart[d] = lo;
+  }
+  __syncthreads();
+  if (d < world) counts[d] = s_start[d + 1] - s_start[d];
+}
+
+struct PackTargets {
+  uint4* local;
+  uint4* peer[kMaxRanks];
+};
+__global__ void __launch_bounds__(256)
+chain_pack_kernel(const uint32_t* __restrict__ rowS, const uint32_t* __restrict__ colS, const uint32_t* __restrict__ lastS,
+                  const float* __restrict__ wS, int64_t n, const int64_t* __restrict__ dstart, int world, PackTargets targets) {
+  __shared__ int64_t s_start[kMaxRanks + 1];
+  if (threadIdx.x <= world) s_start[threadIdx.x] = dstart[threadIdx.x];
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n; p += stride) {
+    uint4 rec;
+    rec.x = ld_stream(colS + p);
+    rec.y = ld_stream(rowS + p);
+    rec.z = ld_stream(lastS + p);
+    rec.w = wS != nullptr ? __float_as_uint(ld_stream(wS + p)) : __float_as_uint(1.f);
+    if (targets.local != nullptr) {
+      targets.local[p] = rec;
+    } else {
+      int d = 0;
+      for (int j = 1; j < world; ++j) d += p >= s_start[j] ? 1 : 0;
+      targets.peer[d][p - s_start[d]] = rec;
+    }
+  }
+}
+
+// ids come back in slot order: global id = owner's first merged edge + returned index.  One scan turns them into the
+// row structure of the next level (local rows = distinct global ids among the local items) and the per-item info words.
+struct UnpackProducer {
+  const uint32_t* back;
+  const int64_t* dstart;
+  const int64_t* edge_offsets;
+  int world;
+  __device__ unsigned long long gid(int64_t i) const {
+    int d = 0;
+    for (int j = 1; j < world; ++j) d += i >= dstart[j] ? 1 : 0;
+    return static_cast<unsigned long long>(edge_offsets[d]) + back[i];
+  }
+  __device__ unsigned long long operator()(int64_t i) const { return (i == 0 || gid(i) != gid(i - 1)) ? 1ull : 0ull; }
+};
+struct UnpackConsumer {
+  UnpackProducer ids;
+  const uint32_t* labS;
+  const uint32_t* lastS;
+  uint32_t* rowid;                   // local row of every slot
+  uint32_t* run_start;               // [local rows + 1]
+  uint32_t* row_value;               // global id of every local row
+  unsigned long long* info_item;     // by label: global id << 32 | last node
+  int64_t n;
+  __device__ void operator()(int64_t i, unsigned long long head, unsigned long long prefix) const {
+    const unsigned long long g = ids.gid(i);
+    const unsigned long long r = prefix + head - 1;
+    rowid[i] = static_cast<uint32_t>(r);
+    if (head) {
+      run_start[r] = static_cast<uint32_t>(i);
+      row_value[r] = static_cast<uint32_t>(g);
+    }
+    if (i == n - 1) run_start[r + 1] = static_cast<uint32_t>(n);
+    info_item[labS[i]] = (g << 32) | lastS[i];
+  }
+};
+
+// ---- owner side
+__global__ void __launch_bounds__(256)
+merge_bounds_kernel(const uint4* __restrict__ records, const int64_t* __restrict__ seg, int world, long long row_lo,
+                    long long rows_per_tile, int64_t n_tiles, uint32_t* __restrict__ bnd) {
+  const int64_t total = (n_tiles + 1) * world;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < total; k += stride) {
+    const int64_t t = k / world;
+    const int s = static_cast<int>(k - t * world);
+    int64_t lo = seg[s], hi = seg[s + 1];
+    if (t == n_tiles) {
+      lo = hi;
+    } else {
+      const long long target = row_lo + t * rows_per_tile;
+      while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if (static_cast<long long>(records[mid].y) >= target) hi = mid; else lo = mid + 1;
+      }
+    }
+    bnd[k] = static_cast<uint32_t>(lo);
+  }
+}
+
+struct MergeArgs {
+  const uint4* records;
+  const uint32_t* bnd;  // [(tiles + 1) * world]
+  int world;
+  long long row_lo, rows_owned, total_nodes, rows_per_tile;
+  uint32_t* inverse;    // [R] merged edge (local index) of every record, arrival order
+  uint32_t *row_m, *col_m, *last_m;
+  float* w_m;
+  unsigned long long* tile_state;
+  unsigned long long* result;  // [0] merged edges, [1] status
+};
+
+__global__ void __launch_bounds__(kMergeBlock)
+merge_tile_kernel(MergeArgs a) {
+  __shared__ unsigned long long s_key[kMergeCap];   // (row - first row of the tile) << 32 | col
+  __shared__ float s_w[kMergeCap];
+  __shared__ uint32_t s_last[kMergeCap];
+  __shared__ uint32_t s_run[kMergeCap];
+  __shared__ uint16_t s_perm[kMergeCap];
+  __shared__ uint32_t s_lo[kMaxRanks], s_off[kMaxRanks + 1];
+  __shared__ uint32_t s_warp_cnt[kMergeBlock / 32];
+  __shared__ unsigned long long s_base_id;
+  __shared__ unsigned long long s_total;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const unsigned lane = lane_id();
+  const unsigned tile = blockIdx.x;
+  const bool last_tile = tile == gridDim.x - 1;
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (int s = 0; s < a.world; ++s) {
+      const uint32_t lo = a.bnd[static_cast<size_t>(tile) * a.world + s];
+      const uint32_t hi = a.bnd[static_cast<size_t>(tile + 1) * a.world + s];
+      s_lo[s] = lo;
+      s_off[s] = run;
+      run += hi - lo;
+    }
+    s_off[a.world] = run;
+  }
+  __syncthreads();
+  const int n = static_cast<int>(s_off[a.world]);
+  if (n == 0 || n > kMergeCap) {
+    if (warp == 0) {
+      if (n > kMergeCap && lane == 0) atomicOr(a.result + 1, kMergeStatusOverflow);
+      if (lane == 0) chain_tile_publish(a.tile_state, tile, 0ull, 1, 2);
+      const unsigned long long before = chain_tile_prefix(a.tile_state, tile, 0ull, 1, 2);
+      if (last_tile && lane == 0) a.result[0] = before;
+    }
+    return;
+  }
+  const long long row0 = a.row_lo + static_cast<long long>(tile) * a.rows_per_tile;
+  // ---- load the slices, sender after sender
+  for (int i = tid; i < n; i += kMergeBlock) {
+    int s = 0;
+    for (int j = 1; j < a.world; ++j) s += static_cast<uint32_t>(i) >= s_off[j] ? 1 : 0;
+    const uint4 r = __ldcs(a.records + s_lo[s] + (i - s_off[s]));
+    const long long row = static_cast<long long>(r.y);
+    if (row < a.row_lo || row >= a.row_lo + a.rows_owned || static_cast<long long>(r.x) >= a.total_nodes)
+      atomicOr(a.result + 1, kChainStatusIdOutOfRange);
+    s_key[i] = (static_cast<unsigned long long>(row - row0) << 32) | r.x;
+    s_w[i] = __uint_as_float(r.w);
+    s_last[i] = r.z;
+  }
+  __syncthreads();
+  // ---- rank of every record in the merge of the runs (stable: earlier senders first among equal keys)
+  for (int i = tid; i < n; i += kMergeBlock) {
+    int s = 0;
+    for (int j = 1; j < a.world; ++j) s += static_cast<uint32_t>(i) >= s_off[j] ? 1 : 0;
+    const unsigned long long key = s_key[i];
+    int rank = i - static_cast<int>(s_off[s]);
+    for (int q = 0; q < a.world; ++q) {
+      if (q == s) continue;
+      int lo = static_cast<int>(s_off[q]), hi = static_cast<int>(s_off[q + 1]);
+      const int begin = lo;
+      if (q < s) {  // records of earlier senders with key <= this key come first
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (s_key[mid] <= key) lo = mid + 1; else hi = mid;
+        }
+      } else {      // of later senders: key < this key
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (s_key[mid] < key) lo = mid + 1; else hi = mid;
+        }
+      }
+      rank += lo - begin;
+    }
+    s_perm[rank] = static_cast<uint16_t>(i);
+  }
+  __syncthreads();
+  // ---- run heads in merged order (a tile starts with a new row, so its first record is a head)
+  {
+    const int p0 = tid * kMergePerThread;
+    unsigned long long prev = ~0ull;
+    if (p0 > 0 && p0 <= n) prev = s_key[s_perm[p0 - 1]];
+    uint32_t run[kMergePerThread];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kMergePerThread; ++k) {
+      const int p = p0 + k;
+      if (p < n) {
+        const unsigned long long key = s_key[s_perm[p]];
+        cnt += (p == 0 || key != prev) ? 1u : 0u;
+        prev = key;
+      }
+      run[k] = cnt;
+    }
+    const uint32_t inc = warp_inclusive_sum(cnt);
+    if (lane == 31) s_warp_cnt[warp] = inc;
+    __syncthreads();
+    uint32_t before = inc - cnt, total = 0;
+#pragma unroll
+    for (int w = 0; w < kMergeBlock / 32; ++w) {
+      if (w < warp) before += s_warp_cnt[w];
+      total += s_warp_cnt[w];
+    }
+#pragma unroll
+    for (int k = 0; k < kMergePerThread; ++k)
+      if (p0 + k < n) s_run[p0 + k] = before + run[k] - 1;
+    if (tid == 0) {
+      s_total = total;
+      chain_tile_publish(a.tile_state, tile, total, 1, 2);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long total = s_total;
+    const unsigned long long prefix = chain_tile_prefix(a.tile_state, tile, total, 1, 2);
+    if (lane == 0) {
+      s_base_id = prefix;
+      if (last_tile) a.result[0] = prefix + total;
+    }
+  }
+  __syncthreads();
+  const unsigned long long base_id = s_base_id;
+  for (int p = tid; p < n; p += kMergeBlock) {
+    const int i = s_perm[p];
+    const uint32_t run = s_run[p];
+    const uint32_t id = static_cast<uint32_t>(base_id + run);
+    int s = 0;
+    for (int j = 1; j < a.world; ++j) s += static_cast<uint32_t>(i) >= s_off[j] ? 1 : 0;
+    a.inverse[s_lo[s] + (i - s_off[s])] = id;
+    if (p == 0 || s_run[p - 1] != run) {
+      const unsigned long long key = s_key[i];
+      float acc = s_w[i];
+      for (int q = p + 1; q < n && s_run[q] == run; ++q) acc += s_w[s_perm[q]];   // merged order = stream order
+      a.row_m[id] = static_cast<uint32_t>(static_cast<long long>(key >> 32) + row0);
+      a.col_m[id] = static_cast<uint32_t>(key);
+      a.last_m[id] = s_last[i];
+      a.w_m[id] = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+merge_sorted_fill_kernel(const uint32_t* __restrict__ row_m, const uint32_t* __restrict__ col_m, const float* __restrict__ w_m,
+                         const uint32_t* __restrict__ last_m, int64_t num_out, int64_t* __restrict__ out_ei,
+                         float* __restrict__ out_w, int64_t* __restrict__ out_last) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < num_out; r += stride) {
+    st_stream(out_ei + r, static_cast<int64_t>(row_m[r]));
+    st_stream(out_ei + num_out + r, static_cast<int64_t>(col_m[r]));
+    st_stream(out_w + r, w_m[r]);
+    st_stream(out_last + r, static_cast<int64_t>(last_m[r]));
   }
 }
 
@@ -638,14 +943,22 @@ static int launch_tiles(ChainTileArgs& a, bool first, cudaStream_t stream) {
   if (a.n_slots == 0) return PPG_OK;
   a.code_partial = 1;
   a.code_inclusive = 2;
-  PPG_REQUIRE(a.tile_state != nullptr && a.run_start_out != nullptr, PPG_ERR_INVALID, "chain: tile state and run_start are required");
+  PPG_REQUIRE(a.tile_state != nullptr, PPG_ERR_INVALID, "chain: tile state is required");
   const int64_t tiles = ceil_div(a.n_slots, kChainTile);
   PPG_REQUIRE(tiles < (1ll << 31), PPG_ERR_INVALID, "chain: %lld pairs are too many", (long long)a.n_slots);
   PPG_CUDA_TRY(cudaMemsetAsync(a.tile_state, 0, static_cast<size_t>(tiles) * sizeof(unsigned long long), stream));
   if (first) {
-    chain_tile_kernel<true><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
+    chain_tile_kernel<true, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
+  } else if (a.info != nullptr) {
+    static bool configured = false;
+    if (!configured) {
+      PPG_CUDA_TRY(cudaFuncSetAttribute(chain_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(kChainTileSmemDist)));
+      configured = true;
+    }
+    chain_tile_kernel<false, true><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmemDist, stream>>>(a);
   } else {
-    chain_tile_kernel<false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
+    chain_tile_kernel<false, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
   }
   PPG_LAUNCHED();
   return PPG_OK;
@@ -813,8 +1126,8 @@ extern "C" size_t ppg_chain_heavy_workspace_bytes(int64_t heavy_slots, int64_t h
 
 // Rows the tiles left in generation order: one stable radix sort over their pairs only, written back in place.
 extern "C" int ppg_chain_heavy_fix(const void* heavy_list, int64_t heavy_rows, int64_t heavy_slots, int64_t n_slots,
-                                   uint32_t* colS, uint32_t* labS, float* wS, void* workspace, size_t workspace_bytes,
-                                   void* stream_) {
+                                   uint32_t* colS, uint32_t* labS, float* wS, uint32_t* extraS, void* workspace,
+                                   size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (heavy_rows == 0 || heavy_slots == 0) return PPG_OK;
   Workspace ws(workspace, workspace_bytes);
@@ -830,9 +1143,153 @@ extern "C" int ppg_chain_heavy_fix(const void* heavy_list, int64_t heavy_rows, i
                                                &in_b, stream));
   const unsigned long long* keys = in_b ? L.keys_b : L.keys_a;
   const uint32_t* vals = in_b ? L.vals_b : L.vals_a;
-  heavy_gather_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(keys, vals, heavy_slots, labS, wS, L.t_lab, L.t_w, L.t_dest);
+  heavy_gather_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(keys, vals, heavy_slots, labS, wS, extraS, L.t_lab, L.t_w, L.t_extra, L.t_dest);
   PPG_LAUNCHED();
-  heavy_write_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(keys, heavy_slots, L.t_lab, L.t_w, L.t_dest, colS, labS, wS);
+  heavy_write_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(keys, heavy_slots, L.t_lab, L.t_w, L.t_extra, L.t_dest, colS, labS, wS, extraS);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
+// =================================================================== distributed build (see the kernels above)
+// Tiles of a level on a rank of a distributed build: `info` by item = global id << 32 | last node; rowid / run_start /
+// row_value describe the LOCAL rows (distinct global ids among the local items, from ppg_chain_unpack); rowS receives
+// global ids.  The run heads the kernel finds are local and unused (the owners merge): idS / id_item may be NULL.
+extern "C" int ppg_chain_tiles_dist(int64_t n_sources, int64_t n_rows, int64_t n_slots, const void* offP, const uint32_t* firstP,
+                                    const uint32_t* lblP, const float* wP, const uint32_t* run_start, const uint32_t* rowid,
+                                    const uint32_t* row_value, const void* info, const uint32_t* via, const uint32_t* srcbound,
+                                    int heavy, uint32_t* rowS, uint32_t* colS, uint32_t* labS, float* wS, uint32_t* lastS,
+                                    uint32_t* tail_out, float* w_item_out, uint32_t* run_start_scratch, void* tile_state,
+                                    void* heavy_list, int64_t* result, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(n_sources > 0 && n_sources < (1ll << 31) && n_slots >= 0 && n_slots < (1ll << 31) && n_rows > 0, PPG_ERR_INVALID,
+              "chain: sizes outside [0, 2^31)");
+  PPG_REQUIRE(heavy >= 1 && heavy <= kChainHeavyMax, PPG_ERR_INVALID, "chain: heavy threshold %d outside [1, %d]", heavy, kChainHeavyMax);
+  PPG_REQUIRE(wP != nullptr && wS != nullptr && info != nullptr && row_value != nullptr && lastS != nullptr, PPG_ERR_INVALID,
+              "chain (distributed): weights, info words, row values and lastS are required");
+  ChainTileArgs a = {};
+  a.offP = static_cast<const unsigned long long*>(offP);
+  a.firstP = firstP;
+  a.lblP = lblP;
+  a.wP = wP;
+  a.run_start = run_start;
+  a.rowid = rowid;
+  a.row_value = row_value;
+  a.info = static_cast<const unsigned long long*>(info);
+  a.via = via;
+  a.srcbound = srcbound;
+  a.n_sources = n_sources;
+  a.n_rows = n_rows;
+  a.n_slots = n_slots;
+  a.heavy = heavy;
+  a.rowS = rowS;
+  a.colS = colS;
+  a.labS = labS;
+  a.wS = wS;
+  a.lastS = lastS;
+  a.tail_out = tail_out;
+  a.w_item_out = w_item_out;
+  a.heavy_list = static_cast<uint2*>(heavy_list);
+  a.result = reinterpret_cast<unsigned long long*>(result);
+  a.run_start_out = run_start_scratch;
+  a.tile_state = static_cast<unsigned long long*>(tile_state);
+  return launch_tiles(a, false, stream);
+}
+
+// First slot of every destination rank (dstart [world + 1], counts [world]; device int64) among slots whose rows ascend.
+extern "C" int ppg_chain_dest_bounds(const uint32_t* rowS, int64_t n_slots, const int64_t* offsets, int world, int64_t* dstart,
+                                     int64_t* counts, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(world >= 1 && world <= kMaxRanks, PPG_ERR_INVALID, "chain: %d ranks outside [1, %d]", world, kMaxRanks);
+  chain_dest_bounds_kernel<<<1, 32, 0, stream>>>(rowS, n_slots, offsets, world, dstart, counts);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
+// Slots -> 16-byte records {col id, row id, last node, weight}, either into one local buffer (slot order = destination
+// order) or straight into the owners' receive buffers (h_peer_records[d] = first record reserved for this sender).
+extern "C" int ppg_chain_pack(const uint32_t* rowS, const uint32_t* colS, const uint32_t* lastS, const float* wS, int64_t n_slots,
+                              const int64_t* dstart, int world, void* out_records, void* const* h_peer_records, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (n_slots == 0) return PPG_OK;
+  PPG_REQUIRE(world >= 1 && world <= kMaxRanks, PPG_ERR_INVALID, "chain: %d ranks outside [1, %d]", world, kMaxRanks);
+  PPG_REQUIRE((out_records != nullptr) != (h_peer_records != nullptr), PPG_ERR_INVALID,
+              "chain_pack: give either a local record buffer or the peers' receive buffers");
+  PackTargets targets = {};
+  targets.local = static_cast<uint4*>(out_records);
+  if (h_peer_records != nullptr)
+    for (int d = 0; d < world; ++d) targets.peer[d] = static_cast<uint4*>(h_peer_records[d]);
+  chain_pack_kernel<<<grid_for(n_slots, 256 * 4), 256, 0, stream>>>(rowS, colS, lastS, wS, n_slots, dstart, world, targets);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
+// The owners' answers (back [n_slots], slot order) -> local row structure of the next level + info word of every item.
+// result[0] = number of local rows.
+extern "C" int ppg_chain_unpack(const uint32_t* back, int64_t n_slots, const int64_t* dstart, const int64_t* edge_offsets, int world,
+                                const uint32_t* labS, const uint32_t* lastS, void* workspace, size_t workspace_bytes,
+                                uint32_t* rowid, uint32_t* run_start, uint32_t* row_value, void* info_item, int64_t* result,
+                                void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(world >= 1 && world <= kMaxRanks && n_slots >= 0 && n_slots < (1ll << 31), PPG_ERR_INVALID, "chain_unpack: bad sizes");
+  const size_t need = ppg_chain_scan_workspace_bytes(n_slots);
+  PPG_REQUIRE(workspace_bytes >= need, PPG_ERR_WORKSPACE, "chain_unpack: workspace %zu < %zu bytes", workspace_bytes, need);
+  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, stream));
+  if (n_slots == 0) {
+    PPG_CUDA_TRY(cudaMemsetAsync(result, 0, sizeof(int64_t), stream));
+    PPG_CUDA_TRY(cudaMemsetAsync(run_start, 0, sizeof(uint32_t), stream));
+    return PPG_OK;
+  }
+  UnpackProducer ids{back, dstart, edge_offsets, world};
+  return launch_scan(ids, UnpackConsumer{ids, labS, lastS, rowid, run_start, row_value, static_cast<unsigned long long*>(info_item), n_slots},
+                     n_slots, static_cast<unsigned long long*>(workspace), reinterpret_cast<unsigned long long*>(result), stream);
+}
+
+extern "C" int64_t ppg_merge_sorted_tiles(int64_t num_records) { return num_records > 0 ? ceil_div(num_records, kMergeTile) : 0; }
+
+// Owner side: `world` runs of records (run s = records [seg[s], seg[s + 1]), each sorted by (row, col)) -> merged edges in
+// compact arrays (row_m, col_m, w_m, last_m: capacity num_records), the merged edge of every record (out_inverse, arrival
+// order), result[0] = merged edges, result[1] = status (1: id out of range, 2: a row range did not fit a tile -- merge
+// these records with ppg_merge_records_sort instead).  bounds: u32 [(tiles + 1) * world], tile_state: u64 [tiles].
+extern "C" int ppg_merge_sorted(const void* records, int64_t num_records, const int64_t* seg, int world, int64_t row_lo,
+                                int64_t rows_owned, int64_t total_nodes, uint32_t* bounds, void* tile_state, uint32_t* out_inverse,
+                                uint32_t* row_m, uint32_t* col_m, float* w_m, uint32_t* last_m, int64_t* result, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(world >= 1 && world <= kMaxRanks, PPG_ERR_INVALID, "merge_sorted: %d ranks outside [1, %d]", world, kMaxRanks);
+  PPG_REQUIRE(num_records >= 0 && num_records < (1ll << 31) && total_nodes <= (1ll << 32), PPG_ERR_INVALID, "merge_sorted: bad sizes");
+  PPG_CUDA_TRY(cudaMemsetAsync(result, 0, 2 * sizeof(int64_t), stream));
+  if (num_records == 0) return PPG_OK;
+  const int64_t tiles = ppg_merge_sorted_tiles(num_records);
+  const int64_t rows_per_tile = rows_owned > 0 ? ceil_div(rows_owned, tiles) : 1;
+  PPG_CUDA_TRY(cudaMemsetAsync(tile_state, 0, static_cast<size_t>(tiles) * sizeof(unsigned long long), stream));
+  merge_bounds_kernel<<<grid_for((tiles + 1) * world, 256), 256, 0, stream>>>(static_cast<const uint4*>(records), seg, world, row_lo,
+                                                                             rows_per_tile, tiles, bounds);
+  PPG_LAUNCHED();
+  MergeArgs a = {};
+  a.records = static_cast<const uint4*>(records);
+  a.bnd = bounds;
+  a.world = world;
+  a.row_lo = row_lo;
+  a.rows_owned = rows_owned;
+  a.total_nodes = total_nodes;
+  a.rows_per_tile = rows_per_tile;
+  a.inverse = out_inverse;
+  a.row_m = row_m;
+  a.col_m = col_m;
+  a.w_m = w_m;
+  a.last_m = last_m;
+  a.tile_state = static_cast<unsigned long long*>(tile_state);
+  a.result = reinterpret_cast<unsigned long long*>(result);
+  merge_tile_kernel<<<static_cast<unsigned>(tiles), kMergeBlock, 0, stream>>>(a);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
+extern "C" int ppg_merge_sorted_fill(const uint32_t* row_m, const uint32_t* col_m, const float* w_m, const uint32_t* last_m,
+                                     int64_t num_out, int64_t* out_edge_index, float* out_weights, int64_t* out_last, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (num_out == 0) return PPG_OK;
+  merge_sorted_fill_kernel<<<grid_for(num_out, 256 * 4), 256, 0, stream>>>(row_m, col_m, w_m, last_m, num_out, out_edge_index, out_weights,
+                                                                          out_last);
   PPG_LAUNCHED();
   return PPG_OK;
 }

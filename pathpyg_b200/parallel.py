@@ -434,6 +434,251 @@ def _exchange_merge(line_index, node_info, weights, own_prefix, offsets, offsets
     return out_ei, out_w, out_last, ids, edge_offsets, edge_offsets_dev, carried
 
 
+# ------------------------------------------------------------------------------------------------
+# distributed lift on the generation-order chain (csrc/chain.cu)
+# ------------------------------------------------------------------------------------------------
+class _MergeSorted:
+    """Owner side on the chain: one (row, col)-sorted run of records per sender, merged in shared-memory tiles of whole
+    row ranges (``ppg_merge_sorted``).  Same surface as ``ops.PendingMerge``: ``result_words`` [merged count, status],
+    ``inverse`` [R] int32, ``finish(num_out)``."""
+
+    def __init__(self, records: torch.Tensor, recv: list[int], row_lo: int, rows_owned: int, total_nodes: int):
+        from .ops import _ptr, _stream
+        lib = _lib.load()
+        self.dev, self.R, world = records.device, records.size(0), len(recv)
+        seg = [0]
+        for c in recv:
+            seg.append(seg[-1] + int(c))
+        n = max(self.R, 1)
+        tiles = int(lib.ppg_merge_sorted_tiles(self.R))
+        self.inverse = torch.empty(n, dtype=torch.int32, device=self.dev)[:self.R]
+        self.compact = [torch.empty(n, dtype=torch.float32 if i == 2 else torch.int32, device=self.dev) for i in range(4)]
+        self.result_words = torch.zeros(2, dtype=torch.int64, device=self.dev)
+        self.keep = (records, torch.tensor(seg, dtype=torch.int64, device=self.dev),
+                     torch.empty((tiles + 1) * world + 1, dtype=torch.int32, device=self.dev),
+                     torch.empty(tiles + 1, dtype=torch.int64, device=self.dev))
+        row_m, col_m, w_m, last_m = self.compact
+        with torch.cuda.device(self.dev):
+            _lib.check(lib.ppg_merge_sorted(_ptr(records), self.R, _ptr(self.keep[1]), world, int(row_lo), int(rows_owned), int(total_nodes),
+                                            _ptr(self.keep[2]), _ptr(self.keep[3]), _ptr(self.inverse), _ptr(row_m), _ptr(col_m), _ptr(w_m),
+                                            _ptr(last_m), _ptr(self.result_words), _stream(self.dev)))
+
+    def finish(self, num_out: int):
+        from .ops import _ptr, _stream
+        out_ei = torch.empty((2, num_out), dtype=torch.int64, device=self.dev)
+        out_w = torch.empty(num_out, dtype=torch.float32, device=self.dev)
+        out_last = torch.empty(num_out, dtype=torch.int64, device=self.dev)
+        row_m, col_m, w_m, last_m = self.compact
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.load().ppg_merge_sorted_fill(_ptr(row_m), _ptr(col_m), _ptr(w_m), _ptr(last_m), int(num_out), _ptr(out_ei),
+                                                         _ptr(out_w), _ptr(out_last), _stream(self.dev)))
+        return out_ei, out_w, out_last
+
+
+def _chain_supported(edge_index, edge_weight, num_nodes, local_ops) -> bool:
+    import os
+    return (local_ops is None and edge_index.is_cuda and os.environ.get("PPG_CHAIN", "1") != "0" and edge_index.dtype == torch.int64
+            and (edge_weight is None or edge_weight.dtype == torch.float32) and num_nodes < (1 << 31))
+
+
+def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, cuts, group, trace) -> dict:
+    """``distributed_temporal_layers`` on the generation-order chain.  Every rank expands its items in the order of their
+    GLOBAL merged ids (known from the previous level's exchange), so its records leave sorted by (row, col) and grouped
+    by owner without a partition pass; the owner merges one sorted run per sender in shared-memory tiles
+    (``ppg_merge_sorted``) instead of radix-sorting what it received.  The exchange itself is unchanged: counts through
+    one all-gather, records into the owners' symmetric buffers over NVLink (or one all-to-all-v), 4-byte indices back.
+
+    Paths that start with a ghost event carry weight 0 from level 1 on (a path inherits the weight of its first event),
+    so they only collect ids.  At level k only the items that start before cut k are expanded (``limit``); the items
+    that start before the later cuts are counted through the row pointer of the level (``starts_before``)."""
+    import ctypes
+    from . import chain as chain_mod
+    from . import ops
+    from .ops import _ptr, _stream
+
+    lib = _lib.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = ext_ei.device
+    m_ext = ext_ei.size(1)
+    heavy, tile = chain_mod.heavy_threshold(), lib.ppg_chain_tile_slots()
+    u32 = torch.int32
+    mark = trace.mark
+    res = torch.zeros((K + 2, 8), dtype=torch.int64, device=dev)
+    peer_to_peer = world > 1 and _PeerArenas.available(dev)
+    layers: dict[int, DistributedLayer] = {}
+
+    def empty32(n, dtype=u32):
+        return torch.empty(max(int(n), 1), dtype=dtype, device=dev)
+
+    def scan_ws(n):
+        return torch.empty(lib.ppg_chain_scan_workspace_bytes(int(n)), dtype=torch.uint8, device=dev)
+
+    with torch.cuda.device(dev):
+        stream = _stream(dev)
+        # ---- level 1: the events of the extended range, grouped by source node, ranked by target node
+        w_item = torch.ones(m_ext, dtype=torch.float32, device=dev) if ext_w is None else ext_w.to(torch.float32).clone()
+        w_item[m_own:] = 0.0
+        n_slots = m_ext
+        slots = {"row": empty32(n_slots), "col": empty32(n_slots), "lab": empty32(n_slots), "w": empty32(n_slots, torch.float32),
+                 "heavy": torch.empty((n_slots // (heavy + 1) + 2, 2), dtype=u32, device=dev)}
+        slots["last"] = slots["col"]
+        tws = views = None
+        if m_ext:
+            tws = ops.lift_order_temporal_group(ext_ei, num_nodes)
+            views = (ctypes.c_void_p * 6)()
+            _lib.check(lib.ppg_lift_temporal_views(_ptr(tws), m_ext, num_nodes, views))
+            state = torch.empty(-(-m_ext // tile) + 1, dtype=torch.int64, device=dev)
+            _lib.check(lib.ppg_chain_first_tiles(_ptr(ext_ei), m_ext, num_nodes, ctypes.c_void_p(views[0]), ctypes.c_void_p(views[1]),
+                                                 ctypes.c_void_p(views[2]), _ptr(w_item), heavy, _ptr(slots["row"]), _ptr(slots["col"]),
+                                                 _ptr(slots["lab"]), _ptr(slots["w"]), None, None, None, _ptr(state), _ptr(slots["heavy"]),
+                                                 _ptr(res[1]), stream))
+        # rows of layer 1 = first-order nodes, owned by node-id range
+        offsets = [-(-num_nodes * p // world) for p in range(world + 1)]
+        offsets_dev = torch.tensor(offsets, dtype=torch.int64, device=dev)
+        total_nodes = num_nodes
+        rows_k, row_lo = torch.arange(offsets[rank], offsets[rank + 1], device=dev).unsqueeze(1), offsets[rank]
+        starts_before = {j: cuts[j] for j in range(2, K + 1)}   # items of the current level that start before cut j
+        first = ptr_next = via = None                           # count results of the level being expanded (raw pointers)
+        tail = None
+        keep = []
+
+        for k in range(1, K + 1):
+            more = k < K
+            mark(f"route_count[{k}]")
+            dstart = torch.empty(world + 1, dtype=torch.int64, device=dev)
+            counts = torch.empty(world, dtype=torch.int64, device=dev)
+            _lib.check(lib.ppg_chain_dest_bounds(_ptr(slots["row"]), n_slots, _ptr(offsets_dev), world, _ptr(dstart), _ptr(counts), stream))
+            # count pass of the next level over this level's items (label order) while the counts travel
+            later = list(range(k + 1, K + 1))
+            sel = torch.zeros(len(later) + 1, dtype=torch.int64, device=dev)     # starts_before of the next level + status bits
+            nxt_first = nxt_ptr = None
+            if more and n_slots:
+                if k == 1:
+                    time, mode, delta_i, delta_f = ops._time_mode(ext_t.contiguous(), delta)
+                    _lib.check(lib.ppg_lift_temporal_count(_ptr(ext_ei), _ptr(time), m_ext, num_nodes, mode | _lib.TIME_GROUPED, delta_i,
+                                                           delta_f, _ptr(tws), tws.numel(), None, stream))
+                    at = views[4] - tws.data_ptr()
+                    ptr_t = tws[at:at + 8 * (m_ext + 1)].view(torch.int64)
+                    nxt_first, nxt_ptr = ctypes.c_void_p(views[3]), ctypes.c_void_p(views[4])
+                    status_word = tws[8:16].view(torch.int64)
+                else:
+                    first_t = empty32(n_slots)
+                    ptr_t = torch.empty(n_slots + 1, dtype=torch.int64, device=dev)
+                    ws = scan_ws(n_slots)
+                    _lib.check(lib.ppg_chain_count(_ptr(tail), ptr_next, n_slots, _ptr(ws), ws.numel(), _ptr(first_t), _ptr(ptr_t),
+                                                   ctypes.c_void_p(res[k].data_ptr() + 8 * 4), stream))
+                    nxt_first, nxt_ptr = ctypes.c_void_p(first_t.data_ptr()), ctypes.c_void_p(ptr_t.data_ptr())
+                    keep = [first_t, ptr_t]
+                    status_word = res[k, 1:2]
+                at_items = torch.tensor([min(starts_before[j], n_slots) for j in later], dtype=torch.int64, device=dev)
+                sel = torch.cat([ptr_t[at_items], status_word])
+            gathered = _gather_counts(torch.cat([counts, res[k, :4], sel]), group)                  # (sync 1)
+            matrix, mine = gathered[:, :world], gathered[rank].tolist()
+            send, recv = matrix[rank].tolist(), matrix[:, rank].tolist()
+            if (int(gathered[:, world + 1].max()) | int(gathered[:, -1].max())) & 1:
+                raise ValueError("distributed lift: node id outside [0, num_nodes)")
+            heavy_slots, heavy_rows = mine[world + 2], mine[world + 3]
+            if heavy_rows:   # hub rows: the tiles left them in generation order
+                ws = torch.empty(lib.ppg_chain_heavy_workspace_bytes(heavy_slots, heavy_rows, n_slots), dtype=torch.uint8, device=dev)
+                extra = None if slots["last"] is slots["col"] else slots["last"]
+                _lib.check(lib.ppg_chain_heavy_fix(_ptr(slots["heavy"]), heavy_rows, heavy_slots, n_slots, _ptr(slots["col"]),
+                                                   _ptr(slots["lab"]), _ptr(slots["w"]), _ptr(extra), _ptr(ws), ws.numel(), stream))
+            next_starts = {j: mine[world + 4 + i] for i, j in enumerate(later)}
+
+            mark(f"route_pack[{k}]")
+            if peer_to_peer:
+                arenas = _PeerArenas.get(group, dev)
+                arenas.ensure(int(matrix.sum(0).max()))
+                which = k & 1
+                ahead = matrix[:rank].sum(0).tolist()
+                peers = (ctypes.c_void_p * world)(*[ctypes.c_void_p(arenas.peer_slot(which, d, ahead[d])) for d in range(world)])
+                _lib.check(lib.ppg_chain_pack(_ptr(slots["row"]), _ptr(slots["col"]), _ptr(slots["last"]), _ptr(slots["w"]), n_slots,
+                                              _ptr(dstart), world, None, peers, stream))
+            else:
+                records = torch.empty((max(n_slots, 1), 2), dtype=torch.int64, device=dev)[:n_slots]
+                _lib.check(lib.ppg_chain_pack(_ptr(slots["row"]), _ptr(slots["col"]), _ptr(slots["last"]), _ptr(slots["w"]), n_slots,
+                                              _ptr(dstart), world, _ptr(records), None, stream))
+                received = torch.empty((sum(recv), 2), dtype=torch.int64, device=dev)
+                work = dist.all_to_all_single(received.view(-1), records.view(-1), [2 * c for c in recv], [2 * c for c in send],
+                                              group=group, async_op=True)
+            mark(f"rows[{k}]")
+            if k > 1:   # owned rows of this layer = merged edges of the previous one (local work while the records travel)
+                rows_k = ops.extend_owned_rows(rows_k, prev_row_lo, prev_ei[0], prev_last)
+            mark(f"records_wait[{k}]")
+            if peer_to_peer:
+                arenas.barrier(which)
+                received = arenas.received(which, sum(recv))
+            else:
+                work.wait()
+                del records
+            mark(f"merge_sort[{k}]")
+            rows_owned = offsets[rank + 1] - offsets[rank]
+            merge = _MergeSorted(received, recv, offsets[rank], rows_owned, total_nodes)
+            mark(f"merge_sync[{k}]")
+            results = _gather_counts(merge.result_words, group)                                     # (sync 2)
+            if int(results[:, 1].max()) & 2:   # a row range did not fit a tile somewhere: those owners sort their records
+                if int(results[rank, 1]) & 2:
+                    merge = ops.merge_records_begin(received.clone() if peer_to_peer else received, offsets[rank], rows_owned, total_nodes)
+                results = _gather_counts(merge.result_words, group)
+            back = torch.empty(max(n_slots, 1), dtype=torch.int32, device=dev)[:n_slots]
+            work = dist.all_to_all_single(back, merge.inverse, send, recv, group=group, async_op=True)
+            if int(results[:, 1].max()) & 1:
+                raise ValueError("distributed lift: a node id outside its layer reached an owner (inconsistent inputs)")
+            edge_offsets = [0]
+            for c in results[:, 0].tolist():
+                edge_offsets.append(edge_offsets[-1] + int(c))
+            if edge_offsets[-1] > (1 << 31):
+                raise ValueError(f"distributed lift: {edge_offsets[-1]} merged edges exceed the 31-bit ids of the chain")
+            edge_offsets_dev = torch.tensor(edge_offsets, dtype=torch.int64, device=dev)
+            mark(f"merge_fill[{k}]")
+            out_ei, out_w, out_last = merge.finish(edge_offsets[rank + 1] - edge_offsets[rank])
+            if k == 2 and edge_offsets[-1] == 0:
+                raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors (distributed lift: no time-respecting pair)")
+            layers[k] = DistributedLayer(k, total_nodes, offsets[rank], rows_k, out_ei, out_w, edge_offsets[rank], edge_offsets[-1])
+            prev_ei, prev_last, prev_row_lo = out_ei, out_last, offsets[rank]
+            mark(f"ids_wait[{k}]")
+            work.wait()
+            if not more:
+                break
+
+            # ---- the ids are back: local rows of the next level, info word of every item, then expand in that order
+            mark(f"route_unpack[{k}]")
+            rowid, run_start, row_value = empty32(n_slots), empty32(n_slots + 1), empty32(n_slots)
+            info = torch.empty(max(n_slots, 1), dtype=torch.int64, device=dev)
+            ws = scan_ws(n_slots)
+            _lib.check(lib.ppg_chain_unpack(_ptr(back), n_slots, _ptr(dstart), _ptr(edge_offsets_dev), world, _ptr(slots["lab"]),
+                                            _ptr(slots["last"]), _ptr(ws), ws.numel(), _ptr(rowid), _ptr(run_start), _ptr(row_value),
+                                            _ptr(info), ctypes.c_void_p(res[k].data_ptr() + 8 * 5), stream))
+            mark(f"lift_next[{k}]")
+            n_next = next_starts.get(k + 1, 0) if n_slots else 0
+            nxt = {"row": empty32(n_next), "col": empty32(n_next), "lab": empty32(n_next), "w": empty32(n_next, torch.float32),
+                   "last": empty32(n_next), "heavy": torch.empty((n_next // (heavy + 1) + 2, 2), dtype=u32, device=dev)}
+            nxt_tail = nxt_w_item = None
+            if n_next:
+                ns = n_slots
+                offP = torch.empty(ns + 1, dtype=torch.int64, device=dev)
+                firstP, lblP, wP = empty32(ns), empty32(ns), empty32(ns, torch.float32)
+                srcbound = torch.empty((-(-n_next // tile), 2), dtype=u32, device=dev)
+                ws = scan_ws(ns)
+                limit = min(starts_before[k + 1], ns)
+                _lib.check(lib.ppg_chain_count_sorted(_ptr(slots["lab"]), ns, nxt_first, nxt_ptr, _ptr(w_item), limit, _ptr(rowid),
+                                                      _ptr(run_start), _ptr(ws), ws.numel(), _ptr(offP), _ptr(firstP), _ptr(lblP), _ptr(wP),
+                                                      _ptr(srcbound), stream))
+                if k + 1 < K:
+                    nxt_tail, nxt_w_item = empty32(n_next), empty32(n_next, torch.float32)
+                state = torch.empty(-(-n_next // tile) + 1, dtype=torch.int64, device=dev)
+                _lib.check(lib.ppg_chain_tiles_dist(ns, 1, n_next, _ptr(offP), _ptr(firstP), _ptr(lblP), _ptr(wP), _ptr(run_start),
+                                                    _ptr(rowid), _ptr(row_value), _ptr(info), ctypes.c_void_p(views[1]) if k == 1 else None,
+                                                    _ptr(srcbound), heavy, _ptr(nxt["row"]), _ptr(nxt["col"]), _ptr(nxt["lab"]),
+                                                    _ptr(nxt["w"]), _ptr(nxt["last"]), _ptr(nxt_tail), _ptr(nxt_w_item), None, _ptr(state),
+                                                    _ptr(nxt["heavy"]), _ptr(res[k + 1]), stream))
+            slots, n_slots, tail, w_item = nxt, n_next, nxt_tail, nxt_w_item
+            first, ptr_next = nxt_first, nxt_ptr
+            starts_before = next_starts
+            offsets, offsets_dev, total_nodes = edge_offsets, edge_offsets_dev, edge_offsets[-1]
+    return layers
+
+
 def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, num_nodes: int, delta, max_order: int,
                                 edge_weight: torch.Tensor | None = None, group=None, local_ops=None) -> dict:
     """``MultiOrderModel.from_temporal_graph`` over a stream that is split across the ranks.
@@ -484,6 +729,11 @@ def distributed_temporal_layers(edge_index: torch.Tensor, time: torch.Tensor, nu
             found = [m_ext if m_own > 0 else 0] * (K - 2)
         for j, c in zip(range(2, K), found):
             cuts[j] = int(c)
+
+    if _chain_supported(ext_ei, ext_w, num_nodes, None if getattr(local_ops, "__name__", "") == "pathpyg_b200.ops" else local_ops):
+        layers = _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, cuts, group, trace)
+        trace.close()
+        return layers
 
     # ---- order 1: nodes are the first-order nodes themselves, rows owned by node-id range
     n1_bounds = [-(-num_nodes * p // world) for p in range(world + 1)]

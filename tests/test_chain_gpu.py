@@ -106,3 +106,38 @@ def test_chain_bad_ids(cuda):
     tg = pp.TemporalGraph.from_tensors(ei, torch.tensor([1, 2, 3], device=cuda), 3)
     with pytest.raises(ValueError):
         pp.MultiOrderModel.from_temporal_graph(tg, delta=2, max_order=2)
+
+
+@pytest.mark.parametrize("R,rows,total,row_lo,world", [(0, 5, 9, 3, 2), (1, 1, 1, 0, 1), (4000, 60, 200, 1000, 3), (700_000, 50_000, 400_000, 123_456, 8),
+                                                       (300_000, 200_000, 9_000_000, 5_000_000, 16), (50_000, 7, 30, 10, 4)])
+def test_merge_sorted_runs_matches_torch(cuda, R, rows, total, row_lo, world):
+    """Owner side of the distributed chain: `world` runs of records, each sorted by (row, col), merged in tiles; against
+    the torch restatement of the owner's merge (stable: equal keys keep sender order, then arrival order).  The last
+    case crams all records into 7 rows: the row ranges overflow their tiles and the status word asks for the sort."""
+    from pathpyg_b200.parallel import _MergeSorted
+    from torch_local_ops import TorchOps
+
+    gen = torch.Generator().manual_seed(R + world)
+    cuts = torch.sort(torch.randint(0, R + 1, (world - 1,), generator=gen)).values.tolist()
+    seg = [0] + cuts + [R]
+    recv = [b - a for a, b in zip(seg[:-1], seg[1:])]
+    src = torch.randint(row_lo, row_lo + rows, (R,), generator=gen)
+    dst = torch.randint(0, total, (R,), generator=gen)
+    for a, b in zip(seg[:-1], seg[1:]):   # every run sorted by (row, col)
+        order = torch.argsort(src[a:b] * (total + 1) + dst[a:b], stable=True)
+        src[a:b], dst[a:b] = src[a:b][order], dst[a:b][order]
+    last = dst % 1000
+    w = torch.rand(R, generator=gen)
+    bits = w.view(torch.int32).to(torch.int64) & 0xffffffff
+    records = torch.stack([(src << 32) | dst, (bits << 32) | last], dim=1).to(cuda)
+    got = _MergeSorted(records, recv, row_lo, rows, total)
+    want = TorchOps.merge_records_begin(records.cpu(), row_lo, rows, total)   # on the host: index_add_ runs in arrival order there
+    words = got.result_words.tolist()
+    if rows == 7:
+        assert words[1] & 2
+        return
+    assert words == want.result_words.tolist()
+    assert torch.equal(got.inverse.cpu(), want.inverse)
+    n_out = words[0]
+    for a, b in zip(got.finish(n_out), want.finish(n_out)):
+        assert torch.equal(a.cpu(), b)
