@@ -61,8 +61,8 @@ def static_config(name: str, world: int) -> dict:
         return out
     out.update(edges=cfg["m"], timestamps=cfg["T"], delta=cfg["delta"])
     if cfg["kind"] == "dist":
-        out["parallelism"] = (f"{world} rank(s): time-range partition of ONE stream, ghost zone (K-1)*delta, per order one "
-                              "all-to-all-v of 16-byte records + 4-byte ids back")
+        out["parallelism"] = (f"{world} rank(s): time-range partition of ONE stream, ghost zone (K-1)*delta, per order 16-byte "
+                              "records to the owner of their row + 4-byte ids back")
     else:
         if cfg["dbgnn"]:
             out["dbgnn"] = {"hidden_dims": [cfg["hidden"]] * 3, "classes": cfg["classes"], "features": "dense randn fp32"}
@@ -216,51 +216,66 @@ def fused_min_bytes_dbgnn(n, e, n2, e2, H, classes):
     return 2 * gcn(n, e) + 2 * gcn(n2, e2) + 4 * n2 + 4 * H * (n2 + n) + 4 * H * n + 4 * n * (H + classes)
 
 
-# ------------------------------------------------------------------------------------------------ in-step pass timing
-def profiled_passes(lib, fn):
-    """Run `fn` once with the library's per-pass CUDA events switched on; returns [(ms, pairs, bytes per pair)] of every
-    radix digit pass launched inside it (the launches of a REAL step, on the launching stream)."""
+# ------------------------------------------------------------------------------------------------ in-step kernel timing
+KERNEL_KINDS = {0: "onesweep_pass_kernel (radix digit pass)", 1: "chain_tile_kernel (expand + rank one level of the layer chain)",
+                2: "merge_tile_kernel (owner-side merge of the senders' sorted runs)", 3: "gcn_tc_kernel (fused tcgen05 GCN layer)"}
+
+
+def profiled_kernels(lib, fn):
+    """Run `fn` once with the library's CUDA-event hook switched on; returns [(ms, items, bytes per item, kind)] of every
+    hot-kernel launch inside it (the launches of a REAL step, on the launching stream)."""
     cap = 512
-    ms, items, bpi, count = (ctypes.c_float * cap)(), (ctypes.c_int64 * cap)(), (ctypes.c_int * cap)(), ctypes.c_int(0)
+    ms, items, bpi, kind = (ctypes.c_float * cap)(), (ctypes.c_int64 * cap)(), (ctypes.c_int * cap)(), (ctypes.c_int * cap)()
+    count = ctypes.c_int(0)
     lib.ppg_profile_begin()
     try:
         fn()
     finally:
-        lib.ppg_profile_end(ms, items, bpi, cap, ctypes.byref(count))
-    return [(ms[i], items[i], bpi[i]) for i in range(count.value)]
+        lib.ppg_profile_end(ms, items, bpi, kind, cap, ctypes.byref(count))
+    return [(ms[i], items[i], bpi[i], kind[i]) for i in range(count.value)]
 
 
-def pass_roofline(passes, peaks, traffic=None):
-    """Dominant kernel = the onesweep digit pass over the LARGEST (key, payload) array of the step (the order-K
-    merge): average over its launches inside the profiled steps."""
-    if not passes:
+def kernel_roofline(launches, peaks, runs, step_ms=None, gcn_bytes=None):
+    """Dominant kernel = the kind with the largest total device time inside the profiled steps; reported for its largest
+    launch shape (average over the launches of that shape).  ``runs``: number of profiled steps; ``gcn_bytes``: nodes of a
+    layer -> compulsory bytes of the fused layer (the library does not know the edge count)."""
+    if not launches:
         return None
-    top_items = max(p[1] for p in passes)
-    top = [p for p in passes if p[1] == top_items and p[2] == max(q[2] for q in passes if q[1] == top_items)]
-    ms = sum(p[0] for p in top) / len(top)
-    bytes_per_launch = top[0][1] * top[0][2]
-    achieved = bytes_per_launch / (ms / 1e3) / 1e9
-    all_ms = sum(p[0] for p in passes)
-    return {"bound": "hbm", "kernel": f"onesweep_pass_kernel<{'u64' if top[0][2] == 24 else 'u32'} key, u32 payload>", "pairs": top_items,
-            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-            "algorithmic_bytes_per_launch": bytes_per_launch, "launch_ms": ms, "launches_averaged": len(top),
-            "all_digit_passes": {"launches": len(passes), "ms_total": all_ms,
-                                 "achieved": sum(p[1] * p[2] for p in passes) / (all_ms / 1e3) / 1e9},
-            "how": "CUDA events around every digit pass launched INSIDE real steps (library profile hook, launching stream); "
-                   "bytes = read + write of key and payload per pair",
-            "peak_source": peaks["source"]}
+    per_kind = {}
+    for ms, items, bpi, kind in launches:
+        nbytes = items * bpi if kind != 3 else (gcn_bytes or {}).get(items, 0)
+        d = per_kind.setdefault(kind, {"launches": 0, "ms_total": 0.0, "bytes": 0})
+        d["launches"] += 1
+        d["ms_total"] += ms
+        d["bytes"] += nbytes
+    top_kind = max(per_kind, key=lambda k: per_kind[k]["ms_total"])
+    mine = [l for l in launches if l[3] == top_kind]
+    top_items = max(l[1] for l in mine)
+    top = [l for l in mine if l[1] == top_items]
+    ms = sum(l[0] for l in top) / len(top)
+    per_launch = top[0][1] * max(l[2] for l in top) if top_kind != 3 else (gcn_bytes or {}).get(top_items, 0)
+    achieved = per_launch / (ms / 1e3) / 1e9
+    out = {"bound": "hbm", "kernel": KERNEL_KINDS[top_kind], "items": top_items, "achieved": achieved, "peak": peaks["hbm_gbs"],
+           "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": ncu_traffic(top_kind, top_items),
+           "algorithmic_bytes_per_launch": per_launch, "launch_ms": ms, "launches_averaged": len(top),
+           "by_kernel": {KERNEL_KINDS[k].split(" ")[0]: {"launches_per_step": d["launches"] / runs, "ms_per_step": d["ms_total"] / runs,
+                                                         "achieved": d["bytes"] / (d["ms_total"] / 1e3) / 1e9 if d["ms_total"] else None}
+                         for k, d in sorted(per_kind.items())},
+           "how": "CUDA events around every launch of the hot kernels INSIDE real steps (library profile hook, launching stream); the "
+                  "dominant kernel is the one with the largest total time; bytes = what the launch must read and write once",
+           "peak_source": peaks["source"]}
+    if step_ms:
+        out["share_of_step"] = per_kind[top_kind]["ms_total"] / runs / step_ms
+    return out
 
 
-def ncu_traffic(key):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-    (profiles/sort_traffic.json); None if not captured for this size."""
-    for name in ("sort_traffic.json", "r01_sort_traffic.json"):
-        path = os.path.join(ROOT, "profiles", name)
-        if os.path.isfile(path):
-            with open(path) as f:
-                v = json.load(f).get(key, {}).get("dram_bytes_per_launch")
-            if v is not None:
-                return v
+def ncu_traffic(kind, items):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+    (profiles/kernel_traffic.json: "<kind>:<items>" -> bytes); None if that launch shape was not captured."""
+    path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f).get(f"{kind}:{items}", {}).get("dram_bytes_per_launch")
     return None
 
 
@@ -381,9 +396,9 @@ def run_lift(args, name, rank, world, local_rank, as_extra=False):
     h2d = ei_pin.numel() * 8 + t_pin.numel() * 8 + (x_pin.numel() * 4 if with_dbgnn else 0)
 
     # ---- dominant kernel: every radix digit pass launched inside three more real steps, timed by the library's hook
-    passes = []
+    launches = []
     for _ in range(3):
-        passes += profiled_passes(lib, lambda: one_step(None))
+        launches += profiled_kernels(lib, lambda: one_step(None))
     lift_ms, dbgnn_ms, e2e_ms = max_over_ranks([lift_ms, dbgnn_ms, e2e_ms], dev, world)
     if rank != 0:
         return None
@@ -408,7 +423,8 @@ def run_lift(args, name, rank, world, local_rank, as_extra=False):
                            "layers_nodes_edges": {str(k): v for k, v in layers.items()},
                            "l2": "flushed between steps (512 MB write)" if flush is not None else "inputs and intermediates larger than L2"},
         "lift_stage_roofline": stage_roofline(lift_bytes, lift_ms / steps, peaks),
-        "roofline": pass_roofline(passes, peaks, traffic=ncu_traffic("pairs_1.8M" if name == "cfg2" else f"pairs_{name}")),
+        "roofline": kernel_roofline(launches, peaks, 3, step_ms=(lift_ms + dbgnn_ms) / steps,
+                                    gcn_bytes={n_: 8 * e_ + 8 * n_ + 8 * H * n_ for n_, e_ in layers.values()} if with_dbgnn else None),
         "e2e": {"value": world * lifted / (e2e_ms / 1e3), "unit": "lifted edges/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h_bytes[0], "ms_per_step": e2e_ms,
                 "what": ("from_temporal_graph(host graph, device=...) + DBGNN forward as ONE timed region: pinned host edge index, "
@@ -554,7 +570,7 @@ def run_dist(args, name, rank, world, local_rank, as_extra=False):
     rec = [e2e_step() for _ in range(3)]
     torch.cuda.synchronize(dev)
     e2e_ms = sum(a.elapsed_time(b) for a, b in rec) / len(rec)
-    passes = profiled_passes(lib, step)
+    launches = profiled_kernels(lib, step)
     step_ms, e2e_ms = max_over_ranks([step_ms, e2e_ms], dev, world)
     h2d_all = torch.tensor([ei_pin.numel() * 8 + t_pin.numel() * 8, d2h[0]], dtype=torch.int64, device=dev)
     if world > 1:
@@ -580,7 +596,7 @@ def run_dist(args, name, rank, world, local_rank, as_extra=False):
         "higher_is_better": True,
         "scaling": "strong",
         "vs_baseline": None,
-        "dtype": "int64 indices (u32 record fields, u64 sort keys inside) + fp32 weights",
+        "dtype": "int64 indices (u32 ids and record fields inside) + fp32 weights",
         "data": "synthetic",
         "config": static_config(name, world),
         "parity_ok": parity_ok,
@@ -590,10 +606,12 @@ def run_dist(args, name, rank, world, local_rank, as_extra=False):
                            "n_gpu_ms": ms, "speedup": one_gpu_ms / ms, "efficiency": one_gpu_ms / ms / world},
         "workload_stats": {"lifted_edges_per_step": lifted, "line_graph_columns": {str(k): v for k, v in line_sizes.items()},
                            "layers_nodes_edges": {str(k): v for k, v in layers_single.items()}, "l2": "inputs and intermediates larger than L2"},
-        "collectives_per_step": {"all_to_all_v (records out, ids back)": 2 * K, "all_gather (counts)": 2 * K, "ghost zone all_to_all_v + 2 all_reduce": 1},
+        "collectives_per_step": {"records into the owners' symmetric buffers (NVLink peer stores; all_to_all_v without peer access)": K,
+                                 "all_to_all_v (merged-edge indices back)": K, "all_gather (counts)": 2 * K,
+                                 "ghost zone all_to_all_v + 2 all_gather": 1},
         "lift_stage_roofline": stage_roofline(lift_bytes, ms, peaks, note="whole-job algorithmic bytes of the single-device formulation / step time; "
                                               "aggregate peak = n_gpus x per-GPU peak", aggregate_frac=lift_bytes / (ms / 1e3) / 1e9 / (peaks["hbm_gbs"] * world)),
-        "roofline": pass_roofline(passes, peaks),
+        "roofline": kernel_roofline(launches, peaks, 1, step_ms=ms),
         "e2e": {"value": lifted / (e2e_ms / 1e3), "unit": "lifted edges/s", "h2d_bytes_per_step": int(h2d_all[0]), "d2h_bytes_per_step": int(h2d_all[1]),
                 "ms_per_step": e2e_ms, "what": "pinned host slices of the stream in (24 B per event), distributed_temporal_layers, the max-order "
                                                "layer's owned edges + weights back to pinned host memory (bytes summed over the ranks)"},

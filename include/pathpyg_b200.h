@@ -70,12 +70,17 @@ int ppg_result_read(const void* workspace, int64_t* h_total, int* h_status_bits,
 const char* ppg_last_error(void);
 /* number of kernels this library has launched in this process (monotonic; for bench accounting) */
 unsigned long long ppg_launch_count(void);
-/* Opt-in timing of the radix digit passes (the dominant kernel of the lift) with CUDA events on the launching
- * stream: between _begin and _end every pass of every sort is bracketed by an event pair (at most 512 passes);
- * _end synchronises the device and returns, per pass, its duration, the number of (key, payload) pairs and the
- * algorithmic bytes per pair (read + write of key and payload).  Benchmark instrumentation; off by default. */
+/* Opt-in timing of the hot kernels with CUDA events on the launching stream: between _begin and _end every launch of a
+ * radix digit pass, a chain tile kernel, an owner merge kernel and a fused tensor-core GCN layer is bracketed by an event
+ * pair (at most 512 launches); _end synchronises the device and returns, per launch, its duration, its kind, the number
+ * of items (pairs / slots / records / nodes) and the algorithmic bytes per item (0 for the GCN layer: the caller knows its
+ * edge count).  Benchmark instrumentation; off by default. */
+#define PPG_PROFILE_DIGIT_PASS 0
+#define PPG_PROFILE_CHAIN_TILES 1
+#define PPG_PROFILE_MERGE_TILES 2
+#define PPG_PROFILE_GCN_LAYER 3
 int ppg_profile_begin(void);
-int ppg_profile_end(float* h_ms, int64_t* h_items, int* h_bytes_per_item, int capacity, int* h_count);
+int ppg_profile_end(float* h_ms, int64_t* h_items, int* h_bytes_per_item, int* h_kind, int capacity, int* h_count);
 
 /* ---------------------------------------------------------------------------------------------
  * a2  lift_order_edge_index            reference: src/pathpyG/algorithms/lift_order.py:48-79

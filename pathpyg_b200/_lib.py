@@ -35,7 +35,7 @@ PROTOTYPES = {
     "ppg_last_error": (c_char_p, []),
     "ppg_launch_count": (ctypes.c_uint64, []),
     "ppg_profile_begin": (c_int, []),
-    "ppg_profile_end": (c_int, [POINTER(ctypes.c_float), _ph_i64, _ph_int, c_int, _ph_int]),
+    "ppg_profile_end": (c_int, [POINTER(ctypes.c_float), _ph_i64, _ph_int, _ph_int, c_int, _ph_int]),
     "ppg_result_read": (c_int, [_p, _ph_i64, _ph_int, _p]),
     "ppg_lift_order_workspace_bytes": (c_size_t, [_i64, _i64]),
     "ppg_lift_order_count": (c_int, [_p, _i64, _i64, _p, c_size_t, _ph_i64, _p]),

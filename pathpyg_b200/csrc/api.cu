@@ -31,7 +31,7 @@ extern "C" int ppg_profile_begin(void) {
   return PPG_OK;
 }
 
-extern "C" int ppg_profile_end(float* h_ms, int64_t* h_items, int* h_bytes_per_item, int capacity, int* h_count) {
+extern "C" int ppg_profile_end(float* h_ms, int64_t* h_items, int* h_bytes_per_item, int* h_kind, int capacity, int* h_count) {
   ppg::PassProfile& p = ppg::g_pass_profile;
   p.enabled = false;
   PPG_CUDA_TRY(cudaDeviceSynchronize());
@@ -40,6 +40,7 @@ extern "C" int ppg_profile_end(float* h_ms, int64_t* h_items, int* h_bytes_per_i
     PPG_CUDA_TRY(cudaEventElapsedTime(&h_ms[i], p.start[i], p.stop[i]));
     h_items[i] = p.items[i];
     h_bytes_per_item[i] = p.bytes_per_item[i];
+    if (h_kind != nullptr) h_kind[i] = p.kind[i];
   }
   *h_count = n;
   p.count = 0;

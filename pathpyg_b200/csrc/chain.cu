@@ -947,6 +947,14 @@ static int launch_tiles(ChainTileArgs& a, bool first, cudaStream_t stream) {
   const int64_t tiles = ceil_div(a.n_slots, kChainTile);
   PPG_REQUIRE(tiles < (1ll << 31), PPG_ERR_INVALID, "chain: %lld pairs are too many", (long long)a.n_slots);
   PPG_CUDA_TRY(cudaMemsetAsync(a.tile_state, 0, static_cast<size_t>(tiles) * sizeof(unsigned long long), stream));
+  // algorithmic bytes of the launch (what the kernel must read and write once), for the live roofline of bench.py
+  const bool dist = !first && a.info != nullptr;
+  const long long per_source = first ? 4 + 4 + 8 + (a.wS != nullptr ? 4 : 0) : 8 + 4 + 4 + 4 + (a.wS != nullptr ? 4 : 0);
+  const long long per_slot = (first ? 0 : (dist ? 8 : 4) + (a.via != nullptr ? 4 : 0)) + 12 + (a.wS != nullptr ? 4 : 0) +
+                             (a.idS != nullptr ? 4 : 0) + (a.id_item != nullptr ? 4 : 0) + (a.tail_out != nullptr ? 4 : 0) +
+                             (a.w_item_out != nullptr ? 4 : 0) + (dist ? 4 : 0);
+  const long long launch_bytes = per_source * a.n_sources + per_slot * a.n_slots;
+  profile_pass_begin(stream);
   if (first) {
     chain_tile_kernel<true, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
   } else if (a.info != nullptr) {
@@ -960,6 +968,7 @@ static int launch_tiles(ChainTileArgs& a, bool first, cudaStream_t stream) {
   } else {
     chain_tile_kernel<false, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
   }
+  profile_pass_end(stream, a.n_slots, static_cast<int>((launch_bytes + a.n_slots / 2) / a.n_slots), PPG_PROFILE_CHAIN_TILES);
   PPG_LAUNCHED();
   return PPG_OK;
 }
@@ -1279,7 +1288,9 @@ extern "C" int ppg_merge_sorted(const void* records, int64_t num_records, const 
   a.last_m = last_m;
   a.tile_state = static_cast<unsigned long long*>(tile_state);
   a.result = reinterpret_cast<unsigned long long*>(result);
+  profile_pass_begin(stream);
   merge_tile_kernel<<<static_cast<unsigned>(tiles), kMergeBlock, 0, stream>>>(a);
+  profile_pass_end(stream, num_records, 16 + 4 + 16, PPG_PROFILE_MERGE_TILES);   // record in, merged index out, merged edge out (upper bound)
   PPG_LAUNCHED();
   return PPG_OK;
 }

@@ -33,7 +33,7 @@ extern unsigned long long g_launch_count;
     ++::ppg::g_launch_count;                                                             \
   } while (0)
 
-// opt-in timing of every radix digit pass with CUDA events on the launching stream (ppg_profile_begin / _end):
+// opt-in timing of the hot kernels (radix digit passes, chain tiles, owner merges, fused GCN layers) with CUDA events on the launching stream (ppg_profile_begin / _end):
 // the benchmark reads the durations of the passes that ran INSIDE a real step instead of probing a synthetic sort
 struct PassProfile {
   static constexpr int kCapacity = 512;
@@ -42,6 +42,7 @@ struct PassProfile {
   cudaEvent_t start[kCapacity], stop[kCapacity];
   long long items[kCapacity];
   int bytes_per_item[kCapacity];
+  int kind[kCapacity];
   bool created = false;
 };
 extern PassProfile g_pass_profile;
@@ -49,12 +50,13 @@ inline void profile_pass_begin(cudaStream_t stream) {
   PassProfile& p = g_pass_profile;
   if (p.enabled && p.count < PassProfile::kCapacity) cudaEventRecord(p.start[p.count], stream);
 }
-inline void profile_pass_end(cudaStream_t stream, long long items, int bytes_per_item) {
+inline void profile_pass_end(cudaStream_t stream, long long items, int bytes_per_item, int kind = PPG_PROFILE_DIGIT_PASS) {
   PassProfile& p = g_pass_profile;
   if (p.enabled && p.count < PassProfile::kCapacity) {
     cudaEventRecord(p.stop[p.count], stream);
     p.items[p.count] = items;
     p.bytes_per_item[p.count] = bytes_per_item;
+    p.kind[p.count] = kind;
     ++p.count;
   }
 }

@@ -694,16 +694,26 @@ extern "C" int ppg_gcn_layer_tc(const int32_t* colptr, const int32_t* src, const
                                 int act, float* out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n == 0) return PPG_OK;
-  static const bool single_role = [] {  // development switch: PPG_GCN_TC_V1=1 runs the single-role kernel (A/B runs)
-    const char* e = getenv("PPG_GCN_TC_V1");
+  // Two kernels with identical results (bit for bit): the single-role one (every warp gathers, then one thread issues
+  // the MMAs, then every warp runs the epilogue) and the warp-specialised one (gather warps fill operand buffer i + 1
+  // while the MMA / epilogue warps work on tile i, two TMEM accumulators).  Measured on B200 at the order-2 layer of
+  // cfg2 (n = 1M, e = 1.8M, 64 -> 64; profiles/r02b_gcn_ws_ab.log): 329 us against 340 us -- the gather itself, not the
+  // serialisation of the phases, is what bounds the layer, so the single-role kernel is the default; PPG_GCN_TC_WS=1
+  // selects the other.
+  static const bool specialised = [] {
+    const char* e = getenv("PPG_GCN_TC_WS");
     return e != nullptr && e[0] == '1';
   }();
+  int rc = -1;
+  profile_pass_begin(stream);
 #define PPG_TC_CASE(FF, HH)                                                                                        \
-  if (F == FF && H == HH)                                                                                          \
-    return single_role ? launch_tc<FF, HH>(colptr, src, val, self_val, X, W, bias, n, act, out, stream)            \
-                       : launch_tc_ws<FF, HH>(colptr, src, val, self_val, X, W, bias, n, act, out, stream)
+  if (rc < 0 && F == FF && H == HH)                                                                                \
+    rc = specialised ? launch_tc_ws<FF, HH>(colptr, src, val, self_val, X, W, bias, n, act, out, stream)           \
+                     : launch_tc<FF, HH>(colptr, src, val, self_val, X, W, bias, n, act, out, stream)
   PPG_TC_CASE(32, 16); PPG_TC_CASE(32, 32); PPG_TC_CASE(32, 64);
   PPG_TC_CASE(64, 16); PPG_TC_CASE(64, 32); PPG_TC_CASE(64, 64);
 #undef PPG_TC_CASE
-  PPG_REQUIRE(false, PPG_ERR_INVALID, "tensor-core layer: widths F=%lld H=%lld not supported", (long long)F, (long long)H);
+  profile_pass_end(stream, n, 0, PPG_PROFILE_GCN_LAYER);
+  PPG_REQUIRE(rc >= 0, PPG_ERR_INVALID, "tensor-core layer: widths F=%lld H=%lld not supported", (long long)F, (long long)H);
+  return rc;
 }
