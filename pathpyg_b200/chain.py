@@ -27,6 +27,17 @@ _u32 = torch.int32  # 32-bit words; the kernels read them unsigned (all values <
 _RES_HEADS, _RES_STATUS, _RES_HEAVY_SLOTS, _RES_HEAVY_ROWS, _RES_NEXT = 0, 1, 2, 3, 4
 
 
+_side_streams: dict = {}
+
+
+def side_stream(dev: torch.device) -> torch.cuda.Stream:
+    """One side stream per device for the output work of a finished layer (fill, node sequences)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(dev)
+    return _side_streams[key]
+
+
 def heavy_threshold() -> int:
     """Rows with more pairs than this are ordered by the radix-sort fallback (``PPG_CHAIN_HEAVY`` overrides, tests)."""
     lib = _lib.load()
@@ -93,6 +104,13 @@ class TemporalChain:
                                            _ptr(out_ei), _ptr(out_w), _stream(self.dev)))
         return out_ei, out_w
 
+    def _emit(self, store, k: int, level: _Level, nodes: int, inverse) -> None:
+        """Finish layer k: merged edges + whatever ``store`` derives from them.  (On one device this output work stays on
+        the main stream: moved to a side stream under the next level's expansion it gained nothing at 10M and 50M events
+        -- both are bound by the same memory system -- and cost 80 us of stream hand-offs at 1M.)"""
+        out_ei, out_w = self._fill(level)
+        store(k, out_ei, out_w, nodes, inverse)
+
     def inverse_idx(self, level: _Level) -> torch.Tensor:
         """``inverse_idx`` of the layer above ``level``: the merged id of every item, int64 as in the reference."""
         out = torch.empty(level.items, dtype=torch.int64, device=self.dev)
@@ -133,7 +151,7 @@ class TemporalChain:
             l1.merged = words[_RES_HEADS]
             if words[_RES_HEAVY_ROWS]:
                 l1.merged = self._heavy_fix(l1, 1, words[_RES_HEAVY_ROWS], words[_RES_HEAVY_SLOTS])
-            store(1, *self._fill(l1), n, None)
+            self._emit(store, 1, l1, n, None)
             if K == 1:
                 return
             pairs = words[4]
@@ -185,7 +203,7 @@ class TemporalChain:
                 cur.merged = words[_RES_HEADS]
                 if words[_RES_HEAVY_ROWS]:
                     cur.merged = self._heavy_fix(cur, k, words[_RES_HEAVY_ROWS], words[_RES_HEAVY_SLOTS])
-                store(k, *self._fill(cur), prev.merged, inverse)
+                self._emit(store, k, cur, prev.merged, inverse)
                 del offP, firstP, lblP, wP, srcbound
                 keep = [nxt_first, nxt_ptr, cur.tail]
                 prev, pairs, w_item, via = cur, words[_RES_NEXT], cur.w_item, None

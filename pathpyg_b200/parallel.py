@@ -515,6 +515,7 @@ def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, 
 
     with torch.cuda.device(dev):
         stream = _stream(dev)
+        main, side = torch.cuda.current_stream(dev), chain_mod.side_stream(dev)
         # ---- level 1: the events of the extended range, grouped by source node, ranked by target node
         w_item = torch.ones(m_ext, dtype=torch.float32, device=dev) if ext_w is None else ext_w.to(torch.float32).clone()
         w_item[m_own:] = 0.0
@@ -601,9 +602,10 @@ def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, 
                 received = torch.empty((sum(recv), 2), dtype=torch.int64, device=dev)
                 work = dist.all_to_all_single(received.view(-1), records.view(-1), [2 * c for c in recv], [2 * c for c in send],
                                               group=group, async_op=True)
-            mark(f"rows[{k}]")
-            if k > 1:   # owned rows of this layer = merged edges of the previous one (local work while the records travel)
-                rows_k = ops.extend_owned_rows(rows_k, prev_row_lo, prev_ei[0], prev_last)
+            if k > 1:   # owned rows of this layer = merged edges of the previous one: output work, on the side stream
+                with torch.cuda.stream(side):
+                    rows_k = ops.extend_owned_rows(rows_k, prev_row_lo, prev_ei[0], prev_last)
+                    rows_k.record_stream(main)
             mark(f"records_wait[{k}]")
             if peer_to_peer:
                 arenas.barrier(which)
@@ -631,7 +633,13 @@ def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, 
                 raise ValueError(f"distributed lift: {edge_offsets[-1]} merged edges exceed the 31-bit ids of the chain")
             edge_offsets_dev = torch.tensor(edge_offsets, dtype=torch.int64, device=dev)
             mark(f"merge_fill[{k}]")
-            out_ei, out_w, out_last = merge.finish(edge_offsets[rank + 1] - edge_offsets[rank])
+            side.wait_stream(main)   # the merged edges are written out under the next level's expansion
+            for t in getattr(merge, "compact", ()):
+                t.record_stream(side)
+            with torch.cuda.stream(side):
+                out_ei, out_w, out_last = merge.finish(edge_offsets[rank + 1] - edge_offsets[rank])
+                for t in (out_ei, out_w, out_last):
+                    t.record_stream(main)
             if k == 2 and edge_offsets[-1] == 0:
                 raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors (distributed lift: no time-respecting pair)")
             layers[k] = DistributedLayer(k, total_nodes, offsets[rank], rows_k, out_ei, out_w, edge_offsets[rank], edge_offsets[-1])
@@ -676,6 +684,7 @@ def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, 
             first, ptr_next = nxt_first, nxt_ptr
             starts_before = next_starts
             offsets, offsets_dev, total_nodes = edge_offsets, edge_offsets_dev, edge_offsets[-1]
+        main.wait_stream(side)
     return layers
 
 
