@@ -584,6 +584,11 @@ def run_dist(args, name, rank, world, local_rank, as_extra=False):
     lifted = sum(line_sizes.values())
     one_gpu_ms = min(single_ms)
     ms = step_ms / steps
+    exchange_ms = ms
+    if world == 1:
+        # one GPU: what a user runs there is MultiOrderModel.from_temporal_graph (no exchange); the exchange path on a
+        # one-rank group (every record routed to the rank itself) is reported beside it
+        ms, step_ms = one_gpu_ms, one_gpu_ms * steps
     lift_bytes = alg_bytes_lift(cfg["n"], cfg["m"], line_sizes, layers_single)
     return {
         "metric": "k-order lift edges/s",
@@ -603,7 +608,8 @@ def run_dist(args, name, rank, world, local_rank, as_extra=False):
         "parity_how": "64-bit order-sensitive digests of edge index, weights and node sequences of every layer, summed over the ranks "
                       "(all-reduce), equal the digests of MultiOrderModel.from_temporal_graph on the whole stream on one GPU (same run)",
         "strong_scaling": {"one_gpu_ms_same_stream": one_gpu_ms, "one_gpu_path": "MultiOrderModel.from_temporal_graph (no exchange), rank 0, same run",
-                           "n_gpu_ms": ms, "speedup": one_gpu_ms / ms, "efficiency": one_gpu_ms / ms / world},
+                           "n_gpu_ms": exchange_ms, "n_gpu_path": "parallel.distributed_temporal_layers (ghost zone + per-order exchange)",
+                           "speedup": one_gpu_ms / exchange_ms, "efficiency": one_gpu_ms / exchange_ms / world},
         "workload_stats": {"lifted_edges_per_step": lifted, "line_graph_columns": {str(k): v for k, v in line_sizes.items()},
                            "layers_nodes_edges": {str(k): v for k, v in layers_single.items()}, "l2": "inputs and intermediates larger than L2"},
         "collectives_per_step": {"records into the owners' symmetric buffers (NVLink peer stores; all_to_all_v without peer access)": K,

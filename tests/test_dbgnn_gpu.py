@@ -12,8 +12,12 @@ RTOL = 1e-5
 
 
 def close(a, b):
+    """Relative fp32 test, scale-invariant: |a - b| <= 1e-5 * max(|b|, rms(b)) element by element.  The floor is the
+    tensor's own root-mean-square -- below it an element is the result of cancellation between summands of that size, so
+    its error is measured against them, not against the (arbitrarily small) difference."""
     a, b = a.double().cpu(), b.double().cpu()
-    return bool(((a - b).abs() <= RTOL * b.abs().clamp(min=1.0)).all())
+    floor = float(b.pow(2).mean().sqrt()) if b.numel() else 0.0
+    return bool(((a - b).abs() <= RTOL * b.abs().clamp(min=floor)).all())
 
 
 def test_gcn_norm_and_spmm_vs_oracle(cuda):
