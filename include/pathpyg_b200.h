@@ -134,32 +134,38 @@ int ppg_lift_temporal_views(const void* workspace, int64_t num_edges, int64_t nu
  *   grouped by row; a tile of whole rows is ranked by column in shared memory (csrc/chain.cu).  Items keep the index
  *   ("label") they have in the reference's line graph.  Per level the caller provides
  *     slot arrays  [pairs]: rowS, colS (merged ids of both ends), labS (label of the pair at every slot; it is the merged
- *                            order P of the next level), wS (optional weights), idS (merged id of every slot)
- *     item arrays  [pairs]: id_item (merged id by label = inverse_idx of the next layer), tail (continuation item by
- *                            label), w_item (optional)
+ *                            order P of the next level), wS (optional weights), idS (merged id of every slot), and for
+ *                            the next level firstS / degS (first continuation of the slot's pair and their number)
+ *     node words   u64 [pairs + 1] by label: merged id (low word; read with stride 2 it is inverse_idx of the next layer)
+ *                            | number of continuations, then -- after ppg_chain_scan_nodes -- row pointer of the next
+ *                            level (high word)
  *     run_start    [merged + 1]: first slot of every merged edge
  *     result       int64[8], zeroed: [0] merged edges, [1] status bits (1: node id out of range), [2] pairs in rows
  *                  longer than `heavy`, [3] such rows (listed in heavy_list: {first slot, length} u32 pairs, capacity
  *                  pairs / (heavy + 1) + 2)
- *   ppg_chain_first_tiles   level 1: rows = source nodes; ptr1 / grouped / sorted_src from ppg_lift_temporal_views
- *   ppg_chain_count         k >= 2: continuation count of every level-k item in label order -> first, ptr_next u64 [E+1]
- *   ppg_chain_count_sorted  the same counts in merged order P (items >= limit are not expanded): offP u64 [n+1], firstP,
- *                           lblP, wP [n], srcbound [ceil(pairs / ppg_chain_tile_slots())][2] (rowid / run_start: the
- *                           previous level's idS / run_start)
- *   ppg_chain_tiles         expand + rank: `via` maps a continuation position to its item (temporal level: `grouped`);
- *                           the run heads are found in the same kernel (tile_state: 8 bytes per tile of
- *                           ppg_chain_tile_slots() pairs) -> idS, id_item (nullable), run_start, result[0]: final unless
- *                           result[3] != 0
+ *   ppg_chain_first_tiles   level 1: rows = source nodes; ptr1 / grouped / sorted_src from ppg_lift_temporal_views; writes
+ *                           the id word of the events' node words, ppg_chain_node_ptr the other word (from the event
+ *                           graph's row pointer)
+ *   ppg_chain_count_sorted  level 2: continuation counts of the events in merged order P (events >= limit are not
+ *                           expanded): offP u64 [n+1], firstP, lblP, wP [n], srcbound [ceil(pairs / tile)][2] (rowid /
+ *                           run_start: the previous level's idS / run_start)
+ *   ppg_chain_count_sorted_next  levels >= 3: the counts are already in merged order (degS); one gather per source
+ *   ppg_chain_tiles         expand + rank: `via` maps a continuation position to its item (level 2: `grouped`);
+ *                           node_prev: node words of the previous level; the run heads are found in the same kernel
+ *                           (tile_state: 8 bytes per tile of ppg_chain_tile_slots() pairs) -> idS, node_out, run_start,
+ *                           result[0]: final unless result[3] != 0
+ *   ppg_chain_scan_nodes    label-order scan of the counts in the node words -> row pointer of the next level, total
  *   ppg_chain_heavy_fix     rows the tiles left in generation order: one radix sort over their pairs; then
- *   ppg_chain_heads         run heads of the slots again -> idS, id_item, run_start, result[0]
+ *   ppg_chain_heads         run heads of the slots again -> idS, id word of the node words, run_start, result[0]
  *   ppg_chain_fill          merged edges [2, merged] int64 + weights (unit weights when wS is NULL)
+ *   ppg_chain_count         (distributed build) continuation counts of level >= 3 in label order from `tail`
  * ------------------------------------------------------------------------------------------- */
 int ppg_chain_heavy_default(void);
 int ppg_chain_tile_slots(void);
 size_t ppg_chain_scan_workspace_bytes(int64_t num_items);
 int ppg_chain_first_tiles(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, const uint32_t* ptr1,
                           const uint32_t* grouped, const uint32_t* sorted_src, const float* weights, int heavy, uint32_t* rowS,
-                          uint32_t* colS, uint32_t* labS, float* wS, uint32_t* idS, uint32_t* id_item, uint32_t* run_start,
+                          uint32_t* colS, uint32_t* labS, float* wS, uint32_t* idS, void* node_out, uint32_t* run_start,
                           void* tile_state, void* heavy_list, int64_t* result, void* stream);
 int ppg_chain_count(const uint32_t* tail, const void* ptr_prev, int64_t num_items, void* workspace, size_t workspace_bytes,
                     uint32_t* first, void* ptr_next, int64_t* total, void* stream);
@@ -169,19 +175,24 @@ int ppg_chain_count_sorted(const uint32_t* P, int64_t num_items, const uint32_t*
                            uint32_t* srcbound, void* stream);
 int ppg_chain_tiles(int64_t num_sources, int64_t num_rows, int64_t num_slots, const void* offP, const uint32_t* firstP,
                     const uint32_t* lblP, const float* wP, const uint32_t* run_start, const uint32_t* rowid,
-                    const uint32_t* colsrc, const uint32_t* via, const uint32_t* srcbound, int heavy, uint32_t* rowS,
-                    uint32_t* colS, uint32_t* labS, float* wS, uint32_t* tail_out, float* w_item_out, uint32_t* idS,
-                    uint32_t* id_item, uint32_t* run_start_out, void* tile_state, void* heavy_list, int64_t* result,
-                    void* stream);
+                    const void* node_prev, const uint32_t* via, const uint32_t* srcbound, int heavy, uint32_t* rowS,
+                    uint32_t* colS, uint32_t* labS, float* wS, uint32_t* idS, void* node_out, uint32_t* firstS, uint32_t* degS,
+                    uint32_t* run_start_out, void* tile_state, void* heavy_list, int64_t* result, void* stream);
+int ppg_chain_node_ptr(const void* off, int64_t num_items, void* node, void* stream);
+int ppg_chain_scan_nodes(void* node, int64_t num_items, void* workspace, size_t workspace_bytes, int64_t* total, void* stream);
+int ppg_chain_count_sorted_next(const uint32_t* P, int64_t num_items, const uint32_t* degS, const void* node, int64_t limit,
+                                const uint32_t* rowid, const uint32_t* run_start, void* workspace, size_t workspace_bytes,
+                                void* offP, uint32_t* lblP, uint32_t* srcbound, void* stream);
 int ppg_chain_heads(const uint32_t* rowS, const uint32_t* colS, const uint32_t* labS, int64_t num_slots, void* workspace,
-                    size_t workspace_bytes, uint32_t* idS, uint32_t* id_item, uint32_t* run_start, int64_t* result,
-                    void* stream);
+                    size_t workspace_bytes, uint32_t* idS, uint32_t* id_item, int id_stride, uint32_t* run_start,
+                    int64_t* result, void* stream);
 size_t ppg_chain_heavy_workspace_bytes(int64_t heavy_slots, int64_t heavy_rows, int64_t num_slots);
 int ppg_chain_heavy_fix(const void* heavy_list, int64_t heavy_rows, int64_t heavy_slots, int64_t num_slots, uint32_t* colS,
-                        uint32_t* labS, float* wS, uint32_t* extraS, void* workspace, size_t workspace_bytes, void* stream);
+                        uint32_t* labS, float* wS, uint32_t* extra0, uint32_t* extra1, uint32_t* extra2, void* workspace,
+                        size_t workspace_bytes, void* stream);
 int ppg_chain_fill(const uint32_t* rowS, const uint32_t* colS, const float* wS, const uint32_t* run_start, int64_t num_out,
                    int64_t* out_edge_index, float* out_weights, void* stream);
-int ppg_chain_widen(const uint32_t* in, int64_t n, int64_t* out, void* stream);
+int ppg_chain_widen(const uint32_t* in, int in_stride, int64_t n, int64_t* out, void* stream);
 
 /* The same chain on a rank of a distributed build (no counterpart in /root/reference).  A rank expands its
  * items in the order of their GLOBAL merged ids, so its pairs are sorted by (row, col) in global ids and the pairs of one

@@ -53,9 +53,12 @@ PROTOTYPES = {
     "ppg_chain_count": (c_int, [_p, _p, _i64, _p, c_size_t, _p, _p, _p, _p]),
     "ppg_chain_count_sorted": (c_int, [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, c_size_t, _p, _p, _p, _p, _p, _p]),
     "ppg_chain_tiles": (c_int, [_i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "ppg_chain_heads": (c_int, [_p, _p, _p, _i64, _p, c_size_t, _p, _p, _p, _p, _p]),
+    "ppg_chain_node_ptr": (c_int, [_p, _i64, _p, _p]),
+    "ppg_chain_scan_nodes": (c_int, [_p, _i64, _p, c_size_t, _p, _p]),
+    "ppg_chain_count_sorted_next": (c_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, c_size_t, _p, _p, _p, _p]),
+    "ppg_chain_heads": (c_int, [_p, _p, _p, _i64, _p, c_size_t, _p, _p, c_int, _p, _p, _p]),
     "ppg_chain_heavy_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
-    "ppg_chain_heavy_fix": (c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, c_size_t, _p]),
+    "ppg_chain_heavy_fix": (c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, c_size_t, _p]),
     "ppg_chain_tiles_dist": (c_int, [_i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                                      _p, _p]),
     "ppg_chain_dest_bounds": (c_int, [_p, _i64, _p, c_int, _p, _p, _p]),
@@ -65,7 +68,7 @@ PROTOTYPES = {
     "ppg_merge_sorted": (c_int, [_p, _i64, _p, c_int, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ppg_merge_sorted_fill": (c_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "ppg_chain_fill": (c_int, [_p, _p, _p, _p, _i64, _p, _p, _p]),
-    "ppg_chain_widen": (c_int, [_p, _i64, _p, _p]),
+    "ppg_chain_widen": (c_int, [_p, c_int, _i64, _p, _p]),
     "ppg_rows_minmax_workspace_bytes": (c_size_t, [_i64]),
     "ppg_rows_minmax": (c_int, [_p, _i64, _i64, _p, c_size_t, _ph_i64, _ph_i64, _ph_int, _p]),
     "ppg_unique_rows_workspace_bytes": (c_size_t, [_i64, c_int]),

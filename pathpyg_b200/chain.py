@@ -58,9 +58,8 @@ class _Level:
         self.heavy_list = torch.empty((n // (heavy + 1) + 2, 2), dtype=_u32, device=dev)
         # needed by the next level only
         self.idS = torch.empty(n, dtype=_u32, device=dev) if keep_items else None
-        self.id_item = torch.empty(n, dtype=_u32, device=dev) if keep_items else None
-        self.tail = None
-        self.w_item = None
+        self.node = torch.empty(n + 1, dtype=torch.int64, device=dev) if keep_items else None   # by label: id | count / pointer << 32
+        self.firstS = self.degS = None   # slot order: first continuation and their number (levels >= 2 with a level above)
         self.merged = 0
 
 
@@ -83,18 +82,16 @@ class TemporalChain:
     def _tile_state(self, slots: int) -> torch.Tensor:
         return torch.empty(-(-slots // self.tile) + 1, dtype=torch.int64, device=self.dev)
 
-    def _heads(self, level: _Level, k: int) -> None:
-        ws = self._scan_ws(level.items)
-        _lib.check(self.lib.ppg_chain_heads(_ptr(level.rowS), _ptr(level.colS), _ptr(level.labS), level.items, _ptr(ws), ws.numel(),
-                                            _ptr(level.idS), _ptr(level.id_item), _ptr(level.run_start), _ptr(self.res[k]),
-                                            _stream(self.dev)))
-
     def _heavy_fix(self, level: _Level, k: int, rows: int, slots: int) -> int:
         """Order the rows the tiles skipped, redo the run heads; returns the merged count (one more synchronisation)."""
         ws = torch.empty(self.lib.ppg_chain_heavy_workspace_bytes(slots, rows, level.items), dtype=torch.uint8, device=self.dev)
         _lib.check(self.lib.ppg_chain_heavy_fix(_ptr(level.heavy_list), rows, slots, level.items, _ptr(level.colS), _ptr(level.labS),
-                                                _ptr(level.wS), None, _ptr(ws), ws.numel(), _stream(self.dev)))
-        self._heads(level, k)
+                                                _ptr(level.wS), _ptr(level.firstS), _ptr(level.degS), None, _ptr(ws), ws.numel(),
+                                                _stream(self.dev)))
+        ws = self._scan_ws(level.items)
+        _lib.check(self.lib.ppg_chain_heads(_ptr(level.rowS), _ptr(level.colS), _ptr(level.labS), level.items, _ptr(ws), ws.numel(),
+                                            _ptr(level.idS), _ptr(level.node), 2, _ptr(level.run_start), _ptr(self.res[k]),
+                                            _stream(self.dev)))
         return int(self.res[k, _RES_HEADS].item())
 
     def _fill(self, level: _Level):
@@ -112,9 +109,10 @@ class TemporalChain:
         store(k, out_ei, out_w, nodes, inverse)
 
     def inverse_idx(self, level: _Level) -> torch.Tensor:
-        """``inverse_idx`` of the layer above ``level``: the merged id of every item, int64 as in the reference."""
+        """``inverse_idx`` of the layer above ``level``: the merged id of every item (the id word of its node word),
+        int64 as in the reference."""
         out = torch.empty(level.items, dtype=torch.int64, device=self.dev)
-        _lib.check(self.lib.ppg_chain_widen(_ptr(level.id_item), level.items, _ptr(out), _stream(self.dev)))
+        _lib.check(self.lib.ppg_chain_widen(_ptr(level.node), 2, level.items, _ptr(out), _stream(self.dev)))
         return out
 
     # ------------------------------------------------------------------ the build
@@ -134,7 +132,7 @@ class TemporalChain:
             # ---- level 1: events grouped by source node, ranked by target node inside every source group
             l1 = _Level(m, dev, self.weighted, K > 1, self.heavy)
             _lib.check(lib.ppg_chain_first_tiles(_ptr(self.ei), m, n, ptr1, grouped, sorted_src, _ptr(self.w), self.heavy,
-                                                 _ptr(l1.rowS), _ptr(l1.colS), _ptr(l1.labS), _ptr(l1.wS), _ptr(l1.idS), _ptr(l1.id_item),
+                                                 _ptr(l1.rowS), _ptr(l1.colS), _ptr(l1.labS), _ptr(l1.wS), _ptr(l1.idS), _ptr(l1.node),
                                                  _ptr(l1.run_start), _ptr(self._tile_state(m)), _ptr(l1.heavy_list), _ptr(self.res[1]),
                                                  stream))
             if K > 1:
@@ -143,6 +141,7 @@ class TemporalChain:
                 time, mode, delta_i, delta_f = ops._time_mode(time.contiguous(), delta)
                 _lib.check(lib.ppg_lift_temporal_count(_ptr(self.ei), _ptr(time), m, n, mode | _lib.TIME_GROUPED, delta_i, delta_f,
                                                        _ptr(tws), tws.numel(), None, stream))
+                _lib.check(lib.ppg_chain_node_ptr(off2, m, _ptr(l1.node), stream))     # node word of an event: id | first pair
                 words = torch.cat([self.res[1, :4], tws[:16].view(torch.int64)]).tolist()      # the synchronisation of order 1
             else:
                 words = self.res[1, :4].tolist() + [0, 0]
@@ -160,9 +159,7 @@ class TemporalChain:
                                           "(lift_order_temporal: no time-respecting pair for this delta)")
 
             # ---- levels 2..K
-            prev, first, ptr_next, via = l1, first2, off2, grouped
-            w_item = self.w
-            keep = [tws]  # arrays the raw pointers above point into
+            prev = l1
             for k in range(2, K + 1):
                 more = k < K
                 if pairs == 0:   # nothing continues: this layer has nodes but no edges, the ones above are empty
@@ -175,38 +172,40 @@ class TemporalChain:
                 cur = _Level(pairs, dev, self.weighted, more, self.heavy)
                 ns = prev.items
                 offP = torch.empty(ns + 1, dtype=torch.int64, device=dev)
-                firstP = torch.empty(ns, dtype=_u32, device=dev)
                 lblP = torch.empty(ns, dtype=_u32, device=dev)
-                wP = torch.empty(ns, dtype=torch.float32, device=dev) if self.weighted else None
                 srcbound = torch.empty((-(-pairs // self.tile), 2), dtype=_u32, device=dev)
                 ws = self._scan_ws(ns)
-                _lib.check(lib.ppg_chain_count_sorted(_ptr(prev.labS), ns, first, ptr_next, _ptr(w_item), ns, _ptr(prev.idS),
-                                                      _ptr(prev.run_start), _ptr(ws), ws.numel(),
-                                                      _ptr(offP), _ptr(firstP), _ptr(lblP), _ptr(wP), _ptr(srcbound), stream))
+                if k == 2:   # the counts of the events are in label order (temporal count): gather them into merged order
+                    firstP = torch.empty(ns, dtype=_u32, device=dev)
+                    _lib.check(lib.ppg_chain_count_sorted(_ptr(prev.labS), ns, first2, off2, None, ns, _ptr(prev.idS),
+                                                          _ptr(prev.run_start), _ptr(ws), ws.numel(), _ptr(offP), _ptr(firstP),
+                                                          _ptr(lblP), None, _ptr(srcbound), stream))
+                    via = grouped
+                else:        # the previous level's tiles left them in merged order
+                    firstP = prev.firstS
+                    _lib.check(lib.ppg_chain_count_sorted_next(_ptr(prev.labS), ns, _ptr(prev.degS), _ptr(prev.node), ns, _ptr(prev.idS),
+                                                               _ptr(prev.run_start), _ptr(ws), ws.numel(), _ptr(offP), _ptr(lblP),
+                                                               _ptr(srcbound), stream))
+                    via = None
                 if more:
-                    cur.tail = torch.empty(pairs, dtype=_u32, device=dev)
-                    cur.w_item = torch.empty(pairs, dtype=torch.float32, device=dev) if self.weighted else None
-                _lib.check(lib.ppg_chain_tiles(ns, prev.merged, pairs, _ptr(offP), _ptr(firstP), _ptr(lblP), _ptr(wP),
-                                               _ptr(prev.run_start), _ptr(prev.idS), _ptr(prev.id_item), via, _ptr(srcbound), self.heavy,
-                                               _ptr(cur.rowS), _ptr(cur.colS), _ptr(cur.labS), _ptr(cur.wS), _ptr(cur.tail),
-                                               _ptr(cur.w_item), _ptr(cur.idS), _ptr(cur.id_item), _ptr(cur.run_start),
+                    cur.firstS = torch.empty(pairs, dtype=_u32, device=dev)
+                    cur.degS = torch.empty(pairs, dtype=_u32, device=dev)
+                # a pair inherits the weight of its source item, which the previous level holds in slot (= merged) order
+                _lib.check(lib.ppg_chain_tiles(ns, prev.merged, pairs, _ptr(offP), _ptr(firstP), _ptr(lblP), _ptr(prev.wS),
+                                               _ptr(prev.run_start), _ptr(prev.idS), _ptr(prev.node), via, _ptr(srcbound), self.heavy,
+                                               _ptr(cur.rowS), _ptr(cur.colS), _ptr(cur.labS), _ptr(cur.wS), _ptr(cur.idS),
+                                               _ptr(cur.node), _ptr(cur.firstS), _ptr(cur.degS), _ptr(cur.run_start),
                                                _ptr(self._tile_state(pairs)), _ptr(cur.heavy_list), _ptr(self.res[k]), stream))
-                nxt_first = nxt_ptr = None
-                if more:
-                    nxt_first = torch.empty(pairs, dtype=_u32, device=dev)
-                    nxt_ptr = torch.empty(pairs + 1, dtype=torch.int64, device=dev)
+                if more:     # label-order scan of the counts: row pointer of the next level + its number of pairs
                     ws2 = self._scan_ws(pairs)
-                    _lib.check(lib.ppg_chain_count(_ptr(cur.tail), ptr_next, pairs, _ptr(ws2), ws2.numel(), _ptr(nxt_first),
-                                                   _ptr(nxt_ptr), ctypes.c_void_p(self.res[k].data_ptr() + 8 * _RES_NEXT), stream))
+                    _lib.check(lib.ppg_chain_scan_nodes(_ptr(cur.node), pairs, _ptr(ws2), ws2.numel(),
+                                                        ctypes.c_void_p(self.res[k].data_ptr() + 8 * _RES_NEXT), stream))
                 inverse = self.inverse_idx(prev) if cached or not more else None
                 words = self.res[k].tolist()                                                      # the synchronisation of order k
                 cur.merged = words[_RES_HEADS]
                 if words[_RES_HEAVY_ROWS]:
                     cur.merged = self._heavy_fix(cur, k, words[_RES_HEAVY_ROWS], words[_RES_HEAVY_SLOTS])
                 self._emit(store, k, cur, prev.merged, inverse)
-                del offP, firstP, lblP, wP, srcbound
-                keep = [nxt_first, nxt_ptr, cur.tail]
-                prev, pairs, w_item, via = cur, words[_RES_NEXT], cur.w_item, None
-                if more:
-                    first, ptr_next = ctypes.c_void_p(nxt_first.data_ptr()), ctypes.c_void_p(nxt_ptr.data_ptr())
-            del keep
+                del offP, firstP, lblP, srcbound
+                prev, pairs = cur, words[_RES_NEXT]
+            del tws

@@ -116,7 +116,7 @@ struct ChainTileArgs {
   const float* wP;                 // [n_sources] weight of the source or nullptr      (FIRST: by event)
   const uint32_t* run_start;       // [n_rows + 1] first source of every row
   const uint32_t* rowid;           // [n_sources] row of every source
-  const uint32_t* colsrc;          // merged id of an item                             (FIRST: unused)
+  const unsigned long long* node_prev;  // by item: merged id | row pointer of THIS level << 32 ([items + 1]; FIRST, DIST: unused)
   const uint32_t* via;             // continuation position -> item (temporal level) or nullptr
   const int64_t* dst;              // FIRST: target node of every event
   const uint32_t* srcbound;        // [tiles][2] (see ChainSortedConsumer)              (FIRST: unused)
@@ -124,14 +124,18 @@ struct ChainTileArgs {
   int heavy;
   uint32_t *rowS, *colS, *labS;
   float* wS;
-  uint32_t* tail_out;              // [n_slots] by label or nullptr
-  float* w_item_out;               // [n_slots] by label or nullptr
+  uint32_t* tail_out;              // DIST: [n_slots] by label or nullptr
+  float* w_item_out;               // DIST: [n_slots] by label or nullptr
+  // what the next level needs (NEXT): by label the merged id | number of continuations << 32 (FIRST: the id word only),
+  // and in slot order -- the merged order P of the next level -- the first continuation and their number
+  unsigned long long* node_out;
+  uint32_t *firstS, *degS;
   uint2* heavy_list;
   unsigned long long* result;
   // run heads, fused: valid when no row of the level is heavy (otherwise ppg_chain_heavy_fix + ppg_chain_heads redo them)
   unsigned long long* tile_state;  // [tiles] zeroed
   unsigned code_partial, code_inclusive;
-  uint32_t *idS, *id_item, *run_start_out;
+  uint32_t *idS, *run_start_out;
   // distributed build (DIST): ids are global, rows are local
   const unsigned long long* info;  // by item: global id << 32 | last first-order node (replaces colsrc)
   const uint32_t* row_value;       // by local row: its global id (what rowS receives)
@@ -196,7 +200,7 @@ __device__ __forceinline__ unsigned long long chain_tile_prefix(unsigned long lo
   return acc;
 }
 
-template <bool FIRST, bool DIST>
+template <bool FIRST, bool DIST, bool NEXT>
 __global__ void __launch_bounds__(kChainBlock)
 chain_tile_kernel(ChainTileArgs a) {
   extern __shared__ __align__(16) uint32_t chain_smem[];
@@ -210,6 +214,8 @@ chain_tile_kernel(ChainTileArgs a) {
   uint32_t* s_len = s_row + kChainCap;                              // at a row's first slot: its length; later: run index of every slot
   uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_len + kChainCap);
   uint32_t* s_last = reinterpret_cast<uint32_t*>(s_perm + kChainCap);  // DIST only: last first-order node of every slot's pair
+  uint32_t* s_nfirst = s_last;                                         // NEXT only: first continuation at the next level ...
+  uint32_t* s_ndeg = s_nfirst + kChainCap;                             // ... and their number
   __shared__ int64_t s_geo[4];
   __shared__ int64_t s_bound[2];
   __shared__ uint32_t s_warp_max[kChainBlock / 32];
@@ -368,11 +374,17 @@ chain_tile_kernel(ChainTileArgs a) {
             const unsigned long long info = a.info[item];
             col = static_cast<uint32_t>(info >> 32);
             s_last[i] = static_cast<uint32_t>(info);
-          } else {
-            col = a.colsrc[item];
+            if (a.tail_out != nullptr) a.tail_out[label] = item;
+            if (a.w_item_out != nullptr) a.w_item_out[label] = s_w[f0];
+          } else {     // merged id | first level-k item whose source is this item << 32
+            const unsigned long long nd = a.node_prev[item];
+            col = static_cast<uint32_t>(nd);
+            if (NEXT) {
+              const uint32_t p0 = static_cast<uint32_t>(nd >> 32);
+              s_nfirst[i] = p0;
+              s_ndeg[i] = static_cast<uint32_t>(a.node_prev[item + 1] >> 32) - p0;
+            }
           }
-          if (a.tail_out != nullptr) a.tail_out[label] = item;
-          if (a.w_item_out != nullptr) a.w_item_out[label] = s_w[f0];
         }
         s_col[i] = col;
         if (i == cn - 1 || static_cast<int>(s_mark[i + 1] >> 16) - 1 != g0) {
@@ -459,15 +471,22 @@ chain_tile_kernel(ChainTileArgs a) {
 
     // ---- write the chunk in its final order: first what does not depend on the tiles before this one ...
     uint32_t label[kChainPerThread];
+    uint32_t ndeg[kChainPerThread];
 #pragma unroll
     for (int k = 0; k < kChainPerThread; ++k) {
       const int p = k * kChainBlock + tid;
+      ndeg[k] = 0;
       if (p < cn) {
         const int i = s_perm[p];
         const int g0 = static_cast<int>(s_mark[p] >> 16) - 1;
         const int f0 = static_cast<int>(s_mark[i] & 0xffffu) - 1;
         const int64_t jj = static_cast<int64_t>(i) - s_soff[f0];
         label[k] = s_lbl[f0] + static_cast<uint32_t>(jj);
+        if (NEXT) {
+          ndeg[k] = s_ndeg[i];
+          st_stream(a.firstS + cb + p, s_nfirst[i]);
+          st_stream(a.degS + cb + p, ndeg[k]);
+        }
         st_stream(a.rowS + cb + p, DIST ? a.row_value[s_row[g0]] : s_row[g0]);
         st_stream(a.colS + cb + p, s_col[i]);
         if (DIST) st_stream(a.lastS + cb + p, s_last[i]);
@@ -496,7 +515,11 @@ chain_tile_kernel(ChainTileArgs a) {
         const uint32_t run = s_len[p];
         const uint32_t id = static_cast<uint32_t>(base_id + run);
         if (a.idS != nullptr) st_stream(a.idS + cb + p, id);
-        if (a.id_item != nullptr) a.id_item[label[k]] = id;
+        if (FIRST) {
+          if (a.node_out != nullptr) reinterpret_cast<uint32_t*>(a.node_out)[2 * static_cast<size_t>(label[k])] = id;
+        } else if (NEXT) {
+          a.node_out[label[k]] = static_cast<unsigned long long>(id) | (static_cast<unsigned long long>(ndeg[k]) << 32);
+        }
         if (a.run_start_out != nullptr && (p == 0 || s_len[p - 1] != run)) a.run_start_out[id] = static_cast<uint32_t>(cb + p);
       }
     }
@@ -506,6 +529,7 @@ chain_tile_kernel(ChainTileArgs a) {
 
 constexpr size_t kChainTileSmem = static_cast<size_t>(kChainCap) * (8 * 4 + 2);
 constexpr size_t kChainTileSmemDist = kChainTileSmem + static_cast<size_t>(kChainCap) * 4;
+constexpr size_t kChainTileSmemNext = kChainTileSmem + static_cast<size_t>(kChainCap) * 8;
 
 // ------------------------------------------------------------------ heads
 struct ChainHeadProducer {
@@ -519,7 +543,8 @@ struct ChainHeadProducer {
 struct ChainHeadConsumer {
   const uint32_t* labS;
   uint32_t* idS;        // merged id of every slot (nullable)
-  uint32_t* id_item;    // merged id of every item, by label (nullable)
+  uint32_t* id_item;    // merged id of every item, by label, `id_stride` words apart (nullable)
+  int id_stride;
   uint32_t* run_start;  // [heads + 1]
   int64_t n;
   __device__ void operator()(int64_t i, unsigned long long head, unsigned long long prefix) const {
@@ -527,7 +552,7 @@ struct ChainHeadConsumer {
     if (head) run_start[prefix] = static_cast<uint32_t>(i);
     if (i == n - 1) run_start[prefix + head] = static_cast<uint32_t>(n);
     if (idS != nullptr) idS[i] = id;
-    if (id_item != nullptr) id_item[ld_stream(labS + i)] = id;
+    if (id_item != nullptr) id_item[static_cast<size_t>(ld_stream(labS + i)) * id_stride] = id;
   }
 };
 
@@ -558,11 +583,48 @@ chain_fill_kernel(const uint32_t* __restrict__ rowS, const uint32_t* __restrict_
 }
 
 __global__ void __launch_bounds__(256)
-chain_widen_kernel(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+chain_widen_kernel(const uint32_t* __restrict__ in, int in_stride, int64_t n, int64_t* __restrict__ out) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-    st_stream(out + i, static_cast<int64_t>(ld_stream(in + i)));
+    st_stream(out + i, static_cast<int64_t>(ld_stream(in + i * in_stride)));
 }
+
+// level 1: the row pointer of the event graph (u64, lift.cu) into the ptr word of the events' node words
+__global__ void __launch_bounds__(256)
+chain_node_ptr_kernel(const unsigned long long* __restrict__ off, int64_t n_plus_1, unsigned long long* __restrict__ node) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_plus_1; i += stride)
+    reinterpret_cast<uint32_t*>(node)[2 * i + 1] = static_cast<uint32_t>(ld_stream(off + i));
+}
+
+// label-order scan of the continuation counts the tiles left in the node words: count -> row pointer of the next level
+struct NodeDegProducer {
+  const unsigned long long* node;
+  __device__ unsigned long long operator()(int64_t i) const { return node[i] >> 32; }
+};
+struct NodePtrConsumer {
+  unsigned long long* node;
+  int64_t n;
+  __device__ void operator()(int64_t i, unsigned long long v, unsigned long long prefix) const {
+    reinterpret_cast<uint32_t*>(node)[2 * i + 1] = static_cast<uint32_t>(prefix);
+    if (i == n - 1) reinterpret_cast<uint32_t*>(node)[2 * n + 1] = static_cast<uint32_t>(prefix + v);
+  }
+};
+
+// count pass of levels >= 3 in merged order: the counts are already in that order (degS of the previous level's tiles);
+// one gather per source fetches the label of its first pair
+struct ChainSortedProducer2 {
+  const uint32_t* P;
+  const uint32_t* degS;
+  const unsigned long long* node;   // by label: id | row pointer of the next level << 32 (after the label-order scan)
+  int64_t limit;
+  uint32_t* lblP;
+  __device__ unsigned long long operator()(int64_t s) const {
+    const uint32_t q = ld_stream(P + s);
+    lblP[s] = static_cast<uint32_t>(node[q] >> 32);
+    return static_cast<int64_t>(q) < limit ? ld_stream(degS + s) : 0u;
+  }
+};
 
 // ------------------------------------------------------------------ heavy rows
 struct HeavyLayout {
@@ -573,7 +635,7 @@ struct HeavyLayout {
   unsigned long long *keys_a, *keys_b;
   uint32_t *vals_a, *vals_b;
   uint32_t* t_lab;
-  uint32_t* t_extra;
+  uint32_t* t_extra[3];
   float* t_w;
   uint32_t* t_dest;
   int bits;
@@ -588,10 +650,13 @@ struct HeavyLayout {
     vals_a = ws.take<uint32_t>(static_cast<size_t>(slots));
     vals_b = ws.take<uint32_t>(static_cast<size_t>(slots));
     t_lab = ws.take<uint32_t>(static_cast<size_t>(slots));
-    t_extra = ws.take<uint32_t>(static_cast<size_t>(slots));
+    for (int j = 0; j < 3; ++j) t_extra[j] = ws.take<uint32_t>(static_cast<size_t>(slots));
     t_w = ws.take<float>(static_cast<size_t>(slots));
     t_dest = ws.take<uint32_t>(static_cast<size_t>(slots));
   }
+};
+struct HeavyExtras {  // further slot arrays that travel with the pairs of a heavy row (firstS, degS, lastS)
+  uint32_t* p[3];
 };
 struct HeavyLenProducer {
   const uint2* list;
@@ -618,8 +683,8 @@ heavy_compact_kernel(const uint2* __restrict__ list, const unsigned long long* _
 
 __global__ void __launch_bounds__(256)
 heavy_gather_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t slots,
-                    const uint32_t* __restrict__ labS, const float* __restrict__ wS, const uint32_t* __restrict__ extraS,
-                    uint32_t* __restrict__ t_lab, float* __restrict__ t_w, uint32_t* __restrict__ t_extra,
+                    const uint32_t* __restrict__ labS, const float* __restrict__ wS, HeavyExtras extraS,
+                    uint32_t* __restrict__ t_lab, float* __restrict__ t_w, HeavyExtras t_extra,
                     uint32_t* __restrict__ t_dest) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slots; i += stride) {
@@ -634,21 +699,25 @@ heavy_gather_kernel(const unsigned long long* __restrict__ keys, const uint32_t*
     t_dest[i] = static_cast<uint32_t>(k >> 32) + static_cast<uint32_t>(i - hi);
     t_lab[i] = labS[src];
     if (wS != nullptr) t_w[i] = wS[src];
-    if (extraS != nullptr) t_extra[i] = extraS[src];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (extraS.p[j] != nullptr) t_extra.p[j][i] = extraS.p[j][src];
   }
 }
 
 __global__ void __launch_bounds__(256)
 heavy_write_kernel(const unsigned long long* __restrict__ keys, int64_t slots, const uint32_t* __restrict__ t_lab,
-                   const float* __restrict__ t_w, const uint32_t* __restrict__ t_extra, const uint32_t* __restrict__ t_dest,
-                   uint32_t* __restrict__ colS, uint32_t* __restrict__ labS, float* __restrict__ wS, uint32_t* __restrict__ extraS) {
+                   const float* __restrict__ t_w, HeavyExtras t_extra, const uint32_t* __restrict__ t_dest,
+                   uint32_t* __restrict__ colS, uint32_t* __restrict__ labS, float* __restrict__ wS, HeavyExtras extraS) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slots; i += stride) {
     const uint32_t d = t_dest[i];
     colS[d] = static_cast<uint32_t>(keys[i]);
     labS[d] = t_lab[i];
     if (wS != nullptr) wS[d] = t_w[i];
-    if (extraS != nullptr) extraS[d] = t_extra[i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (extraS.p[j] != nullptr) extraS.p[j][d] = t_extra.p[j][i];
   }
 }
 
@@ -950,23 +1019,32 @@ static int launch_tiles(ChainTileArgs& a, bool first, cudaStream_t stream) {
   // algorithmic bytes of the launch (what the kernel must read and write once), for the live roofline of bench.py
   const bool dist = !first && a.info != nullptr;
   const long long per_source = first ? 4 + 4 + 8 + (a.wS != nullptr ? 4 : 0) : 8 + 4 + 4 + 4 + (a.wS != nullptr ? 4 : 0);
-  const long long per_slot = (first ? 0 : (dist ? 8 : 4) + (a.via != nullptr ? 4 : 0)) + 12 + (a.wS != nullptr ? 4 : 0) +
-                             (a.idS != nullptr ? 4 : 0) + (a.id_item != nullptr ? 4 : 0) + (a.tail_out != nullptr ? 4 : 0) +
-                             (a.w_item_out != nullptr ? 4 : 0) + (dist ? 4 : 0);
+  const bool next = !first && !dist && a.node_out != nullptr;
+  const long long per_slot = (first ? 0 : 8 + (a.via != nullptr ? 4 : 0)) + 12 + (a.wS != nullptr ? 4 : 0) +
+                             (a.idS != nullptr ? 4 : 0) + (a.node_out != nullptr ? (first ? 4 : 8) : 0) + (next ? 8 : 0) +
+                             (a.tail_out != nullptr ? 4 : 0) + (a.w_item_out != nullptr ? 4 : 0) + (dist ? 4 : 0);
   const long long launch_bytes = per_source * a.n_sources + per_slot * a.n_slots;
   profile_pass_begin(stream);
   if (first) {
-    chain_tile_kernel<true, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
-  } else if (a.info != nullptr) {
+    chain_tile_kernel<true, false, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
+  } else if (dist) {
     static bool configured = false;
     if (!configured) {
-      PPG_CUDA_TRY(cudaFuncSetAttribute(chain_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      PPG_CUDA_TRY(cudaFuncSetAttribute(chain_tile_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(kChainTileSmemDist)));
       configured = true;
     }
-    chain_tile_kernel<false, true><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmemDist, stream>>>(a);
+    chain_tile_kernel<false, true, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmemDist, stream>>>(a);
+  } else if (next) {
+    static bool configured = false;
+    if (!configured) {
+      PPG_CUDA_TRY(cudaFuncSetAttribute(chain_tile_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(kChainTileSmemNext)));
+      configured = true;
+    }
+    chain_tile_kernel<false, false, true><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmemNext, stream>>>(a);
   } else {
-    chain_tile_kernel<false, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
+    chain_tile_kernel<false, false, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
   }
   profile_pass_end(stream, a.n_slots, static_cast<int>((launch_bytes + a.n_slots / 2) / a.n_slots), PPG_PROFILE_CHAIN_TILES);
   PPG_LAUNCHED();
@@ -984,7 +1062,7 @@ extern "C" int ppg_chain_tile_slots(void) { return kChainTile; }
 extern "C" int ppg_chain_first_tiles(const int64_t* edge_index, int64_t m, int64_t N, const uint32_t* ptr1,
                                      const uint32_t* grouped, const uint32_t* sorted_src, const float* weights, int heavy,
                                      uint32_t* rowS, uint32_t* colS, uint32_t* labS, float* wS, uint32_t* idS,
-                                     uint32_t* id_item, uint32_t* run_start, void* tile_state, void* heavy_list,
+                                     void* node_out, uint32_t* run_start, void* tile_state, void* heavy_list,
                                      int64_t* result, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PPG_REQUIRE(m > 0 && N > 0 && m < (1ll << 31) && N < (1ll << 31), PPG_ERR_INVALID, "chain: sizes m=%lld N=%lld outside (0, 2^31)",
@@ -1009,7 +1087,7 @@ extern "C" int ppg_chain_first_tiles(const int64_t* edge_index, int64_t m, int64
   a.heavy_list = static_cast<uint2*>(heavy_list);
   a.result = reinterpret_cast<unsigned long long*>(result);
   a.idS = idS;
-  a.id_item = id_item;
+  a.node_out = static_cast<unsigned long long*>(node_out);
   a.run_start_out = run_start;
   a.tile_state = static_cast<unsigned long long*>(tile_state);
   return launch_tiles(a, true, stream);
@@ -1019,8 +1097,8 @@ extern "C" size_t ppg_chain_scan_workspace_bytes(int64_t n) { return (scan_state
 
 // Run heads of the slots in final order -> merged ids; result[kResHeads] = number of merged edges.
 extern "C" int ppg_chain_heads(const uint32_t* rowS, const uint32_t* colS, const uint32_t* labS, int64_t n, void* workspace,
-                               size_t workspace_bytes, uint32_t* idS, uint32_t* id_item, uint32_t* run_start, int64_t* result,
-                               void* stream_) {
+                               size_t workspace_bytes, uint32_t* idS, uint32_t* id_item, int id_stride, uint32_t* run_start,
+                               int64_t* result, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PPG_REQUIRE(n >= 0 && n < (1ll << 31), PPG_ERR_INVALID, "chain: %lld slots outside [0, 2^31)", (long long)n);
   const size_t need = ppg_chain_scan_workspace_bytes(n);
@@ -1031,7 +1109,7 @@ extern "C" int ppg_chain_heads(const uint32_t* rowS, const uint32_t* colS, const
     PPG_CUDA_TRY(cudaMemsetAsync(run_start, 0, sizeof(uint32_t), stream));
     return PPG_OK;
   }
-  return launch_scan(ChainHeadProducer{rowS, colS}, ChainHeadConsumer{labS, idS, id_item, run_start, n}, n,
+  return launch_scan(ChainHeadProducer{rowS, colS}, ChainHeadConsumer{labS, idS, id_item, id_stride < 1 ? 1 : id_stride, run_start, n}, n,
                      static_cast<unsigned long long*>(workspace), reinterpret_cast<unsigned long long*>(result) + kResHeads, stream);
 }
 
@@ -1044,10 +1122,10 @@ extern "C" int ppg_chain_fill(const uint32_t* rowS, const uint32_t* colS, const 
   return PPG_OK;
 }
 
-extern "C" int ppg_chain_widen(const uint32_t* in, int64_t n, int64_t* out, void* stream_) {
+extern "C" int ppg_chain_widen(const uint32_t* in, int in_stride, int64_t n, int64_t* out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n == 0) return PPG_OK;
-  chain_widen_kernel<<<grid_for(n, 256 * 4), 256, 0, stream>>>(in, n, out);
+  chain_widen_kernel<<<grid_for(n, 256 * 4), 256, 0, stream>>>(in, in_stride < 1 ? 1 : in_stride, n, out);
   PPG_LAUNCHED();
   return PPG_OK;
 }
@@ -1089,10 +1167,10 @@ extern "C" int ppg_chain_count_sorted(const uint32_t* P, int64_t n, const uint32
 // Tiles of level k >= 2: `via` maps a continuation position to its item (temporal level: the events grouped by source).
 extern "C" int ppg_chain_tiles(int64_t n_sources, int64_t n_rows, int64_t n_slots, const void* offP, const uint32_t* firstP,
                                const uint32_t* lblP, const float* wP, const uint32_t* run_start, const uint32_t* rowid,
-                               const uint32_t* colsrc, const uint32_t* via, const uint32_t* srcbound, int heavy, uint32_t* rowS,
-                               uint32_t* colS, uint32_t* labS, float* wS, uint32_t* tail_out, float* w_item_out,
-                               uint32_t* idS, uint32_t* id_item, uint32_t* run_start_out, void* tile_state,
-                               void* heavy_list, int64_t* result, void* stream_) {
+                               const void* node_prev, const uint32_t* via, const uint32_t* srcbound, int heavy, uint32_t* rowS,
+                               uint32_t* colS, uint32_t* labS, float* wS, uint32_t* idS, void* node_out, uint32_t* firstS,
+                               uint32_t* degS, uint32_t* run_start_out, void* tile_state, void* heavy_list, int64_t* result,
+                               void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PPG_REQUIRE(n_sources > 0 && n_sources < (1ll << 31) && n_slots >= 0 && n_slots < (1ll << 31) && n_rows > 0, PPG_ERR_INVALID,
               "chain: sizes outside [0, 2^31)");
@@ -1105,7 +1183,9 @@ extern "C" int ppg_chain_tiles(int64_t n_sources, int64_t n_rows, int64_t n_slot
   a.wP = wP;
   a.run_start = run_start;
   a.rowid = rowid;
-  a.colsrc = colsrc;
+  PPG_REQUIRE(node_prev != nullptr && (node_out == nullptr) == (firstS == nullptr) && (firstS == nullptr) == (degS == nullptr),
+              PPG_ERR_INVALID, "chain: node words of the previous level are required; node_out, firstS and degS come together");
+  a.node_prev = static_cast<const unsigned long long*>(node_prev);
   a.via = via;
   a.srcbound = srcbound;
   a.n_sources = n_sources;
@@ -1116,12 +1196,12 @@ extern "C" int ppg_chain_tiles(int64_t n_sources, int64_t n_rows, int64_t n_slot
   a.colS = colS;
   a.labS = labS;
   a.wS = wS;
-  a.tail_out = tail_out;
-  a.w_item_out = w_item_out;
+  a.node_out = static_cast<unsigned long long*>(node_out);
+  a.firstS = firstS;
+  a.degS = degS;
   a.heavy_list = static_cast<uint2*>(heavy_list);
   a.result = reinterpret_cast<unsigned long long*>(result);
   a.idS = idS;
-  a.id_item = id_item;
   a.run_start_out = run_start_out;
   a.tile_state = static_cast<unsigned long long*>(tile_state);
   return launch_tiles(a, false, stream);
@@ -1135,8 +1215,8 @@ extern "C" size_t ppg_chain_heavy_workspace_bytes(int64_t heavy_slots, int64_t h
 
 // Rows the tiles left in generation order: one stable radix sort over their pairs only, written back in place.
 extern "C" int ppg_chain_heavy_fix(const void* heavy_list, int64_t heavy_rows, int64_t heavy_slots, int64_t n_slots,
-                                   uint32_t* colS, uint32_t* labS, float* wS, uint32_t* extraS, void* workspace,
-                                   size_t workspace_bytes, void* stream_) {
+                                   uint32_t* colS, uint32_t* labS, float* wS, uint32_t* extra0, uint32_t* extra1,
+                                   uint32_t* extra2, void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (heavy_rows == 0 || heavy_slots == 0) return PPG_OK;
   Workspace ws(workspace, workspace_bytes);
@@ -1152,9 +1232,11 @@ extern "C" int ppg_chain_heavy_fix(const void* heavy_list, int64_t heavy_rows, i
                                                &in_b, stream));
   const unsigned long long* keys = in_b ? L.keys_b : L.keys_a;
   const uint32_t* vals = in_b ? L.vals_b : L.vals_a;
-  heavy_gather_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(keys, vals, heavy_slots, labS, wS, extraS, L.t_lab, L.t_w, L.t_extra, L.t_dest);
+  const HeavyExtras extras = {{extra0, extra1, extra2}};
+  const HeavyExtras temps = {{L.t_extra[0], L.t_extra[1], L.t_extra[2]}};
+  heavy_gather_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(keys, vals, heavy_slots, labS, wS, extras, L.t_lab, L.t_w, temps, L.t_dest);
   PPG_LAUNCHED();
-  heavy_write_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(keys, heavy_slots, L.t_lab, L.t_w, L.t_extra, L.t_dest, colS, labS, wS, extraS);
+  heavy_write_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(keys, heavy_slots, L.t_lab, L.t_w, temps, L.t_dest, colS, labS, wS, extras);
   PPG_LAUNCHED();
   return PPG_OK;
 }
@@ -1303,4 +1385,47 @@ extern "C" int ppg_merge_sorted_fill(const uint32_t* row_m, const uint32_t* col_
                                                                           out_last);
   PPG_LAUNCHED();
   return PPG_OK;
+}
+
+// Level 1: ptr word of the events' node words <- row pointer of the event graph (u64 [m + 1] of ppg_lift_temporal_views).
+extern "C" int ppg_chain_node_ptr(const void* off, int64_t num_items, void* node, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  chain_node_ptr_kernel<<<grid_for(num_items + 1, 256 * 4), 256, 0, stream>>>(static_cast<const unsigned long long*>(off), num_items + 1,
+                                                                              static_cast<unsigned long long*>(node));
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
+// Label-order scan of the continuation counts in the node words (in place: count -> row pointer of the next level;
+// node[num_items] receives the total, which is also written to *total).
+extern "C" int ppg_chain_scan_nodes(void* node, int64_t num_items, void* workspace, size_t workspace_bytes, int64_t* total,
+                                    void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(num_items >= 0 && num_items < (1ll << 31), PPG_ERR_INVALID, "chain: %lld items outside [0, 2^31)", (long long)num_items);
+  const size_t need = ppg_chain_scan_workspace_bytes(num_items);
+  PPG_REQUIRE(workspace_bytes >= need, PPG_ERR_WORKSPACE, "chain_scan_nodes: workspace %zu < %zu bytes", workspace_bytes, need);
+  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, stream));
+  if (num_items == 0) {
+    PPG_CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(int64_t), stream));
+    PPG_CUDA_TRY(cudaMemsetAsync(node, 0, sizeof(unsigned long long), stream));
+    return PPG_OK;
+  }
+  unsigned long long* nd = static_cast<unsigned long long*>(node);
+  return launch_scan(NodeDegProducer{nd}, NodePtrConsumer{nd, num_items}, num_items, static_cast<unsigned long long*>(workspace),
+                     reinterpret_cast<unsigned long long*>(total), stream);
+}
+
+// Count pass of levels >= 3 in merged order (see ChainSortedProducer2): degS of the previous level's tiles, limit, node
+// words after ppg_chain_scan_nodes -> offP u64 [n + 1], lblP [n], srcbound.
+extern "C" int ppg_chain_count_sorted_next(const uint32_t* P, int64_t n, const uint32_t* degS, const void* node, int64_t limit,
+                                           const uint32_t* rowid, const uint32_t* run_start, void* workspace, size_t workspace_bytes,
+                                           void* offP, uint32_t* lblP, uint32_t* srcbound, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PPG_REQUIRE(n > 0 && n < (1ll << 31), PPG_ERR_INVALID, "chain: %lld sources outside (0, 2^31)", (long long)n);
+  const size_t need = ppg_chain_scan_workspace_bytes(n);
+  PPG_REQUIRE(workspace_bytes >= need, PPG_ERR_WORKSPACE, "chain_count_sorted_next: workspace %zu < %zu bytes", workspace_bytes, need);
+  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, stream));
+  return launch_scan(ChainSortedProducer2{P, degS, static_cast<const unsigned long long*>(node), limit, lblP},
+                     ChainSortedConsumer{static_cast<unsigned long long*>(offP), reinterpret_cast<uint2*>(srcbound), rowid, run_start, n}, n,
+                     static_cast<unsigned long long*>(workspace), nullptr, stream);
 }

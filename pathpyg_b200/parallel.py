@@ -583,7 +583,7 @@ def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, 
                 ws = torch.empty(lib.ppg_chain_heavy_workspace_bytes(heavy_slots, heavy_rows, n_slots), dtype=torch.uint8, device=dev)
                 extra = None if slots["last"] is slots["col"] else slots["last"]
                 _lib.check(lib.ppg_chain_heavy_fix(_ptr(slots["heavy"]), heavy_rows, heavy_slots, n_slots, _ptr(slots["col"]),
-                                                   _ptr(slots["lab"]), _ptr(slots["w"]), _ptr(extra), _ptr(ws), ws.numel(), stream))
+                                                   _ptr(slots["lab"]), _ptr(slots["w"]), _ptr(extra), None, None, _ptr(ws), ws.numel(), stream))
             next_starts = {j: mine[world + 4 + i] for i, j in enumerate(later)}
 
             mark(f"route_pack[{k}]")
