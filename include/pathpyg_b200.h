@@ -158,7 +158,6 @@ int ppg_lift_temporal_views(const void* workspace, int64_t num_edges, int64_t nu
  *   ppg_chain_heavy_fix     rows the tiles left in generation order: one radix sort over their pairs; then
  *   ppg_chain_heads         run heads of the slots again -> idS, id word of the node words, run_start, result[0]
  *   ppg_chain_fill          merged edges [2, merged] int64 + weights (unit weights when wS is NULL)
- *   ppg_chain_count         (distributed build) continuation counts of level >= 3 in label order from `tail`
  * ------------------------------------------------------------------------------------------- */
 int ppg_chain_heavy_default(void);
 int ppg_chain_tile_slots(void);
@@ -167,8 +166,6 @@ int ppg_chain_first_tiles(const int64_t* edge_index, int64_t num_edges, int64_t 
                           const uint32_t* grouped, const uint32_t* sorted_src, const float* weights, int heavy, uint32_t* rowS,
                           uint32_t* colS, uint32_t* labS, float* wS, uint32_t* idS, void* node_out, uint32_t* run_start,
                           void* tile_state, void* heavy_list, int64_t* result, void* stream);
-int ppg_chain_count(const uint32_t* tail, const void* ptr_prev, int64_t num_items, void* workspace, size_t workspace_bytes,
-                    uint32_t* first, void* ptr_next, int64_t* total, void* stream);
 int ppg_chain_count_sorted(const uint32_t* P, int64_t num_items, const uint32_t* first, const void* ptr_next,
                            const float* w_item, int64_t limit, const uint32_t* rowid, const uint32_t* run_start,
                            void* workspace, size_t workspace_bytes, void* offP, uint32_t* firstP, uint32_t* lblP, float* wP,
@@ -178,11 +175,14 @@ int ppg_chain_tiles(int64_t num_sources, int64_t num_rows, int64_t num_slots, co
                     const void* node_prev, const uint32_t* via, const uint32_t* srcbound, int heavy, uint32_t* rowS,
                     uint32_t* colS, uint32_t* labS, float* wS, uint32_t* idS, void* node_out, uint32_t* firstS, uint32_t* degS,
                     uint32_t* run_start_out, void* tile_state, void* heavy_list, int64_t* result, void* stream);
-int ppg_chain_node_ptr(const void* off, int64_t num_items, void* node, void* stream);
-int ppg_chain_scan_nodes(void* node, int64_t num_items, void* workspace, size_t workspace_bytes, int64_t* total, void* stream);
-int ppg_chain_count_sorted_next(const uint32_t* P, int64_t num_items, const uint32_t* degS, const void* node, int64_t limit,
-                                const uint32_t* rowid, const uint32_t* run_start, void* workspace, size_t workspace_bytes,
-                                void* offP, uint32_t* lblP, uint32_t* srcbound, void* stream);
+/* per-item words: u32 words `stride` apart, the one in question at index `word` (node words: stride 2, pointer word 1;
+ * info words of the distributed build: stride 4, pointer word 2) */
+int ppg_chain_node_ptr(const void* off, int64_t num_items, void* node, int stride, int word, void* stream);
+int ppg_chain_scan_nodes(void* node, int stride, int word, int64_t num_items, void* workspace, size_t workspace_bytes,
+                         int64_t* total, void* stream);
+int ppg_chain_count_sorted_next(const uint32_t* P, int64_t num_items, const uint32_t* degS, const void* node, int stride,
+                                int word, int64_t limit, const uint32_t* rowid, const uint32_t* run_start, void* workspace,
+                                size_t workspace_bytes, void* offP, uint32_t* lblP, uint32_t* srcbound, void* stream);
 int ppg_chain_heads(const uint32_t* rowS, const uint32_t* colS, const uint32_t* labS, int64_t num_slots, void* workspace,
                     size_t workspace_bytes, uint32_t* idS, uint32_t* id_item, int id_stride, uint32_t* run_start,
                     int64_t* result, void* stream);
@@ -195,33 +195,41 @@ int ppg_chain_fill(const uint32_t* rowS, const uint32_t* colS, const float* wS, 
 int ppg_chain_widen(const uint32_t* in, int in_stride, int64_t n, int64_t* out, void* stream);
 
 /* The same chain on a rank of a distributed build (no counterpart in /root/reference).  A rank expands its
- * items in the order of their GLOBAL merged ids, so its pairs are sorted by (row, col) in global ids and the pairs of one
- * owner (owners hold ascending row ranges) are one contiguous slot range; an owner merges one sorted run per sender.
- *   ppg_chain_tiles_dist    as ppg_chain_tiles with `info` by item (global id << 32 | last node) for colsrc, LOCAL rows
- *                           (rowid / run_start / row_value from ppg_chain_unpack), lastS out; rowS receives global ids
+ * items in the order of their GLOBAL merged ids, so its pairs leave as 16-byte records {col, row, last node, weight} sorted
+ * by (row, col) in global ids, and the records of one owner (owners hold ascending row ranges) are one contiguous range of
+ * the sender's buffer; an owner reads one sorted run per sender (peer memory), merges them in shared-memory tiles and
+ * stores the merged-edge index of every record into the sender's answer buffer.
+ *   info words  uint4 [items + 1] by label: {global id, last node, number of continuations -> row pointer, -}
+ *   ppg_chain_pack          level 1: the slot arrays of ppg_chain_first_tiles -> records
+ *   ppg_chain_tiles_dist    levels >= 2: as ppg_chain_tiles with info words for node words and LOCAL rows (rowid /
+ *                           run_start / row_value from ppg_chain_unpack); writes records, labS, firstS / degS and the
+ *                           count word of the new items' info words (info_out)
+ *   ppg_chain_heavy_fix_records  ppg_chain_heavy_fix for record slots
  *   ppg_chain_dest_bounds   first slot of every destination rank: dstart [world + 1], counts [world] (device int64)
- *   ppg_chain_pack          slots -> 16-byte records {col, row, last node, weight} into a local buffer or the owners'
- *                           receive buffers (peer memory), slot order
- *   ppg_merge_sorted        owner: merge the runs in shared-memory tiles of whole row ranges -> compact merged arrays +
- *                           the merged edge of every record; result[1] & 2: a tile overflowed, use ppg_merge_records_*
- *   ppg_chain_unpack        sender: returned indices -> global ids, local rows of the next level, info word of every item */
-int ppg_chain_tiles_dist(int64_t num_sources, int64_t num_rows, int64_t num_slots, const void* offP, const uint32_t* firstP,
-                         const uint32_t* lblP, const float* wP, const uint32_t* run_start, const uint32_t* rowid,
-                         const uint32_t* row_value, const void* info, const uint32_t* via, const uint32_t* srcbound, int heavy,
-                         uint32_t* rowS, uint32_t* colS, uint32_t* labS, float* wS, uint32_t* lastS, uint32_t* tail_out,
-                         float* w_item_out, uint32_t* run_start_scratch, void* tile_state, void* heavy_list, int64_t* result,
-                         void* stream);
-int ppg_chain_dest_bounds(const uint32_t* rowS, int64_t num_slots, const int64_t* offsets, int world, int64_t* dstart,
-                          int64_t* counts, void* stream);
+ *   ppg_merge_sorted        owner: merge the runs -> compact merged arrays + the merged edge of every record (into
+ *                           h_back[s]); result[1] & 2: a tile overflowed, use ppg_merge_records_* on a copy instead
+ *   ppg_chain_unpack        sender: returned indices -> global ids, local rows of the next level, info words */
 int ppg_chain_pack(const uint32_t* rowS, const uint32_t* colS, const uint32_t* lastS, const float* wS, int64_t num_slots,
-                   const int64_t* dstart, int world, void* out_records, void* const* h_peer_records, void* stream);
+                   void* records, void* stream);
+int ppg_chain_tiles_dist(int64_t num_sources, int64_t num_slots, const void* offP, const uint32_t* firstP, const uint32_t* lblP,
+                         const float* wP, int w_stride, const uint32_t* run_start, const uint32_t* rowid,
+                         const uint32_t* row_value, const void* info, const uint32_t* via, const uint32_t* srcbound, int heavy,
+                         void* records, uint32_t* labS, uint32_t* firstS, uint32_t* degS, void* info_out, void* tile_state,
+                         void* heavy_list, int64_t* result, void* stream);
+size_t ppg_chain_heavy_records_workspace_bytes(int64_t heavy_slots, int64_t heavy_rows, int64_t num_slots);
+int ppg_chain_heavy_fix_records(const void* heavy_list, int64_t heavy_rows, int64_t heavy_slots, int64_t num_slots, void* records,
+                                uint32_t* labS, uint32_t* firstS, uint32_t* degS, void* workspace, size_t workspace_bytes,
+                                void* stream);
+int ppg_chain_dest_bounds(const uint32_t* rows, int stride, int64_t num_slots, const int64_t* offsets, int world,
+                          int64_t* dstart, int64_t* counts, void* stream);
 int ppg_chain_unpack(const uint32_t* back, int64_t num_slots, const int64_t* dstart, const int64_t* edge_offsets, int world,
-                     const uint32_t* labS, const uint32_t* lastS, void* workspace, size_t workspace_bytes, uint32_t* rowid,
-                     uint32_t* run_start, uint32_t* row_value, void* info_item, int64_t* result, void* stream);
+                     const uint32_t* labS, const uint32_t* lastS, int last_stride, const uint32_t* degS, void* workspace,
+                     size_t workspace_bytes, uint32_t* rowid, uint32_t* run_start, uint32_t* row_value, void* info_item,
+                     int64_t* result, void* stream);
 int64_t ppg_merge_sorted_tiles(int64_t num_records);
-int ppg_merge_sorted(const void* records, int64_t num_records, const int64_t* seg, int world, int64_t row_lo, int64_t rows_owned,
-                     int64_t total_nodes, uint32_t* bounds, void* tile_state, uint32_t* out_inverse, uint32_t* row_m,
-                     uint32_t* col_m, float* w_m, uint32_t* last_m, int64_t* result, void* stream);
+int ppg_merge_sorted(void* const* h_runs, const int64_t* h_run_len, void* const* h_back, int world, int64_t row_lo,
+                     int64_t rows_owned, int64_t total_nodes, uint32_t* bounds, void* tile_state, uint32_t* row_m, uint32_t* col_m,
+                     float* w_m, uint32_t* last_m, int64_t* result, void* stream);
 int ppg_merge_sorted_fill(const uint32_t* row_m, const uint32_t* col_m, const float* w_m, const uint32_t* last_m,
                           int64_t num_out, int64_t* out_edge_index, float* out_weights, int64_t* out_last, void* stream);
 

@@ -50,22 +50,22 @@ PROTOTYPES = {
     "ppg_chain_tile_slots": (c_int, []),
     "ppg_chain_scan_workspace_bytes": (c_size_t, [_i64]),
     "ppg_chain_first_tiles": (c_int, [_p, _i64, _i64, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "ppg_chain_count": (c_int, [_p, _p, _i64, _p, c_size_t, _p, _p, _p, _p]),
     "ppg_chain_count_sorted": (c_int, [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, c_size_t, _p, _p, _p, _p, _p, _p]),
     "ppg_chain_tiles": (c_int, [_i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "ppg_chain_node_ptr": (c_int, [_p, _i64, _p, _p]),
-    "ppg_chain_scan_nodes": (c_int, [_p, _i64, _p, c_size_t, _p, _p]),
-    "ppg_chain_count_sorted_next": (c_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, c_size_t, _p, _p, _p, _p]),
+    "ppg_chain_node_ptr": (c_int, [_p, _i64, _p, c_int, c_int, _p]),
+    "ppg_chain_scan_nodes": (c_int, [_p, c_int, c_int, _i64, _p, c_size_t, _p, _p]),
+    "ppg_chain_count_sorted_next": (c_int, [_p, _i64, _p, _p, c_int, c_int, _i64, _p, _p, _p, c_size_t, _p, _p, _p, _p]),
     "ppg_chain_heads": (c_int, [_p, _p, _p, _i64, _p, c_size_t, _p, _p, c_int, _p, _p, _p]),
     "ppg_chain_heavy_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
     "ppg_chain_heavy_fix": (c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, c_size_t, _p]),
-    "ppg_chain_tiles_dist": (c_int, [_i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
-                                     _p, _p]),
-    "ppg_chain_dest_bounds": (c_int, [_p, _i64, _p, c_int, _p, _p, _p]),
-    "ppg_chain_pack": (c_int, [_p, _p, _p, _p, _i64, _p, c_int, _p, POINTER(c_void_p), _p]),
-    "ppg_chain_unpack": (c_int, [_p, _i64, _p, _p, c_int, _p, _p, _p, c_size_t, _p, _p, _p, _p, _p, _p]),
+    "ppg_chain_tiles_dist": (c_int, [_i64, _i64, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ppg_chain_dest_bounds": (c_int, [_p, c_int, _i64, _p, c_int, _p, _p, _p]),
+    "ppg_chain_pack": (c_int, [_p, _p, _p, _p, _i64, _p, _p]),
+    "ppg_chain_unpack": (c_int, [_p, _i64, _p, _p, c_int, _p, _p, c_int, _p, _p, c_size_t, _p, _p, _p, _p, _p, _p]),
     "ppg_merge_sorted_tiles": (_i64, [_i64]),
-    "ppg_merge_sorted": (c_int, [_p, _i64, _p, c_int, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "ppg_chain_heavy_records_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),
+    "ppg_chain_heavy_fix_records": (c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, c_size_t, _p]),
+    "ppg_merge_sorted": (c_int, [POINTER(c_void_p), _ph_i64, POINTER(c_void_p), c_int, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "ppg_merge_sorted_fill": (c_int, [_p, _p, _p, _p, _i64, _p, _p, _p, _p]),
     "ppg_chain_fill": (c_int, [_p, _p, _p, _p, _i64, _p, _p, _p]),
     "ppg_chain_widen": (c_int, [_p, c_int, _i64, _p, _p]),

@@ -141,7 +141,7 @@ class TemporalChain:
                 time, mode, delta_i, delta_f = ops._time_mode(time.contiguous(), delta)
                 _lib.check(lib.ppg_lift_temporal_count(_ptr(self.ei), _ptr(time), m, n, mode | _lib.TIME_GROUPED, delta_i, delta_f,
                                                        _ptr(tws), tws.numel(), None, stream))
-                _lib.check(lib.ppg_chain_node_ptr(off2, m, _ptr(l1.node), stream))     # node word of an event: id | first pair
+                _lib.check(lib.ppg_chain_node_ptr(off2, m, _ptr(l1.node), 2, 1, stream))     # node word of an event: id | first pair
                 words = torch.cat([self.res[1, :4], tws[:16].view(torch.int64)]).tolist()      # the synchronisation of order 1
             else:
                 words = self.res[1, :4].tolist() + [0, 0]
@@ -183,7 +183,7 @@ class TemporalChain:
                     via = grouped
                 else:        # the previous level's tiles left them in merged order
                     firstP = prev.firstS
-                    _lib.check(lib.ppg_chain_count_sorted_next(_ptr(prev.labS), ns, _ptr(prev.degS), _ptr(prev.node), ns, _ptr(prev.idS),
+                    _lib.check(lib.ppg_chain_count_sorted_next(_ptr(prev.labS), ns, _ptr(prev.degS), _ptr(prev.node), 2, 1, ns, _ptr(prev.idS),
                                                                _ptr(prev.run_start), _ptr(ws), ws.numel(), _ptr(offP), _ptr(lblP),
                                                                _ptr(srcbound), stream))
                     via = None
@@ -198,7 +198,7 @@ class TemporalChain:
                                                _ptr(self._tile_state(pairs)), _ptr(cur.heavy_list), _ptr(self.res[k]), stream))
                 if more:     # label-order scan of the counts: row pointer of the next level + its number of pairs
                     ws2 = self._scan_ws(pairs)
-                    _lib.check(lib.ppg_chain_scan_nodes(_ptr(cur.node), pairs, _ptr(ws2), ws2.numel(),
+                    _lib.check(lib.ppg_chain_scan_nodes(_ptr(cur.node), 2, 1, pairs, _ptr(ws2), ws2.numel(),
                                                         ctypes.c_void_p(self.res[k].data_ptr() + 8 * _RES_NEXT), stream))
                 inverse = self.inverse_idx(prev) if cached or not more else None
                 words = self.res[k].tolist()                                                      # the synchronisation of order k

@@ -46,18 +46,7 @@ static_assert(kChainCap % kChainBlock == 0 && kChainCap < 65535, "chunk geometry
 enum { kResHeads = 0, kResStatus = 1, kResHeavySlots = 2, kResHeavyRows = 3 };
 constexpr unsigned long long kChainStatusIdOutOfRange = 1ull;
 
-// ------------------------------------------------------------------ count in item order (levels >= 3)
-struct ChainCountProducer {
-  const uint32_t* tail;                  // [E] continuation node (a level-(k-1) item) of every level-k item
-  const unsigned long long* ptr_prev;    // [E_prev + 1] first level-k item of every level-(k-1) item
-  uint32_t* first;                       // out [E]
-  __device__ unsigned long long operator()(int64_t q) const {
-    const uint32_t t = ld_stream(tail + q);
-    const unsigned long long a = ptr_prev[t];
-    first[q] = static_cast<uint32_t>(a);
-    return ptr_prev[t + 1] - a;
-  }
-};
+// ------------------------------------------------------------------ offsets of a scan
 struct ChainOffsetConsumer {
   unsigned long long* off;
   int64_t n;
@@ -124,8 +113,6 @@ struct ChainTileArgs {
   int heavy;
   uint32_t *rowS, *colS, *labS;
   float* wS;
-  uint32_t* tail_out;              // DIST: [n_slots] by label or nullptr
-  float* w_item_out;               // DIST: [n_slots] by label or nullptr
   // what the next level needs (NEXT): by label the merged id | number of continuations << 32 (FIRST: the id word only),
   // and in slot order -- the merged order P of the next level -- the first continuation and their number
   unsigned long long* node_out;
@@ -136,10 +123,12 @@ struct ChainTileArgs {
   unsigned long long* tile_state;  // [tiles] zeroed
   unsigned code_partial, code_inclusive;
   uint32_t *idS, *run_start_out;
-  // distributed build (DIST): ids are global, rows are local
-  const unsigned long long* info;  // by item: global id << 32 | last first-order node (replaces colsrc)
-  const uint32_t* row_value;       // by local row: its global id (what rowS receives)
-  uint32_t* lastS;                 // out: last node of every slot's pair
+  // distributed build (DIST): ids are global, rows are local, the slots leave as 16-byte records
+  const uint4* info;               // by item: {global id, last first-order node, row pointer of THIS level, -} ([items + 1])
+  const uint32_t* row_value;       // by local row: its global id (the record's row)
+  uint4* rec;                      // out [n_slots]: {col id, row id, last node of the pair, weight}
+  uint4* info_out;                 // by label [n_slots + 1]: word 2 receives the pair's number of continuations (or nullptr)
+  int w_stride;                    // wP[s * w_stride] (DIST: the weight word of the previous level's records)
 };
 
 // largest s in [lo, hi) with off[s] <= target; requires off[lo] <= target
@@ -213,9 +202,8 @@ chain_tile_kernel(ChainTileArgs a) {
   uint32_t* s_row = reinterpret_cast<uint32_t*>(s_w + kChainCap);   // at a row's first slot: the row
   uint32_t* s_len = s_row + kChainCap;                              // at a row's first slot: its length; later: run index of every slot
   uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_len + kChainCap);
-  uint32_t* s_last = reinterpret_cast<uint32_t*>(s_perm + kChainCap);  // DIST only: last first-order node of every slot's pair
-  uint32_t* s_nfirst = s_last;                                         // NEXT only: first continuation at the next level ...
-  uint32_t* s_ndeg = s_nfirst + kChainCap;                             // ... and their number
+  uint32_t* s_nfirst = reinterpret_cast<uint32_t*>(s_perm + kChainCap);  // NEXT only: first continuation at the next level ...
+  uint32_t* s_ndeg = s_nfirst + kChainCap;                               // ... and their number
   __shared__ int64_t s_geo[4];
   __shared__ int64_t s_bound[2];
   __shared__ uint32_t s_warp_max[kChainBlock / 32];
@@ -312,7 +300,7 @@ chain_tile_kernel(ChainTileArgs a) {
         s_first[f0] = FIRST ? static_cast<uint32_t>(s) : a.firstP[s];
         const uint32_t lbl = a.lblP[s];
         s_lbl[f0] = lbl;
-        if (a.wS != nullptr) s_w[f0] = FIRST ? a.wP[lbl] : a.wP[s];
+        if (DIST || a.wS != nullptr) s_w[f0] = FIRST ? a.wP[lbl] : a.wP[s * a.w_stride];
         uint32_t mark = static_cast<uint32_t>(f0 + 1);
         if (c0 > 0 && f0 == 0) {  // chunks after the first hold only the tile's last (heavy) row
           mark |= 1u << 16;
@@ -370,12 +358,8 @@ chain_tile_kernel(ChainTileArgs a) {
         } else {
           const uint32_t g = s_first[f0] + static_cast<uint32_t>(jj);
           const uint32_t item = a.via != nullptr ? a.via[g] : g;
-          if (DIST) {  // global id << 32 | last node of the continuation
-            const unsigned long long info = a.info[item];
-            col = static_cast<uint32_t>(info >> 32);
-            s_last[i] = static_cast<uint32_t>(info);
-            if (a.tail_out != nullptr) a.tail_out[label] = item;
-            if (a.w_item_out != nullptr) a.w_item_out[label] = s_w[f0];
+          if (DIST) {  // the other words of the continuation's info are fetched again when the record is written
+            col = a.info[item].x;
           } else {     // merged id | first level-k item whose source is this item << 32
             const unsigned long long nd = a.node_prev[item];
             col = static_cast<uint32_t>(nd);
@@ -487,11 +471,25 @@ chain_tile_kernel(ChainTileArgs a) {
           st_stream(a.firstS + cb + p, s_nfirst[i]);
           st_stream(a.degS + cb + p, ndeg[k]);
         }
-        st_stream(a.rowS + cb + p, DIST ? a.row_value[s_row[g0]] : s_row[g0]);
-        st_stream(a.colS + cb + p, s_col[i]);
-        if (DIST) st_stream(a.lastS + cb + p, s_last[i]);
         st_stream(a.labS + cb + p, label[k]);
-        if (a.wS != nullptr) st_stream(a.wS + cb + p, s_w[f0]);
+        if (DIST) {
+          // the continuation's info words again (this CTA read them a moment ago: L1 / L2), so that neither the last
+          // node nor the next level's counts have to be parked in shared memory
+          const uint32_t g = s_first[f0] + static_cast<uint32_t>(jj);
+          const uint32_t item = a.via != nullptr ? a.via[g] : g;
+          const uint4 nf = a.info[item];
+          if (a.firstS != nullptr) {
+            const uint32_t deg = a.info[item + 1].z - nf.z;
+            st_stream(a.firstS + cb + p, nf.z);
+            st_stream(a.degS + cb + p, deg);
+            reinterpret_cast<uint32_t*>(a.info_out + label[k])[2] = deg;
+          }
+          __stcs(a.rec + cb + p, make_uint4(s_col[i], a.row_value[s_row[g0]], nf.y, __float_as_uint(s_w[f0])));
+        } else {
+          st_stream(a.rowS + cb + p, s_row[g0]);
+          st_stream(a.colS + cb + p, s_col[i]);
+          if (a.wS != nullptr) st_stream(a.wS + cb + p, s_w[f0]);
+        }
       }
     }
     // ... then the merged ids, once the number of run heads before this tile is known
@@ -528,7 +526,6 @@ chain_tile_kernel(ChainTileArgs a) {
 }
 
 constexpr size_t kChainTileSmem = static_cast<size_t>(kChainCap) * (8 * 4 + 2);
-constexpr size_t kChainTileSmemDist = kChainTileSmem + static_cast<size_t>(kChainCap) * 4;
 constexpr size_t kChainTileSmemNext = kChainTileSmem + static_cast<size_t>(kChainCap) * 8;
 
 // ------------------------------------------------------------------ heads
@@ -591,23 +588,27 @@ chain_widen_kernel(const uint32_t* __restrict__ in, int in_stride, int64_t n, in
 
 // level 1: the row pointer of the event graph (u64, lift.cu) into the ptr word of the events' node words
 __global__ void __launch_bounds__(256)
-chain_node_ptr_kernel(const unsigned long long* __restrict__ off, int64_t n_plus_1, unsigned long long* __restrict__ node) {
+chain_node_ptr_kernel(const unsigned long long* __restrict__ off, int64_t n_plus_1, uint32_t* __restrict__ words, int word_stride) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_plus_1; i += stride)
-    reinterpret_cast<uint32_t*>(node)[2 * i + 1] = static_cast<uint32_t>(ld_stream(off + i));
+    words[i * word_stride] = static_cast<uint32_t>(ld_stream(off + i));
 }
 
-// label-order scan of the continuation counts the tiles left in the node words: count -> row pointer of the next level
+// label-order scan of the continuation counts the tiles left in the per-item words: count -> row pointer of the next
+// level.  The word of item i is words[i * stride] (node words: the high word, stride 2; info words of the distributed
+// build: the third word, stride 4).
 struct NodeDegProducer {
-  const unsigned long long* node;
-  __device__ unsigned long long operator()(int64_t i) const { return node[i] >> 32; }
+  const uint32_t* words;
+  int stride;
+  __device__ unsigned long long operator()(int64_t i) const { return words[i * stride]; }
 };
 struct NodePtrConsumer {
-  unsigned long long* node;
+  uint32_t* words;
+  int stride;
   int64_t n;
   __device__ void operator()(int64_t i, unsigned long long v, unsigned long long prefix) const {
-    reinterpret_cast<uint32_t*>(node)[2 * i + 1] = static_cast<uint32_t>(prefix);
-    if (i == n - 1) reinterpret_cast<uint32_t*>(node)[2 * n + 1] = static_cast<uint32_t>(prefix + v);
+    words[i * stride] = static_cast<uint32_t>(prefix);
+    if (i == n - 1) words[n * stride] = static_cast<uint32_t>(prefix + v);
   }
 };
 
@@ -616,12 +617,13 @@ struct NodePtrConsumer {
 struct ChainSortedProducer2 {
   const uint32_t* P;
   const uint32_t* degS;
-  const unsigned long long* node;   // by label: id | row pointer of the next level << 32 (after the label-order scan)
+  const uint32_t* ptr_words;   // by label, `stride` words apart: row pointer of the next level (after the label-order scan)
+  int stride;
   int64_t limit;
   uint32_t* lblP;
   __device__ unsigned long long operator()(int64_t s) const {
     const uint32_t q = ld_stream(P + s);
-    lblP[s] = static_cast<uint32_t>(node[q] >> 32);
+    lblP[s] = ptr_words[static_cast<int64_t>(q) * stride];
     return static_cast<int64_t>(q) < limit ? ld_stream(degS + s) : 0u;
   }
 };
@@ -722,11 +724,14 @@ heavy_write_kernel(const unsigned long long* __restrict__ keys, int64_t slots, c
 }
 
 // ================================================================== distributed build
-// Every rank expands ITS items in the order of their GLOBAL merged ids, so its pairs come out sorted by (row, col) with
-// global ids, ties in stream order; the owners hold ascending row ranges, hence the pairs of one owner are one
-// contiguous range of slots: no partition pass.  An owner receives one sorted run per sender and merges the runs in
-// shared-memory tiles of whole row ranges (rank of a record = its index in its own run + binary searches in the other
-// runs: senders in rank order = stream order, so equal keys stay in the single-device summation order).
+// Every rank expands ITS items in the order of their GLOBAL merged ids, so its pairs come out as 16-byte records sorted by
+// (row, col) in global ids, ties in stream order; the owners hold ascending row ranges, hence the records of one owner are
+// one contiguous range of the sender's buffer: no partition pass, no pack pass.  An owner READS one sorted run per sender
+// straight from the senders' buffers (NVLink peer memory), merges the runs in shared-memory tiles of whole row ranges
+// (rank of a record = its index in its own run + binary searches in the other runs: senders in rank order = stream
+// order, so equal keys stay in the single-device summation order) and WRITES the merged-edge index of every record
+// straight into the sender's answer buffer: the transfer in both directions is the merge kernel's own load and store
+// stream.
 constexpr int kMergeBlock = 256;
 constexpr int kMergeTile = 1024;  // records a tile is sized for
 constexpr int kMergeCap = 2048;   // records a tile can hold (uniform row ranges: load varies)
@@ -734,8 +739,8 @@ constexpr int kMergePerThread = kMergeCap / kMergeBlock;
 constexpr int kMaxRanks = PPG_ROUTE_MAX_RANKS;
 constexpr unsigned long long kMergeStatusOverflow = 2ull;
 
-// first slot of every destination: rows are ascending, owners hold ascending row ranges
-__global__ void chain_dest_bounds_kernel(const uint32_t* __restrict__ rowS, int64_t n, const int64_t* __restrict__ offsets,
+// first slot of every destination: rows are ascending (rows[i * stride]), owners hold ascending row ranges
+__global__ void chain_dest_bounds_kernel(const uint32_t* __restrict__ rows, int stride, int64_t n, const int64_t* __restrict__ offsets,
                                          int world, int64_t* __restrict__ dstart, int64_t* __restrict__ counts) {
   __shared__ int64_t s_start[kMaxRanks + 1];
   const int d = threadIdx.x;
@@ -745,7 +750,7 @@ __global__ void chain_dest_bounds_kernel(const uint32_t* __restrict__ rowS, int6
     const int64_t target = offsets[d];
     while (lo < hi) {
       const int64_t mid = lo + ((hi - lo) >> 1);
-      if (static_cast<int64_t>(rowS[mid]) >= target) hi = mid; else lo = mid + 1;
+      if (static_cast<int64_t>(rows[mid * stride]) >= target) hi = mid; else lo = mid + 1;
     }
     if (d == 0) lo = 0;
     s_start[d] = lo;
@@ -755,35 +760,72 @@ __global__ void chain_dest_bounds_kernel(const uint32_t* __restrict__ rowS, int6
   if (d < world) counts[d] = s_start[d + 1] - s_start[d];
 }
 
-struct PackTargets {
-  uint4* local;
-  uint4* peer[kMaxRanks];
-};
+// level 1: slot arrays -> records
 __global__ void __launch_bounds__(256)
 chain_pack_kernel(const uint32_t* __restrict__ rowS, const uint32_t* __restrict__ colS, const uint32_t* __restrict__ lastS,
-                  const float* __restrict__ wS, int64_t n, const int64_t* __restrict__ dstart, int world, PackTargets targets) {
-  __shared__ int64_t s_start[kMaxRanks + 1];
-  if (threadIdx.x <= world) s_start[threadIdx.x] = dstart[threadIdx.x];
-  __syncthreads();
+                  const float* __restrict__ wS, int64_t n, uint4* __restrict__ rec) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n; p += stride) {
-    uint4 rec;
-    rec.x = ld_stream(colS + p);
-    rec.y = ld_stream(rowS + p);
-    rec.z = ld_stream(lastS + p);
-    rec.w = wS != nullptr ? __float_as_uint(ld_stream(wS + p)) : __float_as_uint(1.f);
-    if (targets.local != nullptr) {
-      targets.local[p] = rec;
-    } else {
-      int d = 0;
-      for (int j = 1; j < world; ++j) d += p >= s_start[j] ? 1 : 0;
-      targets.peer[d][p - s_start[d]] = rec;
+  for (int64_t p = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; p < n; p += stride)
+    __stcs(rec + p, make_uint4(ld_stream(colS + p), ld_stream(rowS + p), ld_stream(lastS + p),
+                               wS != nullptr ? __float_as_uint(ld_stream(wS + p)) : __float_as_uint(1.f)));
+}
+
+// heavy rows of a level whose slots are records: the same fix as ppg_chain_heavy_fix, the record travels as a whole
+__global__ void __launch_bounds__(256)
+heavy_compact_rec_kernel(const uint2* __restrict__ list, const unsigned long long* __restrict__ hoff, int64_t rows, int64_t slots,
+                         const uint4* __restrict__ rec, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t c = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; c < slots; c += stride) {
+    int64_t lo = 0, hi = rows;
+    while (hi - lo > 1) {
+      const int64_t mid = lo + ((hi - lo) >> 1);
+      if (hoff[mid] <= static_cast<unsigned long long>(c)) lo = mid; else hi = mid;
     }
+    const uint2 row = list[lo];
+    const uint32_t slot = row.x + static_cast<uint32_t>(c - static_cast<int64_t>(hoff[lo]));
+    keys[c] = (static_cast<unsigned long long>(row.x) << 32) | rec[slot].x;
+    vals[c] = slot;
+  }
+}
+__global__ void __launch_bounds__(256)
+heavy_gather_rec_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t slots,
+                        const uint4* __restrict__ rec, const uint32_t* __restrict__ labS, HeavyExtras extraS,
+                        uint4* __restrict__ t_rec, uint32_t* __restrict__ t_lab, HeavyExtras t_extra, uint32_t* __restrict__ t_dest) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slots; i += stride) {
+    const unsigned long long k = keys[i];
+    const unsigned long long row_key = k & 0xffffffff00000000ull;
+    int64_t lo = -1, hi = i;
+    while (hi - lo > 1) {
+      const int64_t mid = lo + ((hi - lo) >> 1);
+      if (keys[mid] >= row_key) hi = mid; else lo = mid;
+    }
+    const uint32_t src = vals[i];
+    t_dest[i] = static_cast<uint32_t>(k >> 32) + static_cast<uint32_t>(i - hi);
+    t_rec[i] = rec[src];
+    t_lab[i] = labS[src];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (extraS.p[j] != nullptr) t_extra.p[j][i] = extraS.p[j][src];
+  }
+}
+__global__ void __launch_bounds__(256)
+heavy_write_rec_kernel(int64_t slots, const uint4* __restrict__ t_rec, const uint32_t* __restrict__ t_lab, HeavyExtras t_extra,
+                       const uint32_t* __restrict__ t_dest, uint4* __restrict__ rec, uint32_t* __restrict__ labS, HeavyExtras extraS) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < slots; i += stride) {
+    const uint32_t d = t_dest[i];
+    rec[d] = t_rec[i];
+    labS[d] = t_lab[i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (extraS.p[j] != nullptr) extraS.p[j][d] = t_extra.p[j][i];
   }
 }
 
-// ids come back in slot order: global id = owner's first merged edge + returned index.  One scan turns them into the
-// row structure of the next level (local rows = distinct global ids among the local items) and the per-item info words.
+// The owners' answers (merged-edge index of every record, slot order) -> global ids.  One scan turns them into the row
+// structure of the next level (local rows = distinct global ids among the local items) and the info word of every item
+// {global id, last node, number of continuations (row pointer after ppg_chain_scan_nodes), -}.
 struct UnpackProducer {
   const uint32_t* back;
   const int64_t* dstart;
@@ -799,11 +841,13 @@ struct UnpackProducer {
 struct UnpackConsumer {
   UnpackProducer ids;
   const uint32_t* labS;
-  const uint32_t* lastS;
+  const uint32_t* lastS;             // last node of every slot, `last_stride` words apart (records: the third word)
+  int last_stride;
+  const uint32_t* degS;              // continuations of every slot at the next level or nullptr
   uint32_t* rowid;                   // local row of every slot
   uint32_t* run_start;               // [local rows + 1]
   uint32_t* row_value;               // global id of every local row
-  unsigned long long* info_item;     // by label: global id << 32 | last node
+  uint4* info_item;                  // by label
   int64_t n;
   __device__ void operator()(int64_t i, unsigned long long head, unsigned long long prefix) const {
     const unsigned long long g = ids.gid(i);
@@ -814,27 +858,36 @@ struct UnpackConsumer {
       row_value[r] = static_cast<uint32_t>(g);
     }
     if (i == n - 1) run_start[r + 1] = static_cast<uint32_t>(n);
-    info_item[labS[i]] = (g << 32) | lastS[i];
+    uint32_t* out = reinterpret_cast<uint32_t*>(info_item + labS[i]);
+    *reinterpret_cast<uint2*>(out) = make_uint2(static_cast<uint32_t>(g), lastS[i * last_stride]);
+    if (degS != nullptr) out[2] = degS[i];
   }
 };
 
 // ---- owner side
+struct MergeRuns {
+  const uint4* run[kMaxRanks];   // first record of every sender's run for this owner (peer memory or a local copy)
+  uint32_t len[kMaxRanks];
+  uint32_t* back[kMaxRanks];     // where the merged-edge index of every record of the run goes
+  int world;
+};
+
 __global__ void __launch_bounds__(256)
-merge_bounds_kernel(const uint4* __restrict__ records, const int64_t* __restrict__ seg, int world, long long row_lo,
-                    long long rows_per_tile, int64_t n_tiles, uint32_t* __restrict__ bnd) {
-  const int64_t total = (n_tiles + 1) * world;
+merge_bounds_kernel(MergeRuns runs, long long row_lo, long long rows_per_tile, int64_t n_tiles, uint32_t* __restrict__ bnd) {
+  const int64_t total = (n_tiles + 1) * runs.world;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; k < total; k += stride) {
-    const int64_t t = k / world;
-    const int s = static_cast<int>(k - t * world);
-    int64_t lo = seg[s], hi = seg[s + 1];
+    const int64_t t = k / runs.world;
+    const int s = static_cast<int>(k - t * runs.world);
+    int64_t lo = 0, hi = runs.len[s];
     if (t == n_tiles) {
       lo = hi;
     } else {
+      const uint4* __restrict__ rec = runs.run[s];
       const long long target = row_lo + t * rows_per_tile;
       while (lo < hi) {
         const int64_t mid = lo + ((hi - lo) >> 1);
-        if (static_cast<long long>(records[mid].y) >= target) hi = mid; else lo = mid + 1;
+        if (static_cast<long long>(rec[mid].y) >= target) hi = mid; else lo = mid + 1;
       }
     }
     bnd[k] = static_cast<uint32_t>(lo);
@@ -842,11 +895,9 @@ merge_bounds_kernel(const uint4* __restrict__ records, const int64_t* __restrict
 }
 
 struct MergeArgs {
-  const uint4* records;
-  const uint32_t* bnd;  // [(tiles + 1) * world]
-  int world;
+  MergeRuns runs;
+  const uint32_t* bnd;  // [(tiles + 1) * world]: first record of every run in every tile
   long long row_lo, rows_owned, total_nodes, rows_per_tile;
-  uint32_t* inverse;    // [R] merged edge (local index) of every record, arrival order
   uint32_t *row_m, *col_m, *last_m;
   float* w_m;
   unsigned long long* tile_state;
@@ -869,19 +920,20 @@ merge_tile_kernel(MergeArgs a) {
   const unsigned lane = lane_id();
   const unsigned tile = blockIdx.x;
   const bool last_tile = tile == gridDim.x - 1;
+  const int world = a.runs.world;
   if (tid == 0) {
     uint32_t run = 0;
-    for (int s = 0; s < a.world; ++s) {
-      const uint32_t lo = a.bnd[static_cast<size_t>(tile) * a.world + s];
-      const uint32_t hi = a.bnd[static_cast<size_t>(tile + 1) * a.world + s];
+    for (int s = 0; s < world; ++s) {
+      const uint32_t lo = a.bnd[static_cast<size_t>(tile) * world + s];
+      const uint32_t hi = a.bnd[static_cast<size_t>(tile + 1) * world + s];
       s_lo[s] = lo;
       s_off[s] = run;
       run += hi - lo;
     }
-    s_off[a.world] = run;
+    s_off[world] = run;
   }
   __syncthreads();
-  const int n = static_cast<int>(s_off[a.world]);
+  const int n = static_cast<int>(s_off[world]);
   if (n == 0 || n > kMergeCap) {
     if (warp == 0) {
       if (n > kMergeCap && lane == 0) atomicOr(a.result + 1, kMergeStatusOverflow);
@@ -892,11 +944,11 @@ merge_tile_kernel(MergeArgs a) {
     return;
   }
   const long long row0 = a.row_lo + static_cast<long long>(tile) * a.rows_per_tile;
-  // ---- load the slices, sender after sender
+  // ---- load the slices, sender after sender (remote senders: NVLink peer loads)
   for (int i = tid; i < n; i += kMergeBlock) {
     int s = 0;
-    for (int j = 1; j < a.world; ++j) s += static_cast<uint32_t>(i) >= s_off[j] ? 1 : 0;
-    const uint4 r = __ldcs(a.records + s_lo[s] + (i - s_off[s]));
+    for (int j = 1; j < world; ++j) s += static_cast<uint32_t>(i) >= s_off[j] ? 1 : 0;
+    const uint4 r = a.runs.run[s][s_lo[s] + (i - s_off[s])];
     const long long row = static_cast<long long>(r.y);
     if (row < a.row_lo || row >= a.row_lo + a.rows_owned || static_cast<long long>(r.x) >= a.total_nodes)
       atomicOr(a.result + 1, kChainStatusIdOutOfRange);
@@ -908,10 +960,10 @@ merge_tile_kernel(MergeArgs a) {
   // ---- rank of every record in the merge of the runs (stable: earlier senders first among equal keys)
   for (int i = tid; i < n; i += kMergeBlock) {
     int s = 0;
-    for (int j = 1; j < a.world; ++j) s += static_cast<uint32_t>(i) >= s_off[j] ? 1 : 0;
+    for (int j = 1; j < world; ++j) s += static_cast<uint32_t>(i) >= s_off[j] ? 1 : 0;
     const unsigned long long key = s_key[i];
     int rank = i - static_cast<int>(s_off[s]);
-    for (int q = 0; q < a.world; ++q) {
+    for (int q = 0; q < world; ++q) {
       if (q == s) continue;
       int lo = static_cast<int>(s_off[q]), hi = static_cast<int>(s_off[q + 1]);
       const int begin = lo;
@@ -981,8 +1033,8 @@ merge_tile_kernel(MergeArgs a) {
     const uint32_t run = s_run[p];
     const uint32_t id = static_cast<uint32_t>(base_id + run);
     int s = 0;
-    for (int j = 1; j < a.world; ++j) s += static_cast<uint32_t>(i) >= s_off[j] ? 1 : 0;
-    a.inverse[s_lo[s] + (i - s_off[s])] = id;
+    for (int j = 1; j < world; ++j) s += static_cast<uint32_t>(i) >= s_off[j] ? 1 : 0;
+    a.runs.back[s][s_lo[s] + (i - s_off[s])] = id;   // remote senders: NVLink peer store
     if (p == 0 || s_run[p - 1] != run) {
       const unsigned long long key = s_key[i];
       float acc = s_w[i];
@@ -1018,23 +1070,18 @@ static int launch_tiles(ChainTileArgs& a, bool first, cudaStream_t stream) {
   PPG_CUDA_TRY(cudaMemsetAsync(a.tile_state, 0, static_cast<size_t>(tiles) * sizeof(unsigned long long), stream));
   // algorithmic bytes of the launch (what the kernel must read and write once), for the live roofline of bench.py
   const bool dist = !first && a.info != nullptr;
+  if (a.w_stride < 1) a.w_stride = 1;
   const long long per_source = first ? 4 + 4 + 8 + (a.wS != nullptr ? 4 : 0) : 8 + 4 + 4 + 4 + (a.wS != nullptr ? 4 : 0);
   const bool next = !first && !dist && a.node_out != nullptr;
-  const long long per_slot = (first ? 0 : 8 + (a.via != nullptr ? 4 : 0)) + 12 + (a.wS != nullptr ? 4 : 0) +
-                             (a.idS != nullptr ? 4 : 0) + (a.node_out != nullptr ? (first ? 4 : 8) : 0) + (next ? 8 : 0) +
-                             (a.tail_out != nullptr ? 4 : 0) + (a.w_item_out != nullptr ? 4 : 0) + (dist ? 4 : 0);
+  const long long per_slot = dist ? 16 + (a.via != nullptr ? 4 : 0) + 16 + 4 + (a.firstS != nullptr ? 12 : 0)
+                                  : (first ? 0 : 8 + (a.via != nullptr ? 4 : 0)) + 12 + (a.wS != nullptr ? 4 : 0) +
+                                        (a.idS != nullptr ? 4 : 0) + (a.node_out != nullptr ? (first ? 4 : 8) : 0) + (next ? 8 : 0);
   const long long launch_bytes = per_source * a.n_sources + per_slot * a.n_slots;
   profile_pass_begin(stream);
   if (first) {
     chain_tile_kernel<true, false, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
   } else if (dist) {
-    static bool configured = false;
-    if (!configured) {
-      PPG_CUDA_TRY(cudaFuncSetAttribute(chain_tile_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kChainTileSmemDist)));
-      configured = true;
-    }
-    chain_tile_kernel<false, true, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmemDist, stream>>>(a);
+    chain_tile_kernel<false, true, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
   } else if (next) {
     static bool configured = false;
     if (!configured) {
@@ -1130,25 +1177,6 @@ extern "C" int ppg_chain_widen(const uint32_t* in, int in_stride, int64_t n, int
   return PPG_OK;
 }
 
-// Count pass of level k + 1 in item order (k >= 2): first continuation and row pointer of every level-k item.
-// total[0] = number of level-(k+1) items.
-extern "C" int ppg_chain_count(const uint32_t* tail, const void* ptr_prev, int64_t E, void* workspace, size_t workspace_bytes,
-                               uint32_t* first, void* ptr_next, int64_t* total, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  PPG_REQUIRE(E >= 0 && E < (1ll << 31), PPG_ERR_INVALID, "chain: %lld items outside [0, 2^31)", (long long)E);
-  const size_t need = ppg_chain_scan_workspace_bytes(E);
-  PPG_REQUIRE(workspace_bytes >= need, PPG_ERR_WORKSPACE, "chain_count: workspace %zu < %zu bytes", workspace_bytes, need);
-  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, stream));
-  if (E == 0) {
-    PPG_CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(int64_t), stream));
-    PPG_CUDA_TRY(cudaMemsetAsync(ptr_next, 0, sizeof(unsigned long long), stream));
-    return PPG_OK;
-  }
-  return launch_scan(ChainCountProducer{tail, static_cast<const unsigned long long*>(ptr_prev), first},
-                     ChainOffsetConsumer{static_cast<unsigned long long*>(ptr_next), E}, E,
-                     static_cast<unsigned long long*>(workspace), reinterpret_cast<unsigned long long*>(total), stream);
-}
-
 // Count pass in merged order: slot offsets of the expansion, per-source data in that order, tile boundaries.
 extern "C" int ppg_chain_count_sorted(const uint32_t* P, int64_t n, const uint32_t* first, const void* ptr_next,
                                       const float* w_item, int64_t limit, const uint32_t* rowid, const uint32_t* run_start,
@@ -1242,84 +1270,115 @@ extern "C" int ppg_chain_heavy_fix(const void* heavy_list, int64_t heavy_rows, i
 }
 
 // =================================================================== distributed build (see the kernels above)
-// Tiles of a level on a rank of a distributed build: `info` by item = global id << 32 | last node; rowid / run_start /
-// row_value describe the LOCAL rows (distinct global ids among the local items, from ppg_chain_unpack); rowS receives
-// global ids.  The run heads the kernel finds are local and unused (the owners merge): idS / id_item may be NULL.
-extern "C" int ppg_chain_tiles_dist(int64_t n_sources, int64_t n_rows, int64_t n_slots, const void* offP, const uint32_t* firstP,
-                                    const uint32_t* lblP, const float* wP, const uint32_t* run_start, const uint32_t* rowid,
-                                    const uint32_t* row_value, const void* info, const uint32_t* via, const uint32_t* srcbound,
-                                    int heavy, uint32_t* rowS, uint32_t* colS, uint32_t* labS, float* wS, uint32_t* lastS,
-                                    uint32_t* tail_out, float* w_item_out, uint32_t* run_start_scratch, void* tile_state,
-                                    void* heavy_list, int64_t* result, void* stream_) {
+// Tiles of a level >= 2 on a rank of a distributed build: `info` by item = {global id, last node, row pointer of this
+// level, -}; rowid / run_start / row_value describe the LOCAL rows (distinct global ids among the local items, from
+// ppg_chain_unpack); the slots leave as records (rec), with labS and -- if a level follows -- firstS / degS.
+// wP: weight of every source, w_stride words apart (the weight word of the previous level's records).
+extern "C" int ppg_chain_tiles_dist(int64_t n_sources, int64_t n_slots, const void* offP, const uint32_t* firstP,
+                                    const uint32_t* lblP, const float* wP, int w_stride, const uint32_t* run_start,
+                                    const uint32_t* rowid, const uint32_t* row_value, const void* info, const uint32_t* via,
+                                    const uint32_t* srcbound, int heavy, void* rec, uint32_t* labS, uint32_t* firstS, uint32_t* degS,
+                                    void* info_out, void* tile_state, void* heavy_list, int64_t* result, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  PPG_REQUIRE(n_sources > 0 && n_sources < (1ll << 31) && n_slots >= 0 && n_slots < (1ll << 31) && n_rows > 0, PPG_ERR_INVALID,
+  PPG_REQUIRE(n_sources > 0 && n_sources < (1ll << 31) && n_slots >= 0 && n_slots < (1ll << 31), PPG_ERR_INVALID,
               "chain: sizes outside [0, 2^31)");
   PPG_REQUIRE(heavy >= 1 && heavy <= kChainHeavyMax, PPG_ERR_INVALID, "chain: heavy threshold %d outside [1, %d]", heavy, kChainHeavyMax);
-  PPG_REQUIRE(wP != nullptr && wS != nullptr && info != nullptr && row_value != nullptr && lastS != nullptr, PPG_ERR_INVALID,
-              "chain (distributed): weights, info words, row values and lastS are required");
+  PPG_REQUIRE(wP != nullptr && info != nullptr && row_value != nullptr && rec != nullptr && (firstS == nullptr) == (degS == nullptr) &&
+                  (firstS == nullptr) == (info_out == nullptr),
+              PPG_ERR_INVALID, "chain (distributed): weights, info words, row values and the record buffer are required");
   ChainTileArgs a = {};
   a.offP = static_cast<const unsigned long long*>(offP);
   a.firstP = firstP;
   a.lblP = lblP;
   a.wP = wP;
+  a.w_stride = w_stride;
   a.run_start = run_start;
   a.rowid = rowid;
   a.row_value = row_value;
-  a.info = static_cast<const unsigned long long*>(info);
+  a.info = static_cast<const uint4*>(info);
   a.via = via;
   a.srcbound = srcbound;
   a.n_sources = n_sources;
-  a.n_rows = n_rows;
+  a.n_rows = 1;
   a.n_slots = n_slots;
   a.heavy = heavy;
-  a.rowS = rowS;
-  a.colS = colS;
+  a.rec = static_cast<uint4*>(rec);
   a.labS = labS;
-  a.wS = wS;
-  a.lastS = lastS;
-  a.tail_out = tail_out;
-  a.w_item_out = w_item_out;
+  a.firstS = firstS;
+  a.degS = degS;
+  a.info_out = static_cast<uint4*>(info_out);
   a.heavy_list = static_cast<uint2*>(heavy_list);
   a.result = reinterpret_cast<unsigned long long*>(result);
-  a.run_start_out = run_start_scratch;
   a.tile_state = static_cast<unsigned long long*>(tile_state);
   return launch_tiles(a, false, stream);
 }
 
-// First slot of every destination rank (dstart [world + 1], counts [world]; device int64) among slots whose rows ascend.
-extern "C" int ppg_chain_dest_bounds(const uint32_t* rowS, int64_t n_slots, const int64_t* offsets, int world, int64_t* dstart,
-                                     int64_t* counts, void* stream_) {
+// First slot of every destination rank (dstart [world + 1], counts [world]; device int64) among slots whose rows
+// (rows[i * stride]: stride 1 for a slot array, 4 from the row word of the records) ascend.
+extern "C" int ppg_chain_dest_bounds(const uint32_t* rows, int stride, int64_t n_slots, const int64_t* offsets, int world,
+                                     int64_t* dstart, int64_t* counts, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PPG_REQUIRE(world >= 1 && world <= kMaxRanks, PPG_ERR_INVALID, "chain: %d ranks outside [1, %d]", world, kMaxRanks);
-  chain_dest_bounds_kernel<<<1, 32, 0, stream>>>(rowS, n_slots, offsets, world, dstart, counts);
+  chain_dest_bounds_kernel<<<1, 32, 0, stream>>>(rows, stride < 1 ? 1 : stride, n_slots, offsets, world, dstart, counts);
   PPG_LAUNCHED();
   return PPG_OK;
 }
 
-// Slots -> 16-byte records {col id, row id, last node, weight}, either into one local buffer (slot order = destination
-// order) or straight into the owners' receive buffers (h_peer_records[d] = first record reserved for this sender).
+// Level 1: slot arrays -> records {col, row, last node, weight} in slot order.
 extern "C" int ppg_chain_pack(const uint32_t* rowS, const uint32_t* colS, const uint32_t* lastS, const float* wS, int64_t n_slots,
-                              const int64_t* dstart, int world, void* out_records, void* const* h_peer_records, void* stream_) {
+                              void* rec, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n_slots == 0) return PPG_OK;
-  PPG_REQUIRE(world >= 1 && world <= kMaxRanks, PPG_ERR_INVALID, "chain: %d ranks outside [1, %d]", world, kMaxRanks);
-  PPG_REQUIRE((out_records != nullptr) != (h_peer_records != nullptr), PPG_ERR_INVALID,
-              "chain_pack: give either a local record buffer or the peers' receive buffers");
-  PackTargets targets = {};
-  targets.local = static_cast<uint4*>(out_records);
-  if (h_peer_records != nullptr)
-    for (int d = 0; d < world; ++d) targets.peer[d] = static_cast<uint4*>(h_peer_records[d]);
-  chain_pack_kernel<<<grid_for(n_slots, 256 * 4), 256, 0, stream>>>(rowS, colS, lastS, wS, n_slots, dstart, world, targets);
+  chain_pack_kernel<<<grid_for(n_slots, 256 * 4), 256, 0, stream>>>(rowS, colS, lastS, wS, n_slots, static_cast<uint4*>(rec));
   PPG_LAUNCHED();
   return PPG_OK;
 }
 
-// The owners' answers (back [n_slots], slot order) -> local row structure of the next level + info word of every item.
+extern "C" size_t ppg_chain_heavy_records_workspace_bytes(int64_t heavy_slots, int64_t heavy_rows, int64_t n_slots) {
+  Workspace ws(nullptr, 0);
+  HeavyLayout L(ws, heavy_slots, heavy_rows, n_slots);
+  ws.take<uint4>(static_cast<size_t>(heavy_slots));
+  return ws.used + 256;
+}
+
+// ppg_chain_heavy_fix for a level whose slots are records (distributed build, levels >= 2).
+extern "C" int ppg_chain_heavy_fix_records(const void* heavy_list, int64_t heavy_rows, int64_t heavy_slots, int64_t n_slots,
+                                           void* rec_, uint32_t* labS, uint32_t* firstS, uint32_t* degS, void* workspace,
+                                           size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (heavy_rows == 0 || heavy_slots == 0) return PPG_OK;
+  Workspace ws(workspace, workspace_bytes);
+  HeavyLayout L(ws, heavy_slots, heavy_rows, n_slots);
+  uint4* t_rec = ws.take<uint4>(static_cast<size_t>(heavy_slots));
+  PPG_REQUIRE(ws.fits(), PPG_ERR_WORKSPACE, "chain_heavy_fix_records: workspace %zu < %zu bytes", workspace_bytes, ws.used);
+  PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, L.zero_bytes, stream));
+  uint4* rec = static_cast<uint4*>(rec_);
+  const uint2* list = static_cast<const uint2*>(heavy_list);
+  PPG_TRY(launch_scan(HeavyLenProducer{list}, ChainOffsetConsumer{L.hoff, heavy_rows}, heavy_rows, L.scan_ws, nullptr, stream));
+  heavy_compact_rec_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(list, L.hoff, heavy_rows, heavy_slots, rec, L.keys_a, L.vals_a);
+  PPG_LAUNCHED();
+  int in_b = 0;
+  PPG_TRY(radix_sort_pairs<unsigned long long>(L.keys_a, L.keys_b, L.vals_a, L.vals_b, true, false, heavy_slots, L.bits, L.sort_ws,
+                                               &in_b, stream));
+  const unsigned long long* keys = in_b ? L.keys_b : L.keys_a;
+  const uint32_t* vals = in_b ? L.vals_b : L.vals_a;
+  const HeavyExtras extras = {{firstS, degS, nullptr}};
+  const HeavyExtras temps = {{L.t_extra[0], L.t_extra[1], L.t_extra[2]}};
+  heavy_gather_rec_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(keys, vals, heavy_slots, rec, labS, extras, t_rec, L.t_lab,
+                                                                             temps, L.t_dest);
+  PPG_LAUNCHED();
+  heavy_write_rec_kernel<<<grid_for(heavy_slots, 256 * 4), 256, 0, stream>>>(heavy_slots, t_rec, L.t_lab, temps, L.t_dest, rec, labS, extras);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
+// The owners' answers (back [n_slots], slot order) -> local row structure of the next level + info word of every item
+// (words 0, 1: global id, last node; word 2: degS if given).  lastS: last node of every slot, last_stride words apart.
 // result[0] = number of local rows.
 extern "C" int ppg_chain_unpack(const uint32_t* back, int64_t n_slots, const int64_t* dstart, const int64_t* edge_offsets, int world,
-                                const uint32_t* labS, const uint32_t* lastS, void* workspace, size_t workspace_bytes,
-                                uint32_t* rowid, uint32_t* run_start, uint32_t* row_value, void* info_item, int64_t* result,
-                                void* stream_) {
+                                const uint32_t* labS, const uint32_t* lastS, int last_stride, const uint32_t* degS, void* workspace,
+                                size_t workspace_bytes, uint32_t* rowid, uint32_t* run_start, uint32_t* row_value, void* info_item,
+                                int64_t* result, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PPG_REQUIRE(world >= 1 && world <= kMaxRanks && n_slots >= 0 && n_slots < (1ll << 31), PPG_ERR_INVALID, "chain_unpack: bad sizes");
   const size_t need = ppg_chain_scan_workspace_bytes(n_slots);
@@ -1331,39 +1390,47 @@ extern "C" int ppg_chain_unpack(const uint32_t* back, int64_t n_slots, const int
     return PPG_OK;
   }
   UnpackProducer ids{back, dstart, edge_offsets, world};
-  return launch_scan(ids, UnpackConsumer{ids, labS, lastS, rowid, run_start, row_value, static_cast<unsigned long long*>(info_item), n_slots},
+  return launch_scan(ids, UnpackConsumer{ids, labS, lastS, last_stride < 1 ? 1 : last_stride, degS, rowid, run_start, row_value,
+                                         static_cast<uint4*>(info_item), n_slots},
                      n_slots, static_cast<unsigned long long*>(workspace), reinterpret_cast<unsigned long long*>(result), stream);
 }
 
 extern "C" int64_t ppg_merge_sorted_tiles(int64_t num_records) { return num_records > 0 ? ceil_div(num_records, kMergeTile) : 0; }
 
-// Owner side: `world` runs of records (run s = records [seg[s], seg[s + 1]), each sorted by (row, col)) -> merged edges in
-// compact arrays (row_m, col_m, w_m, last_m: capacity num_records), the merged edge of every record (out_inverse, arrival
-// order), result[0] = merged edges, result[1] = status (1: id out of range, 2: a row range did not fit a tile -- merge
-// these records with ppg_merge_records_sort instead).  bounds: u32 [(tiles + 1) * world], tile_state: u64 [tiles].
-extern "C" int ppg_merge_sorted(const void* records, int64_t num_records, const int64_t* seg, int world, int64_t row_lo,
-                                int64_t rows_owned, int64_t total_nodes, uint32_t* bounds, void* tile_state, uint32_t* out_inverse,
-                                uint32_t* row_m, uint32_t* col_m, float* w_m, uint32_t* last_m, int64_t* result, void* stream_) {
+// Owner side: `world` runs of records, run s = h_runs[s][0 .. h_run_len[s]) sorted by (row, col) -- device addresses, peer
+// memory of the senders or a local copy -- -> merged edges in compact arrays (row_m, col_m, w_m, last_m: capacity = total
+// records) and, for every record, the index of its merged edge stored at h_back[s][position in the run] (the sender's
+// answer buffer, or a local one).  result[0] = merged edges, result[1] = status (1: id out of range, 2: a row range did
+// not fit a tile -- merge these records with ppg_merge_records_sort instead).  bounds: u32 [(tiles + 1) * world],
+// tile_state: u64 [tiles] with tiles = ppg_merge_sorted_tiles(total records).
+extern "C" int ppg_merge_sorted(void* const* h_runs, const int64_t* h_run_len, void* const* h_back, int world, int64_t row_lo,
+                                int64_t rows_owned, int64_t total_nodes, uint32_t* bounds, void* tile_state, uint32_t* row_m,
+                                uint32_t* col_m, float* w_m, uint32_t* last_m, int64_t* result, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PPG_REQUIRE(world >= 1 && world <= kMaxRanks, PPG_ERR_INVALID, "merge_sorted: %d ranks outside [1, %d]", world, kMaxRanks);
-  PPG_REQUIRE(num_records >= 0 && num_records < (1ll << 31) && total_nodes <= (1ll << 32), PPG_ERR_INVALID, "merge_sorted: bad sizes");
+  MergeArgs a = {};
+  int64_t num_records = 0;
+  for (int s = 0; s < world; ++s) {
+    PPG_REQUIRE(h_run_len[s] >= 0 && h_run_len[s] < (1ll << 31), PPG_ERR_INVALID, "merge_sorted: bad run length");
+    a.runs.run[s] = static_cast<const uint4*>(h_runs[s]);
+    a.runs.len[s] = static_cast<uint32_t>(h_run_len[s]);
+    a.runs.back[s] = static_cast<uint32_t*>(h_back[s]);
+    num_records += h_run_len[s];
+  }
+  a.runs.world = world;
+  PPG_REQUIRE(num_records < (1ll << 31) && total_nodes <= (1ll << 32), PPG_ERR_INVALID, "merge_sorted: bad sizes");
   PPG_CUDA_TRY(cudaMemsetAsync(result, 0, 2 * sizeof(int64_t), stream));
   if (num_records == 0) return PPG_OK;
   const int64_t tiles = ppg_merge_sorted_tiles(num_records);
   const int64_t rows_per_tile = rows_owned > 0 ? ceil_div(rows_owned, tiles) : 1;
   PPG_CUDA_TRY(cudaMemsetAsync(tile_state, 0, static_cast<size_t>(tiles) * sizeof(unsigned long long), stream));
-  merge_bounds_kernel<<<grid_for((tiles + 1) * world, 256), 256, 0, stream>>>(static_cast<const uint4*>(records), seg, world, row_lo,
-                                                                             rows_per_tile, tiles, bounds);
+  merge_bounds_kernel<<<grid_for((tiles + 1) * world, 256), 256, 0, stream>>>(a.runs, row_lo, rows_per_tile, tiles, bounds);
   PPG_LAUNCHED();
-  MergeArgs a = {};
-  a.records = static_cast<const uint4*>(records);
   a.bnd = bounds;
-  a.world = world;
   a.row_lo = row_lo;
   a.rows_owned = rows_owned;
   a.total_nodes = total_nodes;
   a.rows_per_tile = rows_per_tile;
-  a.inverse = out_inverse;
   a.row_m = row_m;
   a.col_m = col_m;
   a.w_m = w_m;
@@ -1388,18 +1455,18 @@ extern "C" int ppg_merge_sorted_fill(const uint32_t* row_m, const uint32_t* col_
 }
 
 // Level 1: ptr word of the events' node words <- row pointer of the event graph (u64 [m + 1] of ppg_lift_temporal_views).
-extern "C" int ppg_chain_node_ptr(const void* off, int64_t num_items, void* node, void* stream_) {
+extern "C" int ppg_chain_node_ptr(const void* off, int64_t num_items, void* node, int stride, int word, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   chain_node_ptr_kernel<<<grid_for(num_items + 1, 256 * 4), 256, 0, stream>>>(static_cast<const unsigned long long*>(off), num_items + 1,
-                                                                              static_cast<unsigned long long*>(node));
+                                                                              static_cast<uint32_t*>(node) + word, stride);
   PPG_LAUNCHED();
   return PPG_OK;
 }
 
 // Label-order scan of the continuation counts in the node words (in place: count -> row pointer of the next level;
 // node[num_items] receives the total, which is also written to *total).
-extern "C" int ppg_chain_scan_nodes(void* node, int64_t num_items, void* workspace, size_t workspace_bytes, int64_t* total,
-                                    void* stream_) {
+extern "C" int ppg_chain_scan_nodes(void* node, int stride, int word, int64_t num_items, void* workspace, size_t workspace_bytes,
+                                    int64_t* total, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PPG_REQUIRE(num_items >= 0 && num_items < (1ll << 31), PPG_ERR_INVALID, "chain: %lld items outside [0, 2^31)", (long long)num_items);
   const size_t need = ppg_chain_scan_workspace_bytes(num_items);
@@ -1407,17 +1474,18 @@ extern "C" int ppg_chain_scan_nodes(void* node, int64_t num_items, void* workspa
   PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, stream));
   if (num_items == 0) {
     PPG_CUDA_TRY(cudaMemsetAsync(total, 0, sizeof(int64_t), stream));
-    PPG_CUDA_TRY(cudaMemsetAsync(node, 0, sizeof(unsigned long long), stream));
+    PPG_CUDA_TRY(cudaMemsetAsync(static_cast<uint32_t*>(node) + word, 0, sizeof(uint32_t), stream));
     return PPG_OK;
   }
-  unsigned long long* nd = static_cast<unsigned long long*>(node);
-  return launch_scan(NodeDegProducer{nd}, NodePtrConsumer{nd, num_items}, num_items, static_cast<unsigned long long*>(workspace),
-                     reinterpret_cast<unsigned long long*>(total), stream);
+  uint32_t* words = static_cast<uint32_t*>(node) + word;
+  return launch_scan(NodeDegProducer{words, stride}, NodePtrConsumer{words, stride, num_items}, num_items,
+                     static_cast<unsigned long long*>(workspace), reinterpret_cast<unsigned long long*>(total), stream);
 }
 
 // Count pass of levels >= 3 in merged order (see ChainSortedProducer2): degS of the previous level's tiles, limit, node
 // words after ppg_chain_scan_nodes -> offP u64 [n + 1], lblP [n], srcbound.
-extern "C" int ppg_chain_count_sorted_next(const uint32_t* P, int64_t n, const uint32_t* degS, const void* node, int64_t limit,
+extern "C" int ppg_chain_count_sorted_next(const uint32_t* P, int64_t n, const uint32_t* degS, const void* node, int stride,
+                                           int word, int64_t limit,
                                            const uint32_t* rowid, const uint32_t* run_start, void* workspace, size_t workspace_bytes,
                                            void* offP, uint32_t* lblP, uint32_t* srcbound, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -1425,7 +1493,7 @@ extern "C" int ppg_chain_count_sorted_next(const uint32_t* P, int64_t n, const u
   const size_t need = ppg_chain_scan_workspace_bytes(n);
   PPG_REQUIRE(workspace_bytes >= need, PPG_ERR_WORKSPACE, "chain_count_sorted_next: workspace %zu < %zu bytes", workspace_bytes, need);
   PPG_CUDA_TRY(cudaMemsetAsync(workspace, 0, need, stream));
-  return launch_scan(ChainSortedProducer2{P, degS, static_cast<const unsigned long long*>(node), limit, lblP},
+  return launch_scan(ChainSortedProducer2{P, degS, static_cast<const uint32_t*>(node) + word, stride, limit, lblP},
                      ChainSortedConsumer{static_cast<unsigned long long*>(offP), reinterpret_cast<uint2*>(srcbound), rowid, run_start, n}, n,
                      static_cast<unsigned long long*>(workspace), nullptr, stream);
 }

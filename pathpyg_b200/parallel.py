@@ -437,31 +437,99 @@ def _exchange_merge(line_index, node_info, weights, own_prefix, offsets, offsets
 # ------------------------------------------------------------------------------------------------
 # distributed lift on the generation-order chain (csrc/chain.cu)
 # ------------------------------------------------------------------------------------------------
+class _ChainBuffers:
+    """Record and answer buffers of the distributed chain on one rank: two record buffers (levels alternate: the tiles of
+    level k + 1 read their weights from level k's records while they write their own) and one answer buffer.  With peer
+    access (``torch.distributed._symmetric_memory``: CUDA virtual-memory handles exchanged once, NVLink) the buffers are
+    symmetric allocations mapped into every peer: an owner's merge kernel loads the senders' records and stores the merged
+    indices straight through those mappings, and a device-side barrier over the signal pads orders the phases."""
+
+    _cache: dict = {}
+
+    def __init__(self, group, dev, peer: bool):
+        self.group, self.dev, self.peer, self.capacity = group, dev, peer, 0
+        self.rec, self.back, self.rec_handles, self.back_handle = [None, None], None, [None, None], None
+
+    @classmethod
+    def get(cls, group, dev, peer: bool):
+        key = (id(group) if group is not None else 0, dev.index, peer)
+        if key not in cls._cache:
+            cls._cache[key] = cls(group, dev, peer)
+        return cls._cache[key]
+
+    def ensure(self, slots: int, keep: int | None = None, keep_slots: int = 0) -> None:
+        """Collective when it grows (every rank passes the same number).  ``keep``: record buffer whose first
+        ``keep_slots`` records must survive the growth."""
+        if slots <= self.capacity:
+            return
+        capacity = (int(slots * 1.05) + 4096) // 1024 * 1024
+        saved = self.rec[keep][:2 * keep_slots].clone() if keep is not None and keep_slots else None
+        torch.cuda.synchronize(self.dev)   # kernels in flight may still use the buffers that are about to be released
+        if self.peer:
+            import torch.distributed._symmetric_memory as symm_mem
+            group = self.group if self.group is not None else dist.group.WORLD
+            self.rec_handles, self.back_handle, self.rec, self.back = [None, None], None, [None, None], None   # release first
+            for i in range(2):
+                self.rec[i] = symm_mem.empty(capacity * 2, dtype=torch.int64, device=self.dev)
+                self.rec_handles[i] = symm_mem.rendezvous(self.rec[i], group)
+            self.back = symm_mem.empty(capacity, dtype=torch.int32, device=self.dev)
+            self.back_handle = symm_mem.rendezvous(self.back, group)
+        else:
+            self.rec = [torch.empty(capacity * 2, dtype=torch.int64, device=self.dev) for _ in range(2)]
+            self.back = torch.empty(capacity, dtype=torch.int32, device=self.dev)
+        if saved is not None:
+            self.rec[keep][:saved.numel()] = saved
+        self.capacity = capacity
+
+    def rec_ptr(self, which: int, rank: int, slot: int) -> int:
+        base = int(self.rec_handles[which].buffer_ptrs[rank]) if self.peer else self.rec[which].data_ptr()
+        return base + 16 * int(slot)
+
+    def back_ptr(self, rank: int, slot: int) -> int:
+        base = int(self.back_handle.buffer_ptrs[rank]) if self.peer else self.back.data_ptr()
+        return base + 4 * int(slot)
+
+    def peer_records(self, which: int, rank: int, lo: int, n: int) -> torch.Tensor:
+        """[n, 2] int64 view of records lo .. lo + n of ``rank``'s buffer (the overflow fallback copies them)."""
+        if not self.peer:
+            return self.rec[which][2 * lo:2 * (lo + n)].view(n, 2)
+        return self.rec_handles[which].get_buffer(rank, (self.capacity * 2,), torch.int64)[2 * lo:2 * (lo + n)].view(n, 2)
+
+    def peer_back(self, rank: int, lo: int, n: int) -> torch.Tensor:
+        if not self.peer:
+            return self.back[lo:lo + n]
+        return self.back_handle.get_buffer(rank, (self.capacity,), torch.int32)[lo:lo + n]
+
+    def barrier(self) -> None:
+        if self.peer:
+            self.back_handle.barrier(channel=0)
+
+
 class _MergeSorted:
     """Owner side on the chain: one (row, col)-sorted run of records per sender, merged in shared-memory tiles of whole
-    row ranges (``ppg_merge_sorted``).  Same surface as ``ops.PendingMerge``: ``result_words`` [merged count, status],
-    ``inverse`` [R] int32, ``finish(num_out)``."""
+    row ranges (``ppg_merge_sorted``); the merged-edge index of every record is stored where ``back_ptrs`` say (the
+    senders' answer buffers).  ``result_words`` [merged count, status]; ``finish(num_out)`` as ``ops.PendingMerge``."""
 
-    def __init__(self, records: torch.Tensor, recv: list[int], row_lo: int, rows_owned: int, total_nodes: int):
+    def __init__(self, run_ptrs: list[int], run_lens: list[int], back_ptrs: list[int], row_lo: int, rows_owned: int, total_nodes: int,
+                 dev):
+        import ctypes
         from .ops import _ptr, _stream
         lib = _lib.load()
-        self.dev, self.R, world = records.device, records.size(0), len(recv)
-        seg = [0]
-        for c in recv:
-            seg.append(seg[-1] + int(c))
+        world = len(run_lens)
+        self.dev, self.R = dev, int(sum(run_lens))
         n = max(self.R, 1)
         tiles = int(lib.ppg_merge_sorted_tiles(self.R))
-        self.inverse = torch.empty(n, dtype=torch.int32, device=self.dev)[:self.R]
-        self.compact = [torch.empty(n, dtype=torch.float32 if i == 2 else torch.int32, device=self.dev) for i in range(4)]
-        self.result_words = torch.zeros(2, dtype=torch.int64, device=self.dev)
-        self.keep = (records, torch.tensor(seg, dtype=torch.int64, device=self.dev),
-                     torch.empty((tiles + 1) * world + 1, dtype=torch.int32, device=self.dev),
-                     torch.empty(tiles + 1, dtype=torch.int64, device=self.dev))
+        self.compact = [torch.empty(n, dtype=torch.float32 if i == 2 else torch.int32, device=dev) for i in range(4)]
+        self.result_words = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.keep = (torch.empty((tiles + 1) * world + 1, dtype=torch.int32, device=dev), torch.empty(tiles + 1, dtype=torch.int64, device=dev))
         row_m, col_m, w_m, last_m = self.compact
-        with torch.cuda.device(self.dev):
-            _lib.check(lib.ppg_merge_sorted(_ptr(records), self.R, _ptr(self.keep[1]), world, int(row_lo), int(rows_owned), int(total_nodes),
-                                            _ptr(self.keep[2]), _ptr(self.keep[3]), _ptr(self.inverse), _ptr(row_m), _ptr(col_m), _ptr(w_m),
-                                            _ptr(last_m), _ptr(self.result_words), _stream(self.dev)))
+        runs = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in run_ptrs])
+        backs = (ctypes.c_void_p * world)(*[ctypes.c_void_p(int(p)) for p in back_ptrs])
+        lens = (ctypes.c_int64 * world)(*[int(c) for c in run_lens])
+        with torch.cuda.device(dev):
+            _lib.check(lib.ppg_merge_sorted(runs, lens, backs, world, int(row_lo), int(rows_owned), int(total_nodes), _ptr(self.keep[0]),
+                                            _ptr(self.keep[1]), _ptr(row_m), _ptr(col_m), _ptr(w_m), _ptr(last_m), _ptr(self.result_words),
+                                            _stream(dev)))
 
     def finish(self, num_out: int):
         from .ops import _ptr, _stream
@@ -483,14 +551,19 @@ def _chain_supported(edge_index, edge_weight, num_nodes, local_ops) -> bool:
 
 def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, cuts, group, trace) -> dict:
     """``distributed_temporal_layers`` on the generation-order chain.  Every rank expands its items in the order of their
-    GLOBAL merged ids (known from the previous level's exchange), so its records leave sorted by (row, col) and grouped
-    by owner without a partition pass; the owner merges one sorted run per sender in shared-memory tiles
-    (``ppg_merge_sorted``) instead of radix-sorting what it received.  The exchange itself is unchanged: counts through
-    one all-gather, records into the owners' symmetric buffers over NVLink (or one all-to-all-v), 4-byte indices back.
+    GLOBAL merged ids (known from the previous level's exchange), so its pairs leave as 16-byte records sorted by
+    (row, col) and grouped by owner -- no partition pass, no pack pass.  With peer access the owner's merge kernel READS
+    the senders' runs over NVLink, merges them in shared-memory tiles (``ppg_merge_sorted``) and WRITES the merged-edge
+    index of every record into the sender's answer buffer: the exchange in both directions is the merge kernel's own load
+    / store stream, ordered by two device-side barriers per order.  Without peer access (``PPG_DIST_P2P=0``, or one
+    rank) the same kernels run on copies moved by two all-to-all-v.
+
+    Per order two host synchronisations: (1) all-gather of the per-destination record counts, the first slot of every
+    destination, the heavy-row counts and the sizes of the next level; (2) all-gather of the merged counts.
 
     Paths that start with a ghost event carry weight 0 from level 1 on (a path inherits the weight of its first event),
-    so they only collect ids.  At level k only the items that start before cut k are expanded (``limit``); the items
-    that start before the later cuts are counted through the row pointer of the level (``starts_before``)."""
+    so they only collect ids.  At level k only the items that start before cut k are expanded (``limit``); how many items
+    start before the later cuts is read off the row pointer of the level (``starts_before``)."""
     import ctypes
     from . import chain as chain_mod
     from . import ops
@@ -504,7 +577,8 @@ def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, 
     u32 = torch.int32
     mark = trace.mark
     res = torch.zeros((K + 2, 8), dtype=torch.int64, device=dev)
-    peer_to_peer = world > 1 and _PeerArenas.available(dev)
+    peer = world > 1 and _PeerArenas.available(dev)
+    bufs = _ChainBuffers.get(group, dev, peer)
     layers: dict[int, DistributedLayer] = {}
 
     def empty32(n, dtype=u32):
@@ -513,16 +587,24 @@ def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, 
     def scan_ws(n):
         return torch.empty(lib.ppg_chain_scan_workspace_bytes(int(n)), dtype=torch.uint8, device=dev)
 
+    def word(t: torch.Tensor, index: int) -> ctypes.c_void_p:
+        return ctypes.c_void_p(t.data_ptr() + 4 * index)
+
     with torch.cuda.device(dev):
         stream = _stream(dev)
         main, side = torch.cuda.current_stream(dev), chain_mod.side_stream(dev)
-        # ---- level 1: the events of the extended range, grouped by source node, ranked by target node
-        w_item = torch.ones(m_ext, dtype=torch.float32, device=dev) if ext_w is None else ext_w.to(torch.float32).clone()
-        w_item[m_own:] = 0.0
+        # the buffers hold the largest level of any rank; level 1 = the events of the extended range
+        most = int(_gather_counts(torch.tensor([m_ext], dtype=torch.int64, device=dev), group).max())
+        bufs.ensure(max(most, 1))
+
+        # ---- level 1: events grouped by source node, ranked by target node; ghost events carry weight 0
+        w_event = torch.ones(m_ext, dtype=torch.float32, device=dev) if ext_w is None else ext_w.to(torch.float32).clone()
+        w_event[m_own:] = 0.0
         n_slots = m_ext
-        slots = {"row": empty32(n_slots), "col": empty32(n_slots), "lab": empty32(n_slots), "w": empty32(n_slots, torch.float32),
-                 "heavy": torch.empty((n_slots // (heavy + 1) + 2, 2), dtype=u32, device=dev)}
-        slots["last"] = slots["col"]
+        arrays = {name: empty32(n_slots, torch.float32 if name == "w" else u32) for name in ("row", "col", "lab", "w")}
+        heavy_list = torch.empty((n_slots // (heavy + 1) + 2, 2), dtype=u32, device=dev)
+        labS, firstS, degS = arrays["lab"], None, None
+        info = torch.empty((max(n_slots, 1) + 1, 2), dtype=torch.int64, device=dev)    # by label: {id, last, count -> pointer, -}
         tws = views = None
         if m_ext:
             tws = ops.lift_order_temporal_group(ext_ei, num_nodes)
@@ -530,102 +612,109 @@ def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, 
             _lib.check(lib.ppg_lift_temporal_views(_ptr(tws), m_ext, num_nodes, views))
             state = torch.empty(-(-m_ext // tile) + 1, dtype=torch.int64, device=dev)
             _lib.check(lib.ppg_chain_first_tiles(_ptr(ext_ei), m_ext, num_nodes, ctypes.c_void_p(views[0]), ctypes.c_void_p(views[1]),
-                                                 ctypes.c_void_p(views[2]), _ptr(w_item), heavy, _ptr(slots["row"]), _ptr(slots["col"]),
-                                                 _ptr(slots["lab"]), _ptr(slots["w"]), None, None, None, _ptr(state), _ptr(slots["heavy"]),
+                                                 ctypes.c_void_p(views[2]), _ptr(w_event), heavy, _ptr(arrays["row"]), _ptr(arrays["col"]),
+                                                 _ptr(arrays["lab"]), _ptr(arrays["w"]), None, None, None, _ptr(state), _ptr(heavy_list),
                                                  _ptr(res[1]), stream))
         # rows of layer 1 = first-order nodes, owned by node-id range
         offsets = [-(-num_nodes * p // world) for p in range(world + 1)]
         offsets_dev = torch.tensor(offsets, dtype=torch.int64, device=dev)
         total_nodes = num_nodes
-        rows_k, row_lo = torch.arange(offsets[rank], offsets[rank + 1], device=dev).unsqueeze(1), offsets[rank]
+        rows_k = torch.arange(offsets[rank], offsets[rank + 1], device=dev).unsqueeze(1)
         starts_before = {j: cuts[j] for j in range(2, K + 1)}   # items of the current level that start before cut j
-        first = ptr_next = via = None                           # count results of the level being expanded (raw pointers)
-        tail = None
-        keep = []
 
         for k in range(1, K + 1):
             more = k < K
+            which = k & 1
+            rec = bufs.rec[which]
             mark(f"route_count[{k}]")
             dstart = torch.empty(world + 1, dtype=torch.int64, device=dev)
             counts = torch.empty(world, dtype=torch.int64, device=dev)
-            _lib.check(lib.ppg_chain_dest_bounds(_ptr(slots["row"]), n_slots, _ptr(offsets_dev), world, _ptr(dstart), _ptr(counts), stream))
-            # count pass of the next level over this level's items (label order) while the counts travel
+            rows_at, stride = (_ptr(arrays["row"]), 1) if k == 1 else (word(rec, 1), 4)
+            _lib.check(lib.ppg_chain_dest_bounds(rows_at, stride, n_slots, _ptr(offsets_dev), world, _ptr(dstart), _ptr(counts), stream))
+            # sizes of the next level: row pointer of this level's items in label order
             later = list(range(k + 1, K + 1))
             sel = torch.zeros(len(later) + 1, dtype=torch.int64, device=dev)     # starts_before of the next level + status bits
-            nxt_first = nxt_ptr = None
             if more and n_slots:
+                at_items = torch.tensor([min(starts_before[j], n_slots) for j in later], dtype=torch.int64, device=dev)
                 if k == 1:
                     time, mode, delta_i, delta_f = ops._time_mode(ext_t.contiguous(), delta)
                     _lib.check(lib.ppg_lift_temporal_count(_ptr(ext_ei), _ptr(time), m_ext, num_nodes, mode | _lib.TIME_GROUPED, delta_i,
                                                            delta_f, _ptr(tws), tws.numel(), None, stream))
-                    at = views[4] - tws.data_ptr()
-                    ptr_t = tws[at:at + 8 * (m_ext + 1)].view(torch.int64)
-                    nxt_first, nxt_ptr = ctypes.c_void_p(views[3]), ctypes.c_void_p(views[4])
+                    _lib.check(lib.ppg_chain_node_ptr(ctypes.c_void_p(views[4]), m_ext, _ptr(info), 4, 2, stream))
                     status_word = tws[8:16].view(torch.int64)
                 else:
-                    first_t = empty32(n_slots)
-                    ptr_t = torch.empty(n_slots + 1, dtype=torch.int64, device=dev)
                     ws = scan_ws(n_slots)
-                    _lib.check(lib.ppg_chain_count(_ptr(tail), ptr_next, n_slots, _ptr(ws), ws.numel(), _ptr(first_t), _ptr(ptr_t),
-                                                   ctypes.c_void_p(res[k].data_ptr() + 8 * 4), stream))
-                    nxt_first, nxt_ptr = ctypes.c_void_p(first_t.data_ptr()), ctypes.c_void_p(ptr_t.data_ptr())
-                    keep = [first_t, ptr_t]
+                    _lib.check(lib.ppg_chain_scan_nodes(_ptr(info), 4, 2, n_slots, _ptr(ws), ws.numel(),
+                                                        ctypes.c_void_p(res[k].data_ptr() + 8 * 4), stream))
                     status_word = res[k, 1:2]
-                at_items = torch.tensor([min(starts_before[j], n_slots) for j in later], dtype=torch.int64, device=dev)
-                sel = torch.cat([ptr_t[at_items], status_word])
-            gathered = _gather_counts(torch.cat([counts, res[k, :4], sel]), group)                  # (sync 1)
-            matrix, mine = gathered[:, :world], gathered[rank].tolist()
-            send, recv = matrix[rank].tolist(), matrix[:, rank].tolist()
-            if (int(gathered[:, world + 1].max()) | int(gathered[:, -1].max())) & 1:
+                sel = torch.cat([info.view(torch.int32).view(-1)[at_items * 4 + 2].to(torch.int64), status_word])
+            gathered = _gather_counts(torch.cat([counts, dstart, res[k, :4], sel]), group)          # (sync 1)
+            matrix, starts, mine = gathered[:, :world], gathered[:, world:2 * world + 1], gathered[rank].tolist()
+            recv = matrix[:, rank].tolist()
+            base = 2 * world + 1
+            if (int(gathered[:, base + 1].max()) | int(gathered[:, -1].max())) & 1:
                 raise ValueError("distributed lift: node id outside [0, num_nodes)")
-            heavy_slots, heavy_rows = mine[world + 2], mine[world + 3]
-            if heavy_rows:   # hub rows: the tiles left them in generation order
-                ws = torch.empty(lib.ppg_chain_heavy_workspace_bytes(heavy_slots, heavy_rows, n_slots), dtype=torch.uint8, device=dev)
-                extra = None if slots["last"] is slots["col"] else slots["last"]
-                _lib.check(lib.ppg_chain_heavy_fix(_ptr(slots["heavy"]), heavy_rows, heavy_slots, n_slots, _ptr(slots["col"]),
-                                                   _ptr(slots["lab"]), _ptr(slots["w"]), _ptr(extra), None, None, _ptr(ws), ws.numel(), stream))
-            next_starts = {j: mine[world + 4 + i] for i, j in enumerate(later)}
+            heavy_slots, heavy_rows = mine[base + 2], mine[base + 3]
+            next_starts = {j: mine[base + 4 + i] for i, j in enumerate(later)}
+            next_most = int(gathered[:, base + 4].max()) if later else 0      # largest next level of any rank
 
             mark(f"route_pack[{k}]")
-            if peer_to_peer:
-                arenas = _PeerArenas.get(group, dev)
-                arenas.ensure(int(matrix.sum(0).max()))
-                which = k & 1
-                ahead = matrix[:rank].sum(0).tolist()
-                peers = (ctypes.c_void_p * world)(*[ctypes.c_void_p(arenas.peer_slot(which, d, ahead[d])) for d in range(world)])
-                _lib.check(lib.ppg_chain_pack(_ptr(slots["row"]), _ptr(slots["col"]), _ptr(slots["last"]), _ptr(slots["w"]), n_slots,
-                                              _ptr(dstart), world, None, peers, stream))
-            else:
-                records = torch.empty((max(n_slots, 1), 2), dtype=torch.int64, device=dev)[:n_slots]
-                _lib.check(lib.ppg_chain_pack(_ptr(slots["row"]), _ptr(slots["col"]), _ptr(slots["last"]), _ptr(slots["w"]), n_slots,
-                                              _ptr(dstart), world, _ptr(records), None, stream))
-                received = torch.empty((sum(recv), 2), dtype=torch.int64, device=dev)
-                work = dist.all_to_all_single(received.view(-1), records.view(-1), [2 * c for c in recv], [2 * c for c in send],
-                                              group=group, async_op=True)
+            if k == 1:
+                if heavy_rows:   # hub rows: the tiles left them in generation order
+                    ws = torch.empty(lib.ppg_chain_heavy_workspace_bytes(heavy_slots, heavy_rows, n_slots), dtype=torch.uint8, device=dev)
+                    _lib.check(lib.ppg_chain_heavy_fix(_ptr(heavy_list), heavy_rows, heavy_slots, n_slots, _ptr(arrays["col"]),
+                                                       _ptr(arrays["lab"]), _ptr(arrays["w"]), None, None, None, _ptr(ws), ws.numel(), stream))
+                _lib.check(lib.ppg_chain_pack(_ptr(arrays["row"]), _ptr(arrays["col"]), _ptr(arrays["col"]), _ptr(arrays["w"]), n_slots,
+                                              _ptr(rec), stream))
+            elif heavy_rows:
+                ws = torch.empty(lib.ppg_chain_heavy_records_workspace_bytes(heavy_slots, heavy_rows, n_slots), dtype=torch.uint8, device=dev)
+                _lib.check(lib.ppg_chain_heavy_fix_records(_ptr(heavy_list), heavy_rows, heavy_slots, n_slots, _ptr(rec), _ptr(labS),
+                                                           _ptr(firstS), _ptr(degS), _ptr(ws), ws.numel(), stream))
             if k > 1:   # owned rows of this layer = merged edges of the previous one: output work, on the side stream
                 with torch.cuda.stream(side):
                     rows_k = ops.extend_owned_rows(rows_k, prev_row_lo, prev_ei[0], prev_last)
                     rows_k.record_stream(main)
             mark(f"records_wait[{k}]")
-            if peer_to_peer:
-                arenas.barrier(which)
-                received = arenas.received(which, sum(recv))
-            else:
-                work.wait()
-                del records
+            lo_at = starts[:, rank].tolist()            # first record for this owner in every sender's buffer
+            received = send_back = None
+            if peer:
+                bufs.barrier()                          # every sender's records are complete (and put in order)
+                run_ptrs = [bufs.rec_ptr(which, s, lo_at[s]) for s in range(world)]
+                back_ptrs = [bufs.back_ptr(s, lo_at[s]) for s in range(world)]
+            elif world == 1:
+                run_ptrs, back_ptrs = [bufs.rec_ptr(which, 0, 0)], [bufs.back_ptr(0, 0)]
+            else:                                       # no peer access: the records travel through one all-to-all-v
+                send = matrix[rank].tolist()
+                received = torch.empty((sum(recv), 2), dtype=torch.int64, device=dev)
+                dist.all_to_all_single(received.view(-1), rec[:2 * n_slots], [2 * c for c in recv], [2 * c for c in send], group=group)
+                send_back = torch.empty(max(sum(recv), 1), dtype=torch.int32, device=dev)
+                seg = [0]
+                for c in recv:
+                    seg.append(seg[-1] + c)
+                run_ptrs = [received.data_ptr() + 16 * seg[s] for s in range(world)]
+                back_ptrs = [send_back.data_ptr() + 4 * seg[s] for s in range(world)]
             mark(f"merge_sort[{k}]")
             rows_owned = offsets[rank + 1] - offsets[rank]
-            merge = _MergeSorted(received, recv, offsets[rank], rows_owned, total_nodes)
+            merge = _MergeSorted(run_ptrs, recv, back_ptrs, offsets[rank], rows_owned, total_nodes, dev)
             mark(f"merge_sync[{k}]")
             results = _gather_counts(merge.result_words, group)                                     # (sync 2)
             if int(results[:, 1].max()) & 2:   # a row range did not fit a tile somewhere: those owners sort their records
                 if int(results[rank, 1]) & 2:
-                    merge = ops.merge_records_begin(received.clone() if peer_to_peer else received, offsets[rank], rows_owned, total_nodes)
+                    copy = torch.cat([bufs.peer_records(which, s, lo_at[s], recv[s]) for s in range(world)]) if received is None \
+                        else received
+                    merge = ops.merge_records_begin(copy, offsets[rank], rows_owned, total_nodes)
+                    at = 0
+                    for s in range(world):   # the merged indices go where the tiles would have put them
+                        target = bufs.peer_back(s, lo_at[s], recv[s]) if send_back is None else send_back[at:at + recv[s]]
+                        target.copy_(merge.inverse[at:at + recv[s]])
+                        at += recv[s]
                 results = _gather_counts(merge.result_words, group)
-            back = torch.empty(max(n_slots, 1), dtype=torch.int32, device=dev)[:n_slots]
-            work = dist.all_to_all_single(back, merge.inverse, send, recv, group=group, async_op=True)
             if int(results[:, 1].max()) & 1:
                 raise ValueError("distributed lift: a node id outside its layer reached an owner (inconsistent inputs)")
+            if peer:
+                bufs.barrier()                          # every owner's merged indices have landed in the senders' buffers
+            elif send_back is not None:
+                dist.all_to_all_single(bufs.back[:n_slots], send_back[:sum(recv)], matrix[rank].tolist(), recv, group=group)
             edge_offsets = [0]
             for c in results[:, 0].tolist():
                 edge_offsets.append(edge_offsets[-1] + int(c))
@@ -644,44 +733,53 @@ def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, 
                 raise _lib.EmptyLiftError("torch.cat(): expected a non-empty list of Tensors (distributed lift: no time-respecting pair)")
             layers[k] = DistributedLayer(k, total_nodes, offsets[rank], rows_k, out_ei, out_w, edge_offsets[rank], edge_offsets[-1])
             prev_ei, prev_last, prev_row_lo = out_ei, out_last, offsets[rank]
-            mark(f"ids_wait[{k}]")
-            work.wait()
             if not more:
                 break
 
-            # ---- the ids are back: local rows of the next level, info word of every item, then expand in that order
+            # ---- the ids are back: local rows of the next level, info words of this level's items, then expand in that order
             mark(f"route_unpack[{k}]")
             rowid, run_start, row_value = empty32(n_slots), empty32(n_slots + 1), empty32(n_slots)
-            info = torch.empty(max(n_slots, 1), dtype=torch.int64, device=dev)
             ws = scan_ws(n_slots)
-            _lib.check(lib.ppg_chain_unpack(_ptr(back), n_slots, _ptr(dstart), _ptr(edge_offsets_dev), world, _ptr(slots["lab"]),
-                                            _ptr(slots["last"]), _ptr(ws), ws.numel(), _ptr(rowid), _ptr(run_start), _ptr(row_value),
+            _lib.check(lib.ppg_chain_unpack(_ptr(bufs.back), n_slots, _ptr(dstart), _ptr(edge_offsets_dev), world, _ptr(labS),
+                                            word(rec, 2), 4, None, _ptr(ws), ws.numel(), _ptr(rowid), _ptr(run_start), _ptr(row_value),
                                             _ptr(info), ctypes.c_void_p(res[k].data_ptr() + 8 * 5), stream))
             mark(f"lift_next[{k}]")
             n_next = next_starts.get(k + 1, 0) if n_slots else 0
-            nxt = {"row": empty32(n_next), "col": empty32(n_next), "lab": empty32(n_next), "w": empty32(n_next, torch.float32),
-                   "last": empty32(n_next), "heavy": torch.empty((n_next // (heavy + 1) + 2, 2), dtype=u32, device=dev)}
-            nxt_tail = nxt_w_item = None
+            bufs.ensure(next_most, keep=which, keep_slots=n_slots)
+            rec = bufs.rec[which]
+            nxt_lab = empty32(n_next)
+            nxt_first = nxt_deg = nxt_info = None
+            nxt_heavy = torch.empty((n_next // (heavy + 1) + 2, 2), dtype=u32, device=dev)
+            if k + 1 < K:
+                nxt_first, nxt_deg = empty32(n_next), empty32(n_next)
+                nxt_info = torch.empty((max(n_next, 1) + 1, 2), dtype=torch.int64, device=dev)
             if n_next:
                 ns = n_slots
                 offP = torch.empty(ns + 1, dtype=torch.int64, device=dev)
-                firstP, lblP, wP = empty32(ns), empty32(ns), empty32(ns, torch.float32)
+                lblP = empty32(ns)
                 srcbound = torch.empty((-(-n_next // tile), 2), dtype=u32, device=dev)
                 ws = scan_ws(ns)
                 limit = min(starts_before[k + 1], ns)
-                _lib.check(lib.ppg_chain_count_sorted(_ptr(slots["lab"]), ns, nxt_first, nxt_ptr, _ptr(w_item), limit, _ptr(rowid),
-                                                      _ptr(run_start), _ptr(ws), ws.numel(), _ptr(offP), _ptr(firstP), _ptr(lblP), _ptr(wP),
-                                                      _ptr(srcbound), stream))
-                if k + 1 < K:
-                    nxt_tail, nxt_w_item = empty32(n_next), empty32(n_next, torch.float32)
+                if k == 1:   # the counts of the events are in label order (temporal count): gather them into merged order
+                    firstP = empty32(ns)
+                    _lib.check(lib.ppg_chain_count_sorted(_ptr(labS), ns, ctypes.c_void_p(views[3]), ctypes.c_void_p(views[4]), None, limit,
+                                                          _ptr(rowid), _ptr(run_start), _ptr(ws), ws.numel(), _ptr(offP), _ptr(firstP),
+                                                          _ptr(lblP), None, _ptr(srcbound), stream))
+                    via = ctypes.c_void_p(views[1])
+                else:        # this level's tiles left them in merged order
+                    firstP = firstS
+                    _lib.check(lib.ppg_chain_count_sorted_next(_ptr(labS), ns, _ptr(degS), _ptr(info), 4, 2, limit, _ptr(rowid),
+                                                               _ptr(run_start), _ptr(ws), ws.numel(), _ptr(offP), _ptr(lblP),
+                                                               _ptr(srcbound), stream))
+                    via = None
                 state = torch.empty(-(-n_next // tile) + 1, dtype=torch.int64, device=dev)
-                _lib.check(lib.ppg_chain_tiles_dist(ns, 1, n_next, _ptr(offP), _ptr(firstP), _ptr(lblP), _ptr(wP), _ptr(run_start),
-                                                    _ptr(rowid), _ptr(row_value), _ptr(info), ctypes.c_void_p(views[1]) if k == 1 else None,
-                                                    _ptr(srcbound), heavy, _ptr(nxt["row"]), _ptr(nxt["col"]), _ptr(nxt["lab"]),
-                                                    _ptr(nxt["w"]), _ptr(nxt["last"]), _ptr(nxt_tail), _ptr(nxt_w_item), None, _ptr(state),
-                                                    _ptr(nxt["heavy"]), _ptr(res[k + 1]), stream))
-            slots, n_slots, tail, w_item = nxt, n_next, nxt_tail, nxt_w_item
-            first, ptr_next = nxt_first, nxt_ptr
+                _lib.check(lib.ppg_chain_tiles_dist(ns, n_next, _ptr(offP), _ptr(firstP), _ptr(lblP), word(rec, 3), 4, _ptr(run_start),
+                                                    _ptr(rowid), _ptr(row_value), _ptr(info), via, _ptr(srcbound), heavy,
+                                                    _ptr(bufs.rec[1 - which]), _ptr(nxt_lab), _ptr(nxt_first), _ptr(nxt_deg), _ptr(nxt_info),
+                                                    _ptr(state), _ptr(nxt_heavy), _ptr(res[k + 1]), stream))
+            labS, firstS, degS, heavy_list, n_slots = nxt_lab, nxt_first, nxt_deg, nxt_heavy, n_next
+            if nxt_info is not None:
+                info = nxt_info
             starts_before = next_starts
             offsets, offsets_dev, total_nodes = edge_offsets, edge_offsets_dev, edge_offsets[-1]
         main.wait_stream(side)

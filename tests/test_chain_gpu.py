@@ -114,7 +114,7 @@ def test_merge_sorted_runs_matches_torch(cuda, R, rows, total, row_lo, world):
     """Owner side of the distributed chain: `world` runs of records, each sorted by (row, col), merged in tiles; against
     the torch restatement of the owner's merge (stable: equal keys keep sender order, then arrival order).  The last
     case crams all records into 7 rows: the row ranges overflow their tiles and the status word asks for the sort."""
-    from pathpyg_b200.parallel import _MergeSorted
+    from pathpyg_b200.parallel import _MergeSorted  # noqa
     from torch_local_ops import TorchOps
 
     gen = torch.Generator().manual_seed(R + world)
@@ -130,14 +130,16 @@ def test_merge_sorted_runs_matches_torch(cuda, R, rows, total, row_lo, world):
     w = torch.rand(R, generator=gen)
     bits = w.view(torch.int32).to(torch.int64) & 0xffffffff
     records = torch.stack([(src << 32) | dst, (bits << 32) | last], dim=1).to(cuda)
-    got = _MergeSorted(records, recv, row_lo, rows, total)
+    back = torch.empty(max(R, 1), dtype=torch.int32, device=cuda)
+    got = _MergeSorted([records.data_ptr() + 16 * a for a in seg[:-1]], recv, [back.data_ptr() + 4 * a for a in seg[:-1]], row_lo, rows,
+                       total, cuda)
     want = TorchOps.merge_records_begin(records.cpu(), row_lo, rows, total)   # on the host: index_add_ runs in arrival order there
     words = got.result_words.tolist()
     if rows == 7:
         assert words[1] & 2
         return
     assert words == want.result_words.tolist()
-    assert torch.equal(got.inverse.cpu(), want.inverse)
+    assert torch.equal(back[:R].cpu(), want.inverse)
     n_out = words[0]
     for a, b in zip(got.finish(n_out), want.finish(n_out)):
         assert torch.equal(a.cpu(), b)
