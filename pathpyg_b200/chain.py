@@ -130,6 +130,7 @@ class TemporalChain:
             _lib.check(lib.ppg_lift_temporal_views(_ptr(tws), m, n, views))
             ptr1, grouped, sorted_src, first2, off2, _ = (ctypes.c_void_p(v) for v in views)
             # ---- level 1: events grouped by source node, ranked by target node inside every source group
+            torch.cuda.nvtx.range_push("chain.level[1]")     # NVTX range per order (free without a profiler attached)
             l1 = _Level(m, dev, self.weighted, K > 1, self.heavy)
             _lib.check(lib.ppg_chain_first_tiles(_ptr(self.ei), m, n, ptr1, grouped, sorted_src, _ptr(self.w), self.heavy,
                                                  _ptr(l1.rowS), _ptr(l1.colS), _ptr(l1.labS), _ptr(l1.wS), _ptr(l1.idS), _ptr(l1.node),
@@ -151,6 +152,7 @@ class TemporalChain:
             if words[_RES_HEAVY_ROWS]:
                 l1.merged = self._heavy_fix(l1, 1, words[_RES_HEAVY_ROWS], words[_RES_HEAVY_SLOTS])
             self._emit(store, 1, l1, n, None)
+            torch.cuda.nvtx.range_pop()
             if K == 1:
                 return
             pairs = words[4]
@@ -169,6 +171,7 @@ class TemporalChain:
                         store(j, torch.empty((2, 0), dtype=torch.int64, device=dev), torch.empty(0, dtype=torch.float32, device=dev),
                               nodes, inv)
                     return
+                torch.cuda.nvtx.range_push(f"chain.level[{k}]")
                 cur = _Level(pairs, dev, self.weighted, more, self.heavy)
                 ns = prev.items
                 offP = torch.empty(ns + 1, dtype=torch.int64, device=dev)
@@ -207,5 +210,6 @@ class TemporalChain:
                     cur.merged = self._heavy_fix(cur, k, words[_RES_HEAVY_ROWS], words[_RES_HEAVY_SLOTS])
                 self._emit(store, k, cur, prev.merged, inverse)
                 del offP, firstP, lblP, srcbound
+                torch.cuda.nvtx.range_pop()
                 prev, pairs = cur, words[_RES_NEXT]
             del tws

@@ -186,11 +186,13 @@ class DBGNN(nn.Module):
         n_fo, n_ho = sizes
 
         def first_order(x):
+            torch.cuda.nvtx.range_push("dbgnn.first_order_gcn")
             fo_graph = ops.gcn_prepare(ei, w, n_fo, keep_edge_values=grad, defer_check=True)
             for layer in self.first_order_layers:
                 if drop:
                     x = F.dropout(x, p=self.p_dropout, training=True)
                 x = layer.forward_prepared(x, fo_graph, _lib.ACT_ELU)
+            torch.cuda.nvtx.range_pop()
             return x, fo_graph
 
         # The first-order and the higher-order stack do not depend on each other until the bipartite layer.  Without
@@ -208,11 +210,13 @@ class DBGNN(nn.Module):
         else:
             x, fo_graph = first_order(x)
             bip_graph = None
+        torch.cuda.nvtx.range_push("dbgnn.higher_order_gcn")   # NVTX ranges per stage (free without a profiler attached)
         ho_graph = ops.gcn_prepare(ei_h, w_h, n_ho, keep_edge_values=grad, defer_check=True)
         for layer in self.higher_order_layers:
             if drop:
                 x_h = F.dropout(x_h, p=self.p_dropout, training=True)
             x_h = layer.forward_prepared(x_h, ho_graph, _lib.ACT_ELU)
+        torch.cuda.nvtx.range_pop()
         if fork:
             main.wait_stream(side)
             for t in (x, bip_graph.colptr, bip_graph.src, bip_graph.eid):
@@ -222,7 +226,9 @@ class DBGNN(nn.Module):
             x_h = F.dropout(x_h, p=self.p_dropout, training=True)
         if bip_graph is None:
             bip_graph = ops.csc_build(bip, n_ho, n_fo, defer_check=True)
+        torch.cuda.nvtx.range_push("dbgnn.bipartite")
         x = self.bipartite_layer.forward_prepared((x_h, x), bip_graph, _lib.ACT_ELU)
+        torch.cuda.nvtx.range_pop()
         if drop:
             x = F.dropout(x, p=self.p_dropout, training=True)
         out = _LinearFn.apply(x, self.lin.weight, self.lin.bias)

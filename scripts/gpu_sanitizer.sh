@@ -1,0 +1,43 @@
+#!/bin/bash
+# compute-sanitizer over the kernels with inter-CTA protocols and aliased shared memory:
+#   memcheck + racecheck of (a) the toy order-2 lift + DBGNN forward of __graft_entry__.smoke(), (b) a chain build with the
+#   heavy-row fallback forced on, (c) a multi-tile onesweep sort.  Run under gpurun on one B200; logs go to gpurun_out/.
+#     gpurun --timeout 1500 -- 'bash scripts/gpu_sanitizer.sh r02'
+set -u
+tag=${1:-san}
+out=gpurun_out
+mkdir -p $out
+cat > /tmp/san_case.py <<'PY'
+import os, sys, torch
+sys.path.insert(0, os.getcwd())
+import pathpyg_b200 as pp
+from pathpyg_b200 import ops
+import __graft_entry__ as g
+which = sys.argv[1]
+dev = torch.device("cuda", 0)
+if which == "smoke":
+    g.smoke()
+elif which == "chain":
+    gen = torch.Generator().manual_seed(1)
+    n, m = 300, 20000
+    ei = torch.randint(0, n, (2, m), generator=gen).to(dev)
+    t = torch.sort(torch.randint(0, 400, (m,), generator=gen)).values.to(dev)
+    for heavy in ("256", "3"):
+        os.environ["PPG_CHAIN_HEAVY"] = heavy
+        model = pp.MultiOrderModel.from_temporal_graph(pp.TemporalGraph.from_tensors(ei, t, n), delta=4, max_order=4)
+        print({k: (v.n, v.m) for k, v in model.layers.items()})
+elif which == "sort":
+    gen = torch.Generator().manual_seed(2)
+    keys = torch.randint(0, 1 << 40, (20000,), generator=gen).to(dev)
+    want = torch.sort(keys, stable=True)
+    perm, _ = ops.sort_pairs_u64(keys, 40)
+    assert torch.equal(keys, want.values) and torch.equal(perm.long(), want.indices)
+torch.cuda.synchronize()
+print(which, "ok")
+PY
+for tool in memcheck racecheck; do
+  for c in smoke chain sort; do
+    timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py $c > $out/${tag}_sanitizer_${tool}_${c}.log 2>&1
+    echo "$tool $c: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $out/${tag}_sanitizer_${tool}_${c}.log | tail -1)"
+  done
+done
