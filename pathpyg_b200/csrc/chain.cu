@@ -363,11 +363,13 @@ chain_tile_kernel(ChainTileArgs a) {
           } else {     // merged id | first level-k item whose source is this item << 32
             const unsigned long long nd = a.node_prev[item];
             col = static_cast<uint32_t>(nd);
+#ifndef PPG_NEXT_REREAD
             if (NEXT) {
               const uint32_t p0 = static_cast<uint32_t>(nd >> 32);
               s_nfirst[i] = p0;
               s_ndeg[i] = static_cast<uint32_t>(a.node_prev[item + 1] >> 32) - p0;
             }
+#endif
           }
         }
         s_col[i] = col;
@@ -467,8 +469,19 @@ chain_tile_kernel(ChainTileArgs a) {
         const int64_t jj = static_cast<int64_t>(i) - s_soff[f0];
         label[k] = s_lbl[f0] + static_cast<uint32_t>(jj);
         if (NEXT) {
+#ifndef PPG_NEXT_REREAD
           ndeg[k] = s_ndeg[i];
           st_stream(a.firstS + cb + p, s_nfirst[i]);
+#else
+          // experiment (-DPPG_NEXT_REREAD): the continuation's node word again (L1 / L2) rather than two more shared-memory
+          // words per slot, which cost the fifth resident CTA.  Measured on B200: 6.66 vs 6.13 ms at cfg3, 108.9 vs 107.9 ms at
+          // cfg5 -- the extra dependent load in the store phase costs more than the fifth CTA gains; not the default.
+          const uint32_t g = s_first[f0] + static_cast<uint32_t>(jj);
+          const uint32_t item = a.via != nullptr ? a.via[g] : g;
+          const uint32_t p0 = static_cast<uint32_t>(a.node_prev[item] >> 32);
+          ndeg[k] = static_cast<uint32_t>(a.node_prev[item + 1] >> 32) - p0;
+          st_stream(a.firstS + cb + p, p0);
+#endif
           st_stream(a.degS + cb + p, ndeg[k]);
         }
         st_stream(a.labS + cb + p, label[k]);
@@ -1089,7 +1102,11 @@ static int launch_tiles(ChainTileArgs& a, bool first, cudaStream_t stream) {
                                         static_cast<int>(kChainTileSmemNext)));
       configured = true;
     }
+#ifndef PPG_NEXT_REREAD
     chain_tile_kernel<false, false, true><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmemNext, stream>>>(a);
+#else
+    chain_tile_kernel<false, false, true><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
+#endif
   } else {
     chain_tile_kernel<false, false, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
   }
