@@ -35,8 +35,18 @@
 
 namespace ppg {
 
-constexpr int kChainBlock = 256;
-constexpr int kChainTile = 1024;                         // nominal slots (pairs) per tile
+// Tile geometry, measured on B200 (device time of from_temporal_graph at cfg3 / cfg5; `make variant`):
+//   256 threads x 1024 + 256 slots: 6.13 / 107.9 ms      512 x 1280 + 256: 5.72 / 104.1 ms  (the default)
+//   256 x  768 + 256: 6.17 / 109.0 ms                    512 x  768 + 256: 5.93 / 112.7 ms
+//   512 x 2304 + 256: 6.15 / 108.4 ms                   1024 x 1792 + 256: 5.90 / 109.8 ms
+#ifndef PPG_CHAIN_BLOCK
+#define PPG_CHAIN_BLOCK 512
+#endif
+#ifndef PPG_CHAIN_TILE
+#define PPG_CHAIN_TILE 1280
+#endif
+constexpr int kChainBlock = PPG_CHAIN_BLOCK;
+constexpr int kChainTile = PPG_CHAIN_TILE;               // nominal slots (pairs) per tile
 constexpr int kChainHeavyMax = 256;                      // rows above this never take the in-tile ranking
 constexpr int kChainCap = kChainTile + kChainHeavyMax;   // slots staged per chunk: every non-heavy row of a tile fits
 constexpr int kChainPerThread = kChainCap / kChainBlock; // 5
@@ -1090,6 +1100,16 @@ static int launch_tiles(ChainTileArgs& a, bool first, cudaStream_t stream) {
                                   : (first ? 0 : 8 + (a.via != nullptr ? 4 : 0)) + 12 + (a.wS != nullptr ? 4 : 0) +
                                         (a.idS != nullptr ? 4 : 0) + (a.node_out != nullptr ? (first ? 4 : 8) : 0) + (next ? 8 : 0);
   const long long launch_bytes = per_source * a.n_sources + per_slot * a.n_slots;
+  static bool configured_all = false;   // shared memory beyond the 48 KB default (larger tile geometries, NEXT)
+  if (!configured_all) {
+    PPG_CUDA_TRY(cudaFuncSetAttribute(chain_tile_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(kChainTileSmem)));
+    PPG_CUDA_TRY(cudaFuncSetAttribute(chain_tile_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(kChainTileSmem)));
+    PPG_CUDA_TRY(cudaFuncSetAttribute(chain_tile_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(kChainTileSmem)));
+    configured_all = true;
+  }
   profile_pass_begin(stream);
   if (first) {
     chain_tile_kernel<true, false, false><<<static_cast<unsigned>(tiles), kChainBlock, kChainTileSmem, stream>>>(a);
