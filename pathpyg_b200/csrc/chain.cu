@@ -755,9 +755,15 @@ heavy_write_kernel(const unsigned long long* __restrict__ keys, int64_t slots, c
 // order, so equal keys stay in the single-device summation order) and WRITES the merged-edge index of every record
 // straight into the sender's answer buffer: the transfer in both directions is the merge kernel's own load and store
 // stream.
-constexpr int kMergeBlock = 256;
-constexpr int kMergeTile = 1024;  // records a tile is sized for
-constexpr int kMergeCap = 2048;   // records a tile can hold (uniform row ranges: load varies)
+#ifndef PPG_MERGE_BLOCK
+#define PPG_MERGE_BLOCK 512
+#endif
+#ifndef PPG_MERGE_TILE
+#define PPG_MERGE_TILE 1024
+#endif
+constexpr int kMergeBlock = PPG_MERGE_BLOCK;
+constexpr int kMergeTile = PPG_MERGE_TILE;      // records a tile is sized for
+constexpr int kMergeCap = 2 * PPG_MERGE_TILE;   // records a tile can hold (uniform row ranges: load varies)
 constexpr int kMergePerThread = kMergeCap / kMergeBlock;
 constexpr int kMaxRanks = PPG_ROUTE_MAX_RANKS;
 constexpr unsigned long long kMergeStatusOverflow = 2ull;
