@@ -764,6 +764,8 @@ heavy_write_kernel(const unsigned long long* __restrict__ keys, int64_t slots, c
 constexpr int kMergeBlock = PPG_MERGE_BLOCK;
 constexpr int kMergeTile = PPG_MERGE_TILE;      // records a tile is sized for
 constexpr int kMergeCap = 2 * PPG_MERGE_TILE;   // records a tile can hold (uniform row ranges: load varies)
+constexpr int kMergeRows = 2048;                // rows per tile up to which the merge counts the records of every row
+constexpr size_t kMergeSmem = static_cast<size_t>(kMergeCap) * (8 + 4 + 4 + 4 + 2) + (kMergeRows + 1) * 4;
 constexpr int kMergePerThread = kMergeCap / kMergeBlock;
 constexpr int kMaxRanks = PPG_ROUTE_MAX_RANKS;
 constexpr unsigned long long kMergeStatusOverflow = 2ull;
@@ -935,11 +937,14 @@ struct MergeArgs {
 
 __global__ void __launch_bounds__(kMergeBlock)
 merge_tile_kernel(MergeArgs a) {
-  __shared__ unsigned long long s_key[kMergeCap];   // (row - first row of the tile) << 32 | col
-  __shared__ float s_w[kMergeCap];
-  __shared__ uint32_t s_last[kMergeCap];
-  __shared__ uint32_t s_run[kMergeCap];
-  __shared__ uint16_t s_perm[kMergeCap];
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(merge_smem);   // (row - first row of the tile) << 32 | col
+  float* s_w = reinterpret_cast<float*>(s_key + kMergeCap);
+  uint32_t* s_last = reinterpret_cast<uint32_t*>(s_w + kMergeCap);
+  uint32_t* s_run = s_last + kMergeCap;
+  uint32_t* s_hist = s_run + kMergeCap;                                             // [kMergeRows + 1] records per row of the tile
+  uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_hist + kMergeRows + 1);
+  uint16_t* s_grp = reinterpret_cast<uint16_t*>(s_run);                             // records grouped by row (dead before s_run is written)
   __shared__ uint32_t s_lo[kMaxRanks], s_off[kMaxRanks + 1];
   __shared__ uint32_t s_warp_cnt[kMergeBlock / 32];
   __shared__ unsigned long long s_base_id;
@@ -973,6 +978,11 @@ merge_tile_kernel(MergeArgs a) {
     return;
   }
   const long long row0 = a.row_lo + static_cast<long long>(tile) * a.rows_per_tile;
+  const bool by_rows = a.rows_per_tile <= kMergeRows;   // few enough rows per tile to count the records of every row
+  if (by_rows) {
+    for (int r = tid; r <= kMergeRows; r += kMergeBlock) s_hist[r] = 0;
+    __syncthreads();
+  }
   // ---- load the slices, sender after sender (remote senders: NVLink peer loads)
   for (int i = tid; i < n; i += kMergeBlock) {
     int s = 0;
@@ -981,11 +991,60 @@ merge_tile_kernel(MergeArgs a) {
     const long long row = static_cast<long long>(r.y);
     if (row < a.row_lo || row >= a.row_lo + a.rows_owned || static_cast<long long>(r.x) >= a.total_nodes)
       atomicOr(a.result + 1, kChainStatusIdOutOfRange);
-    s_key[i] = (static_cast<unsigned long long>(row - row0) << 32) | r.x;
+    long long local = row - row0;
+    if (local < 0 || local >= a.rows_per_tile) local = 0;   // a foreign row (flagged above) must not leave the tile's tables
+    s_key[i] = (static_cast<unsigned long long>(local) << 32) | r.x;
     s_w[i] = __uint_as_float(r.w);
     s_last[i] = r.z;
+    if (by_rows) atomicAdd(&s_hist[local], 1u);
   }
   __syncthreads();
+  if (by_rows) {
+    // ---- merge by counting: records per row -> row segments -> every record ranked inside its row by (col, arrival
+    // index).  The arrival index orders senders by rank and a sender's records by position, i.e. stream order, so the
+    // result is the stable merge of the runs -- at a cost of two shared-memory atomics and one pass over a (short) row
+    // per record, where the search-based merge below pays (world - 1) binary searches.
+    {
+      constexpr int PER = (kMergeRows + kMergeBlock - 1) / kMergeBlock;
+      uint32_t v[PER];
+      uint32_t sum = 0;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int r = tid * PER + k;
+        v[k] = r < kMergeRows ? s_hist[r] : 0u;
+        sum += v[k];
+      }
+      const uint32_t inc = warp_inclusive_sum(sum);
+      if (lane == 31) s_warp_cnt[warp] = inc;
+      __syncthreads();
+      uint32_t before = inc - sum;
+#pragma unroll
+      for (int w = 0; w < kMergeBlock / 32; ++w)
+        if (w < warp) before += s_warp_cnt[w];
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int r = tid * PER + k;
+        if (r < kMergeRows) s_hist[r] = before;   // first slot of the row; the scatter below advances it to the row's end
+        before += v[k];
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kMergeBlock) s_grp[atomicAdd(&s_hist[s_key[i] >> 32], 1u)] = static_cast<uint16_t>(i);
+    __syncthreads();
+    for (int i = tid; i < n; i += kMergeBlock) {
+      const unsigned long long key = s_key[i];
+      const uint32_t row = static_cast<uint32_t>(key >> 32);
+      const int lo = row ? static_cast<int>(s_hist[row - 1]) : 0, hi = static_cast<int>(s_hist[row]);
+      int rank = 0;
+      for (int j = lo; j < hi; ++j) {
+        const int other = s_grp[j];
+        const unsigned long long k2 = s_key[other];
+        rank += (k2 < key || (k2 == key && other < i)) ? 1 : 0;
+      }
+      s_perm[lo + rank] = static_cast<uint16_t>(i);
+    }
+    __syncthreads();   // s_grp (aliased with s_run) is dead from here on
+  } else
   // ---- rank of every record in the merge of the runs (stable: earlier senders first among equal keys)
   for (int i = tid; i < n; i += kMergeBlock) {
     int s = 0;
@@ -1481,7 +1540,12 @@ extern "C" int ppg_merge_sorted(void* const* h_runs, const int64_t* h_run_len, v
   a.tile_state = static_cast<unsigned long long*>(tile_state);
   a.result = reinterpret_cast<unsigned long long*>(result);
   profile_pass_begin(stream);
-  merge_tile_kernel<<<static_cast<unsigned>(tiles), kMergeBlock, 0, stream>>>(a);
+  static bool configured = false;
+  if (!configured) {
+    PPG_CUDA_TRY(cudaFuncSetAttribute(merge_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMergeSmem)));
+    configured = true;
+  }
+  merge_tile_kernel<<<static_cast<unsigned>(tiles), kMergeBlock, kMergeSmem, stream>>>(a);
   profile_pass_end(stream, num_records, 16 + 4 + 16, PPG_PROFILE_MERGE_TILES);   // record in, merged index out, merged edge out (upper bound)
   PPG_LAUNCHED();
   return PPG_OK;

@@ -250,6 +250,7 @@ class _Trace:
         self.timed = os.environ.get("PPG_DIST_TRACE", "0") == "1" and dev.type == "cuda"
         self.cuda = dev.type == "cuda"
         self.marks = []
+        self.sizes = []      # (level, sources, sources expanded, pairs) of every expansion, when timed
         self.open = False
         self.mark("start")
 
@@ -273,9 +274,12 @@ class _Trace:
             torch.cuda.synchronize()
             t0 = self.marks[0][1]
             last_trace = [(label, t0.elapsed_time(ev)) for label, ev in self.marks]
+            global last_sizes
+            last_sizes = list(self.sizes)
 
 
 last_trace = None
+last_sizes = None
 
 
 def _gather_counts(mine: torch.Tensor, group) -> torch.Tensor:
@@ -745,6 +749,8 @@ def _distributed_chain_layers(ext_ei, ext_t, ext_w, m_own, num_nodes, delta, K, 
                                             _ptr(info), ctypes.c_void_p(res[k].data_ptr() + 8 * 5), stream))
             mark(f"lift_next[{k}]")
             n_next = next_starts.get(k + 1, 0) if n_slots else 0
+            if trace.timed:
+                trace.sizes.append((k + 1, n_slots, min(starts_before[k + 1], n_slots), n_next))
             bufs.ensure(next_most, keep=which, keep_slots=n_slots)
             rec = bufs.rec[which]
             nxt_lab = empty32(n_next)

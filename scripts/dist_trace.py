@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--workload", default="cfg5")
     ap.add_argument("--events", type=int, default=None)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--last-share", type=float, default=None, help="size of the last rank's range relative to the others")
     a = ap.parse_args()
     cfg = dict(bench.WORKLOADS[a.workload])
     if a.events:
@@ -34,7 +35,7 @@ def main():
     os.environ.setdefault("MASTER_PORT", "29512")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     ei, t = bench.make_stream(cfg, seed=0)
-    lo, hi = parallel.partition_stream(cfg["m"], rank, world, last_share=1.0 + bench.ghost_overhead(cfg, world))
+    lo, hi = parallel.partition_stream(cfg["m"], rank, world, last_share=a.last_share if a.last_share is not None else 1.0 + bench.ghost_overhead(cfg, world))
     ei_l, t_l = ei[:, lo:hi].contiguous().to(dev), t[lo:hi].contiguous().to(dev)
     del ei, t
     K = cfg["order"]
@@ -53,6 +54,8 @@ def main():
     durations = torch.tensor([b[1] - a_[1] for a_, b in zip(tr[:-1], tr[1:])], device=dev)
     worst = durations.clone()
     dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    every = [torch.empty_like(durations) for _ in range(world)]
+    dist.all_gather(every, durations)
     if rank == 0:
         print(f"# distributed lift {a.workload}: {cfg['m']} events, {world} rank(s); best step {total:.2f} ms (max over ranks)")
         print(f"# {'phase':24s} {'rank0 ms':>10s} {'max ms':>10s}")
@@ -63,6 +66,22 @@ def main():
             agg[key] = agg.get(key, 0.0) + dmax
         print("# by phase kind (sum of per-phase max over ranks):", json.dumps({k: round(v, 2) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}))
         print(f"# peak memory rank 0: {torch.cuda.max_memory_allocated(dev) / 2**30:.1f} GiB")
+        kinds = sorted({label.split("[")[0] for label, _ in tr[:-1]})
+        print("# per rank, ms by phase kind (a rank that waits at a synchronisation shows it under route_count / merge_sync):")
+        for r, d in enumerate(every):
+            row = {k: 0.0 for k in kinds}
+            for (label, _), v in zip(tr[:-1], d.tolist()):
+                row[label.split("[")[0]] += v
+            print(f"#   rank {r}: " + "  ".join(f"{k} {v:.1f}" for k, v in row.items()))
+        print("# expansion of every level per rank: lift_next ms")
+        for r, d in enumerate(every):
+            print(f"#   rank {r}: " + "  ".join(f"{label} {v:.2f}" for (label, _), v in zip(tr[:-1], d.tolist()) if label.startswith("lift_next")))
+    sizes = [None] * world
+    dist.all_gather_object(sizes, parallel.last_sizes)
+    if rank == 0:
+        print("# (level, sources, sources expanded, pairs) per rank:")
+        for r, sz in enumerate(sizes):
+            print(f"#   rank {r}: {sz}")
     dist.barrier()
     dist.destroy_process_group()
 

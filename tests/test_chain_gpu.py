@@ -109,11 +109,13 @@ def test_chain_bad_ids(cuda):
 
 
 @pytest.mark.parametrize("R,rows,total,row_lo,world", [(0, 5, 9, 3, 2), (1, 1, 1, 0, 1), (4000, 60, 200, 1000, 3), (700_000, 50_000, 400_000, 123_456, 8),
-                                                       (300_000, 200_000, 9_000_000, 5_000_000, 16), (50_000, 7, 30, 10, 4)])
+                                                       (300_000, 200_000, 9_000_000, 5_000_000, 16), (50_000, 7, 30, 10, 4),
+                                                       (3_000, 10_000_000, 9_000_000, 0, 5)])
 def test_merge_sorted_runs_matches_torch(cuda, R, rows, total, row_lo, world):
     """Owner side of the distributed chain: `world` runs of records, each sorted by (row, col), merged in tiles; against
-    the torch restatement of the owner's merge (stable: equal keys keep sender order, then arrival order).  The last
-    case crams all records into 7 rows: the row ranges overflow their tiles and the status word asks for the sort."""
+    the torch restatement of the owner's merge (stable: equal keys keep sender order, then arrival order).  One case
+    crams all records into 7 rows: the row ranges overflow their tiles and the status word asks for the sort; the last
+    one spreads few records over many rows, which takes the search-based ranking instead of the per-row counts."""
     from pathpyg_b200.parallel import _MergeSorted  # noqa
     from torch_local_ops import TorchOps
 
