@@ -336,10 +336,15 @@ class Graph:
             ptr, perm = ops.sorted_ids_ptr(t[0], self.n), None  # Graph keeps edge_index sorted by row
         if w is None:
             d = (ptr[1:] - ptr[:-1]).to(torch.int32)            # torch_geometric.utils.degree(..., dtype=torch.int)
-        else:
+        elif w.dtype == torch.float32:
             d = ops.segment_sum(ptr, w, perm)
-            if w.dtype.is_floating_point and w.dtype != torch.float32:
-                d = d.to(w.dtype)
+        else:
+            # the reference's scatter(..., reduce="sum") keeps the weight dtype (graph.py:506,512): integer weights are
+            # summed exactly in int64, float64 weights in float64 (differences of one running sum over the grouped order)
+            grouped_w = w if perm is None else w[perm.long()]
+            acc = torch.float64 if w.dtype.is_floating_point else torch.int64
+            run = torch.cat([torch.zeros(1, dtype=acc, device=dev), torch.cumsum(grouped_w.to(acc), 0)])
+            d = (run[ptr[1:].long()] - run[ptr[:-1].long()]).to(w.dtype)
         return _staging.down(d, to_host)
 
     def degrees(self, mode: str = "in", edge_attr: str | None = None, return_tensor: bool = False):
