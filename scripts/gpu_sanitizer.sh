@@ -26,6 +26,20 @@ elif which == "chain":
         os.environ["PPG_CHAIN_HEAVY"] = heavy
         model = pp.MultiOrderModel.from_temporal_graph(pp.TemporalGraph.from_tensors(ei, t, n), delta=4, max_order=4)
         print({k: (v.n, v.m) for k, v in model.layers.items()})
+elif which == "dist":
+    import torch.distributed as dist
+    from pathpyg_b200 import parallel
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29571")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    gen = torch.Generator().manual_seed(3)
+    n, m = 200, 12000
+    ei = torch.randint(0, n, (2, m), generator=gen).to(dev)
+    t = torch.sort(torch.randint(0, 300, (m,), generator=gen)).values.to(dev)
+    for heavy in ("256", "3"):
+        os.environ["PPG_CHAIN_HEAVY"] = heavy
+        layers = parallel.distributed_temporal_layers(ei, t, n, 4, 4)
+        print({k: (v.num_nodes, v.edge_index.size(1)) for k, v in layers.items()})
+    dist.destroy_process_group()
 elif which == "sort":
     gen = torch.Generator().manual_seed(2)
     keys = torch.randint(0, 1 << 40, (20000,), generator=gen).to(dev)
@@ -36,7 +50,7 @@ torch.cuda.synchronize()
 print(which, "ok")
 PY
 for tool in memcheck racecheck; do
-  for c in smoke chain sort; do
+  for c in smoke chain dist sort; do
     timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py $c > $out/${tag}_sanitizer_${tool}_${c}.log 2>&1
     echo "$tool $c: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $out/${tag}_sanitizer_${tool}_${c}.log | tail -1)"
   done
