@@ -14,6 +14,7 @@
 // three MMAs accumulate A_hi W_hi + A_lo W_hi + A_hi W_lo into the same TMEM tile; the dropped term
 // A_lo W_lo is below 2^-21 relative, products of 11-bit significands are exact in the fp32 accumulator.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -117,20 +118,17 @@ struct TmemLoad<32> {
   }
 };
 
-// ELU: expm1 for x <= 0 without the slow library path.  |x| < 0.5: degree-8 Taylor polynomial (truncation
-// < 3e-8 relative); below: exp(x) - 1 with ex2.approx (result magnitude >= 0.39, so no cancellation).
+// ELU: expm1 for x <= 0 without the slow library path.  |x| < 0.125: degree-5 Taylor polynomial (truncation
+// < 5e-8 relative); below: exp(x) - 1 with ex2.approx (result magnitude >= 0.117, absolute error ~2e-7: < 2e-6 relative).
 __device__ __forceinline__ float tc_activate(float x, int act) {
   if (act != PPG_ACT_ELU || x > 0.f) return x;
-  float p = fmaf(x, 1.f / 40320.f, 1.f / 5040.f);
-  p = fmaf(p, x, 1.f / 720.f);
-  p = fmaf(p, x, 1.f / 120.f);
-  p = fmaf(p, x, 1.f / 24.f);
+  float p = fmaf(x, 1.f / 120.f, 1.f / 24.f);
   p = fmaf(p, x, 1.f / 6.f);
   p = fmaf(p, x, 0.5f);
   p = fmaf(p, x, 1.f);
   p *= x;
   const float e = __expf(x) - 1.f;
-  return x > -0.5f ? p : e;
+  return x > -0.125f ? p : e;
 }
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
@@ -645,6 +643,380 @@ gcn_tc_ws_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Staged variant (the default): one persistent CTA per SM, 4 producer warps + 16 consumer warps; the row gather is
+// asynchronous, holds no registers and runs ahead of the arithmetic across tile boundaries.
+//   * The rows of a tile's CSC slots, in slot order, are cut into chunks of 128; a chunk fills one of kSgStages row
+//     buffers in shared memory (128 x F floats, plain row-major).
+//   * Producer warps: a lane reads one src word of the chunk (coalesced, fetched one chunk ahead), the warp requests
+//     its 32 rows with cp.async.cg (16 bytes per lane, L1 bypassed) and the slot values with 4-byte cp.async, then
+//     every producer thread signals the stage's `full` barrier through cp.async.mbarrier.arrive.  Producers only wait
+//     for a free stage, so the rows of tiles t + 1, t + 2 are in flight while tile t is multiplied and written.
+//   * Consumer warps: thread = (16-byte chunk of the row, nodes G, G + groups, ...), accumulators in registers; the
+//     nodes' own rows (contiguous in X) are requested with plain loads at the top of the tile and used at its end; per
+//     stage a thread adds the slots of its nodes that fall into the chunk (ld.shared.v4 + 4 FMA per row and lane),
+//     then releases the stage (`empty` barrier).  Same summation order as the other two kernels: bit-identical.
+//   * One more warp issues the MMAs (the issue of 24 tcgen05.mma blocks its thread for 1.7 us per tile) into one of
+//     two TMEM accumulators as soon as every consumer warp has arrived on the `operands ready` barrier; while they run
+//     the consumers convert, activate and store tile t - 1 straight from TMEM to global memory (thread = one row, 16
+//     consecutive columns).  The operand buffers are rewritten only after the MMAs of the previous tile have
+//     completed.  No CTA-wide barrier inside the tile loop: every hand-over is an mbarrier.
+// Why: the single-role kernel spends 7.8 of 12.2 us per tile in a chain of four dependent memory latencies (pointers ->
+// (src, val) -> first row batch -> second row batch) at 25 % occupancy and executes about 20 000 warp instructions per
+// tile (profiles/r02aa_gcn_trace.log, r02aa ncu capture); here a row costs one LDGSTS per 16 lanes on the producer
+// side and one LDS.128 + 4 FFMA per lane on the consumer side.
+constexpr int kSgConsumers = 512;
+constexpr int kSgProducers = 128;
+constexpr int kSgThreads = kSgConsumers + kSgProducers + 32;   // + the warp whose lane 0 issues the MMAs
+constexpr int kSgChunk = 128;     // rows per stage
+constexpr int kSgStages = 3;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+// the executing thread arrives on the barrier once all its earlier cp.async copies have landed
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// mbarrier wait that parks the thread in hardware (try_wait) instead of polling test_wait: the waiting role must not
+// take issue slots from the working one
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  int spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"   // suspend-time hint (ns)
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1 << 22)) __trap();  // a lost arrival must fail loudly, not hang the device
+  }
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSgConsumers) : "memory"); }
+
+__host__ __device__ constexpr size_t sg_smem_bytes(int F, int H) {
+  return 2 * static_cast<size_t>(kTcTile) * F * 4 + 2 * static_cast<size_t>(H) * F * 4 +
+         static_cast<size_t>(kSgStages) * kSgChunk * F * 4 + static_cast<size_t>(kSgStages) * kSgChunk * 4 + 1024;
+}
+
+template <int F, int H>
+__global__ void __launch_bounds__(kSgThreads, 1)
+gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__ src, const float* __restrict__ val,
+                     const float* __restrict__ self_val, const float* __restrict__ X, const float* __restrict__ W,
+                     const float* __restrict__ bias, int64_t n, int act, float* __restrict__ out) {
+  static_assert(F % 32 == 0 && (H == 16 || H == 32 || H == 64), "unsupported width");
+  constexpr int LPN = F / 4;                                   // lanes per row (one float4 each)
+  constexpr int GPW = 32 / LPN;                                // rows per warp instruction
+  constexpr int GROUPS = kSgConsumers / LPN;                   // consumer lane groups
+  constexpr int NPG = kTcTile / GROUPS;                        // consecutive nodes per lane group
+  constexpr int ROW_BYTES = F * 4;
+  constexpr int STAGE_BYTES = kSgChunk * ROW_BYTES;
+  constexpr int A_BYTES = kTcTile * F * 4;
+  constexpr int W_BYTES = H * F * 4;
+  constexpr int TMEM_COLS = 2 * H < 32 ? 32 : 2 * H;           // two accumulators
+  constexpr int CPT = H >= 32 ? H / 4 : 8;                     // accumulator columns per thread in the epilogue
+  constexpr int CBLOCKS = H / CPT;                             // column blocks (warp / 4 below CBLOCKS takes part)
+  constexpr uint32_t IDESC = umma_idesc_tf32(kTcTile, H);
+  constexpr int C = kSgChunk;
+  static_assert(NPG >= 1, "geometry");
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  unsigned char* sAhi = base;
+  unsigned char* sAlo = base + A_BYTES;
+  unsigned char* sWhi = base + 2 * A_BYTES;
+  unsigned char* sWlo = sWhi + W_BYTES;
+  unsigned char* sRows = sWlo + W_BYTES;                                          // [kSgStages][C][ROW_BYTES]
+  float* sVal = reinterpret_cast<float*>(sRows + kSgStages * STAGE_BYTES);        // [kSgStages][C]
+  __shared__ __align__(8) unsigned long long s_mbar;                // MMAs of a tile complete (phase = tile)
+  __shared__ __align__(8) unsigned long long s_aready;              // operands of a tile complete (phase = tile)
+  __shared__ __align__(8) unsigned long long s_full[kSgStages];     // rows of the stage have landed
+  __shared__ __align__(8) unsigned long long s_empty[kSgStages];    // every consumer warp has left the stage
+  __shared__ uint32_t s_tmem_base;
+  __shared__ int32_t s_ptr[2][kTcTile + 1];
+  __shared__ float s_bias[H];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int64_t num_tiles = ceil_div(n, kTcTile);
+  const int64_t my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  auto row0_of = [&](int64_t t) { return (static_cast<int64_t>(blockIdx.x) + t * gridDim.x) * kTcTile; };
+
+  // ---- one-time setup: W^T split into TF32 hi / lo parts, bias, TMEM allocation, barriers, pointers of tile 0
+  for (int idx = tid; idx < H * F; idx += kSgThreads) {
+    const int h = idx / F, k = idx % F;
+    float hi, lo;
+    split_tf32(W[idx], hi, lo);
+    const uint32_t off = swz_offset(H, h, k);
+    *reinterpret_cast<float*>(sWhi + off) = hi;
+    *reinterpret_cast<float*>(sWlo + off) = lo;
+  }
+  if (tid < H) s_bias[tid] = bias != nullptr ? bias[tid] : 0.f;
+  if (tid <= kTcTile) {
+    const int64_t v = row0_of(0) + tid;
+    s_ptr[0][tid] = colptr[v < n ? v : n];
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_mbar), 1);
+    mbar_init(smem_u32(&s_aready), kSgConsumers / 32);
+    for (int s = 0; s < kSgStages; ++s) {
+      mbar_init(smem_u32(&s_full[s]), kSgProducers);
+      mbar_init(smem_u32(&s_empty[s]), kSgConsumers / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem_base;
+  const uint32_t mbar = smem_u32(&s_mbar), aready = smem_u32(&s_aready);
+  const uint32_t bar_full = smem_u32(&s_full[0]), bar_empty = smem_u32(&s_empty[0]);
+  const uint32_t rows_base = smem_u32(sRows), val_base = smem_u32(sVal);
+
+  if (warp == (kSgConsumers + kSgProducers) / 32) {
+    // ================================================================== MMA issuer
+    // D[128 x H] (TMEM, accumulator t & 1) = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T once the operands of tile t are ready
+    if (lane == 0) {
+      const uint32_t a_hi = smem_u32(sAhi), a_lo = smem_u32(sAlo), w_hi = smem_u32(sWhi), w_lo = smem_u32(sWlo);
+      for (int64_t t = 0; t < my_tiles; ++t) {
+        mbar_wait_parked(aready, static_cast<uint32_t>(t & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>((t & 1) * H);
+        uint32_t accumulate = 0;
+#pragma unroll
+        for (int j = 0; j < F / 8; ++j) {  // K = 8 per tf32 instruction: 32 bytes along the 128-byte swizzled row
+          const uint32_t a_off = (j >> 2) * (kTcTile * 128) + (j & 3) * 32;
+          const uint32_t w_off = (j >> 2) * (H * 128) + (j & 3) * 32;
+          umma_tf32(tmem_d, umma_desc(a_hi + a_off), umma_desc(w_hi + w_off), IDESC, accumulate);
+          accumulate = 1;
+          umma_tf32(tmem_d, umma_desc(a_lo + a_off), umma_desc(w_hi + w_off), IDESC, 1);
+          umma_tf32(tmem_d, umma_desc(a_hi + a_off), umma_desc(w_lo + w_off), IDESC, 1);
+        }
+        // arrives on the barrier when all MMAs above have completed (implies tcgen05.fence::before_thread_sync)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+      }
+    }
+  } else if (warp >= kSgConsumers / 32) {
+    // ================================================================== producers
+    const int pw = warp - kSgConsumers / 32;          // this warp requests rows [32 pw, 32 pw + 32) of every chunk
+    const int h = lane / LPN, c16 = lane % LPN;
+    uint32_t gchunk = 0;
+    auto tile_range = [&](int64_t tt, int32_t& E0, int32_t& E1) {
+      const int64_t r0 = row0_of(tt), r1 = r0 + kTcTile;
+      const bool exists = tt < my_tiles;
+      E0 = colptr[(exists && r0 < n) ? r0 : n];
+      E1 = colptr[(exists && r1 < n) ? r1 : n];
+    };
+    int32_t E0, E1, E0n, E1n;
+    tile_range(0, E0, E1);
+    // src word of this lane's row in the chunk that comes next (fetched one chunk ahead)
+    int32_t idx_next = (E0 + pw * 32 + lane < E1) ? src[E0 + pw * 32 + lane] : 0;
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      tile_range(t + 1, E0n, E1n);
+      const int nchunks = (E1 - E0 + C - 1) / C;
+      for (int k = 0; k < nchunks; ++k, ++gchunk) {
+        const uint32_t st = gchunk % kSgStages, use = gchunk / kSgStages;
+        mbar_wait_parked(bar_empty + 8 * st, (use & 1) ^ 1);
+        const uint32_t stage = rows_base + st * STAGE_BYTES;
+        const int32_t e_l = E0 + k * C + pw * 32 + lane;   // this lane's slot: src word and value
+        const int32_t idx = idx_next;
+        if (k + 1 < nchunks) idx_next = e_l + C < E1 ? src[e_l + C] : 0;
+        if (val != nullptr && e_l < E1) cp_async4(val_base + (st * C + pw * 32 + lane) * 4, val + e_l);
+#pragma unroll
+        for (int j = 0; j < 32 / GPW; ++j) {
+          const int item = j * GPW + h;
+          const int32_t row = __shfl_sync(kFullMask, idx, item);
+          if (e_l - lane + item < E1)
+            cp_async16(stage + static_cast<uint32_t>((pw * 32 + item) * ROW_BYTES + c16 * 16), X + static_cast<int64_t>(row) * F + c16 * 4);
+        }
+        cp_async_arrive(bar_full + 8 * st);
+      }
+      idx_next = (E0n + pw * 32 + lane < E1n) ? src[E0n + pw * 32 + lane] : 0;   // first chunk of the next tile
+      E0 = E0n;
+      E1 = E1n;
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else {
+    // ================================================================== consumers
+    const int c16 = tid % LPN;
+    const int G = tid / LPN;
+    uint32_t gchunk = 0;
+    float cf[NPG], cf_next[NPG];   // coefficients of the own rows, fetched one tile ahead
+    auto load_self = [&](int64_t tt, float* coef) {
+      const int64_t r0 = row0_of(tt);
+#pragma unroll
+      for (int j = 0; j < NPG; ++j) {
+        const int64_t v = r0 + G * NPG + j;
+        coef[j] = (self_val != nullptr && tt < my_tiles && v < n) ? self_val[v] : 0.f;
+      }
+    };
+    // epilogue of tile tt: TMEM accumulator tt & 1 -> registers (thread = one row, CPT consecutive columns) -> bias +
+    // act -> global memory
+    auto epilogue = [&](int64_t tt) {
+      if ((warp >> 2) < CBLOCKS) {
+        uint32_t d[CPT];
+        const int col0 = (warp >> 2) * CPT;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>((tt & 1) * H + col0);
+        TmemLoad<CPT>::run(taddr, d);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int64_t row = row0_of(tt) + (warp & 3) * 32 + lane;
+        if (row < n) {
+          float* o = out + row * H + col0;
+#pragma unroll
+          for (int c = 0; c < CPT; c += 4) {
+            float4 r4;
+            r4.x = tc_activate(__uint_as_float(d[c + 0]) + s_bias[col0 + c + 0], act);
+            r4.y = tc_activate(__uint_as_float(d[c + 1]) + s_bias[col0 + c + 1], act);
+            r4.z = tc_activate(__uint_as_float(d[c + 2]) + s_bias[col0 + c + 2], act);
+            r4.w = tc_activate(__uint_as_float(d[c + 3]) + s_bias[col0 + c + 3], act);
+            __stcs(reinterpret_cast<float4*>(o + c), r4);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+    load_self(0, cf_next);
+    const int v0 = G * NPG;                       // this lane group's nodes: v0 .. v0 + NPG - 1
+    const int w0 = warp * (GPW * NPG);            // this warp's nodes: w0 .. w0 + GPW * NPG - 1
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int b = static_cast<int>(t & 1);
+      const int64_t row0 = row0_of(t);
+      // the pointers of this tile were stored by the threads that have arrived on `operands ready` of tile t - 1
+      if (t > 0) mbar_wait_parked(aready, static_cast<uint32_t>((t - 1) & 1));
+      PPG_TRACE(static_cast<unsigned>(row0 / kTcTile), 0);
+      // pointers of tile t + 1 (registers until this tile's rows are reduced), own rows of this tile (used at its end)
+      int32_t p_next = 0;
+      if (tid <= kTcTile) {
+        const int64_t v = row0_of(t + 1) + tid;
+        p_next = colptr[(t + 1 < my_tiles && v < n) ? v : n];
+      }
+      const int32_t* ptr = s_ptr[b];
+      const int32_t E0 = ptr[0], E1 = ptr[kTcTile];
+      const int32_t wlo = ptr[w0], whi = ptr[w0 + GPW * NPG];   // slots of the whole warp
+      const int nchunks = (E1 - E0 + C - 1) / C;
+      int32_t pn[NPG + 1];
+      float4 own[NPG], acc[NPG];
+#pragma unroll
+      for (int j = 0; j < NPG; ++j) cf[j] = cf_next[j];
+      load_self(t + 1, cf_next);
+#pragma unroll
+      for (int j = 0; j <= NPG; ++j) pn[j] = ptr[v0 + j];
+#pragma unroll
+      for (int j = 0; j < NPG; ++j) {
+        own[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (self_val != nullptr && row0 + v0 + j < n) own[j] = __ldg(reinterpret_cast<const float4*>(X + (row0 + v0 + j) * F + c16 * 4));
+        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+
+      // ---------------- phase 1: segment-reduce the incoming rows of 128 target nodes out of the stages
+      for (int k = 0; k < nchunks; ++k, ++gchunk) {
+        const uint32_t st = gchunk % kSgStages, use = gchunk / kSgStages;
+        const int32_t c0 = E0 + k * C;
+        const int32_t c1 = c0 + C < E1 ? c0 + C : E1;
+        // every warp observes every phase of the `full` barrier (a parity wait is only meaningful to a thread that has
+        // seen the previous phase complete), but only touches the chunks that hold slots of its own nodes
+        mbar_wait_parked(bar_full + 8 * st, use & 1);
+        if (wlo < c1 && whi > c0) {
+          const uint32_t stage = rows_base + st * STAGE_BYTES + c16 * 16;
+          const uint32_t sv = val_base + st * C * 4;
+#pragma unroll
+          for (int j = 0; j < NPG; ++j) {
+            const int32_t a = pn[j] > c0 ? pn[j] : c0;
+            const int32_t z = pn[j + 1] < c1 ? pn[j + 1] : c1;
+            for (int32_t e = a; e < z; ++e) {
+              const float4 x = lds128(stage + static_cast<uint32_t>((e - c0) * ROW_BYTES));
+              const float c = val != nullptr ? lds32(sv + static_cast<uint32_t>((e - c0) * 4)) : 1.f;
+              acc[j].x = fmaf(c, x.x, acc[j].x);
+              acc[j].y = fmaf(c, x.y, acc[j].y);
+              acc[j].z = fmaf(c, x.z, acc[j].z);
+              acc[j].w = fmaf(c, x.w, acc[j].w);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * st);
+      }
+      // the MMAs of tile t - 1 have read the operand buffers (and their accumulator is complete)
+      if (t > 0) {
+        mbar_wait_parked(mbar, static_cast<uint32_t>((t - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+#pragma unroll
+      for (int j = 0; j < NPG; ++j) {   // operand rows: TF32 hi / lo parts of self_v X[v] + sum (no FMA contraction: same bits as the other kernels)
+        const uint32_t off = swz_offset(kTcTile, v0 + j, c16 * 4);
+        float4 h4, l4;
+        split_tf32(__fadd_rn(__fmul_rn(cf[j], own[j].x), acc[j].x), h4.x, l4.x);
+        split_tf32(__fadd_rn(__fmul_rn(cf[j], own[j].y), acc[j].y), h4.y, l4.y);
+        split_tf32(__fadd_rn(__fmul_rn(cf[j], own[j].z), acc[j].z), h4.z, l4.z);
+        split_tf32(__fadd_rn(__fmul_rn(cf[j], own[j].w), acc[j].w), h4.w, l4.w);
+        sts128(smem_u32(sAhi) + off, h4);
+        sts128(smem_u32(sAlo) + off, l4);
+      }
+      if (tid <= kTcTile) s_ptr[b ^ 1][tid] = p_next;   // every warp read tile t - 1's pointers before its arrival for tile t - 1
+      // generic-proxy writes of the operands -> visible to the tensor core (async proxy); hand the tile to the MMA warp
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(aready);
+      PPG_TRACE(static_cast<unsigned>(row0 / kTcTile), 1);  // rows reduced, operands handed over
+      // ---------------- epilogue of the PREVIOUS tile while the tensor core works on this one
+      if (t > 0) epilogue(t - 1);
+      PPG_TRACE(static_cast<unsigned>(row0 / kTcTile), 2);  // previous tile written
+    }
+    mbar_wait_parked(mbar, static_cast<uint32_t>((my_tiles - 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    epilogue(my_tiles - 1);
+    consumer_sync();
+    if (warp == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+  }
+}
+
+template <int F, int H>
+static int launch_tc_staged(const int32_t* colptr, const int32_t* src, const float* val, const float* self_val, const float* X,
+                            const float* W, const float* bias, int64_t n, int act, float* out, cudaStream_t stream) {
+  constexpr size_t smem = sg_smem_bytes(F, H);
+  auto kern = gcn_tc_staged_kernel<F, H>;
+  static bool configured = false;
+  if (!configured) {
+    PPG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    configured = true;
+  }
+  const int64_t tiles = ceil_div(n, kTcTile);
+  const unsigned grid = static_cast<unsigned>(tiles < kNumSMsB200 ? tiles : kNumSMsB200);
+  kern<<<grid, kSgThreads, smem, stream>>>(colptr, src, val, self_val, X, W, bias, n, act, out);
+  PPG_LAUNCHED();
+  return PPG_OK;
+}
+
 template <int F, int H>
 static int launch_tc_ws(const int32_t* colptr, const int32_t* src, const float* val, const float* self_val, const float* X,
                         const float* W, const float* bias, int64_t n, int act, float* out, cudaStream_t stream) {
@@ -694,22 +1066,29 @@ extern "C" int ppg_gcn_layer_tc(const int32_t* colptr, const int32_t* src, const
                                 int act, float* out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n == 0) return PPG_OK;
-  // Two kernels with identical results (bit for bit): the single-role one (every warp gathers, then one thread issues
-  // the MMAs, then every warp runs the epilogue) and the warp-specialised one (gather warps fill operand buffer i + 1
-  // while the MMA / epilogue warps work on tile i, two TMEM accumulators).  Measured on B200 at the order-2 layer of
-  // cfg2 (n = 1M, e = 1.8M, 64 -> 64; profiles/r02b_gcn_ws_ab.log): 329 us against 340 us -- the gather itself, not the
-  // serialisation of the phases, is what bounds the layer, so the single-role kernel is the default; PPG_GCN_TC_WS=1
-  // selects the other.
-  static const bool specialised = [] {
-    const char* e = getenv("PPG_GCN_TC_WS");
-    return e != nullptr && e[0] == '1';
+  // Three kernels with identical results (bit for bit): the staged kernel (producer warps stream the rows into shared
+  // memory stages with cp.async / 1-D bulk copies and run ahead across tiles, consumer warps reduce, multiply and store;
+  // the default), the single-role one (every warp gathers a batch of rows into registers, then one thread issues the
+  // MMAs, then every warp runs the epilogue) and the warp-specialised one (gather warps fill operand buffer i + 1 while
+  // the MMA / epilogue warps work on tile i, two TMEM accumulators).  PPG_GCN_TC=single|ws selects the others
+  // (PPG_GCN_TC_WS=1 is the older spelling of ws); a feature matrix that is not 16-byte aligned takes the single-role
+  // kernel.  Measurements: DESIGN.md section 4.2.
+  const int variant = [] {   // read per call: the tests and the A/B scripts switch kernels inside one process
+    const char* e = getenv("PPG_GCN_TC");
+    const char* w = getenv("PPG_GCN_TC_WS");
+    if (e != nullptr && strcmp(e, "single") == 0) return 1;
+    if ((e != nullptr && strcmp(e, "ws") == 0) || (w != nullptr && w[0] == '1')) return 2;
+    return 0;
   }();
+  const bool aligned = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+  const int which = (variant == 0 && !aligned) ? 1 : variant;
   int rc = -1;
   profile_pass_begin(stream);
 #define PPG_TC_CASE(FF, HH)                                                                                        \
   if (rc < 0 && F == FF && H == HH)                                                                                \
-    rc = specialised ? launch_tc_ws<FF, HH>(colptr, src, val, self_val, X, W, bias, n, act, out, stream)           \
-                     : launch_tc<FF, HH>(colptr, src, val, self_val, X, W, bias, n, act, out, stream)
+    rc = which == 0   ? launch_tc_staged<FF, HH>(colptr, src, val, self_val, X, W, bias, n, act, out, stream)        \
+         : which == 2 ? launch_tc_ws<FF, HH>(colptr, src, val, self_val, X, W, bias, n, act, out, stream)          \
+                      : launch_tc<FF, HH>(colptr, src, val, self_val, X, W, bias, n, act, out, stream)
   PPG_TC_CASE(32, 16); PPG_TC_CASE(32, 32); PPG_TC_CASE(32, 64);
   PPG_TC_CASE(64, 16); PPG_TC_CASE(64, 32); PPG_TC_CASE(64, 64);
 #undef PPG_TC_CASE

@@ -1,5 +1,5 @@
 """Device time of the fused GCN layer (segment-reduce gather + tcgen05 transform + ELU) on the order-2 layer of a
-BASELINE configuration; PPG_GCN_TC_WS=1 selects the warp-specialised kernel, default is the single-role one.
+BASELINE configuration; PPG_GCN_TC=staged|single|ws selects the kernel (default staged).
 Checks the two against each other when run with --check (needs both results, so it calls itself)."""
 import argparse
 import os
@@ -50,7 +50,9 @@ def main():
     alg = 20 * esl + 4 * H * esl + 12 * H * layer.n
     fused_min = 8 * layer.m + 8 * layer.n + 8 * H * layer.n
     med = times[len(times) // 2]
-    which = "warp-specialised" if os.environ.get("PPG_GCN_TC_WS") == "1" else "single-role"
+    which = {"single": "single-role", "ws": "warp-specialised"}.get(os.environ.get("PPG_GCN_TC", "staged"), "staged")
+    if os.environ.get("PPG_GCN_TC_WS") == "1":
+        which = "warp-specialised"
     print(f"gcn_tc ({which}) n={layer.n} e={layer.m} F=H={H}: median {med * 1e3:.1f} us, min {times[0] * 1e3:.1f} us; "
           f"SURVEY bytes {alg / med / 1e6:.0f} GB/s, fused-min bytes {fused_min / med / 1e6:.0f} GB/s")
     if a.save:

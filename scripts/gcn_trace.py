@@ -36,10 +36,16 @@ for it in range(3):
     assert lib.ppg_debug_set_sort_trace(ctypes.c_void_p(0)) == 0
 tr = trace.view(tiles, 8).cpu().double()
 t0 = tr[:, 0].min()
-names = ["tile start", "rows gathered", "product in TMEM", "tile written"]
-print(f"n2={n2} e2={layer.m} tiles={tiles}: per-phase mean duration (us); absolute time of phase end (us since first tile start): min / mean / max")
-for i in range(4):
+variant = os.environ.get("PPG_GCN_TC", "staged")
+if variant in ("single", "ws"):
+    names = ["tile start", "rows gathered", "product in TMEM", "tile written"]
+else:   # staged kernel: time stamps of consumer thread 0
+    names = ["tile start (pointers visible)", "rows reduced, operands handed over", "previous tile written"]
+print(f"[{variant}] n2={n2} e2={layer.m} tiles={tiles}: per-phase mean duration (us); absolute time of phase end (us since first tile start): min / mean / max")
+for i in range(len(names)):
     d = (tr[:, i] - tr[:, i - 1]) / 1e3 if i else tr[:, 0] * 0
     a = (tr[:, i] - t0) / 1e3
-    print(f"  {names[i]:>16}: dur {d.mean():7.2f} (p10 {d.quantile(0.1):6.2f}, p90 {d.quantile(0.9):6.2f})   abs {a.min():8.2f} / {a.mean():8.2f} / {a.max():8.2f}")
-print("  span of kernel (us):", float((tr[:, 3].max() - t0) / 1e3), " tiles per CTA:", tiles / (148 * 2))
+    print(f"  {names[i]:>36}: dur {d.mean():7.2f} (p10 {d.quantile(0.1):6.2f}, p90 {d.quantile(0.9):6.2f})   abs {a.min():8.2f} / {a.mean():8.2f} / {a.max():8.2f}")
+last = len(names) - 1
+ctas = 148 if variant not in ("single",) else 296
+print("  span of kernel (us):", float((tr[:, last].max() - t0) / 1e3), " tiles per CTA:", tiles / ctas)

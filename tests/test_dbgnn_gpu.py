@@ -282,6 +282,44 @@ def test_tensor_core_layer_vs_oracle(cuda, F, H):
     assert bool(((got.double().cpu() - agg2 @ W.double().t()).abs() <= RTOL * scale).all())
 
 
+@pytest.mark.parametrize("F,H", [(64, 64), (32, 16), (64, 32)])
+def test_tensor_core_layer_variants_bit_identical(cuda, monkeypatch, F, H):
+    """The three tcgen05 layer kernels (staged = producer warps stream the rows through shared-memory stages and run ahead
+    across tile boundaries, single-role, warp-specialised) sum in the same order: bit-identical outputs.  Several tiles
+    per CTA, a last tile that is not full, hubs whose slots span many stages, tiles without any slot, nodes without
+    in-edges, and the optional operands (no values, no self term, no bias)."""
+    g = torch.Generator().manual_seed(F + H)
+    n, e = 148 * 128 * 3 + 77, 160_000
+    ei = torch.randint(0, n, (2, e), generator=g)
+    ei[1, :5000] = torch.randint(0, 3, (5000,), generator=g)            # hubs: > 2048 slots in tile 0
+    ei[1, 5000:9000] = n - 1 - torch.randint(0, 2, (4000,), generator=g)  # ... and in the last (partial) tile
+    ei = ei[:, (ei[1] % 5 != 2) & ((ei[1] // 128) % 7 != 3)]           # every seventh tile has no slot at all
+    key = torch.unique(ei[0] * n + ei[1])
+    ei = torch.stack([key // n, key % n])
+    w = torch.rand(ei.size(1), generator=g) + 0.5
+    x, W, b = torch.randn(n, F, generator=g), torch.randn(H, F, generator=g) / F ** 0.5, torch.randn(H, generator=g)
+    graph = ops.gcn_prepare(ei.to(cuda), w.to(cuda), n)
+    x, W, b = x.to(cuda), W.to(cuda), b.to(cuda)
+
+    def run(variant):
+        monkeypatch.setenv("PPG_GCN_TC", variant)
+        outs = [ops.gcn_layer_tc(graph, x, W, b, _lib.ACT_ELU)]
+        val, self_val = graph.val, graph.self_val
+        graph.val = None
+        outs.append(ops.gcn_layer_tc(graph, x, W, None, _lib.ACT_NONE))
+        graph.self_val = None
+        outs.append(ops.gcn_layer_tc(graph, x, W, b, _lib.ACT_NONE))
+        graph.val, graph.self_val = val, self_val
+        torch.cuda.synchronize()
+        return outs
+
+    ring, single, ws = run("staged"), run("single"), run("ws")
+    assert close(ring[0], ops.gcn_layer_fused(graph, x, W, b, _lib.ACT_ELU))
+    for i, (a, s_, w_) in enumerate(zip(ring, single, ws)):
+        assert torch.equal(a, s_), f"staged vs single-role, case {i}"
+        assert torch.equal(a, w_), f"staged vs warp-specialised, case {i}"
+
+
 def test_graph_replay_matches_eager(cuda, monkeypatch):
     """Repeated no-grad inference on the same device-resident graph replays a captured CUDA graph: bit-identical to
     the eager pass, follows feature / parameter VALUES, re-validates when an index tensor is modified in place."""
