@@ -379,10 +379,13 @@ int ppg_bipartite_fused(const int32_t* colptr, const int32_t* src, const float* 
                         void* stream);
 
 /* The same GCN layer with the dense transform on the tcgen05 tensor cores (3xTF32 split, fp32-accurate),
- * accumulator in TMEM; F in {32, 64}, H in {16, 32, 64} (ppg_gcn_tc_supported). */
+ * accumulator in TMEM; F in {32, 64}, H in {16, 32, 64} (ppg_gcn_tc_supported).  `e` = number of CSC slots
+ * (colptr[n]) or 0 if the caller does not know it: sparse graphs (e <= 4 n) take the kernel that streams the rows
+ * through shared-memory stages, dense ones the kernel that gathers them into registers; the results are the same
+ * bit for bit. */
 int ppg_gcn_tc_supported(int64_t F, int64_t H);
 int ppg_gcn_layer_tc(const int32_t* colptr, const int32_t* src, const float* val, const float* self_val, const float* X,
-                     const float* W, const float* bias, int64_t n, int64_t F, int64_t H, int act, float* out,
+                     const float* W, const float* bias, int64_t n, int64_t e, int64_t F, int64_t H, int act, float* out,
                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -100,7 +100,7 @@ PROTOTYPES = {
     "ppg_gcn_layer_fused": (c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, c_int, _p, _p]),
     "ppg_bipartite_fused": (c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, c_int, _p, _p]),
     "ppg_gcn_tc_supported": (c_int, [_i64, _i64]),
-    "ppg_gcn_layer_tc": (c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, c_int, _p, _p]),
+    "ppg_gcn_layer_tc": (c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, c_int, _p, _p]),
     "ppg_act_backward_workspace_bytes": (c_size_t, [_i64, _i64]),
     "ppg_act_backward": (c_int, [_p, _p, _p, _i64, _i64, c_int, _p, _p, _p, _p, c_size_t, _p]),
     "ppg_atb_workspace_bytes": (c_size_t, [_i64, _i64, _i64]),

@@ -185,9 +185,18 @@ __device__ __forceinline__ void sort_trace(unsigned tile, int slot) {
     g_sort_trace[static_cast<size_t>(tile) * 8 + slot] = t;
   }
 }
+__device__ __forceinline__ void sort_trace_if(bool who, unsigned tile, int slot) {
+  if (who && g_sort_trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_sort_trace[static_cast<size_t>(tile) * 8 + slot] = t;
+  }
+}
 #define PPG_TRACE(tile, slot) sort_trace(tile, slot)
+#define PPG_TRACE_IF(who, tile, slot) sort_trace_if(who, tile, slot)
 #else
 #define PPG_TRACE(tile, slot)
+#define PPG_TRACE_IF(who, tile, slot)
 #endif
 
 }  // namespace ppg

@@ -668,8 +668,14 @@ gcn_tc_ws_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__
 constexpr int kSgConsumers = 512;
 constexpr int kSgProducers = 128;
 constexpr int kSgThreads = kSgConsumers + kSgProducers + 32;   // + the warp whose lane 0 issues the MMAs
-constexpr int kSgChunk = 128;     // rows per stage
-constexpr int kSgStages = 3;
+#ifndef PPG_SG_CHUNK
+#define PPG_SG_CHUNK 128
+#endif
+#ifndef PPG_SG_STAGES
+#define PPG_SG_STAGES 3
+#endif
+constexpr int kSgChunk = PPG_SG_CHUNK;     // rows per stage (multiple of 16, at most 128; experiment builds: make variant)
+constexpr int kSgStages = PPG_SG_STAGES;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -738,7 +744,7 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
   constexpr int CBLOCKS = H / CPT;                             // column blocks (warp / 4 below CBLOCKS takes part)
   constexpr uint32_t IDESC = umma_idesc_tf32(kTcTile, H);
   constexpr int C = kSgChunk;
-  static_assert(NPG >= 1, "geometry");
+  static_assert(NPG >= 1 && C % 16 == 0 && C <= 128, "geometry");
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -753,7 +759,7 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
   __shared__ __align__(8) unsigned long long s_full[kSgStages];     // rows of the stage have landed
   __shared__ __align__(8) unsigned long long s_empty[kSgStages];    // every consumer warp has left the stage
   __shared__ uint32_t s_tmem_base;
-  __shared__ int32_t s_ptr[2][kTcTile + 1];
+  __shared__ int32_t s_ptr[3][kTcTile + 1];                         // CSC pointers of tiles t, t + 1, t + 2
   __shared__ float s_bias[H];
 
   const int tid = threadIdx.x;
@@ -774,8 +780,11 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
   }
   if (tid < H) s_bias[tid] = bias != nullptr ? bias[tid] : 0.f;
   if (tid <= kTcTile) {
-    const int64_t v = row0_of(0) + tid;
-    s_ptr[0][tid] = colptr[v < n ? v : n];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int64_t v = row0_of(b) + tid;
+      s_ptr[b][tid] = colptr[(b < my_tiles && v < n) ? v : n];
+    }
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)), "n"(TMEM_COLS) : "memory");
@@ -824,7 +833,10 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
     }
   } else if (warp >= kSgConsumers / 32) {
     // ================================================================== producers
-    const int pw = warp - kSgConsumers / 32;          // this warp requests rows [32 pw, 32 pw + 32) of every chunk
+    constexpr int RPW = C / (kSgProducers / 32);      // rows of a chunk per producer warp
+    static_assert(RPW % GPW == 0 && RPW <= 32, "chunk geometry");
+    const int pw = warp - kSgConsumers / 32;          // this warp requests rows [RPW pw, RPW pw + RPW) of every chunk
+    const bool has_row = lane < RPW;
     const int h = lane / LPN, c16 = lane % LPN;
     uint32_t gchunk = 0;
     auto tile_range = [&](int64_t tt, int32_t& E0, int32_t& E1) {
@@ -836,7 +848,7 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
     int32_t E0, E1, E0n, E1n;
     tile_range(0, E0, E1);
     // src word of this lane's row in the chunk that comes next (fetched one chunk ahead)
-    int32_t idx_next = (E0 + pw * 32 + lane < E1) ? src[E0 + pw * 32 + lane] : 0;
+    int32_t idx_next = (has_row && E0 + pw * RPW + lane < E1) ? src[E0 + pw * RPW + lane] : 0;
     for (int64_t t = 0; t < my_tiles; ++t) {
       tile_range(t + 1, E0n, E1n);
       const int nchunks = (E1 - E0 + C - 1) / C;
@@ -844,20 +856,22 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
         const uint32_t st = gchunk % kSgStages, use = gchunk / kSgStages;
         mbar_wait_parked(bar_empty + 8 * st, (use & 1) ^ 1);
         const uint32_t stage = rows_base + st * STAGE_BYTES;
-        const int32_t e_l = E0 + k * C + pw * 32 + lane;   // this lane's slot: src word and value
+        PPG_TRACE_IF(pw == 0 && lane == 0 && k == 0, static_cast<unsigned>(row0_of(t) / kTcTile), 4);   // first stage of the tile acquired
+        const int32_t e_l = E0 + k * C + pw * RPW + lane;   // this lane's slot (lanes below RPW): src word and value
         const int32_t idx = idx_next;
-        if (k + 1 < nchunks) idx_next = e_l + C < E1 ? src[e_l + C] : 0;
-        if (val != nullptr && e_l < E1) cp_async4(val_base + (st * C + pw * 32 + lane) * 4, val + e_l);
+        if (k + 1 < nchunks) idx_next = (has_row && e_l + C < E1) ? src[e_l + C] : 0;
+        if (val != nullptr && has_row && e_l < E1) cp_async4(val_base + (st * C + pw * RPW + lane) * 4, val + e_l);
 #pragma unroll
-        for (int j = 0; j < 32 / GPW; ++j) {
+        for (int j = 0; j < RPW / GPW; ++j) {
           const int item = j * GPW + h;
           const int32_t row = __shfl_sync(kFullMask, idx, item);
           if (e_l - lane + item < E1)
-            cp_async16(stage + static_cast<uint32_t>((pw * 32 + item) * ROW_BYTES + c16 * 16), X + static_cast<int64_t>(row) * F + c16 * 4);
+            cp_async16(stage + static_cast<uint32_t>((pw * RPW + item) * ROW_BYTES + c16 * 16), X + static_cast<int64_t>(row) * F + c16 * 4);
         }
         cp_async_arrive(bar_full + 8 * st);
+        PPG_TRACE_IF(pw == 0 && lane == 0 && k + 1 == nchunks, static_cast<unsigned>(row0_of(t) / kTcTile), 5);   // last chunk of the tile requested
       }
-      idx_next = (E0n + pw * 32 + lane < E1n) ? src[E0n + pw * 32 + lane] : 0;   // first chunk of the next tile
+      idx_next = (has_row && E0n + pw * RPW + lane < E1n) ? src[E0n + pw * RPW + lane] : 0;   // first chunk of the next tile
       E0 = E0n;
       E1 = E1n;
     }
@@ -885,18 +899,31 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>((tt & 1) * H + col0);
         TmemLoad<CPT>::run(taddr, d);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const int64_t row = row0_of(tt) + (warp & 3) * 32 + lane;
-        if (row < n) {
-          float* o = out + row * H + col0;
+        float4 q[CPT / 4];
 #pragma unroll
-          for (int c = 0; c < CPT; c += 4) {
-            float4 r4;
-            r4.x = tc_activate(__uint_as_float(d[c + 0]) + s_bias[col0 + c + 0], act);
-            r4.y = tc_activate(__uint_as_float(d[c + 1]) + s_bias[col0 + c + 1], act);
-            r4.z = tc_activate(__uint_as_float(d[c + 2]) + s_bias[col0 + c + 2], act);
-            r4.w = tc_activate(__uint_as_float(d[c + 3]) + s_bias[col0 + c + 3], act);
-            __stcs(reinterpret_cast<float4*>(o + c), r4);
-          }
+        for (int c = 0; c < CPT; c += 4) {
+          q[c / 4].x = tc_activate(__uint_as_float(d[c + 0]) + s_bias[col0 + c + 0], act);
+          q[c / 4].y = tc_activate(__uint_as_float(d[c + 1]) + s_bias[col0 + c + 1], act);
+          q[c / 4].z = tc_activate(__uint_as_float(d[c + 2]) + s_bias[col0 + c + 2], act);
+          q[c / 4].w = tc_activate(__uint_as_float(d[c + 3]) + s_bias[col0 + c + 3], act);
+        }
+        // lanes 2i and 2i + 1 trade halves so that every store instruction writes whole 32-byte sectors: the even lane
+        // keeps float4 0 (and 2) of both rows, the odd lane float4 1 (and 3)
+        const bool odd = lane & 1;
+        const int64_t row_e = row0_of(tt) + (warp & 3) * 32 + (lane & ~1);
+#pragma unroll
+        for (int c = 0; c < CPT / 4; c += 2) {
+          const float4 give = odd ? q[c] : q[c + 1];
+          float4 got;
+          got.x = __shfl_xor_sync(kFullMask, give.x, 1);
+          got.y = __shfl_xor_sync(kFullMask, give.y, 1);
+          got.z = __shfl_xor_sync(kFullMask, give.z, 1);
+          got.w = __shfl_xor_sync(kFullMask, give.w, 1);
+          const float4 for_even_row = odd ? got : q[c];        // even lane: own float4 c; odd lane: the even row's float4 c + 1
+          const float4 for_odd_row = odd ? q[c + 1] : got;     // even lane: the odd row's float4 c; odd lane: own float4 c + 1
+          float* o = out + row_e * H + col0 + (c + (odd ? 1 : 0)) * 4;
+          if (row_e < n) __stcs(reinterpret_cast<float4*>(o), for_even_row);
+          if (row_e + 1 < n) __stcs(reinterpret_cast<float4*>(o + H), for_odd_row);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -906,17 +933,19 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
     const int w0 = warp * (GPW * NPG);            // this warp's nodes: w0 .. w0 + GPW * NPG - 1
     for (int64_t t = 0; t < my_tiles; ++t) {
       const int b = static_cast<int>(t & 1);
+      const int pb = static_cast<int>(t % 3);
       const int64_t row0 = row0_of(t);
-      // the pointers of this tile were stored by the threads that have arrived on `operands ready` of tile t - 1
-      if (t > 0) mbar_wait_parked(aready, static_cast<uint32_t>((t - 1) & 1));
+      // No wait here: a warp starts to reduce tile t while slower warps are still on tile t - 1 (the rows of a warp's
+      // nodes vary from tile to tile; the common point of a tile is the MMA, one phase later).  The pointers of this
+      // tile were stored two tiles ago and acquired in the previous iteration (see below).
       PPG_TRACE(static_cast<unsigned>(row0 / kTcTile), 0);
-      // pointers of tile t + 1 (registers until this tile's rows are reduced), own rows of this tile (used at its end)
+      // pointers of tile t + 2 (registers until this tile's rows are reduced), own rows of this tile (used at its end)
       int32_t p_next = 0;
       if (tid <= kTcTile) {
-        const int64_t v = row0_of(t + 1) + tid;
-        p_next = colptr[(t + 1 < my_tiles && v < n) ? v : n];
+        const int64_t v = row0_of(t + 2) + tid;
+        p_next = colptr[(t + 2 < my_tiles && v < n) ? v : n];
       }
-      const int32_t* ptr = s_ptr[b];
+      const int32_t* ptr = s_ptr[pb];
       const int32_t E0 = ptr[0], E1 = ptr[kTcTile];
       const int32_t wlo = ptr[w0], whi = ptr[w0 + GPW * NPG];   // slots of the whole warp
       const int nchunks = (E1 - E0 + C - 1) / C;
@@ -962,10 +991,14 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * st);
       }
+      PPG_TRACE(static_cast<unsigned>(row0 / kTcTile), 1);  // rows reduced
       // the MMAs of tile t - 1 have read the operand buffers (and their accumulator is complete)
       if (t > 0) {
         mbar_wait_parked(mbar, static_cast<uint32_t>((t - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ... which implies that every warp has handed tile t - 1 over: this wait returns at once and acquires what the
+        // other warps stored before their arrival (the pointers of tile t + 1)
+        mbar_wait_parked(aready, static_cast<uint32_t>((t - 1) & 1));
       }
 #pragma unroll
       for (int j = 0; j < NPG; ++j) {   // operand rows: TF32 hi / lo parts of self_v X[v] + sum (no FMA contraction: same bits as the other kernels)
@@ -978,16 +1011,16 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
         sts128(smem_u32(sAhi) + off, h4);
         sts128(smem_u32(sAlo) + off, l4);
       }
-      if (tid <= kTcTile) s_ptr[b ^ 1][tid] = p_next;   // every warp read tile t - 1's pointers before its arrival for tile t - 1
+      if (tid <= kTcTile) s_ptr[(pb + 2) % 3][tid] = p_next;   // buffer of tile t - 1, which every warp read before its arrival for tile t - 1
       // generic-proxy writes of the operands -> visible to the tensor core (async proxy); hand the tile to the MMA warp
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(aready);
-      PPG_TRACE(static_cast<unsigned>(row0 / kTcTile), 1);  // rows reduced, operands handed over
+      PPG_TRACE(static_cast<unsigned>(row0 / kTcTile), 2);  // operands handed over
       // ---------------- epilogue of the PREVIOUS tile while the tensor core works on this one
       if (t > 0) epilogue(t - 1);
-      PPG_TRACE(static_cast<unsigned>(row0 / kTcTile), 2);  // previous tile written
+      PPG_TRACE(static_cast<unsigned>(row0 / kTcTile), 3);  // previous tile written
     }
     mbar_wait_parked(mbar, static_cast<uint32_t>((my_tiles - 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1062,26 +1095,31 @@ extern "C" int ppg_gcn_tc_supported(int64_t F, int64_t H) {
 }
 
 extern "C" int ppg_gcn_layer_tc(const int32_t* colptr, const int32_t* src, const float* val, const float* self_val,
-                                const float* X, const float* W, const float* bias, int64_t n, int64_t F, int64_t H,
-                                int act, float* out, void* stream_) {
+                                const float* X, const float* W, const float* bias, int64_t n, int64_t e, int64_t F,
+                                int64_t H, int act, float* out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (n == 0) return PPG_OK;
   // Three kernels with identical results (bit for bit): the staged kernel (producer warps stream the rows into shared
-  // memory stages with cp.async / 1-D bulk copies and run ahead across tiles, consumer warps reduce, multiply and store;
-  // the default), the single-role one (every warp gathers a batch of rows into registers, then one thread issues the
-  // MMAs, then every warp runs the epilogue) and the warp-specialised one (gather warps fill operand buffer i + 1 while
-  // the MMA / epilogue warps work on tile i, two TMEM accumulators).  PPG_GCN_TC=single|ws selects the others
-  // (PPG_GCN_TC_WS=1 is the older spelling of ws); a feature matrix that is not 16-byte aligned takes the single-role
-  // kernel.  Measurements: DESIGN.md section 4.2.
+  // memory stages with cp.async and run ahead across tiles, consumer warps reduce, a dedicated warp issues the MMAs),
+  // the single-role one (every warp gathers a batch of rows into registers, then one thread issues the MMAs, then
+  // every warp runs the epilogue) and the warp-specialised one (gather warps fill operand buffer i + 1 while the MMA /
+  // epilogue warps work on tile i, two TMEM accumulators).  Sparse graphs (at most 4 slots per node: the higher-order
+  // De Bruijn layers, 248 against 324 us at cfg2) take the staged kernel, dense ones (the first-order layer of cfg2, 10
+  // slots per node: 77 against 101 us) the single-role kernel, where one lane group streams a long slot range with 8
+  // loads in flight while a stage of the staged kernel would serve only one or two consumer warps.
+  // PPG_GCN_TC=staged|single|ws forces one (PPG_GCN_TC_WS=1 is the older spelling of ws); a feature matrix that is not
+  // 16-byte aligned takes the single-role kernel.  Measurements: DESIGN.md section 4.2.
   const int variant = [] {   // read per call: the tests and the A/B scripts switch kernels inside one process
-    const char* e = getenv("PPG_GCN_TC");
+    const char* v = getenv("PPG_GCN_TC");
     const char* w = getenv("PPG_GCN_TC_WS");
-    if (e != nullptr && strcmp(e, "single") == 0) return 1;
-    if ((e != nullptr && strcmp(e, "ws") == 0) || (w != nullptr && w[0] == '1')) return 2;
-    return 0;
+    if (v != nullptr && strcmp(v, "staged") == 0) return 0;
+    if (v != nullptr && strcmp(v, "single") == 0) return 1;
+    if ((v != nullptr && strcmp(v, "ws") == 0) || (w != nullptr && w[0] == '1')) return 2;
+    return -1;
   }();
   const bool aligned = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
-  const int which = (variant == 0 && !aligned) ? 1 : variant;
+  int which = variant >= 0 ? variant : (e > 4 * n ? 1 : 0);
+  if (which == 0 && !aligned) which = 1;
   int rc = -1;
   profile_pass_begin(stream);
 #define PPG_TC_CASE(FF, HH)                                                                                        \

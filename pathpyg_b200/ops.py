@@ -759,7 +759,7 @@ def gcn_layer_tc(g: TargetGroupedEdges, x: torch.Tensor, weight: torch.Tensor, b
     out = torch.empty((g.num_targets, H), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.ppg_gcn_layer_tc(_ptr(g.colptr), _ptr(g.src), _ptr(g.val), _ptr(g.self_val), _ptr(x), _ptr(weight),
-                                        _ptr(bias), g.num_targets, F, H, act, _ptr(out), _stream(dev)))
+                                        _ptr(bias), g.num_targets, g.src.numel(), F, H, act, _ptr(out), _stream(dev)))
     return out
 
 

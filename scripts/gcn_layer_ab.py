@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--layer", type=int, default=None, help="order of the layer (default: the highest one)")
     ap.add_argument("--save", default=None)
     ap.add_argument("--compare", default=None)
     a = ap.parse_args()
@@ -25,7 +26,7 @@ def main():
     ei, t = bench.make_stream(cfg, seed=0)
     tg = pp.TemporalGraph.from_tensors(ei.to(dev), t.to(dev), cfg["n"])
     model = pp.MultiOrderModel.from_temporal_graph(tg, delta=cfg["delta"], max_order=cfg["order"])
-    layer = model.layers[cfg["order"]]
+    layer = model.layers[a.layer or cfg["order"]]
     H = cfg["hidden"]
     gen = torch.Generator().manual_seed(1)
     x = torch.randn(layer.n, H, generator=gen).to(dev)

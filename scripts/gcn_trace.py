@@ -39,8 +39,8 @@ t0 = tr[:, 0].min()
 variant = os.environ.get("PPG_GCN_TC", "staged")
 if variant in ("single", "ws"):
     names = ["tile start", "rows gathered", "product in TMEM", "tile written"]
-else:   # staged kernel: time stamps of consumer thread 0
-    names = ["tile start (pointers visible)", "rows reduced, operands handed over", "previous tile written"]
+else:   # staged kernel: time stamps of consumer thread 0 (slots 0-3) and of lane 0 of the first producer warp (4, 5)
+    names = ["tile start (pointers visible)", "rows reduced", "operands handed over", "previous tile written"]
 print(f"[{variant}] n2={n2} e2={layer.m} tiles={tiles}: per-phase mean duration (us); absolute time of phase end (us since first tile start): min / mean / max")
 for i in range(len(names)):
     d = (tr[:, i] - tr[:, i - 1]) / 1e3 if i else tr[:, 0] * 0
@@ -49,3 +49,10 @@ for i in range(len(names)):
 last = len(names) - 1
 ctas = 148 if variant not in ("single",) else 296
 print("  span of kernel (us):", float((tr[:, last].max() - t0) / 1e3), " tiles per CTA:", tiles / ctas)
+if variant not in ("single", "ws"):
+    ok = (tr[:, 4] > 0) & (tr[:, 5] > 0)
+    lead = (tr[ok, 0] - tr[ok, 4]) / 1e3      # consumer starts the tile this long after the producer acquired its first stage
+    done = (tr[ok, 1] - tr[ok, 5]) / 1e3      # consumer finishes reducing this long after the last chunk was REQUESTED
+    span = (tr[ok, 5] - tr[ok, 4]) / 1e3      # producer: first stage acquired -> last chunk requested
+    for nm, x in (("producer ahead of consumer at tile start", lead), ("last request -> rows reduced", done), ("producer: first stage -> last request", span)):
+        print(f"  {nm:>44}: mean {x.mean():7.2f}  p10 {x.quantile(0.1):7.2f}  p50 {x.quantile(0.5):7.2f}  p90 {x.quantile(0.9):7.2f}")
