@@ -644,14 +644,14 @@ gcn_tc_ws_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// Staged variant (the default): one persistent CTA per SM, 4 producer warps + 16 consumer warps; the row gather is
+// Staged variant (the default): one persistent CTA per SM, 3 producer warps + 16 consumer warps + 1 MMA warp; the row gather is
 // asynchronous, holds no registers and runs ahead of the arithmetic across tile boundaries.
 //   * The rows of a tile's CSC slots, in slot order, are cut into chunks of 128; a chunk fills one of kSgStages row
 //     buffers in shared memory (128 x F floats, plain row-major).
-//   * Producer warps: a lane reads one src word of the chunk (coalesced, fetched one chunk ahead), the warp requests
-//     its 32 rows with cp.async.cg (16 bytes per lane, L1 bypassed) and the slot values with 4-byte cp.async, then
-//     every producer thread signals the stage's `full` barrier through cp.async.mbarrier.arrive.  Producers only wait
-//     for a free stage, so the rows of tiles t + 1, t + 2 are in flight while tile t is multiplied and written.
+//   * Producer warps: one per stage.  Its lanes read the chunk's src words (coalesced) while the stage is awaited, the
+//     warp requests the 128 rows with cp.async.cg (16 bytes per lane, L1 bypassed) and the slot values with 4-byte
+//     cp.async, waits for them (cp.async.wait_all) and signals the stage's `full` barrier with one arrival.  Producers
+//     only wait for their stage, so the rows of tiles t + 1, t + 2 travel while tile t is multiplied and written.
 //   * Consumer warps: thread = (16-byte chunk of the row, nodes G, G + groups, ...), accumulators in registers; the
 //     nodes' own rows (contiguous in X) are requested with plain loads at the top of the tile and used at its end; per
 //     stage a thread adds the slots of its nodes that fall into the chunk (ld.shared.v4 + 4 FMA per row and lane),
@@ -666,8 +666,6 @@ gcn_tc_ws_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__
 // tile (profiles/r02aa_gcn_trace.log, r02aa ncu capture); here a row costs one LDGSTS per 16 lanes on the producer
 // side and one LDS.128 + 4 FFMA per lane on the consumer side.
 constexpr int kSgConsumers = 512;
-constexpr int kSgProducers = 128;
-constexpr int kSgThreads = kSgConsumers + kSgProducers + 32;   // + the warp whose lane 0 issues the MMAs
 #ifndef PPG_SG_CHUNK
 #define PPG_SG_CHUNK 128
 #endif
@@ -676,6 +674,8 @@ constexpr int kSgThreads = kSgConsumers + kSgProducers + 32;   // + the warp who
 #endif
 constexpr int kSgChunk = PPG_SG_CHUNK;     // rows per stage (multiple of 16, at most 128; experiment builds: make variant)
 constexpr int kSgStages = PPG_SG_STAGES;
+constexpr int kSgProducers = 32 * kSgStages;                   // one producer warp per stage
+constexpr int kSgThreads = kSgConsumers + kSgProducers + 32;   // + the warp whose lane 0 issues the MMAs
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -794,7 +794,7 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
     mbar_init(smem_u32(&s_mbar), 1);
     mbar_init(smem_u32(&s_aready), kSgConsumers / 32);
     for (int s = 0; s < kSgStages; ++s) {
-      mbar_init(smem_u32(&s_full[s]), kSgProducers);
+      mbar_init(smem_u32(&s_full[s]), 1);
       mbar_init(smem_u32(&s_empty[s]), kSgConsumers / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -833,49 +833,48 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
     }
   } else if (warp >= kSgConsumers / 32) {
     // ================================================================== producers
-    constexpr int RPW = C / (kSgProducers / 32);      // rows of a chunk per producer warp
-    static_assert(RPW % GPW == 0 && RPW <= 32, "chunk geometry");
-    const int pw = warp - kSgConsumers / 32;          // this warp requests rows [RPW pw, RPW pw + RPW) of every chunk
-    const bool has_row = lane < RPW;
+    // Producer warp pw owns stage pw, i.e. the chunks with (running chunk number) % stages == pw: it requests all rows of
+    // the chunk, waits for them and signals the stage with ONE arrival (every arrival on any mbarrier of the CTA wakes
+    // the warps parked on the others; 128 per-thread arrivals per chunk cost a third of all issued instructions in
+    // re-polls -- profiles/r02ao).  A warp that owns its stage sees every phase of the stage's barriers, which a
+    // parity wait needs.
+    constexpr int WPL = C / 32;                       // src words (= rows) of a chunk per lane
+    static_assert(C % 32 == 0, "chunk geometry");
+    const int pw = warp - kSgConsumers / 32;
     const int h = lane / LPN, c16 = lane % LPN;
     uint32_t gchunk = 0;
-    auto tile_range = [&](int64_t tt, int32_t& E0, int32_t& E1) {
-      const int64_t r0 = row0_of(tt), r1 = r0 + kTcTile;
-      const bool exists = tt < my_tiles;
-      E0 = colptr[(exists && r0 < n) ? r0 : n];
-      E1 = colptr[(exists && r1 < n) ? r1 : n];
-    };
-    int32_t E0, E1, E0n, E1n;
-    tile_range(0, E0, E1);
-    // src word of this lane's row in the chunk that comes next (fetched one chunk ahead)
-    int32_t idx_next = (has_row && E0 + pw * RPW + lane < E1) ? src[E0 + pw * RPW + lane] : 0;
     for (int64_t t = 0; t < my_tiles; ++t) {
-      tile_range(t + 1, E0n, E1n);
+      const int64_t r0 = row0_of(t), r1 = r0 + kTcTile;
+      const int32_t E0 = colptr[r0 < n ? r0 : n], E1 = colptr[r1 < n ? r1 : n];
       const int nchunks = (E1 - E0 + C - 1) / C;
       for (int k = 0; k < nchunks; ++k, ++gchunk) {
         const uint32_t st = gchunk % kSgStages, use = gchunk / kSgStages;
-        mbar_wait_parked(bar_empty + 8 * st, (use & 1) ^ 1);
-        const uint32_t stage = rows_base + st * STAGE_BYTES;
-        PPG_TRACE_IF(pw == 0 && lane == 0 && k == 0, static_cast<unsigned>(row0_of(t) / kTcTile), 4);   // first stage of the tile acquired
-        const int32_t e_l = E0 + k * C + pw * RPW + lane;   // this lane's slot (lanes below RPW): src word and value
-        const int32_t idx = idx_next;
-        if (k + 1 < nchunks) idx_next = (has_row && e_l + C < E1) ? src[e_l + C] : 0;
-        if (val != nullptr && has_row && e_l < E1) cp_async4(val_base + (st * C + pw * RPW + lane) * 4, val + e_l);
+        if (st != static_cast<uint32_t>(pw)) continue;
+        const int32_t c0 = E0 + k * C;
+        int32_t idx[WPL];
 #pragma unroll
-        for (int j = 0; j < RPW / GPW; ++j) {
-          const int item = j * GPW + h;
-          const int32_t row = __shfl_sync(kFullMask, idx, item);
-          if (e_l - lane + item < E1)
-            cp_async16(stage + static_cast<uint32_t>((pw * RPW + item) * ROW_BYTES + c16 * 16), X + static_cast<int64_t>(row) * F + c16 * 4);
+        for (int i = 0; i < WPL; ++i) idx[i] = c0 + i * 32 + lane < E1 ? src[c0 + i * 32 + lane] : 0;   // lands while the stage is awaited
+        mbar_wait_parked(bar_empty + 8 * st, (use & 1) ^ 1);
+        PPG_TRACE_IF(lane == 0 && k == 0, static_cast<unsigned>(r0 / kTcTile), 4);   // first stage of the tile acquired
+        const uint32_t stage = rows_base + st * STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < WPL; ++i) {
+          const int32_t e = c0 + i * 32 + lane;
+          if (val != nullptr && e < E1) cp_async4(val_base + (st * C + i * 32 + lane) * 4, val + e);
+#pragma unroll
+          for (int j = 0; j < 32 / GPW; ++j) {
+            const int item = j * GPW + h;
+            const int32_t row = __shfl_sync(kFullMask, idx[i], item);
+            if (c0 + i * 32 + item < E1)
+              cp_async16(stage + static_cast<uint32_t>((i * 32 + item) * ROW_BYTES + c16 * 16), X + static_cast<int64_t>(row) * F + c16 * 4);
+          }
         }
-        cp_async_arrive(bar_full + 8 * st);
-        PPG_TRACE_IF(pw == 0 && lane == 0 && k + 1 == nchunks, static_cast<unsigned>(row0_of(t) / kTcTile), 5);   // last chunk of the tile requested
+        PPG_TRACE_IF(lane == 0 && k + 1 == nchunks, static_cast<unsigned>(r0 / kTcTile), 5);   // last chunk of the tile requested
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_full + 8 * st);
       }
-      idx_next = (has_row && E0n + pw * RPW + lane < E1n) ? src[E0n + pw * RPW + lane] : 0;   // first chunk of the next tile
-      E0 = E0n;
-      E1 = E1n;
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
   } else {
     // ================================================================== consumers
     const int c16 = tid % LPN;
