@@ -218,7 +218,7 @@ def fused_min_bytes_dbgnn(n, e, n2, e2, H, classes):
 
 # ------------------------------------------------------------------------------------------------ in-step kernel timing
 KERNEL_KINDS = {0: "onesweep_pass_kernel (radix digit pass)", 1: "chain_tile_kernel (expand + rank one level of the layer chain)",
-                2: "merge_tile_kernel (owner-side merge of the senders' sorted runs)", 3: "gcn_tc_kernel (fused tcgen05 GCN layer)"}
+                2: "merge_tile_kernel (owner-side merge of the senders' sorted runs)", 3: "gcn_tc_kernel (fused tcgen05 GCN layer: staged producer / consumer kernel on sparse layers, single-role on dense ones)"}
 
 
 def profiled_kernels(lib, fn):

@@ -1043,7 +1043,11 @@ static int launch_tc_staged(const int32_t* colptr, const int32_t* src, const flo
     configured = true;
   }
   const int64_t tiles = ceil_div(n, kTcTile);
-  const unsigned grid = static_cast<unsigned>(tiles < kNumSMsB200 ? tiles : kNumSMsB200);
+  unsigned grid = static_cast<unsigned>(tiles < kNumSMsB200 ? tiles : kNumSMsB200);
+  if (const char* g = getenv("PPG_GCN_TC_GRID")) {   // test hook: few CTAs with many tiles each (sanitizer runs on small graphs)
+    const long v = atol(g);
+    if (v >= 1 && v < static_cast<long>(grid)) grid = static_cast<unsigned>(v);
+  }
   kern<<<grid, kSgThreads, smem, stream>>>(colptr, src, val, self_val, X, W, bias, n, act, out);
   PPG_LAUNCHED();
   return PPG_OK;

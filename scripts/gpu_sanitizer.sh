@@ -1,7 +1,8 @@
 #!/bin/bash
 # compute-sanitizer over the kernels with inter-CTA protocols and aliased shared memory:
 #   memcheck + racecheck of (a) the toy order-2 lift + DBGNN forward of __graft_entry__.smoke(), (b) a chain build with the
-#   heavy-row fallback forced on, (c) a multi-tile onesweep sort.  Run under gpurun on one B200; logs go to gpurun_out/.
+#   heavy-row fallback forced on, (c) a multi-tile onesweep sort, (d) the staged tcgen05 GCN layer (CASES="gcn" runs only
+#   the named cases).  Run under gpurun on one B200; logs go to gpurun_out/.
 #     gpurun --timeout 1500 -- 'bash scripts/gpu_sanitizer.sh r02'
 set -u
 tag=${1:-san}
@@ -40,6 +41,22 @@ elif which == "dist":
         layers = parallel.distributed_temporal_layers(ei, t, n, 4, 4)
         print({k: (v.num_nodes, v.edge_index.size(1)) for k, v in layers.items()})
     dist.destroy_process_group()
+elif which == "gcn":
+    # the staged tcgen05 GCN layer (producer / consumer / MMA warps, mbarrier hand-overs, cp.async stages): several
+    # tiles per CTA, bit-identical to the single-role kernel
+    from pathpyg_b200 import _lib
+    gen = torch.Generator().manual_seed(4)
+    os.environ["PPG_GCN_TC_GRID"] = "6"          # 6 CTAs x 4-5 tiles
+    n, e, F, H = 128 * 26 + 50, 9000, 32, 32
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    ei[1, :600] = torch.randint(0, 4, (600,), generator=gen)
+    graph = ops.gcn_prepare(ei.to(dev), (torch.rand(e, generator=gen) + 0.5).to(dev), n)
+    x, W, b = torch.randn(n, F, generator=gen).to(dev), (torch.randn(H, F, generator=gen) / 6).to(dev), torch.randn(H, generator=gen).to(dev)
+    outs = []
+    for v in ("staged", "single"):
+        os.environ["PPG_GCN_TC"] = v
+        outs.append(ops.gcn_layer_tc(graph, x, W, b, _lib.ACT_ELU))
+    assert torch.equal(outs[0], outs[1])
 elif which == "sort":
     gen = torch.Generator().manual_seed(2)
     keys = torch.randint(0, 1 << 40, (20000,), generator=gen).to(dev)
@@ -50,7 +67,7 @@ torch.cuda.synchronize()
 print(which, "ok")
 PY
 for tool in memcheck racecheck; do
-  for c in smoke chain dist sort; do
+  for c in ${CASES:-smoke chain dist sort gcn}; do
     timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_case.py $c > $out/${tag}_sanitizer_${tool}_${c}.log 2>&1
     echo "$tool $c: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $out/${tag}_sanitizer_${tool}_${c}.log | tail -1)"
   done

@@ -314,6 +314,14 @@ def test_tensor_core_layer_variants_bit_identical(cuda, monkeypatch, F, H):
         return outs
 
     ring, single, ws = run("staged"), run("single"), run("ws")
+    # the staged kernel hands its tiles over through mbarriers only: repeated launches, and few CTAs with many tiles each
+    # (PPG_GCN_TC_GRID, a test hook), must reproduce the same bits
+    for grid in ("", "", "5", "37"):
+        if grid:
+            monkeypatch.setenv("PPG_GCN_TC_GRID", grid)
+        again = run("staged")
+        assert all(torch.equal(a, b_) for a, b_ in zip(ring, again)), f"staged kernel not reproducible (grid {grid or 'default'})"
+    monkeypatch.delenv("PPG_GCN_TC_GRID", raising=False)
     assert close(ring[0], ops.gcn_layer_fused(graph, x, W, b, _lib.ACT_ELU))
     for i, (a, s_, w_) in enumerate(zip(ring, single, ws)):
         assert torch.equal(a, s_), f"staged vs single-role, case {i}"
