@@ -947,5 +947,18 @@ def main():
             torch.distributed.destroy_process_group()
 
 
+def _only_json_on_stdout(fn):
+    """The contract is ONE JSON line on stdout: libraries that print there (NCCL announces its version on the first
+    communicator) are sent to stderr for the duration of the run; `print` inside this module goes to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+    try:
+        fn()
+    finally:
+        sys.stdout.flush()
+
+
 if __name__ == "__main__":
-    main()
+    _only_json_on_stdout(main)
