@@ -440,6 +440,27 @@ int ppg_weighted_log_sum(const float* freq, const float* prob, const int64_t* id
                          void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Per-walk bookkeeping of a7 / a9: what the reference writes as torch.cumsum, repeat_interleave, bincount and
+ * arange + mask   reference: src/pathpyG/core/multi_order_model.py:217-224,335,354-361,402-405,
+ *                            src/pathpyG/core/path_data.py:139-159
+ * ------------------------------------------------------------------------------------------- */
+/* offsets [n + 1] = exclusive prefix sums of counts [n] (offsets[n] = their sum; the workspace starts with {total,
+ * status}: ppg_result_read).  A count below min_count sets status bit 0 and counts as 0. */
+size_t ppg_counts_to_offsets_workspace_bytes(int64_t n);
+int ppg_counts_to_offsets(const int64_t* counts, int64_t n, int64_t min_count, void* workspace, size_t workspace_bytes,
+                          int64_t* offsets, void* stream);
+/* repeat_interleave: out_values[j] = values[i] (elements of 4 or 8 bytes; nullable) and owner[j] = i (nullable) for
+ * offsets[i] <= j < offsets[i + 1], j < total = offsets[n] */
+int ppg_expand_offsets(const int64_t* offsets, int64_t n, int64_t total, const void* values, int value_bytes,
+                       void* out_values, int64_t* owner, void* stream);
+/* edge_index [2, total - num_walks]: the links p -> p + 1 (plus base) inside every walk, the walks laid end to end at
+ * offsets [num_walks + 1]; every walk has at least one position */
+int ppg_walk_chain(const int64_t* offsets, int64_t num_walks, int64_t total, int64_t base, int64_t* edge_index, void* stream);
+/* counts [num_bins] (int64) = occurrences of every id; bit 0 of the zeroed status_word is set if an id is outside
+ * [0, num_bins) */
+int ppg_bincount(const int64_t* ids, int64_t n, int64_t num_bins, int64_t* counts, void* status_word, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Shortest time-respecting paths   reference: src/pathpyG/algorithms/temporal.py:57-107
  *   edge_index [2,m] time-sorted events, event_graph [2,num_pairs] = the a1 output for the same delta.
  *   For the sources [source_begin, source_end) (source_begin a multiple of 32):

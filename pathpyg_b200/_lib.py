@@ -99,6 +99,11 @@ PROTOTYPES = {
     "ppg_gcn_fused_supported": (c_int, [_i64, _i64]),
     "ppg_gcn_layer_fused": (c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, c_int, _p, _p]),
     "ppg_bipartite_fused": (c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, c_int, _p, _p]),
+    "ppg_counts_to_offsets_workspace_bytes": (c_size_t, [_i64]),
+    "ppg_counts_to_offsets": (c_int, [_p, _i64, _i64, _p, c_size_t, _p, _p]),
+    "ppg_expand_offsets": (c_int, [_p, _i64, _i64, _p, c_int, _p, _p, _p]),
+    "ppg_walk_chain": (c_int, [_p, _i64, _i64, _i64, _p, _p]),
+    "ppg_bincount": (c_int, [_p, _i64, _i64, _p, _p, _p]),
     "ppg_gcn_tc_supported": (c_int, [_i64, _i64]),
     "ppg_gcn_layer_tc": (c_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, c_int, _p, _p]),
     "ppg_act_backward_workspace_bytes": (c_size_t, [_i64, _i64]),

@@ -292,9 +292,9 @@ class MultiOrderModel:
         dev, to_host = _staging.compute_device(pg.edge_index, pg.node_sequence)
         edge_index = _plain(_staging.up(pg.edge_index, dev)).long()
         node_sequence = _plain(_staging.up(pg.node_sequence, dev)).long()
-        edge_weight = _staging.up(pg.dag_weight, dev).repeat_interleave(_staging.up(pg.dag_num_edges, dev))
+        edge_weight = ops.repeat_by_count(_staging.up(pg.dag_weight, dev), _staging.up(pg.dag_num_edges, dev))   # :217
         if mode == "diffusion":
-            outdeg = torch.bincount(edge_index[0], minlength=node_sequence.size(0))
+            outdeg = ops.bincount(edge_index[0], node_sequence.size(0))
             edge_weight = edge_weight / outdeg[edge_index[0]]
             aggr = "mul"
         elif mode == "propagation":
@@ -355,7 +355,7 @@ class MultiOrderModel:
         """``torch.unique(node_sequence, return_counts=True)[1]`` (:335): occurrence counts of the node ids that
         occur, in ascending id order -- ids that never occur are SKIPPED, as in the reference (:336-337)."""
         ids = node_sequence.reshape(-1)
-        counts = torch.bincount(ids)
+        counts = ops.bincount(ids)
         return counts if bool((counts > 0).all()) else counts[counts > 0]
 
     def get_zeroth_order_log_likelihood(self, dag_graph: Data) -> float:
@@ -379,7 +379,7 @@ class MultiOrderModel:
         keep = shrunk > 0
         lengths = shrunk[keep]                                                    # :358
         freq = freq[keep]                                                         # :359
-        starts = torch.cumsum(lengths, 0) - lengths                               # cumsum(.)[:-1] of the zero-prefixed sum, :361
+        starts = ops.counts_to_offsets(lengths)[0][:-1]                           # cumsum(.)[:-1] of the zero-prefixed sum, :361
         prob = self.layers[order].transition_probabilities()                      # unweighted, as in the reference (:363)
         inverse = _staging.up(self.layers[order + 1].data.inverse_idx, dev)
         return ops.weighted_log_sum(freq, _staging.up(prob, dev), starts, inverse)    # :363-369
@@ -398,7 +398,7 @@ class MultiOrderModel:
         # zeroth-order model: weighted node frequencies (:402-407)
         dev, _ = _staging.compute_device(dag_graph.node_sequence, dag_graph.dag_weight)
         ns = _plain(_staging.up(dag_graph.node_sequence, dev)).reshape(-1)
-        w = _staging.up(dag_graph.dag_weight, dev).repeat_interleave(_staging.up(dag_graph.dag_num_nodes, dev))
+        w = ops.repeat_by_count(_staging.up(dag_graph.dag_weight, dev), _staging.up(dag_graph.dag_num_nodes, dev))
         n_ids = int(ns.max()) + 1 if ns.numel() else 0
         # torch.bincount(ids, weights) adds the weights of a node in position order: group the positions by node
         # (stable) and sum every group in slot order

@@ -10,6 +10,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from .. import ops
 from .data import Data
 from .index_map import IndexMap
 
@@ -61,6 +62,18 @@ class PathData:
     def append_index_walks(self, flat_nodes: torch.Tensor, lengths: torch.Tensor, weights: torch.Tensor) -> None:
         """Walks given as one flat index tensor plus per-walk lengths (path_data.py:139-159 vectorised)."""
         dev = self.data.edge_index.device
+        lengths = lengths.to(dev).long()
+        if dev.type == "cuda":   # one scan + one kernel (csrc/walks.cu); the node offset of the container is folded in
+            d = self.data
+            chain = ops.walk_chain(lengths, base=int(d.num_nodes))
+            d.edge_index = torch.cat([d.edge_index, chain], dim=1)
+            d.node_sequence = torch.cat([d.node_sequence, flat_nodes.to(dev).long().unsqueeze(1)])
+            d.dag_weight = torch.cat([d.dag_weight, weights.to(dev).to(d.dag_weight.dtype)])
+            d.dag_num_edges = torch.cat([d.dag_num_edges, lengths - 1])
+            d.dag_num_nodes = torch.cat([d.dag_num_nodes, lengths])
+            d.num_nodes += chain.size(1) + lengths.numel()
+            return
+        # a container that lives in host memory (ingest before the upload): index plumbing on the host
         total = int(lengths.sum())
         pos = torch.arange(total, device=dev)
         chain = torch.stack([pos[:-1], pos[1:]])

@@ -550,6 +550,70 @@ def extend_owned_rows(prev_rows: torch.Tensor, prev_row_lo: int, src_ids: torch.
     return out
 
 
+# --------------------------------------------------------------------------------------- a7 / a9 bookkeeping
+def counts_to_offsets(counts: torch.Tensor, min_count: int = 0, what: str = "counts"):
+    """(offsets [n + 1] int64, total): exclusive prefix sums of int64 counts (``torch.cumsum`` with a leading zero);
+    counts below ``min_count`` raise ValueError.  One host synchronisation (the total sizes what follows)."""
+    lib = _lib.load()
+    dev = _require_cuda(counts)
+    counts = counts.contiguous().long()
+    n = counts.numel()
+    offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        ws = _workspace(lib.ppg_counts_to_offsets_workspace_bytes(n), dev)
+        _lib.check(lib.ppg_counts_to_offsets(_ptr(counts), n, int(min_count), _ptr(ws), ws.numel(), _ptr(offsets), _stream(dev)))
+        total, status = ctypes.c_int64(0), ctypes.c_int(0)
+        _lib.check(lib.ppg_result_read(_ptr(ws), ctypes.byref(total), ctypes.byref(status), _stream(dev)))
+    if status.value & 1:
+        raise ValueError(f"{what}: a count is below {min_count}")
+    return offsets, total.value
+
+
+def repeat_by_count(values: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """``values.repeat_interleave(counts)`` for 1-D values of 4 or 8 bytes per element (multi_order_model.py:217,402)."""
+    lib = _lib.load()
+    dev = _require_cuda(values, counts)
+    values = values.contiguous()
+    if values.dim() != 1 or values.numel() != counts.numel() or values.element_size() not in (4, 8):
+        raise ValueError(f"repeat_by_count: values {tuple(values.shape)} {values.dtype}, counts {tuple(counts.shape)}")
+    offsets, total = counts_to_offsets(counts, 0, "repeat_interleave")
+    out = torch.empty(total, dtype=values.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_expand_offsets(_ptr(offsets), counts.numel(), total, _ptr(values), values.element_size(), _ptr(out),
+                                          None, _stream(dev)))
+    return out
+
+
+def walk_chain(lengths: torch.Tensor, base: int = 0) -> torch.Tensor:
+    """edge_index [2, sum(lengths) - len(lengths)] of the links p -> p + 1 (+ base) inside walks laid end to end
+    (path_data.py:139-159: arange, stack, drop the links between consecutive walks)."""
+    lib = _lib.load()
+    dev = _require_cuda(lengths)
+    offsets, total = counts_to_offsets(lengths, 1, "walk lengths")
+    w = lengths.numel()
+    out = torch.empty((2, total - w), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_walk_chain(_ptr(offsets), w, total, int(base), _ptr(out), _stream(dev)))
+    return out
+
+
+def bincount(ids: torch.Tensor, num_bins: int | None = None) -> torch.Tensor:
+    """``torch.bincount(ids, minlength=num_bins)`` with exactly ``num_bins`` bins (default: largest id + 1); ids outside
+    [0, num_bins) raise ValueError."""
+    lib = _lib.load()
+    dev = _require_cuda(ids)
+    ids = ids.reshape(-1).contiguous().long()
+    if num_bins is None:
+        num_bins = int(ids.max()) + 1 if ids.numel() else 0
+    counts = torch.empty(int(num_bins), dtype=torch.int64, device=dev)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ppg_bincount(_ptr(ids), ids.numel(), int(num_bins), _ptr(counts), _ptr(status), _stream(dev)))
+    if int(status[0]) & 1:
+        raise ValueError(f"bincount: id outside [0, {num_bins})")
+    return counts
+
+
 # --------------------------------------------------------------------------------------- a10 / a11
 class TargetGroupedEdges:
     """CSC view of an edge list: incoming edges of every target node, original order inside a target."""
