@@ -121,14 +121,16 @@ struct TmemLoad<32> {
 // ELU: expm1 for x <= 0 without the slow library path.  |x| < 0.125: degree-5 Taylor polynomial (truncation
 // < 5e-8 relative); below: exp(x) - 1 with ex2.approx (result magnitude >= 0.117, absolute error ~2e-7: < 2e-6 relative).
 __device__ __forceinline__ float tc_activate(float x, int act) {
-  if (act != PPG_ACT_ELU || x > 0.f) return x;
+  // branch-free: both sides are evaluated for every element anyway (a warp holds positive and negative values), and a
+  // branch costs a reconvergence barrier per element
   float p = fmaf(x, 1.f / 120.f, 1.f / 24.f);
   p = fmaf(p, x, 1.f / 6.f);
   p = fmaf(p, x, 0.5f);
   p = fmaf(p, x, 1.f);
   p *= x;
   const float e = __expf(x) - 1.f;
-  return x > -0.125f ? p : e;
+  const float neg = x > -0.125f ? p : e;
+  return (act != PPG_ACT_ELU || x > 0.f) ? x : neg;
 }
 
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
@@ -702,21 +704,31 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 }
 // mbarrier wait that parks the thread in hardware (try_wait) instead of polling test_wait: the waiting role must not
 // take issue slots from the working one
+#ifndef PPG_SG_SLEEP
+#define PPG_SG_SLEEP 128
+#endif
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  // a parked warp polls every PPG_SG_SLEEP ns: re-polling at once (every arrival on any barrier of the CTA wakes it) took
+  // a third of all issued instructions away from the warps that had work (profiles/r02ar)
   int spins = 0;
-  while (!done) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"   // suspend-time hint (ns)
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && ++spins > (1 << 22)) __trap();  // a lost arrival must fail loudly, not hang the device
-  }
+  do {
+    __nanosleep(PPG_SG_SLEEP);
+    if (++spins > (1 << 22)) __trap();  // a lost arrival must fail loudly, not hang the device
+  } while (!mbar_try_wait(bar, parity));
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSgConsumers) : "memory"); }
 
