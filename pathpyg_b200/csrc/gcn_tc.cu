@@ -723,7 +723,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   // a parked warp polls every PPG_SG_SLEEP ns: re-polling at once (every arrival on any barrier of the CTA wakes it) took
-  // a third of all issued instructions away from the warps that had work (profiles/r02ar)
+  // a third of all issued instructions away from the warps that had work
   int spins = 0;
   do {
     __nanosleep(PPG_SG_SLEEP);
@@ -848,7 +848,7 @@ gcn_tc_staged_kernel(const int32_t* __restrict__ colptr, const int32_t* __restri
     // Producer warp pw owns stage pw, i.e. the chunks with (running chunk number) % stages == pw: it requests all rows of
     // the chunk, waits for them and signals the stage with ONE arrival (every arrival on any mbarrier of the CTA wakes
     // the warps parked on the others; 128 per-thread arrivals per chunk cost a third of all issued instructions in
-    // re-polls -- profiles/r02ao).  A warp that owns its stage sees every phase of the stage's barriers, which a
+    // re-polls -- DESIGN.md section 4.2).  A warp that owns its stage sees every phase of the stage's barriers, which a
     // parity wait needs.
     constexpr int WPL = C / 32;                       // src words (= rows) of a chunk per lane
     static_assert(C % 32 == 0, "chunk geometry");
@@ -1119,8 +1119,8 @@ extern "C" int ppg_gcn_layer_tc(const int32_t* colptr, const int32_t* src, const
   // the single-role one (every warp gathers a batch of rows into registers, then one thread issues the MMAs, then
   // every warp runs the epilogue) and the warp-specialised one (gather warps fill operand buffer i + 1 while the MMA /
   // epilogue warps work on tile i, two TMEM accumulators).  Sparse graphs (at most 4 slots per node: the higher-order
-  // De Bruijn layers, 248 against 324 us at cfg2) take the staged kernel, dense ones (the first-order layer of cfg2, 10
-  // slots per node: 77 against 101 us) the single-role kernel, where one lane group streams a long slot range with 8
+  // De Bruijn layers, 217 against 309 us at cfg2) take the staged kernel, dense ones (the first-order layer of cfg2, 10
+  // slots per node: 76 against 92 us) the single-role kernel, where one lane group streams a long slot range with 8
   // loads in flight while a stage of the staged kernel would serve only one or two consumer warps.
   // PPG_GCN_TC=staged|single|ws forces one (PPG_GCN_TC_WS=1 is the older spelling of ws); a feature matrix that is not
   // 16-byte aligned takes the single-role kernel.  Measurements: DESIGN.md section 4.2.
