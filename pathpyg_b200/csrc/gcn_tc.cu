@@ -654,10 +654,12 @@ gcn_tc_ws_kernel(const int32_t* __restrict__ colptr, const int32_t* __restrict__
 //     warp requests the 128 rows with cp.async.cg (16 bytes per lane, L1 bypassed) and the slot values with 4-byte
 //     cp.async, waits for them (cp.async.wait_all) and signals the stage's `full` barrier with one arrival.  Producers
 //     only wait for their stage, so the rows of tiles t + 1, t + 2 travel while tile t is multiplied and written.
-//   * Consumer warps: thread = (16-byte chunk of the row, nodes G, G + groups, ...), accumulators in registers; the
-//     nodes' own rows (contiguous in X) are requested with plain loads at the top of the tile and used at its end; per
-//     stage a thread adds the slots of its nodes that fall into the chunk (ld.shared.v4 + 4 FMA per row and lane),
-//     then releases the stage (`empty` barrier).  Same summation order as the other two kernels: bit-identical.
+//   * Consumer warps: a lane group (F/4 lanes, 16 bytes of the row each) owns 128/groups consecutive nodes and keeps
+//     their sums in registers; the nodes' own rows (contiguous in X) are requested with plain loads at the top of the
+//     tile and used at its end; per stage a thread adds the slots of its nodes that fall into the chunk (ld.shared.v4
+//     + 4 FMA per row and lane), then the warp releases the stage (`empty` barrier).  Same summation order as the
+//     other two kernels: bit-identical.  A warp starts the next tile without waiting for the others (the CSC
+//     pointers are stored two tiles ahead in one of three buffers).
 //   * One more warp issues the MMAs (the issue of 24 tcgen05.mma blocks its thread for 1.7 us per tile) into one of
 //     two TMEM accumulators as soon as every consumer warp has arrived on the `operands ready` barrier; while they run
 //     the consumers convert, activate and store tile t - 1 straight from TMEM to global memory (thread = one row, 16
@@ -674,7 +676,7 @@ constexpr int kSgConsumers = 512;
 #ifndef PPG_SG_STAGES
 #define PPG_SG_STAGES 3
 #endif
-constexpr int kSgChunk = PPG_SG_CHUNK;     // rows per stage (multiple of 16, at most 128; experiment builds: make variant)
+constexpr int kSgChunk = PPG_SG_CHUNK;     // rows per stage (multiple of 32, at most 128; experiment builds: make variant)
 constexpr int kSgStages = PPG_SG_STAGES;
 constexpr int kSgProducers = 32 * kSgStages;                   // one producer warp per stage
 constexpr int kSgThreads = kSgConsumers + kSgProducers + 32;   // + the warp whose lane 0 issues the MMAs
@@ -684,10 +686,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-// the executing thread arrives on the barrier once all its earlier cp.async copies have landed
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ float lds32(uint32_t addr) {
   float v;
@@ -702,8 +700,8 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
-// mbarrier wait that parks the thread in hardware (try_wait) instead of polling test_wait: the waiting role must not
-// take issue slots from the working one
+// mbarrier wait of a role that has nothing else to do: try_wait (which may suspend the thread in hardware), then sleep
+// between polls -- the waiting role must not take issue slots from the working one
 #ifndef PPG_SG_SLEEP
 #define PPG_SG_SLEEP 128
 #endif
