@@ -198,8 +198,9 @@ class DBGNN(nn.Module):
         # The first-order and the higher-order stack do not depend on each other until the bipartite layer.  Without
         # autograd a small (latency-bound) first-order stack runs on a second stream under the higher-order one
         # (cfg2, 1M first-order edges: 1.45 -> 1.39 ms); kernels that fill the GPU on their own only get in each
-        # other's way (cfg3, 10M edges: 19.2 -> 20.7 ms), so large graphs stay on one stream.
-        fork = not grad and not drop and ei.size(1) <= _FORK_MAX_EDGES
+        # other's way (cfg3, 10M edges: 19.2 -> 20.7 ms), so large graphs stay on one stream.  PPG_DBGNN_FORK=0 keeps
+        # everything on one stream (A/B at the end of round 2, with the staged HO kernel: 1.32 against 1.33-1.37 ms).
+        fork = not grad and not drop and ei.size(1) <= _FORK_MAX_EDGES and os.environ.get("PPG_DBGNN_FORK", "1") != "0"
         if fork:
             main = torch.cuda.current_stream(x.device)
             side = _side_stream(x.device)
