@@ -1,4 +1,6 @@
 """Host-side containers and the no-fallback rule.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -92,3 +94,29 @@ def test_product_never_imports_the_oracle():
     for path in root.rglob("*.py"):
         text = path.read_text()
         assert "import oracle" not in text and "from oracle" not in text, path
+
+
+def test_bench_prints_only_the_json_line_on_stdout(tmp_path):
+    """bench.py's contract is ONE JSON line on stdout: whatever a library writes to file descriptor 1 during the run
+    (NCCL announces its version there) must end up on stderr."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, sys; sys.path.insert(0, %r); import bench\n"
+            "bench._only_json_on_stdout(lambda: (os.write(1, b'library chatter\\n'), print('{\"metric\": 1}')))\n" % root)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-500:]
+    assert res.stdout == '{"metric": 1}\n'
+    assert "library chatter" in res.stderr
+
+
+def test_bench_reference_arm_and_gpu_arm_describe_the_same_config():
+    """The driver compares the two arms' `config`: both come from bench.static_config."""
+    import bench
+
+    for name in bench.WORKLOADS:
+        for world in (1, 2, 8):
+            cfg = bench.static_config(name, world)
+            assert cfg["name"] == name and cfg["workload"] == bench.WORKLOADS[name]["label"]
+            assert "model" not in cfg
