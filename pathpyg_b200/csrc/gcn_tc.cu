@@ -725,7 +725,7 @@ __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) 
   int spins = 0;
   do {
     __nanosleep(PPG_SG_SLEEP);
-    if (++spins > (1 << 22)) __trap();  // a lost arrival must fail loudly, not hang the device
+    if (++spins > (1 << 25)) __trap();  // a lost arrival must fail loudly (after ~4 s), not hang the device
   } while (!mbar_try_wait(bar, parity));
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSgConsumers) : "memory"); }
